@@ -1,0 +1,714 @@
+/*
+ * glg_oracle.c -- CPU parity oracle (TEST INFRASTRUCTURE ONLY; see glg_oracle.h for the pinning status).
+ *
+ * Restates, in plain C99 fp64 and in the reference's operation order:
+ *   update()  gl_gym/environments/models/aux_states.hpp:96-1271  (helpers :5-93)
+ *   ODE()     gl_gym/environments/models/ode.hpp:6-124
+ *   the integration contract of greenlight_model.cpp:43-63 as fixed-step RK4 (see header)
+ *   TomatoEnv.step/reset semantics (tomato_env.py, observations.py, rewards.py, noise.py, utils.py)
+ * Variable names follow the GreenLight model's own nomenclature (the names in the reference's comments);
+ * A(k) records the value the reference stores in a[k] so tests can compare all 239 auxiliaries.
+ *
+ * No -ffast-math: cond() relies on IEEE exp overflow -> inf -> 1/(1+inf) = 0.
+ */
+#include "glg_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+#define C2K 273.15
+static const float C2K_F32 = 273.15f; /* airMv's `const float c2k` aux_states.hpp:84 */
+
+/* ---- helpers, aux_states.hpp:5-93 ---- */
+static inline double sat_vp(double t) { return 610.78 * exp(17.2694 * t / (t + 238.3)); }                 /* :5-12 */
+static inline double dens2ppm(double t, double dens) {                                                     /* :14-23 */
+    return 1e6 * 8.3144598 * (t + C2K) * dens / (101325 * 44.01e-3);
+}
+static inline double lay_tau(double t1, double t2, double r1dn, double r2up) {                             /* :25-29 */
+    return t1 * t2 / (1. - r1dn * r2up);
+}
+static inline double lay_rho_up(double t1, double r1up, double r1dn, double r2up) {                        /* :31-35 */
+    return r1up + (t1 * t1 * r2up) / (1. - r1dn * r2up);
+}
+static inline double lay_rho_dn(double t2, double r1dn, double r2up, double r2dn) {                        /* :37-41 */
+    return r2dn + (t2 * t2 * r1dn) / (1. - r1dn * r2up);
+}
+static inline double fir_flux(double area, double e1, double e2, double f12, double t1, double t2, double sg) { /* :48-52 */
+    return area * e1 * e2 * f12 * sg * (pow(t1 + C2K, 4.) - pow(t2 + C2K, 4.));
+}
+static inline double sens(double hec, double t1, double t2) { return fabs(hec) * (t1 - t2); }               /* :54-58 */
+static inline double condens(double hec, double vp1, double vp2) {                                          /* :60-63 */
+    return 1.0 / (1.0 + exp(-0.1 * (vp1 - vp2))) * 6.4e-9 * hec * (vp1 - vp2);
+}
+static inline double smooth_harvest(double v, double cutoff, double smooth, double max_rate) {             /* :75-79 */
+    double k = 2.0 * 4.6052 / smooth;
+    double z = k * (v - cutoff) / 2.0;
+    return max_rate * (tanh(z) + 1.0) / 2.0;
+}
+static inline double air_mv(double f12, double vp1, double vp2, double t1, double t2) {                     /* :81-87 */
+    return 0.002165 * fabs(f12) * (vp1 / (t1 + C2K_F32) - vp2 / (t2 + C2K_F32));
+}
+static inline double air_mc(double f12, double c1, double c2) { return fabs(f12) * (c1 - c2); }             /* :89-93 */
+
+void glgo_aux_rhs(const double *x, const double *u, const double *d, const double *p, double *a, double *dxdt) {
+    double aux_local[GLGO_NA];
+    double *av = a ? a : aux_local;
+#define A(k) av[k]
+    const double co2Air = x[0], co2Top = x[1], tAir = x[2], tTop = x[3], tCan = x[4], tCovIn = x[5], tCovE = x[6];
+    const double tThScr = x[7], tFlr = x[8], tPipe = x[9], tSo1 = x[10], tSo2 = x[11], tSo3 = x[12], tSo4 = x[13];
+    const double tSo5 = x[14], vpAir = x[15], vpTop = x[16], tLamp = x[17], tIntLamp = x[18], tGroPipe = x[19];
+    const double tBlScr = x[20], tCan24 = x[21], cBuf = x[22], cLeaf = x[23], cStem = x[24], cFruit = x[25];
+    const double tCanSum = x[26];
+    const double uBoil = u[0], uCo2 = u[1], thScr = u[2], uVent = u[3], uLamp = u[4], blScr = u[5];
+    const double iGlob = d[0], tOut = d[1], vpOut = d[2], co2Out = d[3], wind = d[4], tSky = d[5], tSoOut = d[6];
+    const double sigma = p[2];
+    int k;
+
+    /* ---- cover optics: roof + thermal screen, PAR then NIR (:111-139) ---- */
+    double tauThScrPar = 1 - thScr * (1 - p[80]);
+    double rhoThScrPar = thScr * p[77];
+    double tauCovThScrPar = lay_tau(p[69], tauThScrPar, p[66], rhoThScrPar);
+    double rhoCovThScrParUp = lay_rho_up(p[69], p[66], p[66], rhoThScrPar);
+    double rhoCovThScrParDn = lay_rho_dn(tauThScrPar, p[66], rhoThScrPar, rhoThScrPar);
+    double tauThScrNir = 1 - thScr * (1 - p[79]);
+    double rhoThScrNir = thScr * p[76];
+    double tauCovThScrNir = lay_tau(p[68], tauThScrNir, p[65], rhoThScrNir);
+    double rhoCovThScrNirUp = lay_rho_up(p[68], p[65], p[65], rhoThScrNir);
+    double rhoCovThScrNirDn = lay_rho_dn(tauThScrNir, p[65], rhoThScrNir, rhoThScrNir);
+    A(0) = tauThScrPar; A(1) = rhoThScrPar; A(2) = tauCovThScrPar; A(3) = rhoCovThScrParUp; A(4) = rhoCovThScrParDn;
+    A(5) = tauThScrNir; A(6) = rhoThScrNir; A(7) = tauCovThScrNir; A(8) = rhoCovThScrNirUp; A(9) = rhoCovThScrNirDn;
+
+    /* ---- + blackout screen (:145-177) ---- */
+    double tauBlScrPar = 1 - blScr * (1 - p[90]);
+    double rhoBlScrPar = blScr * p[88];
+    double tauCovBlScrPar = lay_tau(tauCovThScrPar, tauBlScrPar, rhoCovThScrParDn, rhoBlScrPar);
+    double rhoCovBlScrParUp = lay_rho_up(tauCovThScrPar, rhoCovThScrParUp, rhoCovThScrParDn, rhoBlScrPar);
+    double rhoCovBlScrParDn = lay_rho_dn(tauBlScrPar, rhoCovThScrParDn, rhoBlScrPar, rhoBlScrPar);
+    double tauBlScrNir = 1 - blScr * (1 - p[89]);
+    double rhoBlScrNir = blScr * p[87];
+    double tauCovBlScrNir = lay_tau(tauCovThScrNir, tauBlScrNir, rhoCovThScrNirDn, rhoBlScrNir);
+    double rhoCovBlScrNirUp = lay_rho_up(tauCovThScrNir, rhoCovThScrNirUp, rhoCovThScrNirDn, rhoBlScrNir);
+    double rhoCovBlScrNirDn = lay_rho_dn(tauBlScrNir, rhoCovThScrNirDn, rhoBlScrNir, rhoBlScrNir);
+    A(10) = tauBlScrPar; A(11) = rhoBlScrPar; A(12) = tauCovBlScrPar; A(13) = rhoCovBlScrParUp; A(14) = rhoCovBlScrParDn;
+    A(15) = tauBlScrNir; A(16) = rhoBlScrNir; A(17) = tauCovBlScrNir; A(18) = rhoCovBlScrNirUp; A(19) = rhoCovBlScrNirDn;
+
+    /* ---- + lamp layer => whole cover (:183-227) ---- */
+    double tauCovPar = lay_tau(tauCovBlScrPar, p[176], rhoCovBlScrParDn, p[179]);
+    double rhoCovPar = lay_rho_up(tauCovBlScrPar, rhoCovBlScrParUp, rhoCovBlScrParDn, p[179]);
+    double tauCovNir = lay_tau(tauCovBlScrNir, p[177], rhoCovBlScrNirDn, p[180]);
+    double rhoCovNir = lay_rho_up(tauCovBlScrNir, rhoCovBlScrNirUp, rhoCovBlScrNirDn, p[180]);
+    double tauCovFir = p[70];
+    double rhoCovFir = p[67];
+    double aCovPar = 1 - tauCovPar - rhoCovPar;
+    double aCovNir = 1 - tauCovNir - rhoCovNir;
+    double aCovFir = 1 - tauCovFir - rhoCovFir;
+    double epsCovFir = aCovFir;
+    double capCov = cos(p[45] * M_PI / 180.) * p[73] * p[64] * p[72];
+    A(20) = tauCovPar; A(21) = rhoCovPar; A(22) = tauCovNir; A(23) = rhoCovNir; A(24) = tauCovFir; A(25) = rhoCovFir;
+    A(26) = aCovPar; A(27) = aCovNir; A(28) = aCovFir; A(29) = epsCovFir; A(30) = capCov;
+
+    /* ---- capacities (:233-249) ---- */
+    double lai = p[142] * cLeaf;
+    double capCan = p[16] * lai;
+    double capCovE = 0.1 * capCov;
+    double capCovIn = 0.1 * capCov;
+    double capVpAir = p[38] * p[48] / (p[39] * (tAir + C2K));
+    double capVpTop = p[38] * (p[49] - p[48]) / (p[39] * (tTop + C2K));
+    A(31) = lai; A(32) = capCan; A(33) = capCovE; A(34) = capCovIn; A(35) = capVpAir; A(36) = capVpTop;
+
+    /* ---- lamp/sun radiation above the canopy (:256-295) ---- */
+    double qLampIn = p[172] * uLamp;
+    double qIntLampIn = 0;
+    double rParGhSun = (1 - p[44]) * tauCovPar * p[6] * iGlob;
+    double rParGhLamp = p[174] * qLampIn;
+    double rParGhIntLamp = p[192] * qIntLampIn;
+    double rCanSun = (1 - p[44]) * iGlob * (p[6] * tauCovPar + p[5] * tauCovNir);
+    double rCanLamp = (p[174] + p[175]) * qLampIn;
+    double rCanIntLamp = (p[192] + p[193]) * qIntLampIn;
+    double rCan = rCanSun + rCanLamp + rCanIntLamp;
+    A(37) = qLampIn; A(38) = qIntLampIn; A(39) = rParGhSun; A(40) = rParGhLamp; A(41) = rParGhIntLamp;
+    A(42) = rCanSun; A(43) = rCanLamp; A(44) = rCanIntLamp; A(45) = rCan;
+
+    /* ---- PAR absorbed by the canopy (:299-355) ---- */
+    double rParSunCanDown = rParGhSun * (1 - p[10]) * (1 - exp(-p[32] * lai));
+    double rParLampCanDown = rParGhLamp * (1 - p[10]) * (1 - exp(-p[32] * lai));
+    double fIntLampCanPar = 1 - p[190] * exp(-p[200] * p[189] * lai) + (p[190] - 1) * exp(-p[200] * (1 - p[189]) * lai);
+    double fIntLampCanNir = 1 - p[190] * exp(-p[202] * p[189] * lai) + (p[190] - 1) * exp(-p[202] * (1 - p[189]) * lai);
+    double rParIntLampCanDown = rParGhIntLamp * fIntLampCanPar * (1 - p[10]);
+    double rParSunFlrCanUp = rParGhSun * exp(-p[32] * lai) * p[98] * (1 - p[10]) * (1 - exp(-p[33] * lai));
+    double rParLampFlrCanUp = rParGhLamp * exp(-p[32] * lai) * p[98] * (1 - p[10]) * (1 - exp(-p[33] * lai));
+    double rParIntLampFlrCanUp =
+        rParGhIntLamp * p[190] * exp(-p[200] * p[189] * lai) * p[98] * (1 - p[10]) * (1 - exp(-p[201] * lai));
+    double rParSunCan = rParSunCanDown + rParSunFlrCanUp;
+    double rParLampCan = rParLampCanDown + rParLampFlrCanUp;
+    double rParIntLampCan = rParIntLampCanDown + rParIntLampFlrCanUp;
+    A(46) = rParSunCanDown; A(47) = rParLampCanDown; A(48) = fIntLampCanPar; A(49) = fIntLampCanNir;
+    A(50) = rParIntLampCanDown; A(51) = rParSunFlrCanUp; A(52) = rParLampFlrCanUp; A(53) = rParIntLampFlrCanUp;
+    A(54) = rParSunCan; A(55) = rParLampCan; A(56) = rParIntLampCan;
+
+    /* ---- virtual NIR multilayer cover-canopy-floor (:360-401) ---- */
+    double tauHatCovNir = 1 - rhoCovNir;
+    double tauHatFlrNir = 1 - p[97];
+    double tauHatCanNir = exp(-p[34] * lai);
+    double rhoHatCanNir = p[11] * (1 - tauHatCanNir);
+    double tauCovCanNir = lay_tau(tauHatCovNir, tauHatCanNir, rhoCovNir, rhoHatCanNir);
+    double rhoCovCanNirUp = lay_rho_up(tauHatCovNir, rhoCovNir, rhoCovNir, rhoHatCanNir);
+    double rhoCovCanNirDn = lay_rho_dn(tauHatCanNir, rhoCovNir, rhoHatCanNir, rhoHatCanNir);
+    double tauCovCanFlrNir = lay_tau(tauCovCanNir, tauHatFlrNir, rhoCovCanNirDn, p[97]);
+    double rhoCovCanFlrNir = lay_rho_up(tauCovCanNir, rhoCovCanNirUp, rhoCovCanNirDn, p[97]);
+    double aCanNir = 1 - tauCovCanFlrNir - rhoCovCanFlrNir;
+    double aFlrNir = tauCovCanFlrNir;
+    A(57) = tauHatCovNir; A(58) = tauHatFlrNir; A(59) = tauHatCanNir; A(60) = rhoHatCanNir; A(61) = tauCovCanNir;
+    A(62) = rhoCovCanNirUp; A(63) = rhoCovCanNirDn; A(64) = tauCovCanFlrNir; A(65) = rhoCovCanFlrNir;
+    A(66) = aCanNir; A(67) = aFlrNir;
+
+    /* ---- NIR / PAR absorbed by canopy, floor, air, cover (:406-470) ---- */
+    double rNirSunCan = (1 - p[44]) * aCanNir * p[5] * iGlob;
+    double rNirLampCan = p[175] * qLampIn * (1 - p[11]) * (1 - exp(-p[34] * lai));
+    double rNirIntLampCan = p[193] * qIntLampIn * fIntLampCanNir * (1 - p[11]);
+    double rNirSunFlr = (1 - p[44]) * aFlrNir * p[5] * iGlob;
+    double rNirLampFlr = (1 - p[97]) * exp(-p[34] * lai) * p[175] * qLampIn;
+    double rNirIntLampFlr = p[190] * (1 - p[97]) * exp(-p[202] * lai * p[189]) * p[193] * qIntLampIn;
+    double rParSunFlr = (1 - p[98]) * exp(-p[32] * lai) * rParGhSun;
+    double rParLampFlr = (1 - p[98]) * exp(-p[32] * lai) * rParGhLamp;
+    double rParIntLampFlr = rParGhIntLamp * p[190] * (1 - p[98]) * exp(-p[200] * lai * p[189]);
+    double rLampAir = (p[174] + p[175]) * qLampIn - rParLampCan - rNirLampCan - rParLampFlr - rNirLampFlr;
+    double rIntLampAir =
+        (p[192] + p[193]) * qIntLampIn - rParIntLampCan - rNirIntLampCan - rParIntLampFlr - rNirIntLampFlr;
+    double rGlobSunAir = p[44] * iGlob * (tauCovPar * p[6] + (aCanNir + aFlrNir) * p[5]);
+    double rGlobSunCovE = (aCovPar * p[6] + aCovNir * p[5]) * iGlob;
+    A(68) = rNirSunCan; A(69) = rNirLampCan; A(70) = rNirIntLampCan; A(71) = rNirSunFlr; A(72) = rNirLampFlr;
+    A(73) = rNirIntLampFlr; A(74) = rParSunFlr; A(75) = rParLampFlr; A(76) = rParIntLampFlr; A(77) = rLampAir;
+    A(78) = rIntLampAir; A(79) = rGlobSunAir; A(80) = rGlobSunCovE;
+
+    /* ---- FIR exchange (:476-691) ---- */
+    double tauThScrFirU = 1 - thScr * (1 - p[81]);
+    double tauBlScrFirU = 1 - blScr * (1 - p[91]);
+    double aCan = 1 - exp(-p[35] * lai);
+    A(81) = tauThScrFirU; A(82) = tauBlScrFirU; A(83) = aCan;
+    const double fPipeBlock = 0.49 * M_PI * p[107] * p[105]; /* the `0.49*pi*lPipe*phiPipeE` factor */
+    double rCanCovIn = fir_flux(aCan, p[3], epsCovFir, p[178] * tauThScrFirU * tauBlScrFirU, tCan, tCovIn, sigma);
+    double rCanSky = fir_flux(aCan, p[3], p[4], p[178] * tauCovFir * tauThScrFirU * tauBlScrFirU, tCan, tSky, sigma);
+    double rCanThScr = fir_flux(aCan, p[3], p[74], p[178] * thScr * tauBlScrFirU, tCan, tThScr, sigma);
+    double rCanFlr = fir_flux(aCan, p[3], p[95], p[125], tCan, tFlr, sigma);
+    double rPipeCovIn = fir_flux(p[124], p[104], epsCovFir,
+                                 p[199] * p[178] * tauThScrFirU * tauBlScrFirU * 0.49 * exp(-p[35] * lai), tPipe, tCovIn, sigma);
+    /* reference :520 omits tauBlScrFirU (a[82]) here although its comment includes it */
+    double rPipeSky = fir_flux(p[124], p[104], p[4], p[199] * p[178] * tauCovFir * tauThScrFirU * 0.49 * exp(-p[35] * lai),
+                               tPipe, tSky, sigma);
+    double rPipeThScr = fir_flux(p[124], p[104], p[74], p[199] * p[178] * thScr * tauBlScrFirU * 0.49 * exp(-p[35] * lai),
+                                 tPipe, tThScr, sigma);
+    double rPipeFlr = fir_flux(p[124], p[104], p[95], 0.49, tPipe, tFlr, sigma);
+    double rPipeCan = fir_flux(p[124], p[104], p[3], 0.49 * (1 - exp(-p[35] * lai)), tPipe, tCan, sigma);
+    double rFlrCovIn = fir_flux(1, p[95], epsCovFir,
+                                p[199] * p[178] * tauThScrFirU * tauBlScrFirU * (1 - 0.49 * M_PI * p[107] * p[105]) * exp(-p[35] * lai),
+                                tFlr, tCovIn, sigma);
+    double rFlrSky = fir_flux(1, p[95], p[4],
+                              p[199] * p[178] * tauCovFir * tauThScrFirU * tauBlScrFirU * (1 - 0.49 * M_PI * p[107] * p[105]) * exp(-p[35] * lai),
+                              tFlr, tSky, sigma);
+    double rFlrThScr = fir_flux(1, p[95], p[74],
+                                p[199] * p[178] * thScr * tauBlScrFirU * (1 - 0.49 * M_PI * p[107] * p[105]) * exp(-p[35] * lai),
+                                tFlr, tThScr, sigma);
+    double rThScrCovIn = fir_flux(1, p[74], epsCovFir, thScr, tThScr, tCovIn, sigma);
+    double rThScrSky = fir_flux(1, p[74], p[4], tauCovFir * thScr, tThScr, tSky, sigma);
+    double rCovESky = fir_flux(1, aCovFir, p[4], 1, tCovE, tSky, sigma);
+    double rFirLampFlr = fir_flux(p[181], p[183], p[95], p[199] * (1 - 0.49 * M_PI * p[107] * p[105]) * exp(-p[35] * lai),
+                                  tLamp, tFlr, sigma);
+    double rLampPipe = fir_flux(p[181], p[183], p[104], p[199] * 0.49 * M_PI * p[107] * p[105] * exp(-p[35] * lai),
+                                tLamp, tPipe, sigma);
+    double rFirLampCan = fir_flux(p[181], p[183], p[3], aCan, tLamp, tCan, sigma);
+    double rLampThScr = fir_flux(p[181], p[182], p[74], thScr * tauBlScrFirU, tLamp, tThScr, sigma);
+    double rLampCovIn = fir_flux(p[181], p[182], epsCovFir, tauThScrFirU * tauBlScrFirU, tLamp, tCovIn, sigma);
+    double rLampSky = fir_flux(p[181], p[182], p[4], tauCovFir * tauThScrFirU * tauBlScrFirU, tLamp, tSky, sigma);
+    double rGroPipeCan = fir_flux(p[169], p[165], p[3], 1, tGroPipe, tCan, sigma);
+    double rFlrBlScr = fir_flux(1, p[95], p[85], p[199] * p[178] * blScr * (1 - 0.49 * M_PI * p[107] * p[105]) * exp(-p[35] * lai),
+                                tFlr, tBlScr, sigma);
+    double rPipeBlScr = fir_flux(p[124], p[104], p[85], p[199] * p[178] * blScr * 0.49 * exp(-p[35] * lai), tPipe, tBlScr, sigma);
+    double rCanBlScr = fir_flux(aCan, p[3], p[85], p[178] * blScr, tCan, tBlScr, sigma);
+    double rBlScrThScr = fir_flux(blScr, p[85], p[74], thScr, tBlScr, tThScr, sigma);
+    double rBlScrCovIn = fir_flux(blScr, p[85], epsCovFir, tauThScrFirU, tBlScr, tCovIn, sigma);
+    double rBlScrSky = fir_flux(blScr, p[85], p[4], tauCovFir * tauThScrFirU, tBlScr, tSky, sigma);
+    double rLampBlScr = fir_flux(p[181], p[182], p[85], blScr, tLamp, tBlScr, sigma);
+    double fIntLampCanUp = 1 - exp(-p[203] * (1 - p[189]) * lai);
+    double fIntLampCanDown = 1 - exp(-p[203] * p[189] * lai);
+    double rFirIntLampFlr = fir_flux(p[194], p[195], p[95], (1 - 0.49 * M_PI * p[107] * p[105]) * (1 - fIntLampCanDown),
+                                     tIntLamp, tFlr, sigma);
+    double rIntLampPipe = fir_flux(p[194], p[195], p[104], 0.49 * M_PI * p[107] * p[105] * (1 - fIntLampCanDown),
+                                   tIntLamp, tPipe, sigma);
+    double rFirIntLampCan = fir_flux(p[194], p[195], p[3], fIntLampCanDown + fIntLampCanUp, tIntLamp, tCan, sigma);
+    double rIntLampLamp = fir_flux(p[194], p[195], p[183], (1 - fIntLampCanUp) * p[181], tIntLamp, tLamp, sigma);
+    double rIntLampBlScr = fir_flux(p[194], p[195], p[85], blScr * p[178] * (1 - fIntLampCanUp), tIntLamp, tBlScr, sigma);
+    double rIntLampThScr = fir_flux(p[194], p[195], p[74], thScr * tauBlScrFirU * p[178] * (1 - fIntLampCanUp),
+                                    tIntLamp, tThScr, sigma);
+    double rIntLampCovIn = fir_flux(p[194], p[195], epsCovFir, tauThScrFirU * tauBlScrFirU * p[178] * (1 - fIntLampCanUp),
+                                    tIntLamp, tCovIn, sigma);
+    double rIntLampSky = fir_flux(p[194], p[195], p[4],
+                                  tauCovFir * tauThScrFirU * tauBlScrFirU * p[178] * (1 - fIntLampCanUp), tIntLamp, tSky, sigma);
+    (void)fPipeBlock;
+    A(84) = rCanCovIn; A(85) = rCanSky; A(86) = rCanThScr; A(87) = rCanFlr; A(88) = rPipeCovIn; A(89) = rPipeSky;
+    A(90) = rPipeThScr; A(91) = rPipeFlr; A(92) = rPipeCan; A(93) = rFlrCovIn; A(94) = rFlrSky; A(95) = rFlrThScr;
+    A(96) = rThScrCovIn; A(97) = rThScrSky; A(98) = rCovESky; A(99) = rFirLampFlr; A(100) = rLampPipe;
+    A(101) = rFirLampCan; A(102) = rLampThScr; A(103) = rLampCovIn; A(104) = rLampSky; A(105) = rGroPipeCan;
+    A(106) = rFlrBlScr; A(107) = rPipeBlScr; A(108) = rCanBlScr; A(109) = rBlScrThScr; A(110) = rBlScrCovIn;
+    A(111) = rBlScrSky; A(112) = rLampBlScr; A(113) = fIntLampCanUp; A(114) = fIntLampCanDown;
+    A(115) = rFirIntLampFlr; A(116) = rIntLampPipe; A(117) = rFirIntLampCan; A(118) = rIntLampLamp;
+    A(119) = rIntLampBlScr; A(120) = rIntLampThScr; A(121) = rIntLampCovIn; A(122) = rIntLampSky;
+
+    /* ---- natural ventilation (:698-779) ---- */
+    double aRoofU = uVent * p[55];
+    double aRoofUMax = p[55];
+    double aRoofMin = 0;
+    double aSideU = 0;
+    double etaRoof = 1;
+    double etaRoofNoSide = 1;
+    double etaSide = 0;
+    double cD = p[59];
+    double cW = p[61];
+    double tMeanK = 0.5 * tAir + 0.5 * tOut + C2K;
+    double fVentRoof2 = uVent * p[55] * cD / (2. * p[46]) *
+                        sqrt(fabs(p[26] * p[56] * (tAir - tOut) / (2. * tMeanK) + cW * (wind * wind)));
+    double aMix = aRoofU * aSideU / sqrt(fmax(aRoofU * aRoofU + aSideU * aSideU, 0.01));
+    double fVentRoofSide2 = cD / p[46] *
+                            sqrt(1e-8 + pow(aMix, 2) * (2 * p[26] * p[62] * (tAir - tOut) / tMeanK) +
+                                 (pow((aRoofU + aSideU / 2.), 2) * cW * (wind * wind)));
+    double fVentSide2 = cD * aSideU * wind / (2 * p[46]) * sqrt(cW);
+    double fLeakage = (wind < p[205]) ? p[205] * p[60] : p[60] * wind;
+    double scrMax = fmax(thScr, blScr);
+    double fVentRoof = (etaRoof >= p[8])
+                           ? p[57] * fVentRoof2 + p[204] * fLeakage
+                           : p[57] * (scrMax * fVentRoof2 + (1 - scrMax) * fVentRoofSide2 * etaRoof) + p[204] * fLeakage;
+    double fVentSide = (etaRoof >= p[8])
+                           ? p[57] * fVentSide2 + (1 - p[204]) * fLeakage
+                           : p[57] * (scrMax * fVentSide2 + (1 - scrMax) * fVentRoofSide2 * etaSide) + (1 - p[204]) * fLeakage;
+    A(123) = aRoofU; A(124) = aRoofUMax; A(125) = aRoofMin; A(126) = aSideU; A(127) = etaRoof; A(128) = etaRoofNoSide;
+    A(129) = etaSide; A(130) = cD; A(131) = cW; A(132) = fVentRoof2; A(133) = fVentRoofSide2; A(134) = fVentSide2;
+    A(135) = fLeakage; A(136) = fVentRoof; A(137) = fVentSide;
+
+    /* ---- CO2 ppm, air density, screen air flux (:782-814) ---- */
+    double co2InPpm = dens2ppm(tAir, 1e-6 * co2Air);
+    double rhoTop = p[36] * p[126] / ((tTop + C2K) * p[39]);
+    double rhoAir = p[36] * p[126] / ((tAir + C2K) * p[39]);
+    double rhoAirMean = 0.5 * (rhoTop + rhoAir);
+    double fThScr = thScr * p[84] * pow(fabs(tAir - tTop + 1e-10), 0.66) +
+                    ((1. - thScr) / rhoAirMean) * sqrt(0.5 * rhoAirMean * (1. - thScr) * p[26] * fabs(rhoAir - rhoTop) + 1e-10);
+    double fBlScr = blScr * p[94] * pow(fabs(tAir - tTop + 1e-10), 0.66) +
+                    ((1. - blScr) / rhoAirMean) * sqrt(0.5 * rhoAirMean * (1. - blScr) * p[26] * fabs(rhoAir - rhoTop) + 1e-10);
+    double fScr = fmin(fThScr, fBlScr);
+    A(138) = co2InPpm; A(139) = rhoTop; A(140) = rhoAir; A(141) = rhoAirMean; A(142) = fThScr; A(143) = fBlScr; A(144) = fScr;
+
+    /* ---- convection & conduction (:820-935) ---- */
+    double fVentForced = 0;
+    double hCanAir = sens(2 * p[0] * lai, tCan, tAir);
+    double hAirFlr = (tFlr > tAir) ? sens(1.7 * pow(fabs(tFlr - tAir + 1e-10), (1. / 3.)), tAir, tFlr)
+                                   : sens(1.3 * pow(fabs(tAir - tFlr + 1e-10), (1. / 4.)), tAir, tFlr);
+    double hAirThScr = sens(1.7 * thScr * pow(fabs(tAir - tThScr + 1e-10), (1. / 3.)), tAir, tThScr);
+    double hAirBlScr = sens(1.7 * blScr * pow(fabs(tAir - tBlScr + 1e-10), (1. / 3.)), tAir, tBlScr);
+    double hAirOut = sens(p[111] * p[23] * (fVentSide + fVentForced), tAir, tOut);
+    double hAirTop = sens(p[111] * p[23] * fScr, tAir, tTop);
+    double hThScrTop = sens(1.7 * thScr * pow(fabs(tThScr - tTop + 1e-10), (1. / 3.)), tThScr, tTop);
+    double hBlScrTop = sens(1.7 * blScr * pow(fabs(tBlScr - tTop + 1e-10), (1. / 3.)), tBlScr, tTop);
+    double hTopCovIn = sens(p[50] * pow(fabs(tTop - tCovIn + 1e-10), (1. / 3.)) * p[47] / p[46], tTop, tCovIn);
+    double hTopOut = sens(p[111] * p[23] * fVentRoof, tTop, tOut);
+    double hCovEOut = sens(p[47] / p[46] * (p[51] + p[52] * pow(wind, p[53])), tCovE, tOut);
+    double hPipeAir = sens(1.99 * M_PI * p[105] * p[107] * pow(fabs(tPipe - tAir + 1e-10), 0.32), tPipe, tAir);
+    double hFlrSo1 = sens(2. / (p[101] / p[99] + p[27] / p[103]), tFlr, tSo1);
+    double hSo1So2 = sens(2. * p[103] / (p[27] + p[28]), tSo1, tSo2);
+    double hSo2So3 = sens(2. * p[103] / (p[28] + p[29]), tSo2, tSo3);
+    double hSo3So4 = sens(2. * p[103] / (p[29] + p[30]), tSo3, tSo4);
+    double hSo4So5 = sens(2. * p[103] / (p[30] + p[31]), tSo4, tSo5);
+    double hSo5SoOut = sens(2. * p[103] / (p[31] + p[37]), tSo5, tSoOut);
+    double hCovInCovE = sens(1. / (p[73] / p[71]), tCovIn, tCovE);
+    double hLampAir = sens(p[185], tLamp, tAir);
+    double hGroPipeAir = sens(1.99 * M_PI * p[167] * p[166] * pow(fabs(tGroPipe - tAir + 1e-10), 0.32), tGroPipe, tAir);
+    double hIntLampAir = sens(p[198], tIntLamp, tAir);
+    A(145) = fVentForced; A(146) = hCanAir; A(147) = hAirFlr; A(148) = hAirThScr; A(149) = hAirBlScr; A(150) = hAirOut;
+    A(151) = hAirTop; A(152) = hThScrTop; A(153) = hBlScrTop; A(154) = hTopCovIn; A(155) = hTopOut; A(156) = hCovEOut;
+    A(157) = hPipeAir; A(158) = hFlrSo1; A(159) = hSo1So2; A(160) = hSo2So3; A(161) = hSo3So4; A(162) = hSo4So5;
+    A(163) = hSo5SoOut; A(164) = hCovInCovE; A(165) = hLampAir; A(166) = hGroPipeAir; A(167) = hIntLampAir;
+
+    /* ---- stomata & transpiration (:940-981) ---- */
+    double sRs = 1. / (1. + exp(p[43] * (rCan - p[40])));
+    double cEvap3 = p[20] * (1. - sRs) + p[19] * sRs;
+    double cEvap4 = p[22] * (1. - sRs) + p[21] * sRs;
+    double rfRCan = (rCan + p[17]) / (rCan + p[18]);
+    double rfCo2 = fmin(1.5, 1. + cEvap3 * pow((p[7] * co2Air - 200), 2));
+    double rfVp = fmin(5.8, 1. + cEvap4 * pow((sat_vp(tCan) - vpAir), 2));
+    double rS = p[42] * rfRCan * rfCo2 * rfVp;
+    double vecCanAir = 2. * p[111] * p[23] * lai / (p[1] * p[14] * (p[41] + rS));
+    double mvCanAir = (sat_vp(tCan) - vpAir) * vecCanAir;
+    A(168) = sRs; A(169) = cEvap3; A(170) = cEvap4; A(171) = rfRCan; A(172) = rfCo2; A(173) = rfVp; A(174) = rS;
+    A(175) = vecCanAir; A(176) = mvCanAir;
+
+    /* ---- vapour fluxes (:987-1030) ---- */
+    A(177) = 0; A(178) = 0; A(179) = 0; A(180) = 0;
+    double mvAirThScr = condens(1.7 * thScr * pow(fabs(tAir - tThScr + 1e-10), (1. / 3.)), vpAir, sat_vp(tThScr));
+    double mvAirBlScr = condens(1.7 * blScr * pow(fabs(tAir - tBlScr + 1e-10), (1. / 3.)), vpAir, sat_vp(tBlScr));
+    double mvTopCovIn = condens(p[50] * pow(fabs(tTop - tCovIn + 1e-10), (1. / 3.)) * p[47] / p[46], vpTop, sat_vp(tCovIn));
+    double mvAirTop = air_mv(fScr, vpAir, vpTop, tAir, tTop);
+    double mvTopOut = air_mv(fVentRoof, vpTop, vpOut, tTop, tOut);
+    double mvAirOut = air_mv(fVentSide + fVentForced, vpAir, vpOut, tAir, tOut);
+    double lCanAir = p[1] * mvCanAir;
+    double lAirThScr = p[1] * mvAirThScr;
+    double lAirBlScr = p[1] * mvAirBlScr;
+    double lTopCovIn = p[1] * mvTopCovIn;
+    A(181) = mvAirThScr; A(182) = mvAirBlScr; A(183) = mvTopCovIn; A(184) = mvAirTop; A(185) = mvTopOut; A(186) = mvAirOut;
+    A(187) = lCanAir; A(188) = lAirThScr; A(189) = lAirBlScr; A(190) = lTopCovIn;
+
+    /* ---- canopy photosynthesis (:1041-1097) ---- */
+    double parCan = p[187] * rParLampCan + p[140] * rParSunCan + p[197] * rParIntLampCan;
+    double j25CanMax = lai * p[129];
+    double gamma = (p[129] / j25CanMax) * p[130] * tCan + 20 * p[130] * (1 - (p[129] / j25CanMax));
+    double co2Stom = p[131] * co2InPpm;
+    double jPot = j25CanMax * exp(p[132] * (tCan + C2K - p[133]) / (1e-3 * p[39] * (tCan + C2K) * p[133])) *
+                  (1 + exp((p[134] * p[133] - p[135]) / (1e-3 * p[39] * p[133]))) /
+                  (1 + exp((p[134] * (tCan + C2K) - p[135]) / (1e-3 * p[39] * (tCan + C2K))));
+    double jE = (1. / (2. * p[136])) * (jPot + p[137] * parCan -
+                                        sqrt(pow((jPot + p[137] * parCan), 2) - 4 * p[136] * jPot * p[137] * parCan + 1e-10));
+    double phot = jE * (co2Stom - gamma) / (4 * (co2Stom + 2 * gamma));
+    double photResp = phot * gamma / co2Stom;
+    double hAirBuf = 1. / (1. + exp(5e-4 * (cBuf - p[157])));
+    double mcAirBuf = p[138] * hAirBuf * (phot - photResp);
+    A(191) = parCan; A(192) = j25CanMax; A(193) = gamma; A(194) = co2Stom; A(195) = jPot; A(196) = jE; A(197) = phot;
+    A(198) = photResp; A(199) = hAirBuf; A(200) = mcAirBuf;
+
+    /* ---- carbohydrate flows (:1103-1188) ---- */
+    double gTCan24 = 0.047 * tCan24 + 0.06;
+    double hTCan24 = 1. / (1. + exp(-1.1587 * (tCan24 - p[160]))) * 1. / (1. + exp(1.3904 * (tCan24 - p[159])));
+    double hTCan = 1. / (1. + exp(-0.869 * (tCan - p[162]))) * 1. / (1. + exp(0.5793 * (tCan - p[161])));
+    double hTCanSum = 0.5 * (tCanSum / p[163] + sqrt(pow((tCanSum / p[163]), 2) + 1e-4)) -
+                      0.5 * ((tCanSum - p[163]) / p[163] + sqrt(pow(((tCanSum - p[163]) / p[163]), 2) + 1e-4));
+    double hBufOrg = 1. / (1. + exp(-5e-3 * (cBuf - p[158])));
+    double mcBufLeaf = hBufOrg * hTCan24 * gTCan24 * p[155];
+    double mcBufStem = hBufOrg * hTCan24 * gTCan24 * p[156];
+    double mcBufFruit = hBufOrg * hTCan * hTCan24 * hTCanSum * gTCan24 * p[154];
+    double mcBufAir = p[147] * mcBufLeaf + p[148] * mcBufStem + p[146] * mcBufFruit;
+    double mcLeafAir = (1. - exp(-p[149] * p[143])) * pow(p[150], 0.1 * (tCan24 - 25)) * cLeaf * p[152];
+    double mcStemAir = (1. - exp(-p[149] * p[143])) * pow(p[150], 0.1 * (tCan24 - 25)) * cStem * p[153];
+    double mcFruitAir = (1. - exp(-p[149] * p[143])) * pow(p[150], (0.1 * (tCan24 - 25))) * cFruit * p[151];
+    double mcOrgAir = mcLeafAir + mcStemAir + mcFruitAir;
+    double mcLeafHar = smooth_harvest(cLeaf, p[144], 1e4, 5e4);
+    double mcFruitHar = smooth_harvest(cFruit, p[145], 1e4, 5e4);
+    A(201) = gTCan24; A(202) = hTCan24; A(203) = hTCan; A(204) = hTCanSum; A(205) = hBufOrg; A(206) = mcBufLeaf;
+    A(207) = mcBufStem; A(208) = mcBufFruit; A(209) = mcBufAir; A(210) = mcLeafAir; A(211) = mcStemAir;
+    A(212) = mcFruitAir; A(213) = mcOrgAir; A(214) = mcLeafHar; A(215) = mcFruitHar;
+
+    /* ---- CO2 fluxes, actuators (:1194-1269) ---- */
+    double mcAirCan = (p[139] / p[138]) * (mcAirBuf - mcBufAir - mcOrgAir);
+    double mcAirTop = air_mc(fScr, co2Air, co2Top);
+    double mcTopOut = air_mc(fVentRoof, co2Top, co2Out);
+    double mcAirOut = air_mc(fVentSide + fVentForced, co2Air, co2Out);
+    double hBoilPipe = uBoil * p[108] / p[46];
+    double hBoilGroPipe = 0;
+    double mcExtAir = uCo2 * p[109] / p[46];
+    A(216) = mcAirCan; A(217) = mcAirTop; A(218) = mcTopOut; A(219) = mcAirOut; A(220) = hBoilPipe; A(221) = hBoilGroPipe;
+    A(222) = mcExtAir;
+    for (k = 223; k <= 232; ++k) A(k) = 0;
+    double hLampCool = p[186] * qLampIn;
+    A(233) = hLampCool;
+    for (k = 234; k <= 238; ++k) A(k) = 0;
+
+    if (!dxdt) return;
+    /* ---- ODE(), ode.hpp:12-121: same term order as the reference, read back from the aux vector ---- */
+    dxdt[0] = (1. / p[122]) * (A(223) + A(222) + A(224) - A(216) - A(217) - A(219));
+    dxdt[1] = (1. / p[123]) * (A(217) - A(218));
+    dxdt[2] = (1. / p[112]) * (A(146) + A(225) - A(235) + A(157) + A(226) + A(227) + A(79) - A(147) - A(148) - A(150) -
+                               A(151) - A(229) - A(230) - A(149) + A(165) + A(77) + A(166) + A(167) + A(78));
+    dxdt[3] = (1. / p[120]) * (A(152) + A(151) - A(154) - A(155) + A(153));
+    dxdt[4] = (1. / A(32)) * (A(54) + A(68) + A(92) - A(146) - A(187) - A(84) - A(87) - A(85) - A(86) - A(108) + A(55) +
+                              A(69) + A(101) + A(105) + A(56) + A(70) + A(117));
+    dxdt[5] = (1. / A(34)) * (A(154) + A(190) + A(84) + A(93) + A(88) + A(96) - A(164) + A(103) + A(110) + A(121));
+    dxdt[6] = (1. / A(33)) * (A(80) + A(164) - A(156) - A(98));
+    dxdt[7] = (1. / p[119]) * (A(148) + A(188) + A(86) + A(95) + A(90) - A(152) - A(96) - A(97) + A(109) + A(102) + A(120));
+    dxdt[8] = (1. / p[113]) * (A(147) + A(74) + A(71) + A(87) + A(91) - A(158) - A(93) - A(94) - A(95) + A(75) + A(72) +
+                               A(99) - A(106) + A(76) + A(73) + A(115));
+    dxdt[9] = (1. / p[110]) * (A(220) + A(231) + A(232) - A(89) - A(88) - A(92) - A(91) - A(90) - A(157) + A(100) -
+                               A(107) + A(238) + A(116));
+    dxdt[10] = (1. / p[114]) * (A(158) - A(159));
+    dxdt[11] = (1. / p[115]) * (A(159) - A(160));
+    dxdt[12] = (1. / p[116]) * (A(160) - A(161));
+    dxdt[13] = (1. / p[117]) * (A(161) - A(162));
+    dxdt[14] = (1. / p[118]) * (A(162) - A(163));
+    dxdt[15] = (1. / A(35)) * (A(176) + A(177) + A(178) + A(179) - A(181) - A(184) - A(186) - A(180) - A(236) - A(182));
+    dxdt[16] = (1. / A(36)) * (A(184) - A(183) - A(185));
+    dxdt[17] = (1. / p[184]) * (A(37) - A(165) - A(104) - A(103) - A(102) - A(100) - A(77) - A(112) - A(75) - A(72) -
+                                A(99) - A(55) - A(69) - A(101) - A(233) + A(118));
+    dxdt[18] = (1. / p[191]) * (A(38) - A(167) - A(122) - A(121) - A(120) - A(116) - A(78) - A(119) - A(76) - A(73) -
+                                A(115) - A(56) - A(70) - A(117) - A(118));
+    dxdt[19] = (1. / p[171]) * (A(221) - A(105) - A(166));
+    dxdt[20] = (1. / p[121]) * (A(149) + A(189) + A(108) + A(106) + A(107) - A(153) - A(110) - A(111) - A(109) + A(112) + A(119));
+    dxdt[21] = (1. / 86400.) * (tCan - tCan24);
+    dxdt[22] = A(200) - A(208) - A(206) - A(207) - A(209);
+    dxdt[23] = A(206) - A(210) - A(214);
+    dxdt[24] = A(207) - A(211);
+    dxdt[25] = A(208) - A(212) - A(215);
+    dxdt[26] = (1. / 86400.) * tCan;
+    dxdt[27] = 1. / 86400.;
+#undef A
+}
+
+void glgo_rhs(const double *x, const double *u, const double *d, const double *p, double *dxdt) {
+    glgo_aux_rhs(x, u, d, p, NULL, dxdt);
+}
+
+/* Classical RK4, n_sub equal substeps over [0,dt], inputs held constant (greenlight_model.cpp:59-63 passes
+ * p=[u;d;p] as integrator parameters => zero-order hold).  Stage layout (the GPU kernel uses the same):
+ *   k1=f(x) ; k2=f(x+h/2 k1) ; k3=f(x+h/2 k2) ; k4=f(x+h k3) ; x += h/6 (k1+2k2+2k3+k4)                   */
+int glgo_evalf(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub,
+               double *x_next) {
+    double xc[GLGO_NX], xs[GLGO_NX], k[GLGO_NX], acc[GLGO_NX];
+    const double h = dt / (double)n_sub;
+    int s, i, bad = 0;
+    memcpy(xc, x, sizeof xc);
+    for (s = 0; s < n_sub; ++s) {
+        glgo_rhs(xc, u, d, p, k);
+        for (i = 0; i < GLGO_NX; ++i) { acc[i] = k[i]; xs[i] = xc[i] + (0.5 * h) * k[i]; }
+        glgo_rhs(xs, u, d, p, k);
+        for (i = 0; i < GLGO_NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = xc[i] + (0.5 * h) * k[i]; }
+        glgo_rhs(xs, u, d, p, k);
+        for (i = 0; i < GLGO_NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = xc[i] + h * k[i]; }
+        glgo_rhs(xs, u, d, p, k);
+        for (i = 0; i < GLGO_NX; ++i) xc[i] = xc[i] + (h / 6.0) * (acc[i] + k[i]);
+    }
+    for (i = 0; i < GLGO_NX; ++i) {
+        x_next[i] = xc[i];
+        if (!isfinite(xc[i])) bad = 1;
+    }
+    return bad;
+}
+
+/* tiny fork-join helper: n_threads pthreads, thread t handles items t, t+n, t+2n, ... */
+typedef struct glgo_job {
+    void (*fn)(void *ctx, int item, int tid);
+    void *ctx;
+    int n_items, n_threads, tid;
+} glgo_job;
+static void *glgo_job_main(void *arg) {
+    glgo_job *j = (glgo_job *)arg;
+    int i;
+    for (i = j->tid; i < j->n_items; i += j->n_threads) j->fn(j->ctx, i, j->tid);
+    return NULL;
+}
+static void glgo_parallel_for(void (*fn)(void *, int, int), void *ctx, int n_items, int n_threads) {
+    pthread_t th[256];
+    glgo_job jobs[256];
+    int t;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    if (n_threads > n_items) n_threads = n_items > 0 ? n_items : 1;
+    for (t = 0; t < n_threads; ++t) {
+        jobs[t].fn = fn; jobs[t].ctx = ctx; jobs[t].n_items = n_items; jobs[t].n_threads = n_threads; jobs[t].tid = t;
+        if (t > 0) pthread_create(&th[t], NULL, glgo_job_main, &jobs[t]);
+    }
+    glgo_job_main(&jobs[0]);
+    for (t = 1; t < n_threads; ++t) pthread_join(th[t], NULL);
+}
+
+typedef struct evalf_ctx {
+    const double *x, *u, *d, *p;
+    int p_stride, n_sub;
+    double dt;
+    double *x_next;
+    int bad[256];
+} evalf_ctx;
+static void evalf_item(void *vc, int b, int tid) {
+    evalf_ctx *c = (evalf_ctx *)vc;
+    c->bad[tid] |= glgo_evalf(c->x + (size_t)b * GLGO_NX, c->u + (size_t)b * GLGO_NU, c->d + (size_t)b * GLGO_ND,
+                              c->p + (size_t)b * c->p_stride, c->dt, c->n_sub, c->x_next + (size_t)b * GLGO_NX);
+}
+int glgo_evalf_batch(const double *x, const double *u, const double *d, const double *p, int p_stride, double dt,
+                     int n_sub, double *x_next, int B, int n_threads) {
+    evalf_ctx c;
+    int bad = 0, t;
+    memset(&c, 0, sizeof c);
+    c.x = x; c.u = u; c.d = d; c.p = p; c.p_stride = p_stride; c.n_sub = n_sub; c.dt = dt; c.x_next = x_next;
+    glgo_parallel_for(evalf_item, &c, B, n_threads);
+    for (t = 0; t < 256; ++t) bad |= c.bad[t];
+    return bad;
+}
+
+/* ===================== step semantics ===================== */
+
+/* environments/utils.py:13-46 (rhMax=90, time_in_days=0) */
+void glgo_init_state(const double *d0, double *x) {
+    const double t0 = 16.5;
+    int i;
+    for (i = 0; i < GLGO_NX; ++i) x[i] = t0;
+    x[0] = d0[3];
+    x[1] = x[0];
+    x[4] = t0 + 4;
+    x[11] = 0.25 * (3. * t0 + d0[6]);
+    x[12] = 0.25 * (2. * t0 + 2 * d0[6]);
+    x[13] = 0.25 * (t0 + 3 * d0[6]);
+    x[14] = d0[6];
+    x[15] = 90 / 100. * sat_vp(t0);
+    x[16] = x[15];
+    x[21] = x[4];
+    x[22] = 0.;
+    x[23] = 9.5283e4;
+    x[24] = 2.5107e5;
+    x[25] = 5.5338e4;
+    x[26] = 3.0978e3;
+    x[27] = 0;
+}
+
+/* tomato_env.py:231-270 */
+void glgo_env_reset(glgo_env *e, const double *weather, int rows, double start_day) {
+    memset(e->u, 0, sizeof e->u);
+    e->weather = weather;
+    e->weather_rows = rows;
+    glgo_init_state(weather, e->x);
+    memcpy(e->x_prev, e->x, sizeof e->x);
+    e->day_of_year = start_day;
+    e->hour_of_day = 0;
+    e->timestep = 0;
+    e->terminated = 0;
+}
+
+/* noise.py:3-23.  The reference array is float32 (parameters.py:5): `p[i] += noise*p[i]` computes in float64
+ * (float64 noise array * float32 array -> float64) and the in-place add casts back to float32;
+ * p[144] = p[141]/p[142] is a float32/float32 division. Result widened to double (pybind). */
+void glgo_param_noise(const double *p_nom, const double *noise34, double *p_out) {
+    int i;
+    memcpy(p_out, p_nom, sizeof(double) * GLGO_NP);
+    for (i = 0; i < 34; ++i) {
+        double pv = p_nom[128 + i];
+        p_out[128 + i] = (double)(float)(pv + noise34[i] * pv);
+    }
+    p_out[144] = (double)((float)p_out[141] / (float)p_out[142]);
+}
+
+static inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* observations.py:59-182, evaluated with the pre-increment timestep (tomato_env.py:130,137) */
+void glgo_env_obs(const glgo_env_cfg *c, const glgo_env *e, double *obs) {
+    const double *w = e->weather + (size_t)e->timestep * GLGO_ND;
+    int i, j;
+    obs[0] = dens2ppm(e->x[2], e->x[0] * 1e-6);
+    obs[1] = e->x[2];
+    obs[2] = clampd(100 * e->x[15] / sat_vp(e->x[2]), 0., 100.);
+    obs[3] = e->x[9];
+    obs[4] = e->x[21];
+    obs[5] = e->x[25];
+    obs[6] = e->x[26];
+    for (i = 0; i < 6; ++i) obs[7 + i] = e->u[i];
+    for (i = 0; i < 5; ++i) obs[13 + i] = w[i];
+    obs[15] = clampd(100 * w[2] / sat_vp(w[1]), 0., 100.);
+    obs[16] = dens2ppm(w[1], w[3] * 1e-6);
+    obs[18] = (double)e->timestep;
+    obs[19] = sin(2 * M_PI * e->day_of_year / 365.0);
+    obs[20] = cos(2 * M_PI * e->day_of_year / 365.0);
+    obs[21] = sin(2 * M_PI * e->hour_of_day / 24.0);
+    obs[22] = cos(2 * M_PI * e->hour_of_day / 24.0);
+    for (i = 1; i <= c->Np; ++i)
+        for (j = 0; j < 5; ++j) obs[23 + (i - 1) * 5 + j] = e->weather[(size_t)(e->timestep + i) * GLGO_ND + j];
+}
+
+/* tomato_env.py:115-146 (+ :148-173 for raw control) ; rewards.py:156-231 */
+int glgo_env_step(const glgo_env_cfg *c, glgo_env *e, const double *p_nom, const void *action, int raw_control,
+                  const double *noise34, double *obs, double *reward, double *info) {
+    double p_step[GLGO_NP], x_next[GLGO_NX];
+    const double *pp = p_nom;
+    int i, bad;
+    if (raw_control) {
+        const double *uc = (const double *)action;
+        for (i = 0; i < 6; ++i) e->u[i] = uc[i];
+    } else {
+        /* float32 action * float32 delta -> float32 product; + float64 u ; clip (tomato_env.py:109-113) */
+        const float *a = (const float *)action;
+        for (i = 0; i < 6; ++i) {
+            float prod = a[i] * (float)c->delta_u_max_f32;
+            e->u[i] = clampd(e->u[i] + (double)prod, c->u_min[i], c->u_max[i]);
+        }
+    }
+    if (noise34) {
+        glgo_param_noise(p_nom, noise34, p_step);
+        pp = p_step;
+    }
+    bad = glgo_evalf(e->x, e->u, e->weather + (size_t)e->timestep * GLGO_ND, pp, c->dt, c->n_sub, x_next);
+    memcpy(e->x, x_next, sizeof x_next);
+    if (bad) e->terminated = 1; /* mirrors the bare except -> terminated (tomato_env.py:121-123) */
+
+    e->day_of_year += fmod(c->dt / 86400.0, 365.0);
+    e->hour_of_day += c->dt / 3600.0;
+    e->hour_of_day = fmod(e->hour_of_day, 24.0);
+
+    glgo_env_obs(c, e, obs);
+    if (e->timestep >= c->N) e->terminated = 1;
+
+    {
+        const double dt = c->dt;
+        double heating_energy = e->u[0] * p_nom[108] / p_nom[46] * dt / 3600 * 1e-3;
+        double elec_use = e->u[4] * p_nom[172] * dt / 3600 * 1e-3;
+        double co2_dosing = e->u[1] * p_nom[109] / p_nom[46] * dt * 1e-6;
+        double heat_costs = heating_energy * c->heating_price;
+        double co2_costs = co2_dosing * c->co2_price;
+        double elec_costs = elec_use * c->elec_price;
+        double variable_costs = 0 + heat_costs + co2_costs + elec_costs; /* python sum([...]) starts at 0 */
+        double gains = (e->x[25] - e->x_prev[25]) * 1e-6 / c->dmfm * c->fruit_price;
+        double profit = gains - variable_costs;
+        double viol[3], scaled_pen = 0.0;
+        const double max_viol[3] = {2500, 15, 15};
+        double max_profit = p_nom[154] * dt * 1e-6 / c->dmfm * c->fruit_price;
+        double max_heating = p_nom[108] / p_nom[46] * dt / 3600 * 1e-3 * c->heating_price;
+        double max_elec = p_nom[172] * dt / 3600 * 1e-3 * c->elec_price;
+        double max_co2 = p_nom[109] / p_nom[46] * dt * 1e-6 * c->co2_price;
+        double min_profit = -(0 + max_heating + max_elec + max_co2);
+        for (i = 0; i < 3; ++i) {
+            double lo = c->con_low[i] - obs[i], hi = obs[i] - c->con_high[i];
+            if (lo < 0) lo = 0;
+            if (hi < 0) hi = 0;
+            viol[i] = lo + hi;
+            scaled_pen += (viol[i] - 0.0) / (max_viol[i] - 0.0);
+        }
+        *reward = (profit - min_profit) / (max_profit - min_profit) - scaled_pen - 0.0 /* lamp penalty is 0: rewards.py:203-216 */;
+        if (info) {
+            /* EPI, revenue, variable_costs, fixed_costs, co2, heat, elec, temp_v, co2_v, rh_v, lamp_v */
+            info[0] = profit; info[1] = gains; info[2] = variable_costs; info[3] = c->fixed_costs;
+            info[4] = co2_costs; info[5] = heat_costs; info[6] = elec_costs;
+            info[7] = viol[1]; info[8] = viol[0]; info[9] = viol[2]; info[10] = 0.0;
+        }
+    }
+    e->timestep += 1;
+    memcpy(e->x_prev, e->x, sizeof e->x);
+    return e->terminated;
+}
+
+typedef struct rollout_ctx {
+    const glgo_env_cfg *c;
+    const double *p_nom, *weather;
+    int rows, B, n_steps;
+    const float *actions;
+    long total[256];
+    double rsum[256];
+} rollout_ctx;
+static void rollout_item(void *vc, int b, int tid) {
+    rollout_ctx *r = (rollout_ctx *)vc;
+    const int nobs = GLGO_NOBS_FIXED + 5 * r->c->Np;
+    double *obs = (double *)malloc(sizeof(double) * nobs);
+    double rew, info[GLGO_NINFO];
+    glgo_env e;
+    int s;
+    glgo_env_reset(&e, r->weather, r->rows, 0.0);
+    for (s = 0; s < r->n_steps; ++s) {
+        int done = glgo_env_step(r->c, &e, r->p_nom, r->actions + ((size_t)s * r->B + b) * 6, 0, NULL, obs, &rew, info);
+        r->rsum[tid] += rew;
+        r->total[tid] += 1;
+        if (done) glgo_env_reset(&e, r->weather, r->rows, 0.0);
+    }
+    free(obs);
+}
+long glgo_rollout(const glgo_env_cfg *c, const double *p_nom, const double *weather, int rows, int B, int n_steps,
+                  const float *actions, int n_threads, double *reward_sum_out) {
+    rollout_ctx r;
+    long total = 0;
+    double rsum = 0.0;
+    int t;
+    memset(&r, 0, sizeof r);
+    r.c = c; r.p_nom = p_nom; r.weather = weather; r.rows = rows; r.B = B; r.n_steps = n_steps; r.actions = actions;
+    glgo_parallel_for(rollout_item, &r, B, n_threads);
+    for (t = 0; t < 256; ++t) { total += r.total[t]; rsum += r.rsum[t]; }
+    if (reward_sum_out) *reward_sum_out = rsum;
+    return total;
+}

@@ -1,0 +1,89 @@
+/*
+ * glg_oracle.h -- CPU parity oracle for the GreenLight env-step path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C fp64 restatement of the reference algorithm; only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may link or call it.  The product (libglgym.so)
+ * never does.
+ *
+ * Parity pinning status:
+ *   - RHS (R1,R2: aux_states.hpp:96-1271, ode.hpp:6-124): PINNED against golden vectors produced from the
+ *     reference's own source text (tests/golden/make_golden.py -> tests/golden/rhs_golden.npz).
+ *   - Step semantics (S1-S8: tomato_env.py, observations.py, rewards.py, noise.py, utils.py:init_state):
+ *     PINNED against traces produced by executing the reference's own Python env on top of this
+ *     oracle's evalF (reference-shell, tests/golden/make_golden.py -> tests/golden/shell_trace.npz).
+ *   - Integrator (R3: greenlight_model.cpp:43-63): the reference integrates with CasADi 3.6.7 / SUNDIALS
+ *     CVODES (BDF, abstol=reltol=1e-6), a third-party dependency absent from /root/reference and from
+ *     this image => PARITY UNPINNED at the CVODES boundary.  The contract here is BASELINE.json's: fixed
+ *     step classical RK4, n_sub substeps, u/d/p held constant over [0,dt] (zero-order hold, same as
+ *     greenlight_model.cpp:59-63).  Method error vs. a tight implicit solve is measured in tests.
+ */
+#ifndef GLG_ORACLE_H
+#define GLG_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLGO_NX 28
+#define GLGO_NU 6
+#define GLGO_ND 10
+#define GLGO_NP 208
+#define GLGO_NA 239
+#define GLGO_NOBS_FIXED 23 /* obs = 23 + 5*Np */
+#define GLGO_NINFO 11
+
+/* R1: update() -- 239 auxiliary values. a may be NULL. dxdt may be NULL. */
+void glgo_aux_rhs(const double *x, const double *u, const double *d, const double *p, double *a, double *dxdt);
+/* R2: ODE() */
+void glgo_rhs(const double *x, const double *u, const double *d, const double *p, double *dxdt);
+/* R3/R4: x_next = RK4^n_sub(x; u,d,p const).  returns 0, or 1 if the result is not finite */
+int glgo_evalf(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub,
+               double *x_next);
+/* batched, AoS rows: x[B][28] u[B][6] d[B][10] p[B][208] (p_stride = 0 => shared p) ; OpenMP over envs */
+int glgo_evalf_batch(const double *x, const double *u, const double *d, const double *p, int p_stride, double dt,
+                     int n_sub, double *x_next, int B, int n_threads);
+
+/* ---- step semantics (S1..S8) ---- */
+typedef struct glgo_env_cfg {
+    double dt;              /* 900 */
+    int n_sub;              /* RK4 substeps per step */
+    int N;                  /* season_length*86400/dt, last step index */
+    int Np;                 /* forecast horizon in steps */
+    double delta_u_max_f32; /* float32(0.1) widened */
+    double u_min[6], u_max[6];
+    double con_low[3], con_high[3]; /* co2 ppm, temp, rh */
+    double elec_price, heating_price, co2_price, fruit_price, dmfm;
+    double uncertainty_scale;
+    double fixed_costs;     /* rewards.py:69-70,154: yearly/365/(86400//dt); reported in info only */
+} glgo_env_cfg;
+
+typedef struct glgo_env {
+    double x[28], x_prev[28], u[6];
+    double day_of_year, hour_of_day;
+    int timestep;
+    int terminated;
+    const double *weather; /* [rows][10] */
+    int weather_rows;
+} glgo_env;
+
+void glgo_init_state(const double *d0, double *x);                                   /* utils.py:13-46 */
+void glgo_env_reset(glgo_env *e, const double *weather, int rows, double start_day); /* tomato_env.py:231-270 */
+/* S2: noise.py:3-23 given the 34 uniform draws n_i in (-s/2, s/2) (already scaled). p_out float32-rounded. */
+void glgo_param_noise(const double *p_nom, const double *noise34, double *p_out);
+/* obs for the current (x,u,timestep,time) -- observations.py:59-182 ; obs has 23+5*Np entries */
+void glgo_env_obs(const glgo_env_cfg *c, const glgo_env *e, double *obs);
+/* tomato_env.py:115-146.  action: 6 float32 values (raw_control=0) or 6 doubles u (raw_control=1,
+ * step_raw_control :148-173).  noise34 may be NULL (scale 0).  Outputs obs[23+5Np], reward, info[11].
+ * returns terminated flag. */
+int glgo_env_step(const glgo_env_cfg *c, glgo_env *e, const double *p_nom, const void *action, int raw_control,
+                  const double *noise34, double *obs, double *reward, double *info);
+
+/* multi-threaded rollout used for the CPU baseline: B envs, each stepped n_steps with the given actions
+ * (float32 [n_steps][B][6]); envs auto-reset on termination. returns total env-steps executed. */
+long glgo_rollout(const glgo_env_cfg *c, const double *p_nom, const double *weather, int rows, int B, int n_steps,
+                  const float *actions, int n_threads, double *reward_sum_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
