@@ -1,0 +1,493 @@
+// glg_capi.cu -- C-ABI (include/glgym.h) over the sm_100a kernels.  Host side: handle, device buffers, launches.
+// No CPU fallback anywhere: every entry point either launches CUDA work or fails with GLG_ERR_CUDA.
+#include "../../include/glgym.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#undef GLG_NX
+#undef GLG_NU
+#undef GLG_ND
+#undef GLG_NP
+#undef GLG_NINFO
+#undef GLG_NSTATS
+#include "glg_kernels.cuh"
+
+static thread_local std::string g_create_error = "";
+
+struct glg_handle {
+    glg_config cfg;
+    int B = 0, obs_dim = 0, nt = 64;
+    bool have_params = false, have_weather = false, general = false, is_reset = false;
+    GlgUniform uni;
+    // device buffers
+    double *x = nullptr, *u = nullptr, *time = nullptr, *ep_return = nullptr, *ep_info = nullptr;
+    int *timestep = nullptr, *table = nullptr, *ep_len = nullptr;
+    unsigned int *step_ctr = nullptr;
+    float *obs = nullptr, *term_obs = nullptr, *actions = nullptr;
+    double *reward = nullptr, *info = nullptr, *stats = nullptr;
+    unsigned char *done = nullptr;
+    double *weather = nullptr, *start_day = nullptr;
+    int *reset_tables = nullptr;
+    int n_tables = 0, rows = 0, n_reset_tables = 0;
+    // pinned host staging for glg_step_host
+    float *h_actions = nullptr, *h_obs = nullptr;
+    double *h_reward = nullptr;
+    unsigned char *h_done = nullptr;
+    cudaStream_t own_stream = nullptr;
+    long long launches = 0;
+    std::string err;
+};
+
+#define GLG_CUDA(h, call)                                                                            \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char buf__[512];                                                                         \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            (h)->err = buf__;                                                                        \
+            return GLG_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+static int fail(glg_handle *h, int code, const char *msg) {
+    h->err = msg;
+    return code;
+}
+
+extern "C" void glg_default_config(glg_config *c) {
+    memset(c, 0, sizeof *c);
+    c->num_envs = 1;
+    c->device = 0;
+    c->dt = 900.0;
+    c->n_sub = 600;
+    c->N = 5760;
+    c->Np = 48;
+    c->precision = 0;
+    c->auto_reset = 1;
+    for (int i = 0; i < 6; ++i) {
+        c->u_min[i] = 0.0;
+        c->u_max[i] = 1.0;
+    }
+    c->delta_u_max = (double)0.1f;
+    c->con_low[0] = 300.; c->con_low[1] = 15.; c->con_low[2] = 50.;
+    c->con_high[0] = 1600.; c->con_high[1] = 34.; c->con_high[2] = 85.;
+    c->elec_price = 0.3; c->heating_price = 0.09; c->co2_price = 0.3; c->fruit_price = 1.6; c->dmfm = 0.065;
+    c->fixed_costs = (15. + 0.015 + 0.07 * 116 + 2.) / 365 / (86400 / 900);
+    c->uncertainty_scale = 0.0;
+    c->seed = 0;
+    c->env_id_offset = 0;
+    c->block_threads = 0;
+}
+
+extern "C" const char *glg_last_error(const glg_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+template <typename T>
+static cudaError_t dev_alloc(T **p, size_t n) {
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+    return e;
+}
+
+extern "C" void glg_destroy(glg_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->x); cudaFree(h->u); cudaFree(h->time); cudaFree(h->ep_return); cudaFree(h->ep_info);
+    cudaFree(h->timestep); cudaFree(h->table); cudaFree(h->ep_len); cudaFree(h->step_ctr);
+    cudaFree(h->obs); cudaFree(h->term_obs); cudaFree(h->actions); cudaFree(h->reward); cudaFree(h->info);
+    cudaFree(h->stats); cudaFree(h->done); cudaFree(h->weather); cudaFree(h->start_day); cudaFree(h->reset_tables);
+    if (h->h_actions) cudaFreeHost(h->h_actions);
+    if (h->h_obs) cudaFreeHost(h->h_obs);
+    if (h->h_reward) cudaFreeHost(h->h_reward);
+    if (h->h_done) cudaFreeHost(h->h_done);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
+    if (!cfg || !out) {
+        g_create_error = "glg_create: null argument";
+        return GLG_ERR_ARG;
+    }
+    *out = nullptr;
+    if (cfg->num_envs < 1 || cfg->n_sub < 1 || cfg->N < 0 || cfg->Np < 0 || !(cfg->dt > 0) || cfg->precision != 0) {
+        g_create_error = cfg->precision != 0 ? "glg_create: precision=1 (fp32 throughput mode) is not built in this version"
+                                             : "glg_create: invalid num_envs / n_sub / N / Np / dt";
+        return GLG_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+        g_create_error = std::string("glg_create: no usable CUDA device (") + cudaGetErrorString(ce) +
+                         "); this library has no CPU fallback";
+        return GLG_ERR_CUDA;
+    }
+    glg_handle *h = new (std::nothrow) glg_handle();
+    if (!h) return GLG_ERR_ALLOC;
+    h->cfg = *cfg;
+    h->B = cfg->num_envs;
+    h->obs_dim = GLG_NOBS_FIXED + 5 * cfg->Np;
+    h->nt = 64;
+    const size_t B = (size_t)h->B;
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e == cudaSuccess) e = dev_alloc(&h->x, GLG_NX * B);
+    if (e == cudaSuccess) e = dev_alloc(&h->u, GLG_NU * B);
+    if (e == cudaSuccess) e = dev_alloc(&h->time, 2 * B);
+    if (e == cudaSuccess) e = dev_alloc(&h->ep_return, B);
+    if (e == cudaSuccess) e = dev_alloc(&h->ep_info, GLG_NINFO * B);
+    if (e == cudaSuccess) e = dev_alloc(&h->timestep, B);
+    if (e == cudaSuccess) e = dev_alloc(&h->table, B);
+    if (e == cudaSuccess) e = dev_alloc(&h->ep_len, B);
+    if (e == cudaSuccess) e = dev_alloc(&h->step_ctr, B);
+    if (e == cudaSuccess) e = dev_alloc(&h->obs, (size_t)h->obs_dim * B);
+    if (e == cudaSuccess) e = dev_alloc(&h->term_obs, (size_t)h->obs_dim * B);
+    if (e == cudaSuccess) e = dev_alloc(&h->actions, GLG_NU * B);
+    if (e == cudaSuccess) e = dev_alloc(&h->reward, B);
+    if (e == cudaSuccess) e = dev_alloc(&h->info, GLG_NINFO * B);
+    if (e == cudaSuccess) e = dev_alloc(&h->stats, (size_t)GLG_NSTATS);
+    if (e == cudaSuccess) e = dev_alloc(&h->done, B);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("glg_create: ") + cudaGetErrorString(e);
+        glg_destroy(h);
+        return GLG_ERR_CUDA;
+    }
+    *out = h;
+    return GLG_OK;
+}
+
+extern "C" int glg_set_params(glg_handle *h, const double *p_host) {
+    if (!h || !p_host) return GLG_ERR_ARG;
+    for (int i = 0; i < GLG_NP; ++i) h->uni.P[i] = p_host[i];
+    glg_make_k(p_host, h->uni.K);
+    glg_make_c(p_host, h->uni.C);
+    h->general = !glg_params_nominal_structure(p_host);
+    h->have_params = true;
+    return GLG_OK;
+}
+
+extern "C" int glg_set_weather(glg_handle *h, const double *tables_host, int32_t n_tables, int32_t rows,
+                               const double *start_day_host) {
+    if (!h || !tables_host || n_tables < 1) return GLG_ERR_ARG;
+    if (rows < h->cfg.N + h->cfg.Np + 1) return fail(h, GLG_ERR_ARG, "glg_set_weather: rows < N + Np + 1");
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaFree(h->weather); cudaFree(h->start_day); cudaFree(h->reset_tables);
+    h->weather = nullptr; h->start_day = nullptr; h->reset_tables = nullptr;
+    const size_t n = (size_t)n_tables * rows * GLG_ND;
+    GLG_CUDA(h, cudaMalloc((void **)&h->weather, n * sizeof(double)));
+    GLG_CUDA(h, cudaMemcpy(h->weather, tables_host, n * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<double> sd(n_tables, 0.0);
+    if (start_day_host) sd.assign(start_day_host, start_day_host + n_tables);
+    GLG_CUDA(h, cudaMalloc((void **)&h->start_day, n_tables * sizeof(double)));
+    GLG_CUDA(h, cudaMemcpy(h->start_day, sd.data(), n_tables * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<int> ids(n_tables);
+    for (int i = 0; i < n_tables; ++i) ids[i] = i;
+    GLG_CUDA(h, cudaMalloc((void **)&h->reset_tables, n_tables * sizeof(int)));
+    GLG_CUDA(h, cudaMemcpy(h->reset_tables, ids.data(), n_tables * sizeof(int), cudaMemcpyHostToDevice));
+    h->n_tables = n_tables;
+    h->rows = rows;
+    h->n_reset_tables = n_tables;
+    h->have_weather = true;
+    return GLG_OK;
+}
+
+extern "C" int glg_set_reset_tables(glg_handle *h, const int32_t *ids, int32_t n) {
+    if (!h || !ids || n < 1) return GLG_ERR_ARG;
+    if (!h->have_weather) return fail(h, GLG_ERR_STATE, "glg_set_reset_tables: set the weather bank first");
+    for (int i = 0; i < n; ++i)
+        if (ids[i] < 0 || ids[i] >= h->n_tables) return fail(h, GLG_ERR_ARG, "glg_set_reset_tables: id out of range");
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaFree(h->reset_tables);
+    h->reset_tables = nullptr;
+    GLG_CUDA(h, cudaMalloc((void **)&h->reset_tables, n * sizeof(int)));
+    GLG_CUDA(h, cudaMemcpy(h->reset_tables, ids, n * sizeof(int), cudaMemcpyHostToDevice));
+    h->n_reset_tables = n;
+    return GLG_OK;
+}
+
+static void fill_args(const glg_handle *h, GlgStepArgs *a) {
+    memset(a, 0, sizeof *a);
+    const glg_config &c = h->cfg;
+    a->B = h->B; a->n_sub = c.n_sub; a->N = c.N; a->Np = c.Np; a->rows = h->rows; a->n_tables = h->n_tables;
+    a->obs_dim = h->obs_dim; a->auto_reset = c.auto_reset; a->n_reset_tables = h->n_reset_tables;
+    a->dt = c.dt;
+    for (int i = 0; i < GLG_NU; ++i) {
+        a->u_min[i] = c.u_min[i];
+        a->u_max[i] = c.u_max[i];
+    }
+    a->delta_u_max_f32 = (float)c.delta_u_max;
+    for (int i = 0; i < 3; ++i) {
+        a->con_low[i] = c.con_low[i];
+        a->con_high[i] = c.con_high[i];
+    }
+    a->elec_price = c.elec_price; a->heating_price = c.heating_price; a->co2_price = c.co2_price;
+    a->fruit_price = c.fruit_price; a->dmfm = c.dmfm; a->fixed_costs = c.fixed_costs;
+    a->uncertainty_scale = c.uncertainty_scale;
+    a->seed = c.seed; a->env_id_offset = c.env_id_offset;
+    a->weather = h->weather; a->start_day = h->start_day; a->reset_tables = h->reset_tables;
+    a->x = h->x; a->u = h->u; a->time = h->time; a->ep_return = h->ep_return; a->ep_info = h->ep_info;
+    a->timestep = h->timestep; a->table = h->table; a->ep_len = h->ep_len; a->step_ctr = h->step_ctr;
+    a->obs = h->obs; a->term_obs = h->term_obs; a->reward = h->reward; a->info = h->info; a->stats = h->stats;
+    a->done = h->done;
+}
+
+static int check_ready(glg_handle *h) {
+    if (!h) return GLG_ERR_ARG;
+    if (!h->have_params) return fail(h, GLG_ERR_STATE, "parameters not set (glg_set_params)");
+    if (!h->have_weather) return fail(h, GLG_ERR_STATE, "weather bank not set (glg_set_weather)");
+    return GLG_OK;
+}
+
+extern "C" int glg_reset(glg_handle *h, const uint8_t *mask_dev, const int32_t *table_ids_dev, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    GlgStepArgs a;
+    fill_args(h, &a);
+    const int NT = 128;
+    glg_reset_kernel<NT><<<(h->B + NT - 1) / NT, NT, 0, (cudaStream_t)stream>>>(a, mask_dev, table_ids_dev);
+    h->launches += 1;
+    GLG_CUDA(h, cudaGetLastError());
+    h->is_reset = true;
+    return GLG_OK;
+}
+
+template <bool GENERAL, bool NOISY>
+static cudaError_t launch_step(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
+    constexpr int NT = 64;
+    const size_t smem = GlgStepSmem<NT, NOISY>::bytes(a.Np);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(glg_step_kernel<GENERAL, NOISY, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    glg_step_kernel<GENERAL, NOISY, NT><<<(a.B + NT - 1) / NT, NT, smem, s>>>(h->uni, a);
+    return cudaGetLastError();
+}
+
+static int step_common(glg_handle *h, const float *actions_dev, const double *controls_dev, const double *noise_dev,
+                       void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!h->is_reset) return fail(h, GLG_ERR_STATE, "step before reset");
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    GlgStepArgs a;
+    fill_args(h, &a);
+    a.actions = actions_dev;
+    a.controls = controls_dev;
+    a.raw_control = controls_dev ? 1 : 0;
+    a.noise = noise_dev;
+    const bool noisy = (h->cfg.uncertainty_scale != 0.0) || (noise_dev != nullptr);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+    if (h->general) e = noisy ? launch_step<true, true>(h, a, s) : launch_step<true, false>(h, a, s);
+    else e = noisy ? launch_step<false, true>(h, a, s) : launch_step<false, false>(h, a, s);
+    h->launches += 1;
+    GLG_CUDA(h, e);
+    return GLG_OK;
+}
+
+extern "C" int glg_step(glg_handle *h, const float *actions_dev, const double *noise_dev, void *stream) {
+    if (!h || !actions_dev) return GLG_ERR_ARG;
+    return step_common(h, actions_dev, nullptr, noise_dev, stream);
+}
+
+extern "C" int glg_step_raw_control(glg_handle *h, const double *controls_dev, const double *noise_dev, void *stream) {
+    if (!h || !controls_dev) return GLG_ERR_ARG;
+    return step_common(h, nullptr, controls_dev, noise_dev, stream);
+}
+
+extern "C" int glg_step_host(glg_handle *h, const float *actions_host, float *obs_host, double *reward_host,
+                             uint8_t *done_host) {
+    if (!h || !actions_host) return GLG_ERR_ARG;
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t B = (size_t)h->B;
+    if (!h->h_actions) {
+        GLG_CUDA(h, cudaMallocHost((void **)&h->h_actions, GLG_NU * B * sizeof(float)));
+        GLG_CUDA(h, cudaMallocHost((void **)&h->h_obs, (size_t)h->obs_dim * B * sizeof(float)));
+        GLG_CUDA(h, cudaMallocHost((void **)&h->h_reward, B * sizeof(double)));
+        GLG_CUDA(h, cudaMallocHost((void **)&h->h_done, B));
+    }
+    cudaStream_t s = h->own_stream;
+    memcpy(h->h_actions, actions_host, GLG_NU * B * sizeof(float));
+    GLG_CUDA(h, cudaMemcpyAsync(h->actions, h->h_actions, GLG_NU * B * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = step_common(h, h->actions, nullptr, nullptr, s);
+    if (rc) return rc;
+    if (obs_host) GLG_CUDA(h, cudaMemcpyAsync(h->h_obs, h->obs, (size_t)h->obs_dim * B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (reward_host) GLG_CUDA(h, cudaMemcpyAsync(h->h_reward, h->reward, B * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (done_host) GLG_CUDA(h, cudaMemcpyAsync(h->h_done, h->done, B, cudaMemcpyDeviceToHost, s));
+    GLG_CUDA(h, cudaStreamSynchronize(s));
+    if (obs_host) memcpy(obs_host, h->h_obs, (size_t)h->obs_dim * B * sizeof(float));
+    if (reward_host) memcpy(reward_host, h->h_reward, B * sizeof(double));
+    if (done_host) memcpy(done_host, h->h_done, B);
+    return GLG_OK;
+}
+
+extern "C" int32_t glg_obs_dim(const glg_handle *h) { return h ? h->obs_dim : 0; }
+extern "C" float *glg_obs_dev(glg_handle *h) { return h ? h->obs : nullptr; }
+extern "C" float *glg_terminal_obs_dev(glg_handle *h) { return h ? h->term_obs : nullptr; }
+extern "C" double *glg_reward_dev(glg_handle *h) { return h ? h->reward : nullptr; }
+extern "C" uint8_t *glg_done_dev(glg_handle *h) { return h ? h->done : nullptr; }
+extern "C" double *glg_info_dev(glg_handle *h) { return h ? h->info : nullptr; }
+extern "C" double *glg_state_dev(glg_handle *h) { return h ? h->x : nullptr; }
+extern "C" double *glg_controls_dev(glg_handle *h) { return h ? h->u : nullptr; }
+extern "C" int32_t *glg_timestep_dev(glg_handle *h) { return h ? h->timestep : nullptr; }
+extern "C" int32_t *glg_table_dev(glg_handle *h) { return h ? h->table : nullptr; }
+extern "C" double *glg_time_dev(glg_handle *h) { return h ? h->time : nullptr; }
+extern "C" double *glg_stats_dev(glg_handle *h) { return h ? h->stats : nullptr; }
+extern "C" int64_t glg_launch_count(const glg_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int glg_clear_stats(glg_handle *h, void *stream) {
+    if (!h) return GLG_ERR_ARG;
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    GLG_CUDA(h, cudaMemsetAsync(h->stats, 0, GLG_NSTATS * sizeof(double), (cudaStream_t)stream));
+    return GLG_OK;
+}
+
+// [B][n] row-major host  <->  [n][B] device SoA
+static void to_soa(const double *aos, double *soa, int B, int n) {
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < n; ++i) soa[(size_t)i * B + b] = aos[(size_t)b * n + i];
+}
+static void to_aos(const double *soa, double *aos, int B, int n) {
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < n; ++i) aos[(size_t)b * n + i] = soa[(size_t)i * B + b];
+}
+
+extern "C" int glg_set_state(glg_handle *h, const double *x_host, const double *u_host, const int32_t *timestep_host) {
+    if (!h) return GLG_ERR_ARG;
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    GLG_CUDA(h, cudaDeviceSynchronize());
+    const int B = h->B;
+    std::vector<double> tmp;
+    if (x_host) {
+        tmp.resize((size_t)GLG_NX * B);
+        to_soa(x_host, tmp.data(), B, GLG_NX);
+        GLG_CUDA(h, cudaMemcpy(h->x, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (u_host) {
+        tmp.resize((size_t)GLG_NU * B);
+        to_soa(u_host, tmp.data(), B, GLG_NU);
+        GLG_CUDA(h, cudaMemcpy(h->u, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (timestep_host) GLG_CUDA(h, cudaMemcpy(h->timestep, timestep_host, (size_t)B * sizeof(int), cudaMemcpyHostToDevice));
+    return GLG_OK;
+}
+
+extern "C" int glg_get_state(glg_handle *h, double *x_host, double *u_host, int32_t *timestep_host) {
+    if (!h) return GLG_ERR_ARG;
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    GLG_CUDA(h, cudaDeviceSynchronize());
+    const int B = h->B;
+    std::vector<double> tmp;
+    if (x_host) {
+        tmp.resize((size_t)GLG_NX * B);
+        GLG_CUDA(h, cudaMemcpy(tmp.data(), h->x, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        to_aos(tmp.data(), x_host, B, GLG_NX);
+    }
+    if (u_host) {
+        tmp.resize((size_t)GLG_NU * B);
+        GLG_CUDA(h, cudaMemcpy(tmp.data(), h->u, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        to_aos(tmp.data(), u_host, B, GLG_NU);
+    }
+    if (timestep_host) GLG_CUDA(h, cudaMemcpy(timestep_host, h->timestep, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost));
+    return GLG_OK;
+}
+
+// ---- batched evalF (handle-free) ------------------------------------------------------------------------
+static thread_local std::string g_evalf_error;
+
+template <bool GENERAL, bool PER_ENV_P>
+static cudaError_t launch_evalf(const GlgUniform &uni, const double *x, const double *u, const double *d, const double *p,
+                                double *xn, unsigned char *bad, int B, double dt, int n_sub, cudaStream_t s) {
+    constexpr int NT = 64;
+    const size_t smem = sizeof(double) * (size_t)(2 * GLG_NX + H_COUNT) * NT;
+    cudaError_t e = cudaFuncSetAttribute(glg_evalf_kernel<GENERAL, PER_ENV_P, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    glg_evalf_kernel<GENERAL, PER_ENV_P, NT><<<(B + NT - 1) / NT, NT, smem, s>>>(uni, x, u, d, p, xn, bad, B, dt, n_sub);
+    return cudaGetLastError();
+}
+
+extern "C" int glg_evalf_batch(const double *x_dev, const double *u_dev, const double *d_dev, const double *p_dev,
+                               int32_t p_stride, double *x_next_dev, uint8_t *bad_dev, int32_t B, double dt, int32_t n_sub,
+                               int32_t device, void *stream) {
+    if (!x_dev || !u_dev || !d_dev || !p_dev || !x_next_dev || B < 1 || n_sub < 1 || (p_stride != 0 && p_stride != GLG_NP)) {
+        g_create_error = "glg_evalf_batch: invalid argument";
+        return GLG_ERR_ARG;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    static GlgUniform uni;  // only read by the shared-p variants
+    if (e == cudaSuccess) {
+        if (p_stride == 0) {
+            double ph[GLG_NP];
+            e = cudaMemcpyAsync(ph, p_dev, sizeof ph, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e == cudaSuccess) {
+                for (int i = 0; i < GLG_NP; ++i) uni.P[i] = ph[i];
+                glg_make_k(ph, uni.K);
+                glg_make_c(ph, uni.C);
+                e = glg_params_nominal_structure(ph)
+                        ? launch_evalf<false, false>(uni, x_dev, u_dev, d_dev, p_dev, x_next_dev, bad_dev, B, dt, n_sub, s)
+                        : launch_evalf<true, false>(uni, x_dev, u_dev, d_dev, p_dev, x_next_dev, bad_dev, B, dt, n_sub, s);
+            }
+        } else {
+            e = launch_evalf<true, true>(uni, x_dev, u_dev, d_dev, p_dev, x_next_dev, bad_dev, B, dt, n_sub, s);
+        }
+    }
+    if (e != cudaSuccess) {
+        g_create_error = std::string("glg_evalf_batch: ") + cudaGetErrorString(e);
+        return GLG_ERR_CUDA;
+    }
+    return GLG_OK;
+}
+
+// ---- roofline denominators ------------------------------------------------------------------------------
+template <typename T>
+static int measure_peak(int device, double *out) {
+    if (!out) return GLG_ERR_ARG;
+    cudaError_t e = cudaSetDevice(device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("glg_measure_peak: ") + cudaGetErrorString(e);
+        return GLG_ERR_CUDA;
+    }
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    T *buf = nullptr;
+    cudaMalloc((void **)&buf, (size_t)blocks * threads * sizeof(T));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        glg_fma_peak_kernel<T><<<blocks, threads>>>(buf, iters, (T)0.999999, (T)1e-7);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads / (ms * 1e-3);
+        if (rep > 0 && flops > best) best = flops;
+    }
+    e = cudaGetLastError();
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(buf);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("glg_measure_peak: ") + cudaGetErrorString(e);
+        return GLG_ERR_CUDA;
+    }
+    *out = best;
+    return GLG_OK;
+}
+extern "C" int glg_measure_fp64_peak(int32_t device, double *flops) { return measure_peak<double>(device, flops); }
+extern "C" int glg_measure_fp32_peak(int32_t device, double *flops) { return measure_peak<float>(device, flops); }

@@ -1,0 +1,602 @@
+// glg_kernels.cuh -- sm_100a kernels of the env-step path.  One thread = one greenhouse env.
+//
+//   glg_step_kernel   : fused TomatoEnv.step (tomato_env.py:115-146): action->control (S1), parametric noise (S2),
+//                       weather row fetch (TMA bulk copy of the block's rows k..k+Np into shared memory when the
+//                       block is in lock-step), hoisting of the (u,d,p)-only work, n_sub RK4 substeps with the stage
+//                       state in registers (R1-R3), time update (S3), observation (S4), reward + info (S5,S7),
+//                       termination (S6), episode statistics (warp-shuffle reduction) and auto-reset (S8).
+//   glg_reset_kernel  : TomatoEnv.reset (tomato_env.py:231-270) for a masked subset.
+//   glg_evalf_kernel  : batched GreenLight::evalF (greenlight_model.cpp:96-120) as a pure function.
+//   glg_fma_peak_*    : FMA throughput micro-benchmarks used as roofline denominators.
+//
+// HBM layout (all per-env data structure-of-arrays, index [field][env], so a warp's loads are 256-B contiguous):
+//   x[28][B] f64, u[6][B] f64, timestep[B] i32, table[B] i32, time[2][B] f64, step_ctr[B] u32,
+//   ep_return[B] f64, ep_len[B] i32, ep_info[11][B] f64 ; outputs obs[B][obs_dim] f32 (row-major: the layout SB3 /
+//   torch policies consume), term_obs same, reward[B] f64, done[B] u8, info[11][B] f64.
+//   Weather bank W[n_tables][rows][10] f64: row stride 80 B (16-B aligned => legal cp.async.bulk source).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "glg_model.h"
+#include "glg_philox.h"
+#include "glg_rk4.h"
+
+#define GLG_NOBS_FIXED 23
+#define GLG_NINFO 11
+#define GLG_NSTATS 16
+
+struct GlgUniform {  // passed as a __grid_constant__ kernel parameter: lives in the constant bank, no global state
+    double P[GLG_NP];
+    double K[K_COUNT];
+    double C[C_COUNT];
+};
+
+struct GlgStepArgs {
+    int B, n_sub, N, Np, rows, n_tables, obs_dim, auto_reset, raw_control, n_reset_tables;
+    double dt;
+    double u_min[GLG_NU], u_max[GLG_NU];
+    float delta_u_max_f32;
+    double con_low[3], con_high[3];
+    double elec_price, heating_price, co2_price, fruit_price, dmfm, fixed_costs;
+    double uncertainty_scale;
+    unsigned long long seed;
+    long long env_id_offset;
+    const float *actions;     // [B][6]
+    const double *controls;   // [B][6] (raw control mode)
+    const double *noise;      // [B][34] or null
+    const double *weather;    // [n_tables][rows][10]
+    const double *start_day;  // [n_tables]
+    const int *reset_tables;  // [n_reset_tables]
+    double *x, *u, *time, *ep_return, *ep_info;
+    int *timestep, *table, *ep_len;
+    unsigned int *step_ctr;
+    float *obs, *term_obs;
+    double *reward, *info, *stats;
+    unsigned char *done;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// shared-memory column views: element i of thread t lives at base[i*NT + t]  (conflict-free for 8-byte words)
+// ---------------------------------------------------------------------------------------------------------
+template <int NT>
+struct GlgCol {
+    double *b;
+    __device__ __forceinline__ double &operator[](int i) { return b[i * NT]; }
+    __device__ __forceinline__ double operator[](int i) const { return b[i * NT]; }
+};
+template <int NT>
+struct GlgSmemStore {
+    double *b;  // x at rows [0,28), acc at rows [28,56)
+    __device__ __forceinline__ double &x(int i) { return b[i * NT]; }
+    __device__ __forceinline__ double &acc(int i) { return b[(GLG_NX + i) * NT]; }
+};
+struct GlgConstView {  // read-only view of a constant-bank array
+    const double *b;
+    __device__ __forceinline__ double operator[](int i) const { return b[i]; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA (1-D bulk async copy) + mbarrier wrappers, sm_90+ PTX
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t glg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void glg_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(glg_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void glg_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(glg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void glg_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     glg_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(glg_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void glg_mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = glg_smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// env-step semantics shared by the step and reset kernels
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double glg_dens2ppm(double t, double dens) {  // utils.py:352-361
+    return 1e6 * 8.3144598 * (t + 273.15) * dens / (101325 * 44.01e-3);
+}
+__device__ __forceinline__ double glg_clamp(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+__device__ __forceinline__ double glg_rh(double t, double vp) {  // utils.py:363-364
+    return glg_clamp(100 * vp / glg_satvp(t), 0., 100.);
+}
+
+// init_state(): environments/utils.py:13-46 (rhMax=90, time 0)
+__device__ __forceinline__ void glg_init_state(const double *w0, double *x) {
+    const double t0 = 16.5;
+#pragma unroll
+    for (int i = 0; i < GLG_NX; ++i) x[i] = t0;
+    x[0] = w0[3];
+    x[1] = x[0];
+    x[4] = t0 + 4;
+    x[11] = 0.25 * (3. * t0 + w0[6]);
+    x[12] = 0.25 * (2. * t0 + 2 * w0[6]);
+    x[13] = 0.25 * (t0 + 3 * w0[6]);
+    x[14] = w0[6];
+    x[15] = 90 / 100. * glg_satvp(t0);
+    x[16] = x[15];
+    x[21] = x[4];
+    x[22] = 0.;
+    x[23] = 9.5283e4;
+    x[24] = 2.5107e5;
+    x[25] = 5.5338e4;
+    x[26] = 3.0978e3;
+    x[27] = 0.;
+}
+
+// The 23 non-forecast observation entries (observations.py:59-161) for state x, controls u, weather row w,
+// timestep k (pre-increment), day_of_year, hour_of_day.  o3[3] receives obs[0:3] in fp64 for the reward.
+__device__ __forceinline__ void glg_obs_head(const double *x, const double *u, const double *w, int k, double doy,
+                                             double hod, float *row, double *o3) {
+    const double two_pi = 2 * 3.14159265358979323846;
+    o3[0] = glg_dens2ppm(x[2], x[0] * 1e-6);
+    o3[1] = x[2];
+    o3[2] = glg_rh(x[2], x[15]);
+    row[0] = (float)o3[0];
+    row[1] = (float)o3[1];
+    row[2] = (float)o3[2];
+    row[3] = (float)x[9];
+    row[4] = (float)x[21];
+    row[5] = (float)x[25];
+    row[6] = (float)x[26];
+#pragma unroll
+    for (int i = 0; i < GLG_NU; ++i) row[7 + i] = (float)u[i];
+    row[13] = (float)w[0];
+    row[14] = (float)w[1];
+    row[15] = (float)glg_rh(w[1], w[2]);
+    row[16] = (float)glg_dens2ppm(w[1], w[3] * 1e-6);
+    row[17] = (float)w[4];
+    row[18] = (float)k;
+    double s, c;
+    sincos(two_pi * doy / 365.0, &s, &c);
+    row[19] = (float)s;
+    row[20] = (float)c;
+    sincos(two_pi * hod / 24.0, &s, &c);
+    row[21] = (float)s;
+    row[22] = (float)c;
+}
+
+__device__ __forceinline__ double glg_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused step kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int NT, bool NOISY>
+struct GlgStepSmem {
+    static constexpr int kColRows = 2 * GLG_NX + H_COUNT + (NOISY ? C_COUNT : 0);
+    __host__ __device__ static size_t bytes(int Np) {
+        return sizeof(double) * ((size_t)kColRows * NT + (size_t)(Np + 1) * GLG_ND) + 16 /*mbarrier*/ + sizeof(int) * 5 * NT;
+    }
+};
+
+template <bool GENERAL, bool NOISY, int NT>
+__global__ void __launch_bounds__(NT) glg_step_kernel(const __grid_constant__ GlgUniform U, const __grid_constant__ GlgStepArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_wtile = reinterpret_cast<double *>(smem_raw);                         // [(Np+1)][10], 16-B aligned
+    double *s_cols = s_wtile + (size_t)(A.Np + 1) * GLG_ND;                          // [kColRows][NT]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_cols + (size_t)GlgStepSmem<NT, NOISY>::kColRows * NT);
+    int *s_tbl = reinterpret_cast<int *>(s_bar + 2);  // obs source table per row
+    int *s_k = s_tbl + NT;                            // obs source timestep per row (-1: no env)
+    int *s_tbl_t = s_k + NT;                          // terminal-obs source (done rows)
+    int *s_k_t = s_tbl_t + NT;                        // -1: not done
+    int *s_misc = s_k_t + NT;
+
+    const int tid = threadIdx.x;
+    const int e = blockIdx.x * NT + tid;
+    const bool active = e < A.B;
+    const int B = A.B;
+    const size_t table_stride = (size_t)A.rows * GLG_ND;
+
+    // ---- per-env scalars
+    int k = 0, tbl = 0;
+    if (active) {
+        k = A.timestep[e];
+        tbl = A.table[e];
+    }
+    // weather row used by this step; clamped so a terminated env without auto-reset never reads past its table
+    const int kw = min(k, A.rows - A.Np - 1);
+    // ---- stage the block's weather rows k..k+Np with one TMA bulk copy when the block is in lock-step
+    if (tid == 0) {
+        s_misc[0] = kw;
+        s_misc[1] = tbl;
+        glg_mbar_init(s_bar, 1);
+    }
+    __syncthreads();
+    const int bk = s_misc[0], bt = s_misc[1];
+    const int uniform = __syncthreads_and(!active || (kw == bk && tbl == bt));
+    const uint32_t tile_bytes = (uint32_t)((A.Np + 1) * GLG_ND * sizeof(double));
+    if (uniform) {
+        if (tid == 0) {
+            glg_mbar_expect_tx(s_bar, tile_bytes);
+            glg_bulk_g2s(s_wtile, A.weather + (size_t)bt * table_stride + (size_t)bk * GLG_ND, tile_bytes, s_bar);
+        }
+        glg_mbar_wait(s_bar, 0);
+    }
+
+    GlgCol<NT> Hc{s_cols + (size_t)(2 * GLG_NX) * NT + tid};
+    GlgSmemStore<NT> st{s_cols + tid};
+    double reward = 0.0;
+    int done = 0, bad = 0;
+    double info[GLG_NINFO];
+    double fin_ret = 0.0, fin_len = 0.0, fin_info[GLG_NINFO];  // finished-episode sums (zero unless done)
+#pragma unroll
+    for (int j = 0; j < GLG_NINFO; ++j) fin_info[j] = 0.0;
+    int k_obs = -1, tbl_obs = 0, k_term = -1, tbl_term = 0;
+
+    if (active) {
+        const double *wrow = uniform ? s_wtile : (A.weather + (size_t)tbl * table_stride + (size_t)kw * GLG_ND);
+        double d[GLG_ND];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) d[i] = wrow[i];
+
+        // ---- S1: action -> control (tomato_env.py:109-113) or raw control (:148-149)
+        double u[GLG_NU];
+        if (A.raw_control) {
+#pragma unroll
+            for (int i = 0; i < GLG_NU; ++i) u[i] = A.controls[(size_t)e * GLG_NU + i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < GLG_NU; ++i) {
+                const float prod = __fmul_rn(A.actions[(size_t)e * GLG_NU + i], A.delta_u_max_f32);  // float32 product
+                u[i] = glg_clamp(A.u[(size_t)i * B + e] + (double)prod, A.u_min[i], A.u_max[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < GLG_NU; ++i) A.u[(size_t)i * B + e] = u[i];
+
+        // ---- state in
+        double x[GLG_NX];
+#pragma unroll
+        for (int i = 0; i < GLG_NX; ++i) x[i] = A.x[(size_t)i * B + e];
+        const double fruit_prev = x[25];
+
+        // ---- S2 + hoisting + R1-R3
+        const unsigned int ctr = A.step_ctr[e];
+        if (NOISY) {
+            // per-env crop parameters: p'[i] = f32(p[i] + n_i p[i]), i in 128..161 ; p'[144] = f32(p'[141]/p'[142])
+            GlgCol<NT> Cc{s_cols + (size_t)(2 * GLG_NX + H_COUNT) * NT + tid};
+            double pl[GLG_NP];  // local copy; only 128..161 differ
+            double n34[34];
+            if (A.noise) {
+#pragma unroll 1
+                for (int i = 0; i < 34; ++i) n34[i] = A.noise[(size_t)e * 34 + i];
+            } else {
+                glg_noise34(A.seed, (unsigned long long)(A.env_id_offset + e), ctr, A.uncertainty_scale, n34);
+            }
+#pragma unroll 1
+            for (int i = 0; i < GLG_NP; ++i) pl[i] = U.P[i];
+#pragma unroll 1
+            for (int i = 0; i < 34; ++i) {
+                const double pv = U.P[128 + i];
+                pl[128 + i] = (double)__double2float_rn(pv + n34[i] * pv);
+            }
+            pl[144] = (double)__fdiv_rn(__double2float_rn(pl[141]), __double2float_rn(pl[142]));
+            double Cl[C_COUNT];
+            glg_make_c(pl, Cl);
+#pragma unroll
+            for (int i = 0; i < C_COUNT; ++i) Cc[i] = Cl[i];
+            glg_hoist(pl, u, d, Hc);
+            bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, Cc, Hc, GlgConstView{U.P}, u, d, x, A.dt, A.n_sub, st);
+        } else {
+            glg_hoist(GlgConstView{U.P}, u, d, Hc);
+            bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, GlgConstView{U.C}, Hc, GlgConstView{U.P}, u, d, x, A.dt,
+                                        A.n_sub, st);
+        }
+        if (bad) {
+            // reference: evalF raised -> x unchanged, terminated (tomato_env.py:119-123)
+#pragma unroll
+            for (int i = 0; i < GLG_NX; ++i) x[i] = A.x[(size_t)i * B + e];
+            done = 1;
+        }
+
+        // ---- S3: time update (tomato_env.py:126-128)
+        double doy = A.time[e], hod = A.time[(size_t)B + e];
+        doy += fmod(A.dt / 86400.0, 365.0);
+        hod = fmod(hod + A.dt / 3600.0, 24.0);
+
+        // ---- S4: observation head with the pre-increment timestep
+#pragma unroll
+        for (int i = 0; i < GLG_NU; ++i) u[i] = A.u[(size_t)i * B + e];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) d[i] = wrow[i];
+        float row[GLG_NOBS_FIXED];
+        double o3[3];
+        glg_obs_head(x, u, d, k, doy, hod, row, o3);
+
+        // ---- S6: termination (tomato_env.py:68-75,131-132)
+        if (k >= A.N) done = 1;
+
+        // ---- S5/S7: reward and info, nominal parameters (rewards.py:156-231)
+        {
+            const double dt = A.dt;
+            const double heat_costs = u[0] * U.P[108] / U.P[46] * dt / 3600 * 1e-3 * A.heating_price;
+            const double elec_costs = u[4] * U.P[172] * dt / 3600 * 1e-3 * A.elec_price;
+            const double co2_costs = u[1] * U.P[109] / U.P[46] * dt * 1e-6 * A.co2_price;
+            const double variable_costs = 0 + heat_costs + co2_costs + elec_costs;
+            const double gains = (x[25] - fruit_prev) * 1e-6 / A.dmfm * A.fruit_price;
+            const double profit = gains - variable_costs;
+            const double max_profit = U.P[154] * dt * 1e-6 / A.dmfm * A.fruit_price;
+            const double max_heating = U.P[108] / U.P[46] * dt / 3600 * 1e-3 * A.heating_price;
+            const double max_elec = U.P[172] * dt / 3600 * 1e-3 * A.elec_price;
+            const double max_co2 = U.P[109] / U.P[46] * dt * 1e-6 * A.co2_price;
+            const double min_profit = -(0 + max_heating + max_elec + max_co2);
+            const double max_viol[3] = {2500, 15, 15};
+            double viol[3], pen = 0.0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double lo = fmax(A.con_low[j] - o3[j], 0.0), hi = fmax(o3[j] - A.con_high[j], 0.0);
+                viol[j] = lo + hi;
+                pen += viol[j] / max_viol[j];
+            }
+            reward = (profit - min_profit) / (max_profit - min_profit) - pen - 0.0;
+            info[0] = profit; info[1] = gains; info[2] = variable_costs; info[3] = A.fixed_costs;
+            info[4] = co2_costs; info[5] = heat_costs; info[6] = elec_costs;
+            info[7] = viol[1]; info[8] = viol[0]; info[9] = viol[2]; info[10] = 0.0;
+        }
+        A.reward[e] = reward;
+        A.done[e] = (unsigned char)done;
+#pragma unroll
+        for (int j = 0; j < GLG_NINFO; ++j) A.info[(size_t)j * B + e] = info[j];
+
+        // ---- episode accumulators
+        double ep_ret = A.ep_return[e] + reward;
+        int ep_len = A.ep_len[e] + 1;
+#pragma unroll
+        for (int j = 0; j < GLG_NINFO; ++j) info[j] += A.ep_info[(size_t)j * B + e];
+
+        k += 1;
+        k_obs = kw;
+        tbl_obs = tbl;
+        float *orow = A.obs + (size_t)e * A.obs_dim;
+        if (done && A.auto_reset) {
+            // SB3 VecEnv semantics: keep the terminal observation, then reset in place (tomato_env.py:231-270)
+            float *trow = A.term_obs + (size_t)e * A.obs_dim;
+#pragma unroll
+            for (int i = 0; i < GLG_NOBS_FIXED; ++i) trow[i] = row[i];
+            k_term = k_obs;
+            tbl_term = tbl;
+            tbl = A.n_reset_tables > 1
+                      ? A.reset_tables[glg_rand_below(A.seed, (unsigned long long)(A.env_id_offset + e), ctr, (uint32_t)A.n_reset_tables)]
+                      : A.reset_tables[0];
+            const double *w0 = A.weather + (size_t)tbl * table_stride;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) d[i] = w0[i];
+            glg_init_state(d, x);
+#pragma unroll
+            for (int i = 0; i < GLG_NU; ++i) {
+                u[i] = 0.0;
+                A.u[(size_t)i * B + e] = 0.0;
+            }
+            k = 0;
+            doy = A.start_day[tbl];
+            hod = 0.0;
+            glg_obs_head(x, u, d, 0, doy, hod, row, o3);
+            k_obs = 0;
+            tbl_obs = tbl;
+        }
+#pragma unroll
+        for (int i = 0; i < GLG_NOBS_FIXED; ++i) orow[i] = row[i];
+
+        // ---- state out
+#pragma unroll
+        for (int i = 0; i < GLG_NX; ++i) A.x[(size_t)i * B + e] = x[i];
+        A.timestep[e] = k;
+        A.table[e] = tbl;
+        A.time[e] = doy;
+        A.time[(size_t)B + e] = hod;
+        A.step_ctr[e] = ctr + 1u;
+        if (done) {
+            A.ep_return[e] = 0.0;
+            A.ep_len[e] = 0;
+#pragma unroll
+            for (int j = 0; j < GLG_NINFO; ++j) A.ep_info[(size_t)j * B + e] = 0.0;
+        } else {
+            A.ep_return[e] = ep_ret;
+            A.ep_len[e] = ep_len;
+#pragma unroll
+            for (int j = 0; j < GLG_NINFO; ++j) A.ep_info[(size_t)j * B + e] = info[j];
+        }
+        if (done) {
+            fin_ret = ep_ret;
+            fin_len = (double)ep_len;
+#pragma unroll
+            for (int j = 0; j < GLG_NINFO; ++j) fin_info[j] = info[j];
+        }
+        s_tbl_t[tid] = tbl_term;
+        s_k_t[tid] = k_term;
+        s_tbl[tid] = tbl_obs;
+        s_k[tid] = k_obs;
+    } else {
+        s_tbl_t[tid] = 0;
+        s_k_t[tid] = -1;
+        s_tbl[tid] = 0;
+        s_k[tid] = -1;
+    }
+
+    // ---- finished-episode statistics (all 32 lanes participate; non-done lanes carry zeros)
+    {
+        const unsigned any_done = __ballot_sync(0xffffffffu, active && done);
+        if (any_done) {
+            const double cnt = glg_warp_sum((active && done) ? 1.0 : 0.0);
+            const double ret = glg_warp_sum(fin_ret);
+            const double len = glg_warp_sum(fin_len);
+            const double nbad = glg_warp_sum((active && bad) ? 1.0 : 0.0);
+            double isum[GLG_NINFO];
+#pragma unroll
+            for (int j = 0; j < GLG_NINFO; ++j) isum[j] = glg_warp_sum(fin_info[j]);
+            if ((tid & 31) == 0) {
+                atomicAdd(A.stats + 0, cnt);
+                atomicAdd(A.stats + 1, ret);
+                atomicAdd(A.stats + 2, len);
+#pragma unroll
+                for (int j = 0; j < GLG_NINFO; ++j) atomicAdd(A.stats + 3 + j, isum[j]);
+                atomicAdd(A.stats + 14, nbad);
+            }
+        }
+    }
+
+    // ---- S4 forecast block: obs[23 + 5*(i-1) + c] = weather[k+i][c], i=1..Np, c<5 (observations.py:179-182),
+    //      written cooperatively so that each row's 5*Np floats are stored with coalesced accesses
+    __syncthreads();
+    const int nf = 5 * A.Np;
+    const int row0 = blockIdx.x * NT;
+#pragma unroll 1
+    for (int r = 0; r < NT; ++r) {
+        const int kk = s_k[r];
+        if (kk < 0) continue;
+        const int tb = s_tbl[r];
+        const double *src = (uniform && tb == bt && kk == bk) ? s_wtile : (A.weather + (size_t)tb * table_stride + (size_t)kk * GLG_ND);
+        float *orow = A.obs + (size_t)(row0 + r) * A.obs_dim + GLG_NOBS_FIXED;
+        for (int j = tid; j < nf; j += NT) {
+            const int i = j / 5, c = j - 5 * i;
+            orow[j] = (float)src[(size_t)(1 + i) * GLG_ND + c];
+        }
+        const int kt = s_k_t[r];
+        if (kt >= 0) {
+            const int tt = s_tbl_t[r];
+            const double *srct = A.weather + (size_t)tt * table_stride + (size_t)kt * GLG_ND;
+            float *trow = A.term_obs + (size_t)(row0 + r) * A.obs_dim + GLG_NOBS_FIXED;
+            for (int j = tid; j < nf; j += NT) {
+                const int i = j / 5, c = j - 5 * i;
+                trow[j] = (float)srct[(size_t)(1 + i) * GLG_ND + c];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// reset kernel: tomato_env.py:231-270 for the envs selected by mask (NULL = all)
+// ---------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) glg_reset_kernel(const __grid_constant__ GlgStepArgs A, const unsigned char *mask,
+                                                       const int *table_ids) {
+    const int e = blockIdx.x * NT + threadIdx.x;
+    if (e >= A.B) return;
+    if (mask && !mask[e]) return;
+    const int B = A.B;
+    const unsigned int ctr = A.step_ctr[e];
+    int tbl;
+    if (table_ids) tbl = table_ids[e];
+    else
+        tbl = A.n_reset_tables > 1
+                  ? A.reset_tables[glg_rand_below(A.seed, (unsigned long long)(A.env_id_offset + e), ctr, (uint32_t)A.n_reset_tables)]
+                  : A.reset_tables[0];
+    const double *w0 = A.weather + (size_t)tbl * (size_t)A.rows * GLG_ND;
+    double d[GLG_ND], x[GLG_NX], u[GLG_NU], o3[3];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) d[i] = w0[i];
+    glg_init_state(d, x);
+#pragma unroll
+    for (int i = 0; i < GLG_NU; ++i) {
+        u[i] = 0.0;
+        A.u[(size_t)i * B + e] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < GLG_NX; ++i) A.x[(size_t)i * B + e] = x[i];
+    const double doy = A.start_day[tbl];
+    A.timestep[e] = 0;
+    A.table[e] = tbl;
+    A.time[e] = doy;
+    A.time[(size_t)B + e] = 0.0;
+    A.step_ctr[e] = ctr + 1u;
+    A.ep_return[e] = 0.0;
+    A.ep_len[e] = 0;
+#pragma unroll
+    for (int j = 0; j < GLG_NINFO; ++j) A.ep_info[(size_t)j * B + e] = 0.0;
+    A.done[e] = 0;
+    A.reward[e] = 0.0;
+    float row[GLG_NOBS_FIXED];
+    glg_obs_head(x, u, d, 0, doy, 0.0, row, o3);
+    float *orow = A.obs + (size_t)e * A.obs_dim;
+#pragma unroll
+    for (int i = 0; i < GLG_NOBS_FIXED; ++i) orow[i] = row[i];
+    const int nf = 5 * A.Np;
+    for (int j = 0; j < nf; ++j) {
+        const int i = j / 5, c = j - 5 * i;
+        orow[GLG_NOBS_FIXED + j] = (float)w0[(size_t)(1 + i) * GLG_ND + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batched evalF: x_next[b] = RK4^n_sub(x[b]; u[b], d[b], p[b or shared])   (greenlight_model.cpp:96-120)
+// Row-major [B][n] inputs (the layout of B stacked evalF argument vectors).
+// ---------------------------------------------------------------------------------------------------------
+struct GlgLocalView {
+    const double *b;
+    __device__ __forceinline__ double operator[](int i) const { return b[i]; }
+};
+
+template <bool GENERAL, bool PER_ENV_P, int NT>
+__global__ void __launch_bounds__(NT) glg_evalf_kernel(const __grid_constant__ GlgUniform U, const double *xin, const double *uin,
+                                                       const double *din, const double *pin, double *xout,
+                                                       unsigned char *bad_out, int B, double dt, int n_sub) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_cols = reinterpret_cast<double *>(smem_raw);  // [2*28 + H_COUNT][NT]
+    const int tid = threadIdx.x;
+    const int e = blockIdx.x * NT + tid;
+    if (e >= B) return;
+    double x[GLG_NX], u[GLG_NU], d[GLG_ND];
+#pragma unroll
+    for (int i = 0; i < GLG_NX; ++i) x[i] = xin[(size_t)e * GLG_NX + i];
+#pragma unroll
+    for (int i = 0; i < GLG_NU; ++i) u[i] = uin[(size_t)e * GLG_NU + i];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) d[i] = din[(size_t)e * GLG_ND + i];
+    GlgCol<NT> Hc{s_cols + (size_t)(2 * GLG_NX) * NT + tid};
+    GlgSmemStore<NT> st{s_cols + tid};
+    int bad;
+    if (PER_ENV_P) {
+        const double *pe = pin + (size_t)e * GLG_NP;
+        double Kl[K_COUNT], Cl[C_COUNT];
+        glg_make_k(GlgLocalView{pe}, Kl);
+        glg_make_c(GlgLocalView{pe}, Cl);
+        glg_hoist(GlgLocalView{pe}, u, d, Hc);
+        bad = glg_rk4_step<GENERAL>(GlgLocalView{Kl}, GlgLocalView{Cl}, Hc, GlgLocalView{pe}, u, d, x, dt, n_sub, st);
+    } else {
+        glg_hoist(GlgConstView{U.P}, u, d, Hc);
+        bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, GlgConstView{U.C}, Hc, GlgConstView{U.P}, u, d, x, dt, n_sub, st);
+    }
+#pragma unroll
+    for (int i = 0; i < GLG_NX; ++i) xout[(size_t)e * GLG_NX + i] = x[i];
+    if (bad_out) bad_out[e] = (unsigned char)bad;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FMA throughput micro-benchmarks (roofline denominators; MEASURED_PEAKS.json has no FP64/FP32 pipe figure)
+// 8 independent accumulators per thread so the pipe, not the dependency chain, is the limit.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) glg_fma_peak_kernel(T *out, int iters, T a, T b) {
+    T v0 = (T)threadIdx.x, v1 = v0 + (T)1, v2 = v0 + (T)2, v3 = v0 + (T)3, v4 = v0 + (T)4, v5 = v0 + (T)5, v6 = v0 + (T)6,
+      v7 = v0 + (T)7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            v0 = v0 * a + b; v1 = v1 * a + b; v2 = v2 * a + b; v3 = v3 * a + b;
+            v4 = v4 * a + b; v5 = v5 * a + b; v6 = v6 * a + b; v7 = v7 * a + b;
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+}

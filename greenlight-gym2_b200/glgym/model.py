@@ -1,0 +1,49 @@
+"""`GreenLight` -- mirror of the reference's pybind11 class (greenlight_model.cpp:130-136):
+`GreenLight(nx, nu, nd, np, dt).evalF(x, u, d, p) -> list[float]`, executed by the CUDA evalF kernel.
+
+`evalF_batch` is the batched form the B200 path is built for (B independent evalF calls in one launch).
+The integrator is fixed-step RK4 with `n_sub` substeps (BASELINE.json north_star); the reference's CVODES
+(abstol=reltol=1e-6) is a third-party solver that is not available here -- see DESIGN.md.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class GreenLight:
+    def __init__(self, nx=28, nu=6, nd=10, np_=208, dt=900.0, n_sub=600, device=0):
+        if (nx, nu, nd, np_) != (_lib.NX, _lib.NU, _lib.ND, _lib.NP):
+            raise ValueError("GreenLight model dimensions are fixed: nx=28, nu=6, nd=10, np=208")
+        self.dt = float(dt)
+        self.n_sub = int(n_sub)
+        self.device = int(device)
+        self._lib = _lib.load()
+
+    def evalF_batch(self, x, u, d, p, return_bad=False):
+        """x [B,28], u [B,6], d [B,10], p [208] or [B,208]; torch CUDA float64 tensors or array-likes.
+        Returns x_next [B,28] as a CUDA float64 tensor."""
+        dev = torch.device("cuda", self.device)
+        as_t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64) if not torch.is_tensor(a) else a,
+                                         dtype=torch.float64, device=dev).contiguous()
+        x, u, d, p = as_t(x), as_t(u), as_t(d), as_t(p)
+        B = x.shape[0]
+        assert x.shape == (B, 28) and u.shape == (B, 6) and d.shape == (B, 10)
+        p_stride = 0 if p.dim() == 1 else _lib.NP
+        assert p.shape[-1] == _lib.NP and (p.dim() == 1 or p.shape[0] == B)
+        out = torch.empty_like(x)
+        bad = torch.zeros(B, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = self._lib.glg_evalf_batch(x.data_ptr(), u.data_ptr(), d.data_ptr(), p.data_ptr(), p_stride, out.data_ptr(),
+                                       bad.data_ptr(), B, self.dt, self.n_sub, self.device, stream)
+        _lib.check(rc, None, "glg_evalf_batch")
+        return (out, bad) if return_bad else out
+
+    def evalF(self, x, u, d, p):
+        """Single-env call with the reference's signature; returns a list of 28 floats. Raises RuntimeError if the
+        integration produced a non-finite state (the reference raises from CVODES; tomato_env.py:119-123 catches)."""
+        out, bad = self.evalF_batch(np.asarray(x, dtype=np.float64)[None], np.asarray(u, dtype=np.float64)[None],
+                                    np.asarray(d, dtype=np.float64)[None], np.asarray(p, dtype=np.float64), True)
+        if int(bad[0]) != 0:
+            raise RuntimeError("GreenLight.evalF: non-finite state")
+        return out[0].cpu().tolist()

@@ -1,0 +1,341 @@
+"""GreenLightVecEnv -- the batched, GPU-resident replacement for the reference's
+`SubprocVecEnv([TomatoEnv ...])` stack (gl_gym/RL/utils.py:44-69, gl_gym/environments/tomato_env.py).
+
+One object = B greenhouse envs on one B200; every `step` is ONE fused CUDA kernel launch (csrc/glg_kernels.cuh)
+behind the C-ABI in include/glgym.h.  Two ways to drive it:
+
+  * SB3 `VecEnv` protocol with numpy in/out (`reset`, `step_async`/`step_wait`/`step`, `get_attr`, `env_method`,
+    ...): drop-in for code written against the reference.  Host<->device copies happen inside `glg_step_host`.
+  * tensor fast path (`reset_tensor`, `step_tensor`, `step_raw_control_tensor`): actions are CUDA tensors, the
+    returned obs/reward/done are zero-copy torch views of handle-owned device memory; nothing touches the host.
+
+Constructor arguments mirror the reference's YAML (`gl_gym/configs/envs/TomatoEnv.yml`): `base_env_params` =
+the GreenLightEnv section, `constraints`, `reward_params`, `observation_modules`, `uncertainty_scale`.
+"""
+import ctypes as C
+from os.path import join
+
+import numpy as np
+import torch
+
+from . import _lib
+from .params import init_default_params
+from .spaces import Box
+from .weather import DEFAULT_WEATHER_DIR, load_weather_data
+
+DEFAULT_OBSERVATION_MODULES = [
+    "IndoorClimateObservations", "BasicCropObservations", "ControlObservations", "WeatherObservations",
+    "TimeObservations", "WeatherForecastObservations",
+]
+DEFAULT_BASE_ENV_PARAMS = dict(
+    weather_data_dir=DEFAULT_WEATHER_DIR, location="Bleiswijk", data_source="GL", num_params=208, nx=28, nu=6, nd=10,
+    dt=900, u_min=[0, 0, 0, 0, 0, 0], u_max=[1, 1, 1, 1, 1, 1], delta_u_max=0.1, pred_horizon=0.5, season_length=60,
+    start_train_year=2009, end_train_year=2009, start_train_day=0, end_train_day=0, training=True,
+)
+DEFAULT_CONSTRAINTS = dict(co2_min=300.0, co2_max=1600.0, temp_min=15.0, temp_max=34.0, rh_min=50.0, rh_max=85.0)
+DEFAULT_REWARD_PARAMS = dict(
+    fixed_greenhouse_cost=15.0, fixed_co2_cost=0.015, fixed_lamp_cost=0.07, fixed_screen_cost=2.0, elec_price=0.3,
+    heating_price=0.09, co2_price=0.3, fruit_price=1.6, dmfm=0.065, pen_weights=[4.0e-4, 5.0e-3, 7.0e-4], pen_lamp=0.1,
+)
+INFO_KEYS = ("EPI", "revenue", "variable_costs", "fixed_costs", "co2_cost", "heat_cost", "elec_cost",
+             "temp_violation", "co2_violation", "rh_violation", "lamp_violation")
+
+
+class _DevArray:
+    """Zero-copy view of handle-owned device memory through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def obs_names(Np):
+    """Same names as TomatoEnv.get_obs_names() (tomato_env.py:200-206) for the default module stack."""
+    names = ["co2_air", "temp_air", "rh_air", "pipe_temp", "24CanTemp", "cFruit", "tSum",
+             "uBoil", "uCo2", "uThScr", "uVent", "uLamp", "uBlScr",
+             "glob_rad", "temp_out", "rh_out", "co2_out", "wind_speed",
+             "timestep", "day of year sin", "day of year cos", "hour of day sin", "hour of day cos"]
+    return names + ["glob_rad", "temp_out", "rh_out", "co2_out", "wind_speed"] * Np
+
+
+class GreenLightVecEnv:
+    """B TomatoEnv instances advanced in lock-step on one GPU.  See the module docstring."""
+
+    metadata = {"render_modes": []}
+
+    def __init__(self, num_envs, reward_function="GreenhouseReward", observation_modules=None, constraints=None,
+                 eval_options=None, reward_params=None, base_env_params=None, uncertainty_scale=0.0,
+                 n_sub=600, device=0, seed=0, auto_reset=True, env_id_offset=0, weather_tables=None,
+                 table_start_days=None, params=None, info_mode=None):
+        if reward_function != "GreenhouseReward":
+            raise ValueError("only GreenhouseReward exists in the reference (tomato_env.py:14)")
+        mods = list(observation_modules or DEFAULT_OBSERVATION_MODULES)
+        if mods != DEFAULT_OBSERVATION_MODULES:
+            raise ValueError("the fused kernel implements the default observation stack of configs/envs/TomatoEnv.yml: "
+                             f"{DEFAULT_OBSERVATION_MODULES}")
+        bp = dict(DEFAULT_BASE_ENV_PARAMS)
+        bp.update(base_env_params or {})
+        self.base_env_params = bp
+        con = dict(DEFAULT_CONSTRAINTS)
+        con.update(constraints or {})
+        rp = dict(DEFAULT_REWARD_PARAMS)
+        rp.update(reward_params or {})
+        self.eval_options = eval_options
+        self.uncertainty_scale = float(uncertainty_scale)
+        self.num_envs = int(num_envs)
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        # --- derived quantities, base_env.py:65-88
+        self.c = 86400
+        self.nx, self.nu, self.nd, self.num_params = bp["nx"], bp["nu"], bp["nd"], bp["num_params"]
+        self.dt = bp["dt"]
+        self.u_min = np.array(bp["u_min"], dtype=np.float32)
+        self.u_max = np.array(bp["u_max"], dtype=np.float32)
+        self.delta_u_max = np.ones(self.nu, dtype=np.float32) * bp["delta_u_max"]
+        self.Np = int(bp["pred_horizon"] * self.c / self.dt)
+        self.N = int(bp["season_length"] * self.c / self.dt)
+        self.season_length = bp["season_length"]
+        self.location, self.data_source = bp["location"], bp["data_source"]
+        self.weather_data_dir = bp["weather_data_dir"]
+        self.training = bp["training"]
+        self.train_years = list(range(bp["start_train_year"], bp["end_train_year"] + 1))
+        self.train_days = list(range(bp["start_train_day"], bp["end_train_day"] + 1))
+        self.n_sub = int(n_sub)
+        self.observation_modules = mods
+        self.obs_dim = 23 + 5 * self.Np
+        # spaces: tomato_env.py:83-98 / observations.py observation_space() of each module
+        low = np.concatenate([np.full(4, -1e-4), np.full(3, -1e-4), np.zeros(6), np.full(5, -1e-4), np.full(5, -1e-4),
+                              np.full(5 * self.Np, -1e-4)]).astype(np.float32)
+        high = np.concatenate([np.full(4, 1e4), np.full(3, 1e4), np.ones(6), np.full(5, 1e4), np.full(5, 1e4),
+                               np.full(5 * self.Np, 1e4)]).astype(np.float32)
+        self.observation_space = Box(low=low, high=high, dtype=np.float32)
+        self.action_space = Box(low=-1, high=1, shape=(self.nu,), dtype=np.float32)
+        self.constraints_low = np.array([con["co2_min"], con["temp_min"], con["rh_min"]])
+        self.constraints_high = np.array([con["co2_max"], con["temp_max"], con["rh_max"]])
+        self.render_mode = None
+        self.reset_infos = [{} for _ in range(self.num_envs)]
+        self.info_mode = info_mode or ("full" if self.num_envs <= 256 else "minimal")
+
+        # --- parameters (parameters.py) : float32 table widened to float64, as pybind does for evalF
+        self.p = np.asarray(params if params is not None else init_default_params(self.num_params), dtype=np.float32)
+        # --- weather bank: one table per (year, start_day) the env may be reset to (tomato_env.py:236-260)
+        if weather_tables is None:
+            years = self.train_years if self.training else list(eval_options["eval_years"])
+            days = self.train_days if self.training else list(eval_options["eval_days"])
+            loc = self.location if self.training else eval_options["location"]
+            src = self.data_source if self.training else eval_options["data_source"]
+            tabs, sdays, keys = [], [], []
+            for y in years:
+                for sd in days:
+                    tabs.append(load_weather_data(self.weather_data_dir, loc, src, y, sd, self.season_length,
+                                                  self.Np + 1, self.dt, self.nd))
+                    sdays.append(float(sd))
+                    keys.append((y, sd))
+            self.table_keys = keys
+            weather_tables = np.stack(tabs)
+            table_start_days = np.array(sdays)
+        weather_tables = np.ascontiguousarray(weather_tables, dtype=np.float64)
+        if weather_tables.ndim == 2:
+            weather_tables = weather_tables[None]
+        self.weather_tables = weather_tables
+        n_tables, rows, _ = weather_tables.shape
+        self.table_start_days = np.ascontiguousarray(
+            table_start_days if table_start_days is not None else np.zeros(n_tables), dtype=np.float64)
+
+        # --- handle
+        self._lib = _lib.load()
+        cfg = _lib.GlgConfig()
+        self._lib.glg_default_config(C.byref(cfg))
+        cfg.num_envs, cfg.device, cfg.dt, cfg.n_sub, cfg.N, cfg.Np = self.num_envs, self.device_index, float(self.dt), \
+            self.n_sub, self.N, self.Np
+        cfg.precision = 0
+        cfg.auto_reset = 1 if auto_reset else 0
+        for i in range(self.nu):
+            cfg.u_min[i], cfg.u_max[i] = float(self.u_min[i]), float(self.u_max[i])
+        cfg.delta_u_max = float(np.float32(bp["delta_u_max"]))
+        for i in range(3):
+            cfg.con_low[i], cfg.con_high[i] = float(self.constraints_low[i]), float(self.constraints_high[i])
+        cfg.elec_price, cfg.heating_price, cfg.co2_price = rp["elec_price"], rp["heating_price"], rp["co2_price"]
+        cfg.fruit_price, cfg.dmfm = rp["fruit_price"], rp["dmfm"]
+        yearly = rp["fixed_greenhouse_cost"] + rp["fixed_co2_cost"] + rp["fixed_lamp_cost"] * 116 + rp["fixed_screen_cost"]
+        cfg.fixed_costs = yearly / 365 / (86400 // self.dt)  # rewards.py:69-70,154
+        cfg.uncertainty_scale = self.uncertainty_scale
+        cfg.seed = int(seed) & (2**64 - 1)
+        cfg.env_id_offset = int(env_id_offset)
+        self.reward_params = rp
+        self._seed = int(seed)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.glg_create(C.byref(cfg), C.byref(self._h)), None, "glg_create")
+        p64 = np.ascontiguousarray(self.p, dtype=np.float64)
+        _lib.check(self._lib.glg_set_params(self._h, p64.ctypes.data), self._h, "glg_set_params")
+        _lib.check(self._lib.glg_set_weather(self._h, weather_tables.ctypes.data, n_tables, rows,
+                                             self.table_start_days.ctypes.data), self._h, "glg_set_weather")
+        B, dev = self.num_envs, self.device
+        view = lambda ptr, shape, ts: torch.as_tensor(_DevArray(ptr, shape, ts), device=dev)
+        L = self._lib
+        self.obs_t = view(L.glg_obs_dev(self._h), (B, self.obs_dim), "<f4")
+        self.terminal_obs_t = view(L.glg_terminal_obs_dev(self._h), (B, self.obs_dim), "<f4")
+        self.reward_t = view(L.glg_reward_dev(self._h), (B,), "<f8")
+        self.done_t = view(L.glg_done_dev(self._h), (B,), "|u1")
+        self.info_t = view(L.glg_info_dev(self._h), (_lib.NINFO, B), "<f8")
+        self.state_t = view(L.glg_state_dev(self._h), (_lib.NX, B), "<f8")
+        self.controls_t = view(L.glg_controls_dev(self._h), (_lib.NU, B), "<f8")
+        self.timestep_t = view(L.glg_timestep_dev(self._h), (B,), "<i4")
+        self.table_t = view(L.glg_table_dev(self._h), (B,), "<i4")
+        self.time_t = view(L.glg_time_dev(self._h), (2, B), "<f8")
+        self.stats_t = view(L.glg_stats_dev(self._h), (_lib.NSTATS,), "<f8")
+        self._actions = None
+        self._obs_host = np.empty((B, self.obs_dim), dtype=np.float32)
+        self._rew_host = np.empty(B, dtype=np.float64)
+        self._done_host = np.empty(B, dtype=np.uint8)
+
+    # ------------------------------------------------------------------ tensor fast path
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset_tensor(self, mask=None, table_ids=None):
+        m = 0 if mask is None else mask.to(torch.uint8).contiguous().data_ptr()
+        t = 0 if table_ids is None else table_ids.to(torch.int32).contiguous().data_ptr()
+        _lib.check(self._lib.glg_reset(self._h, m, t, self._stream()), self._h, "glg_reset")
+        return self.obs_t
+
+    def step_tensor(self, actions, noise=None):
+        """actions: CUDA float32 [B,6].  Returns (obs [B,obs_dim] f32, reward [B] f64, done [B] u8) device views
+        that are overwritten by the next step."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        n = 0 if noise is None else noise.to(device=self.device, dtype=torch.float64).contiguous().data_ptr()
+        _lib.check(self._lib.glg_step(self._h, a.data_ptr(), n, self._stream()), self._h, "glg_step")
+        return self.obs_t, self.reward_t, self.done_t
+
+    def step_raw_control_tensor(self, controls, noise=None):
+        """TomatoEnv.step_raw_control (tomato_env.py:148-173) for the batch: controls CUDA float64 [B,6]."""
+        u = controls.to(device=self.device, dtype=torch.float64).contiguous()
+        n = 0 if noise is None else noise.to(device=self.device, dtype=torch.float64).contiguous().data_ptr()
+        _lib.check(self._lib.glg_step_raw_control(self._h, u.data_ptr(), n, self._stream()), self._h, "glg_step_raw_control")
+        return self.obs_t, self.reward_t, self.done_t
+
+    # ------------------------------------------------------------------ SB3 VecEnv protocol (numpy)
+    def reset(self):
+        self.reset_tensor()
+        torch.cuda.synchronize(self.device)
+        self.reset_infos = [{} for _ in range(self.num_envs)]
+        return self.obs_t.cpu().numpy()
+
+    def step_async(self, actions):
+        self._actions = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, self.nu)
+
+    def step_wait(self):
+        _lib.check(self._lib.glg_step_host(self._h, self._actions.ctypes.data, self._obs_host.ctypes.data,
+                                           self._rew_host.ctypes.data, self._done_host.ctypes.data), self._h, "glg_step_host")
+        dones = self._done_host.astype(bool)
+        return self._obs_host.copy(), self._rew_host.astype(np.float32), dones, self._make_infos(dones)
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def step_raw_control(self, controls):
+        u = torch.as_tensor(np.asarray(controls, dtype=np.float64).reshape(self.num_envs, self.nu), device=self.device)
+        self.step_raw_control_tensor(u)
+        torch.cuda.synchronize(self.device)
+        dones = self.done_t.cpu().numpy().astype(bool)
+        return self.obs_t.cpu().numpy(), self.reward_t.cpu().numpy(), dones, self._make_infos(dones)
+
+    def _make_infos(self, dones):
+        if self.info_mode == "full":
+            info = self.info_t.cpu().numpy()
+            ctrl = self.controls_t.cpu().numpy()
+            infos = [dict(zip(INFO_KEYS, info[:, i].tolist()), controls=ctrl[:, i].copy(), **{"TimeLimit.truncated": False})
+                     for i in range(self.num_envs)]
+        else:
+            infos = [{} for _ in range(self.num_envs)]
+        idx = np.nonzero(dones)[0]
+        if idx.size:
+            term = self.terminal_obs_t[torch.as_tensor(idx, device=self.device)].cpu().numpy()
+            for j, i in enumerate(idx):
+                infos[i]["terminal_observation"] = term[j]
+                infos[i]["TimeLimit.truncated"] = False
+        return infos
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.glg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, int):
+            return [indices]
+        return indices
+
+    def get_attr(self, attr_name, indices=None):
+        idx = list(self._indices(indices))
+        if attr_name == "u":
+            u = self.controls_t.cpu().numpy()
+            return [u[:, i].copy() for i in idx]
+        if attr_name == "x":
+            x = self.state_t.cpu().numpy()
+            return [x[:, i].copy() for i in idx]
+        if attr_name == "timestep":
+            k = self.timestep_t.cpu().numpy()
+            return [int(k[i]) for i in idx]
+        if attr_name in ("start_day", "growth_year"):
+            tb = self.table_t.cpu().numpy()
+            keys = getattr(self, "table_keys", None)
+            if attr_name == "start_day":
+                return [float(self.table_start_days[tb[i]]) for i in idx]
+            return [keys[tb[i]][0] if keys else None for i in idx]
+        return [getattr(self, attr_name) for _ in idx]
+
+    def set_attr(self, attr_name, value, indices=None):
+        setattr(self, attr_name, value)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        idx = list(self._indices(indices))
+        if method_name == "get_obs_names":
+            return [obs_names(self.Np) for _ in idx]
+        if method_name == "set_seed":
+            return [None for _ in idx]  # RNG streams are keyed by (seed, global env id); see seed()
+        raise AttributeError(f"env_method {method_name!r} is not provided by the batched env")
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False for _ in self._indices(indices)]
+
+    def seed(self, seed=None):
+        return [None if seed is None else seed + i for i in range(self.num_envs)]
+
+    def get_obs_names(self):
+        return obs_names(self.Np)
+
+    # ------------------------------------------------------------------ helpers
+    def set_state(self, x=None, u=None, timestep=None):
+        """Teacher forcing / checkpoint restore: x [B,28], u [B,6] float64, timestep [B] int32 (host arrays)."""
+        ptr = lambda a, dt: 0 if a is None else np.ascontiguousarray(a, dtype=dt).ctypes.data
+        keep = [None if a is None else np.ascontiguousarray(a, dtype=dt) for a, dt in
+                ((x, np.float64), (u, np.float64), (timestep, np.int32))]
+        _lib.check(self._lib.glg_set_state(self._h, *[0 if a is None else a.ctypes.data for a in keep]), self._h, "glg_set_state")
+
+    def get_state(self):
+        x = np.empty((self.num_envs, _lib.NX))
+        u = np.empty((self.num_envs, _lib.NU))
+        k = np.empty(self.num_envs, dtype=np.int32)
+        _lib.check(self._lib.glg_get_state(self._h, x.ctypes.data, u.ctypes.data, k.ctypes.data), self._h, "glg_get_state")
+        return x, u, k
+
+    def launch_count(self):
+        return int(self._lib.glg_launch_count(self._h))
+
+    def episode_stats(self, clear=False):
+        s = self.stats_t.cpu().numpy().copy()
+        if clear:
+            _lib.check(self._lib.glg_clear_stats(self._h, self._stream()), self._h, "glg_clear_stats")
+        out = {"episodes": s[0], "return_sum": s[1], "length_sum": s[2], "nonfinite": s[14]}
+        out.update({k: s[3 + i] for i, k in enumerate(INFO_KEYS)})
+        return out

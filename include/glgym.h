@@ -1,0 +1,144 @@
+/*
+ * glgym.h -- C-ABI of libglgym.so: the B200-native batched GreenLight env-step path.
+ *
+ * Drop-in boundary for two reference interfaces (see INTEGRATION.md for the binding stubs):
+ *   (1) the pybind11 class `GreenLight(nx,nu,nd,np,dt).evalF(x,u,d,p) -> x_next`
+ *       gl_gym/environments/models/greenlight_model.cpp:31,96-120,130-136    -> glg_evalf_batch()
+ *   (2) the env-step path `TomatoEnv.reset()/step()/step_raw_control()` as consumed through SB3's VecEnv
+ *       gl_gym/environments/tomato_env.py:115-173,231-270, gl_gym/RL/utils.py:44-69 -> glg_reset()/glg_step*()
+ *
+ * Conventions: every function returns 0 on success or a negative glg_status; no C++ types or exceptions cross the
+ * boundary; `stream` is a cudaStream_t passed as void* (NULL = default stream); functions taking a stream only
+ * enqueue work (no hidden synchronisation) unless documented otherwise; pointers named *_dev are device pointers
+ * on the handle's device, *_host are host pointers.  Inputs are owned by the caller; state and outputs are owned
+ * by the handle for its lifetime.  A handle is bound to one device and is not thread-safe (like the reference
+ * object it replaces, greenlight_model.cpp:22-24).  There is no CPU fallback: without a CUDA device
+ * glg_create() fails with GLG_ERR_CUDA.
+ */
+#ifndef GLGYM_H
+#define GLGYM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLG_NX 28
+#define GLG_NU 6
+#define GLG_ND 10
+#define GLG_NP 208
+#define GLG_NINFO 11
+#define GLG_NSTATS 16
+#define GLG_NNOISE 34
+
+typedef enum glg_status {
+    GLG_OK = 0,
+    GLG_ERR_ARG = -1,   /* invalid argument */
+    GLG_ERR_CUDA = -2,  /* CUDA runtime error; see glg_last_error() */
+    GLG_ERR_STATE = -3, /* call order (e.g. step before params/weather were set) */
+    GLG_ERR_ALLOC = -4
+} glg_status;
+
+typedef struct glg_handle glg_handle;
+
+/* Mirrors the constructor arguments of TomatoEnv / GreenLightEnv (base_env.py:41-88, tomato_env.py:27-66,
+ * configs/envs/TomatoEnv.yml) plus the batch/GPU knobs. */
+typedef struct glg_config {
+    int32_t num_envs;        /* B: envs owned by this handle (this GPU's shard) */
+    int32_t device;          /* CUDA device ordinal */
+    double dt;               /* control interval [s] (900) */
+    int32_t n_sub;           /* RK4 substeps per control interval (default 600) */
+    int32_t N;               /* int(season_length*86400/dt): index of the last step (base_env.py:88) */
+    int32_t Np;              /* int(pred_horizon*86400/dt): forecast rows in the observation (base_env.py:80) */
+    int32_t precision;       /* 0 = fp64 parity mode ; 1 = fp32 RHS / fp64 state (throughput mode) */
+    int32_t auto_reset;      /* 1: SB3 VecEnv semantics (terminal obs saved, env re-initialised in the same launch) */
+    double u_min[GLG_NU];    /* base_env.py:72 */
+    double u_max[GLG_NU];    /* base_env.py:73 */
+    double delta_u_max;      /* float32(0.1) widened to double (base_env.py:74) */
+    double con_low[3];       /* co2_min [ppm], temp_min, rh_min  (tomato_env.py:51-55) */
+    double con_high[3];      /* co2_max, temp_max, rh_max        (tomato_env.py:57-61) */
+    double elec_price, heating_price, co2_price, fruit_price, dmfm; /* rewards.py:46-94 */
+    double fixed_costs;      /* rewards.py:69-70,154 (reported in info only) */
+    double uncertainty_scale;/* tomato_env.py:34,118 ; 0 = nominal parameters */
+    uint64_t seed;           /* Philox key */
+    int64_t env_id_offset;   /* global index of local env 0 (multi-GPU sharding; RNG streams follow the global id) */
+    int32_t block_threads;   /* 0 = default */
+    int32_t reserved;
+} glg_config;
+
+/* Fills *cfg with the defaults of configs/envs/TomatoEnv.yml (dt 900, N 5760, Np 48, n_sub 600, ...). */
+void glg_default_config(glg_config *cfg);
+
+int glg_create(const glg_config *cfg, glg_handle **out);
+void glg_destroy(glg_handle *h);
+/* Last error text of the handle (or of the failed glg_create when h is NULL). Never NULL. */
+const char *glg_last_error(const glg_handle *h);
+
+/* Nominal parameter table, 208 doubles (float32-rounded values as produced by init_default_params,
+ * parameters.py:4-261).  Derives the parameter-only constants on the host and selects the kernel variant. */
+int glg_set_params(glg_handle *h, const double *p_host);
+/* Weather bank: n_tables tables of `rows` rows x 10 columns (utils.py:75-84), row-major doubles, plus the start
+ * day of each table (day_of_year after reset, tomato_env.py:246).  rows >= N + Np + 1. */
+int glg_set_weather(glg_handle *h, const double *tables_host, int32_t n_tables, int32_t rows, const double *start_day_host);
+/* Tables a reset may pick (uniformly, Philox); default = all tables.  Mirrors rng.choice(train_days), tomato_env.py:236-244 */
+int glg_set_reset_tables(glg_handle *h, const int32_t *table_ids_host, int32_t n);
+
+/* reset(): tomato_env.py:231-270.  mask_dev: uint8[B] (1 = reset) or NULL for all.  table_ids_dev: int32[B]
+ * explicit table per env or NULL to draw from the reset list.  Writes obs. */
+int glg_reset(glg_handle *h, const uint8_t *mask_dev, const int32_t *table_ids_dev, void *stream);
+
+/* step(): tomato_env.py:115-146, fused in one kernel: action->control, parametric noise, weather row fetch,
+ * n_sub RK4 substeps, time update, observation, reward, info, termination, auto-reset.
+ *   actions_dev : float32 [B][6] in [-1,1]
+ *   noise_dev   : NULL (device Philox when uncertainty_scale > 0) or double [B][34] external multipliers n_i
+ *                 (p_i <- f32(p_i + n_i p_i)), for bit-parity with a host RNG (noise.py:16-19) */
+int glg_step(glg_handle *h, const float *actions_dev, const double *noise_dev, void *stream);
+/* step_raw_control(): tomato_env.py:148-173.  controls_dev: double [B][6], used as-is (no clip / rate limit). */
+int glg_step_raw_control(glg_handle *h, const double *controls_dev, const double *noise_dev, void *stream);
+
+/* End-to-end convenience for host callers (the SB3 VecEnv numpy path): copies actions host->device, runs
+ * glg_step on the handle's own stream, copies obs/reward/done device->host and synchronises.  Any output may be
+ * NULL.  obs_host float32 [B][obs_dim], reward_host double [B], done_host uint8 [B]. */
+int glg_step_host(glg_handle *h, const float *actions_host, float *obs_host, double *reward_host, uint8_t *done_host);
+
+/* Output / state accessors: device pointers owned by the handle, valid until glg_destroy. */
+int32_t glg_obs_dim(const glg_handle *h);          /* 23 + 5*Np */
+float *glg_obs_dev(glg_handle *h);                 /* float32 [B][obs_dim]  (observations.py:59-182) */
+float *glg_terminal_obs_dev(glg_handle *h);        /* float32 [B][obs_dim], rows valid where done=1 */
+double *glg_reward_dev(glg_handle *h);             /* double [B]  (rewards.py:218-231) */
+uint8_t *glg_done_dev(glg_handle *h);              /* uint8 [B]   terminated (tomato_env.py:131-132) */
+double *glg_info_dev(glg_handle *h);               /* double [11][B]: EPI, revenue, variable_costs, fixed_costs, co2_cost,
+                                                      heat_cost, elec_cost, temp_violation, co2_violation, rh_violation,
+                                                      lamp_violation (tomato_env.py:208-222) */
+double *glg_state_dev(glg_handle *h);              /* double [28][B] structure-of-arrays */
+double *glg_controls_dev(glg_handle *h);           /* double [6][B] */
+int32_t *glg_timestep_dev(glg_handle *h);          /* int32 [B] */
+int32_t *glg_table_dev(glg_handle *h);             /* int32 [B] weather table of each env */
+double *glg_time_dev(glg_handle *h);               /* double [2][B]: day_of_year, hour_of_day */
+/* Finished-episode statistics (sums since the last clear): [0] episodes, [1] sum return, [2] sum length,
+ * [3..13] sums of the 11 info entries, [14] non-finite terminations, [15] reserved. */
+double *glg_stats_dev(glg_handle *h);
+int glg_clear_stats(glg_handle *h, void *stream);
+
+/* Test / checkpoint helpers (host arrays, synchronous).  x_host double [B][28], u_host double [B][6]. */
+int glg_set_state(glg_handle *h, const double *x_host, const double *u_host, const int32_t *timestep_host);
+int glg_get_state(glg_handle *h, double *x_host, double *u_host, int32_t *timestep_host);
+
+/* evalF for a batch (pure function; replaces B calls of GreenLight::evalF, greenlight_model.cpp:96-120).
+ * Row-major device arrays x[B][28], u[B][6], d[B][10], p[B][208] (p_stride = 208) or one shared p (p_stride = 0),
+ * x_next[B][28].  bad_dev: optional uint8[B], 1 where the result is not finite. */
+int glg_evalf_batch(const double *x_dev, const double *u_dev, const double *d_dev, const double *p_dev, int32_t p_stride,
+                    double *x_next_dev, uint8_t *bad_dev, int32_t B, double dt, int32_t n_sub, int32_t device, void *stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t glg_launch_count(const glg_handle *h);
+/* Measured FP64 FMA throughput of the device [FLOP/s] (dependent-chain-free DFMA loop, all SMs); the roofline
+ * denominator for this FP64-pipe-bound path. Synchronous. */
+int glg_measure_fp64_peak(int32_t device, double *flops_per_s);
+int glg_measure_fp32_peak(int32_t device, double *flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

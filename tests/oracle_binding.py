@@ -1,0 +1,149 @@
+"""ctypes binding of the CPU parity oracle (oracle/libglg_oracle.so).  TEST INFRASTRUCTURE: imported only by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(_ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "libglg_oracle.so")
+_DP = C.POINTER(C.c_double)
+
+
+class EnvCfg(C.Structure):
+    _fields_ = [("dt", C.c_double), ("n_sub", C.c_int), ("N", C.c_int), ("Np", C.c_int),
+                ("delta_u_max_f32", C.c_double), ("u_min", C.c_double * 6), ("u_max", C.c_double * 6),
+                ("con_low", C.c_double * 3), ("con_high", C.c_double * 3),
+                ("elec_price", C.c_double), ("heating_price", C.c_double), ("co2_price", C.c_double),
+                ("fruit_price", C.c_double), ("dmfm", C.c_double), ("uncertainty_scale", C.c_double),
+                ("fixed_costs", C.c_double)]
+
+
+class Env(C.Structure):
+    _fields_ = [("x", C.c_double * 28), ("x_prev", C.c_double * 28), ("u", C.c_double * 6),
+                ("day_of_year", C.c_double), ("hour_of_day", C.c_double), ("timestep", C.c_int),
+                ("terminated", C.c_int), ("weather", _DP), ("weather_rows", C.c_int)]
+
+
+def build():
+    subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+    return LIB
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        lib = C.CDLL(LIB)
+        lib.glgo_aux_rhs.argtypes = [_DP] * 6
+        lib.glgo_rhs.argtypes = [_DP] * 5
+        lib.glgo_evalf.argtypes = [_DP, _DP, _DP, _DP, C.c_double, C.c_int, _DP]
+        lib.glgo_evalf.restype = C.c_int
+        lib.glgo_evalf_batch.argtypes = [_DP, _DP, _DP, _DP, C.c_int, C.c_double, C.c_int, _DP, C.c_int, C.c_int]
+        lib.glgo_evalf_batch.restype = C.c_int
+        lib.glgo_init_state.argtypes = [_DP, _DP]
+        lib.glgo_env_reset.argtypes = [C.POINTER(Env), _DP, C.c_int, C.c_double]
+        lib.glgo_param_noise.argtypes = [_DP, _DP, _DP]
+        lib.glgo_env_obs.argtypes = [C.POINTER(EnvCfg), C.POINTER(Env), _DP]
+        lib.glgo_env_step.argtypes = [C.POINTER(EnvCfg), C.POINTER(Env), _DP, C.c_void_p, C.c_int, _DP, _DP, _DP, _DP]
+        lib.glgo_env_step.restype = C.c_int
+        lib.glgo_rollout.argtypes = [C.POINTER(EnvCfg), _DP, _DP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                     C.c_int, _DP]
+        lib.glgo_rollout.restype = C.c_long
+        _lib = lib
+    return _lib
+
+
+def P(a):
+    return a.ctypes.data_as(_DP)
+
+
+def default_cfg(n_sub=600, N=5760, Np=48, dt=900.0):
+    c = EnvCfg()
+    c.dt, c.n_sub, c.N, c.Np = dt, n_sub, N, Np
+    c.delta_u_max_f32 = float(np.float32(0.1))
+    for i in range(6):
+        c.u_min[i], c.u_max[i] = 0.0, 1.0
+    lo, hi = (300.0, 15.0, 50.0), (1600.0, 34.0, 85.0)
+    for i in range(3):
+        c.con_low[i], c.con_high[i] = lo[i], hi[i]
+    c.elec_price, c.heating_price, c.co2_price, c.fruit_price, c.dmfm = 0.3, 0.09, 0.3, 1.6, 0.065
+    c.uncertainty_scale = 0.0
+    c.fixed_costs = (15.0 + 0.015 + 0.07 * 116 + 2.0) / 365 / (86400 // 900)
+    return c
+
+
+def rhs(x, u, d, p):
+    f = np.zeros(28)
+    load().glgo_rhs(P(x), P(u), P(d), P(p), P(f))
+    return f
+
+
+def aux_rhs(x, u, d, p):
+    a, f = np.zeros(239), np.zeros(28)
+    load().glgo_aux_rhs(P(x), P(u), P(d), P(p), P(a), P(f))
+    return a, f
+
+
+def evalf(x, u, d, p, dt=900.0, n_sub=600):
+    y = np.zeros(28)
+    bad = load().glgo_evalf(P(np.ascontiguousarray(x, dtype=np.float64)), P(np.ascontiguousarray(u, dtype=np.float64)),
+                            P(np.ascontiguousarray(d, dtype=np.float64)), P(np.ascontiguousarray(p, dtype=np.float64)),
+                            dt, n_sub, P(y))
+    return y, bad
+
+
+def evalf_batch(x, u, d, p, dt=900.0, n_sub=600, n_threads=0):
+    x, u, d, p = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, u, d, p))
+    B = x.shape[0]
+    y = np.zeros((B, 28))
+    stride = 0 if p.ndim == 1 else 208
+    n_threads = n_threads or os.cpu_count() or 1
+    load().glgo_evalf_batch(P(x), P(u), P(d), P(p), stride, dt, n_sub, P(y), B, n_threads)
+    return y
+
+
+class OracleEnv:
+    """One reference-semantics env stepped by the C oracle."""
+
+    def __init__(self, weather, p_nom, cfg=None, start_day=0.0):
+        self.cfg = cfg or default_cfg()
+        self.W = np.ascontiguousarray(weather, dtype=np.float64)
+        self.p = np.ascontiguousarray(p_nom, dtype=np.float64)
+        self.e = Env()
+        self.start_day = start_day
+        self.nobs = 23 + 5 * self.cfg.Np
+        self.reset()
+
+    def reset(self):
+        load().glgo_env_reset(C.byref(self.e), P(self.W), self.W.shape[0], self.start_day)
+        obs = np.zeros(self.nobs)
+        load().glgo_env_obs(C.byref(self.cfg), C.byref(self.e), P(obs))
+        return obs
+
+    def step(self, action=None, control=None, noise34=None):
+        obs, r, info = np.zeros(self.nobs), C.c_double(0.0), np.zeros(11)
+        if control is not None:
+            a = np.ascontiguousarray(control, dtype=np.float64)
+            raw = 1
+        else:
+            a = np.ascontiguousarray(action, dtype=np.float32)
+            raw = 0
+        n = None if noise34 is None else P(np.ascontiguousarray(noise34, dtype=np.float64))
+        done = load().glgo_env_step(C.byref(self.cfg), C.byref(self.e), P(self.p), a.ctypes.data, raw, n, P(obs),
+                                    C.cast(C.byref(r), _DP), P(info))
+        return obs, r.value, bool(done), info
+
+    @property
+    def x(self):
+        return np.array(self.e.x[:])
+
+    @property
+    def u(self):
+        return np.array(self.e.u[:])
