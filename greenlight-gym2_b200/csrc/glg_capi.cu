@@ -19,6 +19,7 @@
 #undef GLG_NINFO
 #undef GLG_NSTATS
 #include "glg_kernels.cuh"
+#include "glg_roles.cuh"
 
 static thread_local std::string g_create_error = "";
 
@@ -84,7 +85,7 @@ extern "C" void glg_default_config(glg_config *c) {
     c->uncertainty_scale = 0.0;
     c->seed = 0;
     c->env_id_offset = 0;
-    c->block_threads = 0;
+    c->role_warps = 0;
 }
 
 extern "C" const char *glg_last_error(const glg_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -117,7 +118,8 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
         return GLG_ERR_ARG;
     }
     *out = nullptr;
-    if (cfg->num_envs < 1 || cfg->n_sub < 1 || cfg->N < 0 || cfg->Np < 0 || !(cfg->dt > 0) || cfg->precision != 0) {
+    if (cfg->num_envs < 1 || cfg->n_sub < 1 || cfg->N < 0 || cfg->Np < 0 || !(cfg->dt > 0) || cfg->precision != 0 ||
+        (cfg->role_warps != 0 && cfg->role_warps != 1 && cfg->role_warps != 4)) {
         g_create_error = cfg->precision != 0 ? "glg_create: precision=1 (fp32 throughput mode) is not built in this version"
                                              : "glg_create: invalid num_envs / n_sub / N / Np / dt";
         return GLG_ERR_ARG;
@@ -273,6 +275,27 @@ static cudaError_t launch_step(glg_handle *h, const GlgStepArgs &a, cudaStream_t
     return cudaGetLastError();
 }
 
+template <bool GENERAL, bool NOISY>
+static cudaError_t launch_step_roles(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
+    const size_t smem = GlgRoleSmem<NOISY>::bytes(a.Np);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(glg_step_roles_kernel<GENERAL, NOISY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    glg_step_roles_kernel<GENERAL, NOISY><<<(a.B + GLG_ROLE_LANES - 1) / GLG_ROLE_LANES, GLG_ROLE_THREADS, smem, s>>>(h->uni, a);
+    return cudaGetLastError();
+}
+
+// kernel B (role warps) pays two CTA barriers per RHS evaluation but runs 4x the warps per env; it wins until
+// kernel A alone can keep every SM sub-partition busy.
+static bool use_role_kernel(const glg_handle *h) {
+    if (h->cfg.role_warps == 1) return false;
+    if (h->cfg.role_warps == 4) return true;
+    return h->B <= 8192;  // measured cross-over on B200 (profiles/): below ~2 waves of kernel A the role kernel wins
+}
+
 static int step_common(glg_handle *h, const float *actions_dev, const double *controls_dev, const double *noise_dev,
                        void *stream) {
     int rc = check_ready(h);
@@ -288,8 +311,13 @@ static int step_common(glg_handle *h, const float *actions_dev, const double *co
     const bool noisy = (h->cfg.uncertainty_scale != 0.0) || (noise_dev != nullptr);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
-    if (h->general) e = noisy ? launch_step<true, true>(h, a, s) : launch_step<true, false>(h, a, s);
-    else e = noisy ? launch_step<false, true>(h, a, s) : launch_step<false, false>(h, a, s);
+    if (use_role_kernel(h)) {
+        if (h->general) e = noisy ? launch_step_roles<true, true>(h, a, s) : launch_step_roles<true, false>(h, a, s);
+        else e = noisy ? launch_step_roles<false, true>(h, a, s) : launch_step_roles<false, false>(h, a, s);
+    } else {
+        if (h->general) e = noisy ? launch_step<true, true>(h, a, s) : launch_step<true, false>(h, a, s);
+        else e = noisy ? launch_step<false, true>(h, a, s) : launch_step<false, false>(h, a, s);
+    }
     h->launches += 1;
     GLG_CUDA(h, e);
     return GLG_OK;
@@ -491,3 +519,14 @@ static int measure_peak(int device, double *out) {
 }
 extern "C" int glg_measure_fp64_peak(int32_t device, double *flops) { return measure_peak<double>(device, flops); }
 extern "C" int glg_measure_fp32_peak(int32_t device, double *flops) { return measure_peak<float>(device, flops); }
+
+extern "C" int glg_debug_math(int32_t op, const double *in_dev, double *out_dev, int32_t n, void *stream) {
+    if (!in_dev || !out_dev || n < 1) return GLG_ERR_ARG;
+    glg_math_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(op, in_dev, out_dev, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_create_error = std::string("glg_debug_math: ") + cudaGetErrorString(e);
+        return GLG_ERR_CUDA;
+    }
+    return GLG_OK;
+}

@@ -180,13 +180,269 @@ __device__ __forceinline__ double glg_warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// fused step kernel
+// building blocks shared by the two step kernels
+// ---------------------------------------------------------------------------------------------------------
+
+// Stages the block's weather rows kw..kw+Np of table tbl with ONE TMA bulk copy when every env of the block is in
+// lock-step (same table, same timestep).  Returns 1 and the common (bk, bt) in that case; all threads must call it.
+__device__ __forceinline__ int glg_stage_weather(const GlgStepArgs &A, double *s_wtile, uint64_t *s_bar, int *s_misc,
+                                                 bool active, int kw, int tbl, int &bk, int &bt) {
+    if (threadIdx.x == 0) {
+        s_misc[0] = kw;
+        s_misc[1] = tbl;
+        glg_mbar_init(s_bar, 1);
+    }
+    __syncthreads();
+    bk = s_misc[0];
+    bt = s_misc[1];
+    const int uniform = __syncthreads_and(!active || (kw == bk && tbl == bt));
+    if (uniform) {
+        const uint32_t tile_bytes = (uint32_t)((A.Np + 1) * GLG_ND * sizeof(double));
+        if (threadIdx.x == 0) {
+            glg_mbar_expect_tx(s_bar, tile_bytes);
+            glg_bulk_g2s(s_wtile, A.weather + ((size_t)bt * A.rows + (size_t)bk) * GLG_ND, tile_bytes, s_bar);
+        }
+        glg_mbar_wait(s_bar, 0);
+    }
+    return uniform;
+}
+
+// S1 (action -> control), state load, S2 (parametric noise) and hoisting for env e.  Fills x[28], u[6], d[7..],
+// the H column and (NOISY) the per-env crop-constant column.
+template <bool NOISY, class HC, class CC>
+__device__ __forceinline__ void glg_env_prologue(const GlgUniform &U, const GlgStepArgs &A, int e, const double *wrow,
+                                                 unsigned int ctr, HC &Hc, CC &Cc, double *x, double *u, double *d) {
+    const int B = A.B;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) d[i] = wrow[i];
+    // S1: tomato_env.py:109-113 (float32 action * float32 delta, then float64 add and clip) or raw control :148-149
+    if (A.raw_control) {
+#pragma unroll
+        for (int i = 0; i < GLG_NU; ++i) u[i] = A.controls[(size_t)e * GLG_NU + i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < GLG_NU; ++i) {
+            const float prod = __fmul_rn(A.actions[(size_t)e * GLG_NU + i], A.delta_u_max_f32);
+            u[i] = glg_clamp(A.u[(size_t)i * B + e] + (double)prod, A.u_min[i], A.u_max[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < GLG_NU; ++i) A.u[(size_t)i * B + e] = u[i];
+#pragma unroll
+    for (int i = 0; i < GLG_NX; ++i) x[i] = A.x[(size_t)i * B + e];
+    if (NOISY) {
+        // noise.py:16-22: p'[i] = f32(p[i] + n_i p[i]), i in 128..161 ; p'[144] = f32(p'[141] / p'[142])
+        double pl[GLG_NP];
+        double n34[34];
+        if (A.noise) {
+#pragma unroll 1
+            for (int i = 0; i < 34; ++i) n34[i] = A.noise[(size_t)e * 34 + i];
+        } else {
+            glg_noise34(A.seed, (unsigned long long)(A.env_id_offset + e), ctr, A.uncertainty_scale, n34);
+        }
+#pragma unroll 1
+        for (int i = 0; i < GLG_NP; ++i) pl[i] = U.P[i];
+#pragma unroll 1
+        for (int i = 0; i < 34; ++i) {
+            const double pv = U.P[128 + i];
+            pl[128 + i] = (double)__double2float_rn(pv + n34[i] * pv);
+        }
+        pl[144] = (double)__fdiv_rn(__double2float_rn(pl[141]), __double2float_rn(pl[142]));
+        double Cl[C_COUNT];
+        glg_make_c(pl, Cl);
+#pragma unroll
+        for (int i = 0; i < C_COUNT; ++i) Cc[i] = Cl[i];
+        glg_hoist(pl, u, d, Hc);
+    } else {
+        glg_hoist(GlgConstView{U.P}, u, d, Hc);
+    }
+}
+
+struct GlgEnvOut {  // what the per-env epilogue hands to the block-level phases
+    int done, k_obs, tbl_obs, k_term, tbl_term;
+    double fin_ret, fin_len, fin_info[GLG_NINFO];
+};
+
+// S3..S8 for env e after the integration: time update, observation head, termination, reward/info, episode
+// accumulators, SB3-style auto-reset, state write-back.  x holds the integrated state (restored if bad).
+__device__ __forceinline__ void glg_env_epilogue(const GlgUniform &U, const GlgStepArgs &A, int e, int k, int kw, int tbl,
+                                                 const double *wrow, double *x, double fruit_prev, int bad,
+                                                 unsigned int ctr, GlgEnvOut &o) {
+    const int B = A.B;
+    const size_t table_stride = (size_t)A.rows * GLG_ND;
+    int done = 0;
+    if (bad) {
+        // reference: evalF raised -> x unchanged, terminated (tomato_env.py:119-123)
+#pragma unroll
+        for (int i = 0; i < GLG_NX; ++i) x[i] = A.x[(size_t)i * B + e];
+        done = 1;
+    }
+    // S3: time update (tomato_env.py:126-128)
+    double doy = A.time[e], hod = A.time[(size_t)B + e];
+    doy += fmod(A.dt / 86400.0, 365.0);
+    hod = fmod(hod + A.dt / 3600.0, 24.0);
+    // S4: observation head with the pre-increment timestep
+    double u[GLG_NU], d[GLG_ND];
+#pragma unroll
+    for (int i = 0; i < GLG_NU; ++i) u[i] = A.u[(size_t)i * B + e];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) d[i] = wrow[i];
+    float row[GLG_NOBS_FIXED];
+    double o3[3];
+    glg_obs_head(x, u, d, k, doy, hod, row, o3);
+    // S6: termination (tomato_env.py:68-75,131-132)
+    if (k >= A.N) done = 1;
+    // S5/S7: reward and info with the nominal parameters (rewards.py:156-231), same operation order
+    double reward, info[GLG_NINFO];
+    {
+        const double dt = A.dt;
+        const double heat_costs = u[0] * U.P[108] / U.P[46] * dt / 3600 * 1e-3 * A.heating_price;
+        const double elec_costs = u[4] * U.P[172] * dt / 3600 * 1e-3 * A.elec_price;
+        const double co2_costs = u[1] * U.P[109] / U.P[46] * dt * 1e-6 * A.co2_price;
+        const double variable_costs = 0 + heat_costs + co2_costs + elec_costs;
+        const double gains = (x[25] - fruit_prev) * 1e-6 / A.dmfm * A.fruit_price;
+        const double profit = gains - variable_costs;
+        const double max_profit = U.P[154] * dt * 1e-6 / A.dmfm * A.fruit_price;
+        const double max_heating = U.P[108] / U.P[46] * dt / 3600 * 1e-3 * A.heating_price;
+        const double max_elec = U.P[172] * dt / 3600 * 1e-3 * A.elec_price;
+        const double max_co2 = U.P[109] / U.P[46] * dt * 1e-6 * A.co2_price;
+        const double min_profit = -(0 + max_heating + max_elec + max_co2);
+        const double max_viol[3] = {2500, 15, 15};
+        double viol[3], pen = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double lo = fmax(A.con_low[j] - o3[j], 0.0), hi = fmax(o3[j] - A.con_high[j], 0.0);
+            viol[j] = lo + hi;
+            pen += viol[j] / max_viol[j];
+        }
+        reward = (profit - min_profit) / (max_profit - min_profit) - pen - 0.0;  // lamp penalty is 0: rewards.py:203-216
+        info[0] = profit; info[1] = gains; info[2] = variable_costs; info[3] = A.fixed_costs;
+        info[4] = co2_costs; info[5] = heat_costs; info[6] = elec_costs;
+        info[7] = viol[1]; info[8] = viol[0]; info[9] = viol[2]; info[10] = 0.0;
+    }
+    A.reward[e] = reward;
+    A.done[e] = (unsigned char)done;
+#pragma unroll
+    for (int j = 0; j < GLG_NINFO; ++j) A.info[(size_t)j * B + e] = info[j];
+    // episode accumulators
+    const double ep_ret = A.ep_return[e] + reward;
+    const int ep_len = A.ep_len[e] + 1;
+#pragma unroll
+    for (int j = 0; j < GLG_NINFO; ++j) info[j] += A.ep_info[(size_t)j * B + e];
+
+    k += 1;
+    o.k_obs = kw;
+    o.tbl_obs = tbl;
+    o.k_term = -1;
+    o.tbl_term = 0;
+    float *orow = A.obs + (size_t)e * A.obs_dim;
+    if (done && A.auto_reset) {
+        // SB3 VecEnv semantics: keep the terminal observation, then reset in place (tomato_env.py:231-270)
+        float *trow = A.term_obs + (size_t)e * A.obs_dim;
+#pragma unroll
+        for (int i = 0; i < GLG_NOBS_FIXED; ++i) trow[i] = row[i];
+        o.k_term = kw;
+        o.tbl_term = tbl;
+        tbl = A.n_reset_tables > 1
+                  ? A.reset_tables[glg_rand_below(A.seed, (unsigned long long)(A.env_id_offset + e), ctr, (uint32_t)A.n_reset_tables)]
+                  : A.reset_tables[0];
+        const double *w0 = A.weather + (size_t)tbl * table_stride;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) d[i] = w0[i];
+        glg_init_state(d, x);
+#pragma unroll
+        for (int i = 0; i < GLG_NU; ++i) {
+            u[i] = 0.0;
+            A.u[(size_t)i * B + e] = 0.0;
+        }
+        k = 0;
+        doy = A.start_day[tbl];
+        hod = 0.0;
+        glg_obs_head(x, u, d, 0, doy, hod, row, o3);
+        o.k_obs = 0;
+        o.tbl_obs = tbl;
+    }
+#pragma unroll
+    for (int i = 0; i < GLG_NOBS_FIXED; ++i) orow[i] = row[i];
+    // state out
+#pragma unroll
+    for (int i = 0; i < GLG_NX; ++i) A.x[(size_t)i * B + e] = x[i];
+    A.timestep[e] = k;
+    A.table[e] = tbl;
+    A.time[e] = doy;
+    A.time[(size_t)B + e] = hod;
+    A.step_ctr[e] = ctr + 1u;
+    A.ep_return[e] = done ? 0.0 : ep_ret;
+    A.ep_len[e] = done ? 0 : ep_len;
+#pragma unroll
+    for (int j = 0; j < GLG_NINFO; ++j) A.ep_info[(size_t)j * B + e] = done ? 0.0 : info[j];
+    o.done = done;
+    o.fin_ret = done ? ep_ret : 0.0;
+    o.fin_len = done ? (double)ep_len : 0.0;
+#pragma unroll
+    for (int j = 0; j < GLG_NINFO; ++j) o.fin_info[j] = done ? info[j] : 0.0;
+}
+
+// Finished-episode statistics: warp-shuffle reduction, one atomic per warp and entry.  Full-warp call.
+__device__ __forceinline__ void glg_stats_reduce(const GlgStepArgs &A, bool active, int bad, const GlgEnvOut &o) {
+    const unsigned any_done = __ballot_sync(0xffffffffu, active && o.done);
+    if (!any_done) return;
+    const double cnt = glg_warp_sum((active && o.done) ? 1.0 : 0.0);
+    const double ret = glg_warp_sum(o.fin_ret);
+    const double len = glg_warp_sum(o.fin_len);
+    const double nbad = glg_warp_sum((active && bad) ? 1.0 : 0.0);
+    double isum[GLG_NINFO];
+#pragma unroll
+    for (int j = 0; j < GLG_NINFO; ++j) isum[j] = glg_warp_sum(o.fin_info[j]);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(A.stats + 0, cnt);
+        atomicAdd(A.stats + 1, ret);
+        atomicAdd(A.stats + 2, len);
+#pragma unroll
+        for (int j = 0; j < GLG_NINFO; ++j) atomicAdd(A.stats + 3 + j, isum[j]);
+        atomicAdd(A.stats + 14, nbad);
+    }
+}
+
+// S4 forecast block: obs[23 + 5*(i-1) + c] = weather[k+i][c], i=1..Np, c<5 (observations.py:179-182), written
+// cooperatively by the whole block so each row's 5*Np floats are stored with coalesced accesses.  NR rows/block.
+__device__ __forceinline__ void glg_write_forecast(const GlgStepArgs &A, int NR, const int *s_tbl, const int *s_k,
+                                                   const int *s_tbl_t, const int *s_k_t, const double *s_wtile,
+                                                   int uniform, int bk, int bt) {
+    const size_t table_stride = (size_t)A.rows * GLG_ND;
+    const int nf = 5 * A.Np;
+    const int row0 = blockIdx.x * NR;
+#pragma unroll 1
+    for (int r = 0; r < NR; ++r) {
+        const int kk = s_k[r];
+        if (kk < 0) continue;
+        const int tb = s_tbl[r];
+        const double *src = (uniform && tb == bt && kk == bk) ? s_wtile : (A.weather + (size_t)tb * table_stride + (size_t)kk * GLG_ND);
+        float *orow = A.obs + (size_t)(row0 + r) * A.obs_dim + GLG_NOBS_FIXED;
+        for (int j = threadIdx.x; j < nf; j += blockDim.x) {
+            const int i = j / 5, c = j - 5 * i;
+            orow[j] = (float)src[(size_t)(1 + i) * GLG_ND + c];
+        }
+        const int kt = s_k_t[r];
+        if (kt >= 0) {
+            const double *srct = A.weather + (size_t)s_tbl_t[r] * table_stride + (size_t)kt * GLG_ND;
+            float *trow = A.term_obs + (size_t)(row0 + r) * A.obs_dim + GLG_NOBS_FIXED;
+            for (int j = threadIdx.x; j < nf; j += blockDim.x) {
+                const int i = j / 5, c = j - 5 * i;
+                trow[j] = (float)srct[(size_t)(1 + i) * GLG_ND + c];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// step kernel A: one thread = one env, the whole RHS in one instruction stream (large batches)
 // ---------------------------------------------------------------------------------------------------------
 template <int NT, bool NOISY>
 struct GlgStepSmem {
     static constexpr int kColRows = 2 * GLG_NX + H_COUNT + (NOISY ? C_COUNT : 0);
     __host__ __device__ static size_t bytes(int Np) {
-        return sizeof(double) * ((size_t)kColRows * NT + (size_t)(Np + 1) * GLG_ND) + 16 /*mbarrier*/ + sizeof(int) * 5 * NT;
+        return sizeof(double) * ((size_t)kColRows * NT + (size_t)(Np + 1) * GLG_ND) + 16 /*mbarrier*/ + sizeof(int) * (4 * NT + 4);
     }
 };
 
@@ -205,10 +461,6 @@ __global__ void __launch_bounds__(NT) glg_step_kernel(const __grid_constant__ Gl
     const int tid = threadIdx.x;
     const int e = blockIdx.x * NT + tid;
     const bool active = e < A.B;
-    const int B = A.B;
-    const size_t table_stride = (size_t)A.rows * GLG_ND;
-
-    // ---- per-env scalars
     int k = 0, tbl = 0;
     if (active) {
         k = A.timestep[e];
@@ -216,273 +468,34 @@ __global__ void __launch_bounds__(NT) glg_step_kernel(const __grid_constant__ Gl
     }
     // weather row used by this step; clamped so a terminated env without auto-reset never reads past its table
     const int kw = min(k, A.rows - A.Np - 1);
-    // ---- stage the block's weather rows k..k+Np with one TMA bulk copy when the block is in lock-step
-    if (tid == 0) {
-        s_misc[0] = kw;
-        s_misc[1] = tbl;
-        glg_mbar_init(s_bar, 1);
-    }
-    __syncthreads();
-    const int bk = s_misc[0], bt = s_misc[1];
-    const int uniform = __syncthreads_and(!active || (kw == bk && tbl == bt));
-    const uint32_t tile_bytes = (uint32_t)((A.Np + 1) * GLG_ND * sizeof(double));
-    if (uniform) {
-        if (tid == 0) {
-            glg_mbar_expect_tx(s_bar, tile_bytes);
-            glg_bulk_g2s(s_wtile, A.weather + (size_t)bt * table_stride + (size_t)bk * GLG_ND, tile_bytes, s_bar);
-        }
-        glg_mbar_wait(s_bar, 0);
-    }
+    int bk, bt;
+    const int uniform = glg_stage_weather(A, s_wtile, s_bar, s_misc, active, kw, tbl, bk, bt);
 
-    GlgCol<NT> Hc{s_cols + (size_t)(2 * GLG_NX) * NT + tid};
-    GlgSmemStore<NT> st{s_cols + tid};
-    double reward = 0.0;
-    int done = 0, bad = 0;
-    double info[GLG_NINFO];
-    double fin_ret = 0.0, fin_len = 0.0, fin_info[GLG_NINFO];  // finished-episode sums (zero unless done)
+    GlgEnvOut o;
+    o.done = 0; o.k_obs = -1; o.tbl_obs = 0; o.k_term = -1; o.tbl_term = 0; o.fin_ret = 0.0; o.fin_len = 0.0;
 #pragma unroll
-    for (int j = 0; j < GLG_NINFO; ++j) fin_info[j] = 0.0;
-    int k_obs = -1, tbl_obs = 0, k_term = -1, tbl_term = 0;
-
+    for (int j = 0; j < GLG_NINFO; ++j) o.fin_info[j] = 0.0;
+    int bad = 0;
     if (active) {
-        const double *wrow = uniform ? s_wtile : (A.weather + (size_t)tbl * table_stride + (size_t)kw * GLG_ND);
-        double d[GLG_ND];
-#pragma unroll
-        for (int i = 0; i < 7; ++i) d[i] = wrow[i];
-
-        // ---- S1: action -> control (tomato_env.py:109-113) or raw control (:148-149)
-        double u[GLG_NU];
-        if (A.raw_control) {
-#pragma unroll
-            for (int i = 0; i < GLG_NU; ++i) u[i] = A.controls[(size_t)e * GLG_NU + i];
-        } else {
-#pragma unroll
-            for (int i = 0; i < GLG_NU; ++i) {
-                const float prod = __fmul_rn(A.actions[(size_t)e * GLG_NU + i], A.delta_u_max_f32);  // float32 product
-                u[i] = glg_clamp(A.u[(size_t)i * B + e] + (double)prod, A.u_min[i], A.u_max[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < GLG_NU; ++i) A.u[(size_t)i * B + e] = u[i];
-
-        // ---- state in
-        double x[GLG_NX];
-#pragma unroll
-        for (int i = 0; i < GLG_NX; ++i) x[i] = A.x[(size_t)i * B + e];
-        const double fruit_prev = x[25];
-
-        // ---- S2 + hoisting + R1-R3
+        const double *wrow = uniform ? s_wtile : (A.weather + ((size_t)tbl * A.rows + (size_t)kw) * GLG_ND);
+        GlgCol<NT> Hc{s_cols + (size_t)(2 * GLG_NX) * NT + tid};
+        GlgCol<NT> Cc{s_cols + (size_t)(2 * GLG_NX + H_COUNT) * NT + tid};
+        GlgSmemStore<NT> st{s_cols + tid};
+        double x[GLG_NX], u[GLG_NU], d[GLG_ND];
         const unsigned int ctr = A.step_ctr[e];
-        if (NOISY) {
-            // per-env crop parameters: p'[i] = f32(p[i] + n_i p[i]), i in 128..161 ; p'[144] = f32(p'[141]/p'[142])
-            GlgCol<NT> Cc{s_cols + (size_t)(2 * GLG_NX + H_COUNT) * NT + tid};
-            double pl[GLG_NP];  // local copy; only 128..161 differ
-            double n34[34];
-            if (A.noise) {
-#pragma unroll 1
-                for (int i = 0; i < 34; ++i) n34[i] = A.noise[(size_t)e * 34 + i];
-            } else {
-                glg_noise34(A.seed, (unsigned long long)(A.env_id_offset + e), ctr, A.uncertainty_scale, n34);
-            }
-#pragma unroll 1
-            for (int i = 0; i < GLG_NP; ++i) pl[i] = U.P[i];
-#pragma unroll 1
-            for (int i = 0; i < 34; ++i) {
-                const double pv = U.P[128 + i];
-                pl[128 + i] = (double)__double2float_rn(pv + n34[i] * pv);
-            }
-            pl[144] = (double)__fdiv_rn(__double2float_rn(pl[141]), __double2float_rn(pl[142]));
-            double Cl[C_COUNT];
-            glg_make_c(pl, Cl);
-#pragma unroll
-            for (int i = 0; i < C_COUNT; ++i) Cc[i] = Cl[i];
-            glg_hoist(pl, u, d, Hc);
-            bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, Cc, Hc, GlgConstView{U.P}, u, d, x, A.dt, A.n_sub, st);
-        } else {
-            glg_hoist(GlgConstView{U.P}, u, d, Hc);
-            bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, GlgConstView{U.C}, Hc, GlgConstView{U.P}, u, d, x, A.dt,
-                                        A.n_sub, st);
-        }
-        if (bad) {
-            // reference: evalF raised -> x unchanged, terminated (tomato_env.py:119-123)
-#pragma unroll
-            for (int i = 0; i < GLG_NX; ++i) x[i] = A.x[(size_t)i * B + e];
-            done = 1;
-        }
-
-        // ---- S3: time update (tomato_env.py:126-128)
-        double doy = A.time[e], hod = A.time[(size_t)B + e];
-        doy += fmod(A.dt / 86400.0, 365.0);
-        hod = fmod(hod + A.dt / 3600.0, 24.0);
-
-        // ---- S4: observation head with the pre-increment timestep
-#pragma unroll
-        for (int i = 0; i < GLG_NU; ++i) u[i] = A.u[(size_t)i * B + e];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) d[i] = wrow[i];
-        float row[GLG_NOBS_FIXED];
-        double o3[3];
-        glg_obs_head(x, u, d, k, doy, hod, row, o3);
-
-        // ---- S6: termination (tomato_env.py:68-75,131-132)
-        if (k >= A.N) done = 1;
-
-        // ---- S5/S7: reward and info, nominal parameters (rewards.py:156-231)
-        {
-            const double dt = A.dt;
-            const double heat_costs = u[0] * U.P[108] / U.P[46] * dt / 3600 * 1e-3 * A.heating_price;
-            const double elec_costs = u[4] * U.P[172] * dt / 3600 * 1e-3 * A.elec_price;
-            const double co2_costs = u[1] * U.P[109] / U.P[46] * dt * 1e-6 * A.co2_price;
-            const double variable_costs = 0 + heat_costs + co2_costs + elec_costs;
-            const double gains = (x[25] - fruit_prev) * 1e-6 / A.dmfm * A.fruit_price;
-            const double profit = gains - variable_costs;
-            const double max_profit = U.P[154] * dt * 1e-6 / A.dmfm * A.fruit_price;
-            const double max_heating = U.P[108] / U.P[46] * dt / 3600 * 1e-3 * A.heating_price;
-            const double max_elec = U.P[172] * dt / 3600 * 1e-3 * A.elec_price;
-            const double max_co2 = U.P[109] / U.P[46] * dt * 1e-6 * A.co2_price;
-            const double min_profit = -(0 + max_heating + max_elec + max_co2);
-            const double max_viol[3] = {2500, 15, 15};
-            double viol[3], pen = 0.0;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const double lo = fmax(A.con_low[j] - o3[j], 0.0), hi = fmax(o3[j] - A.con_high[j], 0.0);
-                viol[j] = lo + hi;
-                pen += viol[j] / max_viol[j];
-            }
-            reward = (profit - min_profit) / (max_profit - min_profit) - pen - 0.0;
-            info[0] = profit; info[1] = gains; info[2] = variable_costs; info[3] = A.fixed_costs;
-            info[4] = co2_costs; info[5] = heat_costs; info[6] = elec_costs;
-            info[7] = viol[1]; info[8] = viol[0]; info[9] = viol[2]; info[10] = 0.0;
-        }
-        A.reward[e] = reward;
-        A.done[e] = (unsigned char)done;
-#pragma unroll
-        for (int j = 0; j < GLG_NINFO; ++j) A.info[(size_t)j * B + e] = info[j];
-
-        // ---- episode accumulators
-        double ep_ret = A.ep_return[e] + reward;
-        int ep_len = A.ep_len[e] + 1;
-#pragma unroll
-        for (int j = 0; j < GLG_NINFO; ++j) info[j] += A.ep_info[(size_t)j * B + e];
-
-        k += 1;
-        k_obs = kw;
-        tbl_obs = tbl;
-        float *orow = A.obs + (size_t)e * A.obs_dim;
-        if (done && A.auto_reset) {
-            // SB3 VecEnv semantics: keep the terminal observation, then reset in place (tomato_env.py:231-270)
-            float *trow = A.term_obs + (size_t)e * A.obs_dim;
-#pragma unroll
-            for (int i = 0; i < GLG_NOBS_FIXED; ++i) trow[i] = row[i];
-            k_term = k_obs;
-            tbl_term = tbl;
-            tbl = A.n_reset_tables > 1
-                      ? A.reset_tables[glg_rand_below(A.seed, (unsigned long long)(A.env_id_offset + e), ctr, (uint32_t)A.n_reset_tables)]
-                      : A.reset_tables[0];
-            const double *w0 = A.weather + (size_t)tbl * table_stride;
-#pragma unroll
-            for (int i = 0; i < 7; ++i) d[i] = w0[i];
-            glg_init_state(d, x);
-#pragma unroll
-            for (int i = 0; i < GLG_NU; ++i) {
-                u[i] = 0.0;
-                A.u[(size_t)i * B + e] = 0.0;
-            }
-            k = 0;
-            doy = A.start_day[tbl];
-            hod = 0.0;
-            glg_obs_head(x, u, d, 0, doy, hod, row, o3);
-            k_obs = 0;
-            tbl_obs = tbl;
-        }
-#pragma unroll
-        for (int i = 0; i < GLG_NOBS_FIXED; ++i) orow[i] = row[i];
-
-        // ---- state out
-#pragma unroll
-        for (int i = 0; i < GLG_NX; ++i) A.x[(size_t)i * B + e] = x[i];
-        A.timestep[e] = k;
-        A.table[e] = tbl;
-        A.time[e] = doy;
-        A.time[(size_t)B + e] = hod;
-        A.step_ctr[e] = ctr + 1u;
-        if (done) {
-            A.ep_return[e] = 0.0;
-            A.ep_len[e] = 0;
-#pragma unroll
-            for (int j = 0; j < GLG_NINFO; ++j) A.ep_info[(size_t)j * B + e] = 0.0;
-        } else {
-            A.ep_return[e] = ep_ret;
-            A.ep_len[e] = ep_len;
-#pragma unroll
-            for (int j = 0; j < GLG_NINFO; ++j) A.ep_info[(size_t)j * B + e] = info[j];
-        }
-        if (done) {
-            fin_ret = ep_ret;
-            fin_len = (double)ep_len;
-#pragma unroll
-            for (int j = 0; j < GLG_NINFO; ++j) fin_info[j] = info[j];
-        }
-        s_tbl_t[tid] = tbl_term;
-        s_k_t[tid] = k_term;
-        s_tbl[tid] = tbl_obs;
-        s_k[tid] = k_obs;
-    } else {
-        s_tbl_t[tid] = 0;
-        s_k_t[tid] = -1;
-        s_tbl[tid] = 0;
-        s_k[tid] = -1;
+        glg_env_prologue<NOISY>(U, A, e, wrow, ctr, Hc, Cc, x, u, d);
+        const double fruit_prev = x[25];
+        if (NOISY) bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, Cc, Hc, GlgConstView{U.P}, u, d, x, A.dt, A.n_sub, st);
+        else bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, GlgConstView{U.C}, Hc, GlgConstView{U.P}, u, d, x, A.dt, A.n_sub, st);
+        glg_env_epilogue(U, A, e, k, kw, tbl, wrow, x, fruit_prev, bad, ctr, o);
     }
-
-    // ---- finished-episode statistics (all 32 lanes participate; non-done lanes carry zeros)
-    {
-        const unsigned any_done = __ballot_sync(0xffffffffu, active && done);
-        if (any_done) {
-            const double cnt = glg_warp_sum((active && done) ? 1.0 : 0.0);
-            const double ret = glg_warp_sum(fin_ret);
-            const double len = glg_warp_sum(fin_len);
-            const double nbad = glg_warp_sum((active && bad) ? 1.0 : 0.0);
-            double isum[GLG_NINFO];
-#pragma unroll
-            for (int j = 0; j < GLG_NINFO; ++j) isum[j] = glg_warp_sum(fin_info[j]);
-            if ((tid & 31) == 0) {
-                atomicAdd(A.stats + 0, cnt);
-                atomicAdd(A.stats + 1, ret);
-                atomicAdd(A.stats + 2, len);
-#pragma unroll
-                for (int j = 0; j < GLG_NINFO; ++j) atomicAdd(A.stats + 3 + j, isum[j]);
-                atomicAdd(A.stats + 14, nbad);
-            }
-        }
-    }
-
-    // ---- S4 forecast block: obs[23 + 5*(i-1) + c] = weather[k+i][c], i=1..Np, c<5 (observations.py:179-182),
-    //      written cooperatively so that each row's 5*Np floats are stored with coalesced accesses
+    s_tbl[tid] = o.tbl_obs;
+    s_k[tid] = o.k_obs;
+    s_tbl_t[tid] = o.tbl_term;
+    s_k_t[tid] = o.k_term;
+    glg_stats_reduce(A, active, bad, o);
     __syncthreads();
-    const int nf = 5 * A.Np;
-    const int row0 = blockIdx.x * NT;
-#pragma unroll 1
-    for (int r = 0; r < NT; ++r) {
-        const int kk = s_k[r];
-        if (kk < 0) continue;
-        const int tb = s_tbl[r];
-        const double *src = (uniform && tb == bt && kk == bk) ? s_wtile : (A.weather + (size_t)tb * table_stride + (size_t)kk * GLG_ND);
-        float *orow = A.obs + (size_t)(row0 + r) * A.obs_dim + GLG_NOBS_FIXED;
-        for (int j = tid; j < nf; j += NT) {
-            const int i = j / 5, c = j - 5 * i;
-            orow[j] = (float)src[(size_t)(1 + i) * GLG_ND + c];
-        }
-        const int kt = s_k_t[r];
-        if (kt >= 0) {
-            const int tt = s_tbl_t[r];
-            const double *srct = A.weather + (size_t)tt * table_stride + (size_t)kt * GLG_ND;
-            float *trow = A.term_obs + (size_t)(row0 + r) * A.obs_dim + GLG_NOBS_FIXED;
-            for (int j = tid; j < nf; j += NT) {
-                const int i = j / 5, c = j - 5 * i;
-                trow[j] = (float)srct[(size_t)(1 + i) * GLG_ND + c];
-            }
-        }
-    }
+    glg_write_forecast(A, NT, s_tbl, s_k, s_tbl_t, s_k_t, s_wtile, uniform, bk, bt);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -599,4 +612,10 @@ __global__ void __launch_bounds__(256) glg_fma_peak_kernel(T *out, int iters, T 
         }
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+}
+
+// accuracy probe for glg_math.h (tests only; not on the step path)
+__global__ void glg_math_kernel(int op, const double *in, double *out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = glg_math_eval(op, in[i]);
 }

@@ -1,0 +1,198 @@
+// glg_math.h -- branch-free fp64 elementary functions for the GreenLight RHS.
+//
+// Why not libdevice: exp/log/cbrt/sqrt/div from libdevice carry a special-case test and an out-of-line slow path
+// each (~70 BSSY/BSYNC regions and 34 CALLs per RHS in the first build, ncu: branch_resolving + no_instruction
+// stalls), which chops the 2.5k-instruction RHS into small basic blocks so ptxas cannot interleave the ~30
+// independent transcendental chains, and their polynomial coefficients are materialised with two MOVs each.
+// Here every function is straight-line code, so the whole RHS is ONE basic block, and coefficients are
+// `static const` doubles that ptxas folds into constant-bank operands of the DFMA.
+//
+// Accuracy (checked in tests/test_math_host.py against libm on 1e6 points each): <= 4e-16 relative, i.e. within
+// a couple of ulp of the oracle's libm; the parity gate is 1e-9 per env-step.
+// Domain: the arguments the model can produce.  Out-of-range inputs saturate instead of trapping:
+//   glg_exp  : saturates at 2^-1021 / 2^1023 (never returns inf/0; 1/(1+exp(709)) flushes to 0, which
+//              is the IEEE behaviour the reference's cond() relies on, aux_states.hpp:60-63)
+//   glg_rcp / glg_sqrt / glg_cbrt / glg_log : positive normal arguments (the model adds 1e-10-type epsilons);
+//              NaN propagates, so a diverged env still ends up flagged non-finite.
+// Host build (tests only): same algorithms, seeds from libm.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define GLG_HD __host__ __device__ __forceinline__
+#else
+#define GLG_HD inline
+#endif
+
+// Polynomial coefficients live in the constant bank on the device: a DFMA can take one c[bank][offset] operand, so
+// no instruction is spent on materialising 64-bit immediates (the first build spent ~400 IMAD.MOV/UMOV per RHS on
+// that, which also pushed the RK4 loop past the 32 KB instruction cache of an SM).
+#if defined(__CUDA_ARCH__)
+#define GLG_COEF __constant__
+#else
+#define GLG_COEF static const
+#endif
+GLG_COEF double glg_kExp[13] = {
+    0x1.af631d0059becp-26, 0x1.28b4057f44145p-22, 0x1.71ddf5749d126p-19, 0x1.a01991ac8730ap-16, 0x1.a01a01b14378fp-13,
+    0x1.6c16c187fbe02p-10, 0x1.111111110f225p-7,  0x1.555555554f0cfp-5,  0x1.555555555555ap-3,  0x1.0000000000011p-1,
+    0x1.71547652b82fep+0 /*log2(e)*/, -0x1.62e42fee00000p-1 /*-ln2_hi*/, -0x1.a39ef35793c76p-33 /*-ln2_lo*/};
+GLG_COEF double glg_kLog[9] = {
+    0x1.2b584aae78a57p-3, 0x1.39fe606542ddep-3, 0x1.7462b4ab2ef6bp-3, 0x1.c71c62e5800a1p-3, 0x1.2492492df148dp-2,
+    0x1.99999999952e2p-2, 0x1.5555555555558p-1, 0x1.62e42fee00000p-1 /*ln2_hi*/, 0x1.a39ef35793c76p-33 /*ln2_lo*/};
+
+GLG_HD double glg_bits2d(long long b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+GLG_HD long long glg_d2bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(d);
+#else
+    long long b;
+    memcpy(&b, &d, 8);
+    return b;
+#endif
+}
+GLG_HD double glg_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+
+// ---- reciprocal: ~20-bit hardware seed (MUFU.RCP64H) + one cubic correction: r = r0 (1 + e + e^2), e = 1 - x r0
+GLG_HD double glg_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    const double e = __fma_rn(-x, r0, 1.0);
+    const double t = __fma_rn(e, e, e);
+    return __fma_rn(r0, t, r0);  // seed error 2^-20 -> e^3 = 2^-60
+#else
+    return 1.0 / x;
+#endif
+}
+GLG_HD double glg_div(double a, double b) { return a * glg_rcp(b); }
+
+// ---- sqrt for x > 0: rsqrt seed (MUFU.RSQ64H) + two coupled Goldschmidt steps + a final residual correction
+GLG_HD double glg_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double g = x * r, h = 0.5 * r;
+    double e = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, e, g);
+    h = __fma_rn(h, e, h);
+    e = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, e, g);
+    h = __fma_rn(h, e, h);
+    const double d = __fma_rn(-g, g, x);
+    return __fma_rn(d, h, g);
+#else
+    return sqrt(x);
+#endif
+}
+
+// ---- exp: Cody-Waite reduction r = x - n ln2, |r| <= ln2/2; degree-11 near-minimax polynomial (4e-18);
+//      scaling by 2^n through the exponent field, n clamped so the result stays a normal number.
+GLG_HD double glg_exp(double x) {
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to nearest integer in the low word
+    const double t = glg_fma(x, glg_kExp[10], MAGIC);
+    const double n = t - MAGIC;
+    double r = glg_fma(n, glg_kExp[11], x);
+    r = glg_fma(n, glg_kExp[12], r);
+    double p = glg_kExp[0];
+    p = glg_fma(p, r, glg_kExp[1]);
+    p = glg_fma(p, r, glg_kExp[2]);
+    p = glg_fma(p, r, glg_kExp[3]);
+    p = glg_fma(p, r, glg_kExp[4]);
+    p = glg_fma(p, r, glg_kExp[5]);
+    p = glg_fma(p, r, glg_kExp[6]);
+    p = glg_fma(p, r, glg_kExp[7]);
+    p = glg_fma(p, r, glg_kExp[8]);
+    p = glg_fma(p, r, glg_kExp[9]);
+    p = glg_fma(p, r, 1.0);
+    p = glg_fma(p, r, 1.0);
+    // 2^n: n sits in the low 32 bits of t (two's complement, valid for |x| < 2^30); add it to the exponent field
+    // of p.  p is in [0.70, 1.42]; clamping n to [-1021, 1023] on the integer pipe keeps the result a normal
+    // number and makes the function saturate (~1e-308 / ~1e308) instead of wrapping for |x| > 708.
+    int ni = (int)(uint32_t)(uint64_t)glg_d2bits(t);
+    ni = ni < -1021 ? -1021 : (ni > 1023 ? 1023 : ni);
+    return glg_bits2d(glg_d2bits(p) + ((long long)ni << 52));
+}
+
+// ---- 1/(1+exp(z)) -- the model's ubiquitous sigmoid building block
+GLG_HD double glg_inv1pexp(double z) { return glg_rcp(1.0 + glg_exp(z)); }
+
+// ---- natural log for positive normal x: x = m 2^e, m in [sqrt(1/2), sqrt(2)); f = (m-1)/(m+1);
+//      log m = 2f + f^3 P(f^2), P degree 6 (abs err 3e-16 on P => < 2e-18 on the log)
+GLG_HD double glg_log(double x) {
+    const long long SQRT_HALF_BITS = 0x3FE6A09E667F3BCDLL;  // bits of sqrt(1/2)
+    long long b = glg_d2bits(x);
+    // exponent such that the remaining mantissa lies in [sqrt(1/2), sqrt(2))
+    const long long eb = (b - SQRT_HALF_BITS) >> 52;
+    b -= eb << 52;
+    const double m = glg_bits2d(b);
+    const double e = (double)(int)eb;
+    const double f = (m - 1.0) * glg_rcp(m + 1.0);
+    const double s = f * f;
+    double p = glg_kLog[0];
+    p = glg_fma(p, s, glg_kLog[1]);
+    p = glg_fma(p, s, glg_kLog[2]);
+    p = glg_fma(p, s, glg_kLog[3]);
+    p = glg_fma(p, s, glg_kLog[4]);
+    p = glg_fma(p, s, glg_kLog[5]);
+    p = glg_fma(p, s, glg_kLog[6]);
+    const double lm = glg_fma(f * s, p, 2.0 * f);
+    return glg_fma(e, glg_kLog[7], glg_fma(e, glg_kLog[8], lm));
+}
+GLG_HD double glg_pow(double b, double e) { return glg_exp(e * glg_log(b)); }  // b > 0
+
+// ---- cube root for x > 0: fp32 seed of x^(-1/3) (MUFU.LG2/EX2), two Newton steps on r -> r + r(1 - x r^3)/3,
+//      then cbrt = x r^2 with a final Newton correction on y^3 = x.
+GLG_HD double glg_cbrt(double x) {
+#if defined(__CUDA_ARCH__)
+    // seed in fp32 on the MUFU pipe; clamped so x = 0 gives a finite r (and then cbrt = 0 * r^2 = 0)
+    const float xf = fmaxf(__double2float_rn(x), 1e-36f);
+    float lg, sd;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(-0.33333334f * lg));
+    double r = (double)sd;
+#else
+    double r = (double)(float)(1.0 / cbrt(fmax(x, 1e-36))) * (1.0 + 1e-7);  // deliberately imperfect seed, like the device's
+#endif
+    const double third = 0x1.5555555555555p-2;
+    double r2 = r * r;
+    double e = glg_fma(-x * r, r2, 1.0);
+    r = glg_fma(r * third, e, r);
+    r2 = r * r;
+    e = glg_fma(-x * r, r2, 1.0);
+    r = glg_fma(r * third, e, r);
+    double y = x * (r * r);
+    // y <- y - (y^3 - x)/(3 y^2) = y + (x - y^3) * (r^2/3) * ...; use r ~ x^(-1/3): 1/(3y^2) ~ r^2/3
+    const double d = glg_fma(-y * y, y, x);
+    return glg_fma(d, (r * r) * third, y);
+}
+
+// dispatcher used by the accuracy tests (host build and the glg_debug_math kernel)
+GLG_HD double glg_math_eval(int op, double v) {
+    switch (op) {
+        case 0: return glg_exp(v);
+        case 1: return glg_log(v);
+        case 2: return glg_rcp(v);
+        case 3: return glg_sqrt(v);
+        case 4: return glg_cbrt(v);
+        case 5: return glg_pow(v, 0.66);
+        case 6: return glg_pow(v, 0.32);
+        case 7: return glg_inv1pexp(v);
+        default: return v;
+    }
+}

@@ -26,7 +26,7 @@ class GlgConfig(C.Structure):
         ("elec_price", C.c_double), ("heating_price", C.c_double), ("co2_price", C.c_double),
         ("fruit_price", C.c_double), ("dmfm", C.c_double), ("fixed_costs", C.c_double),
         ("uncertainty_scale", C.c_double), ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
-        ("block_threads", C.c_int32), ("reserved", C.c_int32),
+        ("role_warps", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -64,6 +64,7 @@ SIGNATURES = {
     "glg_launch_count": (C.c_int64, [C.c_void_p]),
     "glg_measure_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "glg_measure_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
+    "glg_debug_math": (C.c_int, [C.c_int32, _DP, _DP, C.c_int32, _VP]),
 }
 
 _lib = None

@@ -63,7 +63,7 @@ typedef struct glg_config {
     double uncertainty_scale;/* tomato_env.py:34,118 ; 0 = nominal parameters */
     uint64_t seed;           /* Philox key */
     int64_t env_id_offset;   /* global index of local env 0 (multi-GPU sharding; RNG streams follow the global id) */
-    int32_t block_threads;   /* 0 = default */
+    int32_t role_warps;      /* kernel variant: 0 = auto, 1 = one thread per env (kernel A), 4 = four role warps per 32 envs (kernel B) */
     int32_t reserved;
 } glg_config;
 
@@ -137,6 +137,10 @@ int64_t glg_launch_count(const glg_handle *h);
  * denominator for this FP64-pipe-bound path. Synchronous. */
 int glg_measure_fp64_peak(int32_t device, double *flops_per_s);
 int glg_measure_fp32_peak(int32_t device, double *flops_per_s);
+
+/* Accuracy probe of the kernel's branch-free fp64 math (csrc/glg_math.h): out[i] = f_op(in[i]) on the device.
+ * op: 0 exp, 1 log, 2 rcp, 3 sqrt, 4 cbrt, 5 pow(x,0.66), 6 pow(x,0.32), 7 1/(1+exp(x)).  Tests only. */
+int glg_debug_math(int32_t op, const double *in_dev, double *out_dev, int32_t n, void *stream);
 
 #ifdef __cplusplus
 }
