@@ -1,0 +1,54 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "greenlight-gym2_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_test_libs():
+    """The oracle and the host build of the device math are test infrastructure: compile them once per session."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    so = os.path.join(ROOT, "tests", "hostmath", "libhostmath.so")
+    src = os.path.join(ROOT, "tests", "hostmath", "hostmath.cpp")
+    hdrs = [os.path.join(ROOT, "greenlight-gym2_b200", "csrc", h) for h in ("glg_model.h", "glg_math.h", "glg_rk4.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src], check=True)
+
+
+@pytest.fixture(scope="session")
+def params64():
+    from glgym.params import init_default_params
+    return init_default_params().astype(np.float64)
+
+
+@pytest.fixture(scope="session")
+def weather0():
+    from glgym.weather import load_weather_data
+    return load_weather_data(None, "Bleiswijk", "GL", 2009, 0, 60, 49, 900, 10)
+
+
+@pytest.fixture(scope="session")
+def rhs_golden():
+    return np.load(os.path.join(GOLDEN, "rhs_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def shell_trace():
+    return np.load(os.path.join(GOLDEN, "shell_trace.npz"))
+
+
+def rel_err(a, b, floor=1e-3):
+    """max |a-b| / max(|b|, floor): relative error with an absolute floor for states that pass through zero."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))

@@ -1,0 +1,151 @@
+"""CPU tier: host-side mirror of the reference interface (parameters, weather, controller), the host build of the
+kernel math against the oracle, and the C-ABI library's exported surface."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from conftest import GOLDEN, ROOT, rel_err
+
+DP = C.POINTER(C.c_double)
+
+
+def P(a):
+    return a.ctypes.data_as(DP)
+
+
+@pytest.fixture(scope="module")
+def hm():
+    lib = C.CDLL(os.path.join(ROOT, "tests", "hostmath", "libhostmath.so"))
+    lib.hm_evalf.argtypes = [DP, DP, DP, DP, C.c_double, C.c_int, C.c_int, DP]
+    return lib
+
+
+def test_parameter_table_matches_reference():
+    from glgym.params import init_default_params, PARAM_NAMES
+    ref = np.load(os.path.join(GOLDEN, "params_numpy2.npy"))
+    assert init_default_params(208, legacy_promotion=False).dtype == np.float32
+    assert np.array_equal(init_default_params(208, legacy_promotion=False), ref)  # what the reference yields under numpy 2
+    legacy = init_default_params(208)
+    assert list(np.nonzero(legacy != ref)[0]) == [169, 171]  # numpy-1.26 promotion changes exactly these
+    assert float(legacy[169]) == 0.18197675049304962 and float(legacy[171]) == 6746.373046875
+    assert len(PARAM_NAMES) == 208 and PARAM_NAMES[46] == "aFlr" and PARAM_NAMES[154] == "rgFruit"
+    with pytest.raises(ValueError):
+        init_default_params(100)
+
+
+def test_weather_builder_matches_reference(weather0):
+    from glgym.weather import load_weather_data, init_state
+    g = np.load(os.path.join(GOLDEN, "weather_golden.npz"))
+    assert tuple(g["shape"]) == weather0.shape == (10464, 10)
+    assert np.array_equal(weather0[::97], g["sample_sd0"])
+    assert np.array_equal(init_state(weather0[0]), g["x0"])
+    for sd in (0, 7, 18):
+        W = weather0 if sd == 0 else load_weather_data(None, "Bleiswijk", "GL", 2009, sd, 60, 49, 900, 10)
+        assert np.array_equal(W[0], g["first"][sd]) and np.array_equal(W[-1], g["last"][sd])
+        assert np.allclose([W.sum(), (W * np.arange(1, 11)).sum(), np.abs(W).max()], g["sums"][sd], rtol=1e-14, atol=0)
+    with pytest.raises(ValueError):  # start day 19 runs out of rows even with GL2010 appended
+        load_weather_data(None, "Bleiswijk", "GL", 2009, 19, 60, 49, 900, 10)
+
+
+def test_rule_based_controller_matches_reference(shell_trace, weather0):
+    from glgym.controller import RuleBasedController
+    from glgym.weather import init_state
+    t, c = shell_trace, RuleBasedController()
+    x, hod, doy = init_state(weather0[0]), 0.0, 0.0
+    for s in range(t["rb_u"].shape[0]):
+        assert np.array_equal(c.predict(x, weather0[s], hod, doy)[0], t["rb_u"][s]), s
+        x, hod, doy = t["rb_x"][s], (hod + 0.25) % 24, doy + 900 / 86400
+    # batch form = row-wise form
+    X = np.stack([t["rb_x"][3], t["rb_x"][30]])
+    U = c.predict(X, np.stack([weather0[4], weather0[31]]), np.array([1.0, 7.75]), np.array([0.04, 0.32]))
+    assert np.array_equal(U[1], c.predict(X[1], weather0[31], 7.75, 0.32)[0])
+
+
+def test_kernel_math_restructuring_matches_oracle(hm, rhs_golden):
+    """The hoisted / streaming RHS of csrc/glg_model.h (host build) and its role-split form against the oracle."""
+    g = rhs_golden
+    worst = np.zeros(28)
+    for i in range(g["x"].shape[0]):
+        x, u, d, p = (g[k][i].copy() for k in ("x", "u", "d", "p"))
+        general = 0 if hm.hm_nominal_structure(P(p)) else 1
+        assert general == (1 if i % 4 == 3 else 0)
+        f, s1, s2 = g["f"][i], np.zeros(28), np.zeros(28)
+        hm.hm_rhs(P(x), P(u), P(d), P(p), general, P(s1))
+        hm.hm_rhs_roles(P(x), P(u), P(d), P(p), general, P(s2))
+        scale = np.maximum(np.abs(f), 1e-12 * np.maximum(1.0, np.abs(x)))
+        worst = np.maximum(worst, np.abs(s1 - f) / scale)
+        assert np.all(np.abs(s1 - s2) <= 1e-12 * np.maximum(np.abs(s1), 1e-9 * np.maximum(1, np.abs(x)))), i
+    # derivative-level agreement; the two carbohydrate balances cancel to ~1e-8 of their terms
+    assert np.all(np.delete(worst, [22, 23, 25]) <= 1e-9) and np.all(worst <= 1e-6), worst
+
+
+def test_kernel_rk4_matches_oracle_per_step(hm, weather0, params64):
+    """Teacher-forced: identical (x,u,d,p) into both; gate 1e-9 relative per state per step (measured ~2e-15)."""
+    from glgym.weather import init_state
+    rng = np.random.default_rng(5)
+    x, u, worst = init_state(weather0[0]), np.zeros(6), 0.0
+    for k in range(12):
+        u = np.clip(u + (rng.uniform(-1, 1, 6).astype(np.float32) * np.float32(0.1)), 0, 1)
+        ya, bad = ob.evalf(x, u, weather0[k], params64, 900.0, 600)
+        yb = np.zeros(28)
+        assert hm.hm_evalf(P(x), P(u), P(weather0[k].copy()), P(params64), 900.0, 600, 0, P(yb)) == 0 and not bad
+        worst = max(worst, rel_err(yb, ya))
+        x = ya
+    assert worst <= 1e-9, worst
+
+
+def test_branch_free_math_accuracy(hm):
+    rng = np.random.default_rng(0)
+
+    def run(op, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        hm.hm_math(op, P(x), P(y), len(x))
+        return y
+    x = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-2, 2, 200000)])
+    assert np.max(np.abs(run(0, x) / np.exp(x) - 1)) <= 4e-16
+    sat = run(0, np.array([-1e4, 1e4]))
+    assert 0 < sat[0] < 1e-300 and 1e300 < sat[1] < np.inf  # saturates, never 0 / inf
+    x = np.exp(rng.uniform(-40, 40, 200000))
+    assert np.max(np.abs(run(1, x) - np.log(x))) <= 4e-16 * 40
+    x = np.exp(rng.uniform(-25, 6, 200000))
+    assert np.max(np.abs(run(4, x) / np.cbrt(x) - 1)) <= 4e-16
+    assert np.max(np.abs(run(5, x) / x ** 0.66 - 1)) <= 4e-15 and np.max(np.abs(run(6, x) / x ** 0.32 - 1)) <= 2e-15
+    assert run(4, np.array([0.0]))[0] == 0.0
+
+
+def test_capi_exports_every_declared_symbol():
+    """Every function include/glgym.h declares is exported by the built library and bound in glgym._lib."""
+    from glgym import _lib
+    hdr = open(os.path.join(ROOT, "include", "glgym.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(glg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()  # raises if the CUDA extension has not been built
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_capi_config_defaults_and_no_cpu_fallback():
+    from glgym import _lib
+    lib = _lib.load()
+    cfg = _lib.GlgConfig()
+    lib.glg_default_config(C.byref(cfg))
+    assert (cfg.n_sub, cfg.N, cfg.Np, cfg.dt, cfg.auto_reset) == (600, 5760, 48, 900.0, 1)
+    assert cfg.delta_u_max == float(np.float32(0.1)) and list(cfg.con_high) == [1600.0, 34.0, 85.0]
+    assert abs(cfg.fixed_costs - (15 + 0.015 + 0.07 * 116 + 2) / 365 / 96) < 1e-18 and cfg.env_id_offset == 0
+    import torch
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert lib.glg_create(C.byref(cfg), C.byref(h)) == _lib.GLG_ERR_CUDA  # loud failure, no CPU path
+        assert b"no CPU fallback" in lib.glg_last_error(None)
+        with pytest.raises(_lib.GlgError):
+            _lib.check(_lib.GLG_ERR_CUDA, None, "glg_create")
+    cfg.num_envs = 0
+    h = C.c_void_p()
+    assert lib.glg_create(C.byref(cfg), C.byref(h)) == _lib.GLG_ERR_ARG

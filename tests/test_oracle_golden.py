@@ -1,0 +1,128 @@
+"""CPU tier: the oracle (oracle/glg_oracle.c) against the golden vectors produced from the reference
+(tests/golden/make_golden.py) and against the structural expectations of the reference's own tests
+(/root/reference/tests/env_test.py:17-92)."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from conftest import GOLDEN, rel_err
+
+
+def test_rhs_matches_reference_source(rhs_golden):
+    """R1/R2: all 239 auxiliaries and 28 derivatives at 400 points, incl. perturbed crop parameters and the
+    parameter sets that switch on the normally-zero terms.  Same libm, same operation order => bit-identical."""
+    g = rhs_golden
+    worst_a = worst_f = 0.0
+    for i in range(g["x"].shape[0]):
+        a, f = ob.aux_rhs(g["x"][i].copy(), g["u"][i].copy(), g["d"][i].copy(), g["p"][i].copy())
+        worst_a = max(worst_a, rel_err(a, g["a"][i], 1e-300))
+        worst_f = max(worst_f, rel_err(f, g["f"][i], 1e-300))
+    assert worst_a <= 1e-14 and worst_f <= 1e-14, (worst_a, worst_f)
+
+
+def test_rhs_survey_anchor(rhs_golden):
+    """SURVEY.md Appendix E anchor: f(x0, u=0, d=W[0]) incl. the float Kelvin offset of airMv (aux_states.hpp:84)."""
+    f = ob.rhs(rhs_golden["x"][0].copy(), rhs_golden["u"][0].copy(), rhs_golden["d"][0].copy(), rhs_golden["p"][0].copy())
+    assert abs(f[0] - (-3.9363845622433037e-02)) < 1e-15
+    assert abs(f[15] - 1.1276861623873362) < 1e-13
+    assert abs(f[16] - (-1.7698364535644129e-01)) < 1e-14
+    assert f[27] == 1.0 / 86400.0
+
+
+def test_step_semantics_match_reference_env(shell_trace, weather0, params64):
+    """S1,S3-S7: the reference's own TomatoEnv.step() trace (40 random float32 actions) reproduced by the C oracle."""
+    t = shell_trace
+    env = ob.OracleEnv(weather0, params64, ob.default_cfg(n_sub=int(t["n_sub"])))
+    assert rel_err(env.reset(), t["reset_obs"], 1e-12) <= 1e-13
+    for s in range(t["step_actions"].shape[0]):
+        obs, r, done, info = env.step(action=t["step_actions"][s])
+        assert rel_err(obs, t["step_obs"][s], 1e-9) <= 1e-11, s
+        # numpy's SIMD exp and glibc's differ in the last ulp of satVp => RH and its penalty term differ by ~1e-11
+        assert abs(r - t["step_reward"][s]) <= 1e-10, s
+        assert rel_err(info[[0, 1, 2, 4, 5, 6, 7, 8, 9, 10]], t["step_info"][s][[0, 1, 2, 4, 5, 6, 7, 8, 9, 10]], 1e-9) <= 1e-9, s
+        assert abs(info[3] - t["step_info"][s][3]) <= 1e-15
+        assert rel_err(env.x, t["step_x"][s], 1e-9) <= 1e-12, s
+        assert np.array_equal(env.u, t["step_u"][s]), s
+        assert done == bool(t["step_term"][s])
+    assert abs(env.e.day_of_year - float(t["doy"])) < 1e-12 and abs(env.e.hour_of_day - float(t["hod"])) < 1e-12
+
+
+def test_raw_control_matches_reference_env(shell_trace, weather0, params64):
+    """step_raw_control (tomato_env.py:148-173) with the reference's rule-based controller outputs."""
+    t = shell_trace
+    env = ob.OracleEnv(weather0, params64, ob.default_cfg(n_sub=int(t["n_sub"])))
+    for s in range(t["rb_u"].shape[0]):
+        obs, r, done, info = env.step(control=t["rb_u"][s])
+        assert rel_err(obs, t["rb_obs"][s], 1e-9) <= 1e-11, s
+        assert abs(r - t["rb_reward"][s]) <= 1e-10, s
+    # SURVEY.md B.7 smoke anchor (first rule-based step): reward -0.2777, CO2 778.35 ppm, tAir 17.14, RH 95.6
+    assert abs(t["rb_reward"][0] - (-0.27769688624)) < 1e-6 and abs(t["rb_obs"][0][0] - 778.35055) < 1e-3
+
+
+def test_parametric_noise_matches_reference(shell_trace, weather0, params64):
+    """S2: noise.py:3-23 applied to the float32 table; then a step() with those parameters."""
+    t = shell_trace
+    lib = ob.load()
+    for n34, p_ref in zip(t["noise_draws"], t["noise_params"]):
+        out = np.zeros(208)
+        lib.glgo_param_noise(ob.P(params64), ob.P(np.ascontiguousarray(n34)), ob.P(out))
+        assert np.array_equal(out, p_ref)
+    env = ob.OracleEnv(weather0, params64, ob.default_cfg(n_sub=int(t["n_sub"])))
+    for s in range(t["noise_actions"].shape[0]):
+        obs, r, done, info = env.step(action=t["noise_actions"][s], noise34=t["noise_draws"][s])
+        assert rel_err(obs, t["noise_obs"][s], 1e-9) <= 1e-11, s
+        assert rel_err(env.x, t["noise_x"][s], 1e-9) <= 1e-12, s
+
+
+def test_reference_unit_test_expectations(weather0, params64, shell_trace):
+    """What /root/reference/tests/env_test.py pins: reward normalisation constant, obs length, timestep counting,
+    zero variable cost for action -1 from u=0, control bounds, episode length N+1 = 5761."""
+    t = shell_trace
+    assert abs(float(t["max_profit"]) - 0.328 * 900 * 1e-6 / 0.065 * 1.6) < 1e-7  # test_reward_normalisation (7 places)
+    cfg = ob.default_cfg(n_sub=300)
+    env = ob.OracleEnv(weather0, params64, cfg)
+    obs = env.reset()
+    assert obs.shape[0] == 263 and env.e.timestep == 0 and env.e.terminated == 0  # test_reset
+    obs, r, done, info = env.step(action=-np.ones(6, dtype=np.float32))
+    assert obs.shape[0] == 263 and env.e.timestep == 1 and isinstance(r, float)  # test_step
+    assert info[2] == 0.0  # test_reward: variable_costs == 0
+    assert np.all(env.u >= 0.0) and np.all(env.u <= 1.0)  # test_action_scaling
+    env.step(action=np.full(6, 7.0, dtype=np.float32))
+    assert np.all(env.u <= 1.0)
+    # test_episode_termination: the step with timestep == N is the terminal one => 5761 steps per episode
+    assert int(t["N"]) == 5760 and list(t["term_at_N"]) == [False, True]
+    env.e.timestep = cfg.N - 1
+    assert env.step(action=np.zeros(6, dtype=np.float32))[2] is False
+    assert env.step(action=np.zeros(6, dtype=np.float32))[2] is True
+
+
+def test_rk4_method_error_vs_tight_implicit_solve(params64):
+    """R3: RK4(n_sub) against Radau rtol=atol=1e-12 on the reference-translated RHS (tests/golden/truth_step.npz).
+    The reference's CVODES runs at 1e-6 tolerances; RK4 with the default n_sub=600 is far inside that band."""
+    g = np.load(f"{GOLDEN}/truth_step.npz")
+    # quiet steps sit at 1e-10..2e-9 for n_sub=600; the hardest fixture (a control jump, CO2 state) at 2.8e-7,
+    # i.e. still inside the reference integrator's own 1e-6 tolerance band; the error falls with h^4.
+    for n_sub, tol in ((300, 2e-6), (600, 5e-7), (900, 1e-7), (1800, 1e-8)):
+        worst = 0.0
+        for x, u, d, y in zip(g["x"], g["u"], g["d"], g["y"]):
+            yo, bad = ob.evalf(x, u, d, g["p"], 900.0, n_sub)
+            assert not bad
+            worst = max(worst, rel_err(yo, y, 1e-3))
+        assert worst <= tol, (n_sub, worst)
+
+
+def test_rk4_unstable_step_is_flagged(weather0, params64):
+    """h = 15 s is beyond the stability limit: the oracle reports a non-finite result instead of garbage."""
+    from glgym.weather import init_state
+    y, bad = ob.evalf(init_state(weather0[0]), np.zeros(6), weather0[0], params64, 900.0, 60)
+    assert bad == 1
+
+
+def test_batch_evalf_threads_agree(rhs_golden, params64):
+    g = rhs_golden
+    sel = [i for i in range(0, 64) if i % 3 != 2 and i % 4 != 3][:16]
+    x, u, d = g["x"][sel], g["u"][sel], g["d"][sel]
+    y1 = ob.evalf_batch(x, u, d, params64, n_sub=300, n_threads=1)
+    y4 = ob.evalf_batch(x, u, d, params64, n_sub=300, n_threads=4)
+    assert np.array_equal(y1, y4)
+    assert np.array_equal(y1[3], ob.evalf(x[3], u[3], d[3], params64, 900.0, 300)[0])
