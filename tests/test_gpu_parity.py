@@ -1,0 +1,358 @@
+"""GPU tier (pytest -m gpu on a B200): the CUDA path, called through the C-ABI (libglgym.so via glgym._lib),
+against the oracle and the committed golden fixtures.  Nothing here reads /root/reference.
+
+Tolerances (BASELINE.json north_star): fp64 parity mode <= 1e-9 relative per state per step with identical inputs,
+<= 1e-6 relative over a full free-running episode.  rel_err uses an absolute floor of 1e-3 for states that pass
+through zero (cBuf starts at 0, time starts at 0).  Observations are float32 outputs: compared after rounding the
+oracle's float64 observation to float32, allowing 1 float32 ulp.
+"""
+import concurrent.futures as cf
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import philox_ref
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+STEP_TOL = 1e-9
+EPISODE_TOL = 1e-6
+F32_ULP = 2.0 ** -23
+
+
+def obs_close(gpu_obs, oracle_obs):
+    ref = np.asarray(oracle_obs, dtype=np.float64).astype(np.float32)
+    return np.all(np.abs(gpu_obs.astype(np.float64) - ref) <= F32_ULP * np.maximum(np.abs(ref), 1e-30) * 1.01)
+
+
+@pytest.fixture(scope="module")
+def L():
+    from glgym import _lib
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return _lib.load()
+
+
+def make_env(B, **kw):
+    from glgym.vec_env import GreenLightVecEnv
+    return GreenLightVecEnv(B, **kw)
+
+
+# ------------------------------------------------------------------------------------------------ math + evalF
+def test_device_math_accuracy(L):
+    rng = np.random.default_rng(0)
+
+    def dev(op, x):
+        xi = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device="cuda")
+        yo = torch.empty_like(xi)
+        assert L.glg_debug_math(op, xi.data_ptr(), yo.data_ptr(), xi.numel(), 0) == 0
+        torch.cuda.synchronize()
+        return yo.cpu().numpy()
+    x = np.concatenate([rng.uniform(-700, 700, 1 << 18), rng.uniform(-2, 2, 1 << 18)])
+    assert np.max(np.abs(dev(0, x) / np.exp(x) - 1)) <= 4e-16
+    x = np.exp(rng.uniform(-40, 40, 1 << 18))
+    assert np.max(np.abs(dev(1, x) - np.log(x))) <= 2e-14
+    assert np.max(np.abs(dev(2, x) * x - 1)) <= 4e-16 and np.max(np.abs(dev(3, x) / np.sqrt(x) - 1)) <= 4e-16
+    x = np.exp(rng.uniform(-25, 6, 1 << 18))
+    assert np.max(np.abs(dev(4, x) / np.cbrt(x) - 1)) <= 4e-16
+    assert np.max(np.abs(dev(5, x) / x ** 0.66 - 1)) <= 4e-15 and np.max(np.abs(dev(6, x) / x ** 0.32 - 1)) <= 2e-15
+    z = rng.uniform(-800, 800, 1 << 16)
+    assert np.max(np.abs(dev(7, z) - 1 / (1 + np.exp(np.clip(z, -708, 709))))) <= 4e-16
+    sat = dev(0, np.array([-1e4, 1e4, np.nan]))
+    assert 0 < sat[0] < 1e-300 and 1e300 < sat[1] < np.inf and np.isnan(sat[2])
+    assert dev(4, np.array([0.0]))[0] == 0.0
+
+
+def test_evalf_batch_matches_oracle_on_golden_points(rhs_golden, params64):
+    """glg_evalf_batch == B independent GreenLight::evalF calls (greenlight_model.cpp:96-120): shared nominal p,
+    shared non-default-structure p (GENERAL kernel) and per-env p."""
+    from glgym.model import GreenLight
+    g = rhs_golden
+    gl = GreenLight(28, 6, 10, 208, 900.0, n_sub=600)
+    # states from the golden set that are physically reasonable starting points for a 900 s integration
+    sel = np.array([i for i in range(g["x"].shape[0]) if i % 3 != 2 and i % 4 != 3][:96])
+    x, u, d = g["x"][sel], g["u"][sel], g["d"][sel]
+    y, bad = gl.evalF_batch(x, u, d, params64, return_bad=True)
+    yo = ob.evalf_batch(x, u, d, params64, n_sub=600)
+    ok = np.isfinite(yo).all(axis=1)
+    assert ok.sum() >= 64 and np.array_equal(bad.cpu().numpy().astype(bool), ~ok)
+    assert rel_err(y.cpu().numpy()[ok], yo[ok]) <= STEP_TOL
+    # per-env parameter rows (crop-parameter noise and the normally-zero terms switched on)
+    sel2 = np.array([i for i in range(g["x"].shape[0]) if i % 3 == 2 or i % 4 == 3][:48])
+    x, u, d, p = g["x"][sel2], g["u"][sel2], g["d"][sel2], g["p"][sel2]
+    y = gl.evalF_batch(x, u, d, p).cpu().numpy()
+    yo = ob.evalf_batch(x, u, d, p, n_sub=600)
+    ok = np.isfinite(yo).all(axis=1)
+    assert ok.sum() >= 24 and rel_err(y[ok], yo[ok]) <= STEP_TOL
+    # one shared non-default table -> GENERAL variant selected on the host
+    pg = g["p"][3]
+    y = gl.evalF_batch(g["x"][sel][:16], g["u"][sel][:16], g["d"][sel][:16], pg).cpu().numpy()
+    yo = ob.evalf_batch(g["x"][sel][:16], g["u"][sel][:16], g["d"][sel][:16], pg, n_sub=600)
+    ok = np.isfinite(yo).all(axis=1)
+    assert rel_err(y[ok], yo[ok]) <= STEP_TOL
+    # single-call form with the reference's signature
+    out = gl.evalF(list(g["x"][0]), list(g["u"][0]), list(g["d"][0]), list(params64))
+    assert isinstance(out, list) and len(out) == 28 and rel_err(np.array(out), ob.evalf(g["x"][0], g["u"][0], g["d"][0], params64)[0]) <= STEP_TOL
+
+
+def test_evalf_nonfinite_raises_like_reference(weather0, params64):
+    from glgym.model import GreenLight
+    from glgym.weather import init_state
+    gl = GreenLight(n_sub=60)  # h = 15 s: unstable => the reference's caller sees an exception (tomato_env.py:119-123)
+    with pytest.raises(RuntimeError):
+        gl.evalF(init_state(weather0[0]), np.zeros(6), weather0[0], params64)
+
+
+# ------------------------------------------------------------------------------------------------ fused step
+@pytest.mark.parametrize("role_warps", [1, 4])
+def test_step_matches_reference_env_trace(role_warps, shell_trace, weather0):
+    """GPU step() against the trace of the reference's own TomatoEnv (golden, n_sub=300): obs, reward, info, state."""
+    t = shell_trace
+    env = make_env(3, n_sub=int(t["n_sub"]), role_warps=role_warps, info_mode="full")
+    obs = env.reset()
+    assert obs.shape == (3, 263) and obs.dtype == np.float32 and obs_close(obs[1], t["reset_obs"])
+    for s in range(t["step_actions"].shape[0]):
+        a = np.tile(t["step_actions"][s], (3, 1))
+        obs, rew, done, infos = env.step(a)
+        x, u, k = env.get_state()
+        assert obs_close(obs[2], t["step_obs"][s]), s
+        assert abs(env.reward_t.cpu().numpy()[0] - t["step_reward"][s]) <= 1e-9, s
+        assert rel_err(x[1], t["step_x"][s]) <= STEP_TOL * (s + 1), s  # free-running: errors may add up per step
+        assert np.array_equal(u[0], t["step_u"][s]) and k[0] == s + 1 and not done.any()
+        info = np.array([infos[0][key] for key in ("EPI", "revenue", "variable_costs", "fixed_costs", "co2_cost", "heat_cost",
+                                                  "elec_cost", "temp_violation", "co2_violation", "rh_violation", "lamp_violation")])
+        assert rel_err(info, t["step_info"][s], 1e-9) <= 1e-6, s
+    env.close()
+
+
+@pytest.mark.parametrize("role_warps", [1, 4])
+def test_step_teacher_forced_vs_oracle(role_warps, weather0, params64):
+    """Per-step gate: identical (x,u,d,p) into GPU and oracle each step, 96 envs with different actions
+    (one full + one partial CTA for kernel A, three CTAs for kernel B), n_sub=600."""
+    rng = np.random.default_rng(11)
+    B = 96
+    env = make_env(B, n_sub=600, role_warps=role_warps)
+    env.reset()
+    orc = [ob.OracleEnv(weather0, params64) for _ in range(B)]
+    for s in range(3):
+        A = rng.uniform(-1, 1, (B, 6)).astype(np.float32)
+        obs, rew, done, _ = env.step(A)
+        x, u, k = env.get_state()
+        r64 = env.reward_t.cpu().numpy()
+        with cf.ThreadPoolExecutor(16) as ex:
+            res = list(ex.map(lambda b: orc[b].step(action=A[b]), range(B)))
+        for b in range(B):
+            o, r, dn, info = res[b]
+            assert rel_err(x[b], orc[b].x) <= STEP_TOL, (s, b)
+            assert obs_close(obs[b], o) and abs(r64[b] - r) <= 1e-9 and done[b] == dn
+            assert np.array_equal(u[b], orc[b].u)
+            # teacher forcing: continue both from the oracle's state
+        env.set_state(x=np.stack([o_.x for o_ in orc]))
+    env.close()
+
+
+def test_raw_control_and_rule_based_trace(shell_trace):
+    """step_raw_control (tomato_env.py:148-173) with the reference controller's outputs (golden)."""
+    t = shell_trace
+    env = make_env(2, n_sub=int(t["n_sub"]))
+    env.reset()
+    for s in range(t["rb_u"].shape[0]):
+        obs, rew, done, _ = env.step_raw_control(np.tile(t["rb_u"][s], (2, 1)))
+        assert obs_close(obs[1], t["rb_obs"][s]) and abs(rew[0] - t["rb_reward"][s]) <= 1e-9, s
+    x, _, _ = env.get_state()
+    assert rel_err(x[0], t["rb_x"][-1]) <= 1e-7
+    env.close()
+
+
+def test_parametric_noise_external_and_philox(shell_trace, weather0, params64):
+    """S2: (a) external multipliers = the reference env's numpy draws (golden) reproduce its trajectory;
+    (b) the device Philox stream equals its numpy restatement and is keyed by the GLOBAL env id."""
+    t = shell_trace
+    env = make_env(2, n_sub=int(t["n_sub"]), uncertainty_scale=0.3)
+    env.reset()
+    for s in range(t["noise_actions"].shape[0]):
+        a = torch.as_tensor(np.tile(t["noise_actions"][s], (2, 1)), device="cuda")
+        n = torch.as_tensor(np.tile(t["noise_draws"][s], (2, 1)), device="cuda")
+        obs, rew, done = env.step_tensor(a, noise=n)
+        torch.cuda.synchronize()
+        assert obs_close(obs.cpu().numpy()[0], t["noise_obs"][s]), s
+    x, _, _ = env.get_state()
+    assert rel_err(x[1], t["noise_x"][-1]) <= 1e-7
+    env.close()
+    # device Philox: env j of a handle with env_id_offset=o uses stream (seed, o+j, step counter)
+    seed, off, scale = 1234567, 1000, 0.3
+    env = make_env(4, n_sub=300, uncertainty_scale=scale, seed=seed, env_id_offset=off)
+    env.reset()
+    orc = [ob.OracleEnv(weather0, params64, ob.default_cfg(n_sub=300)) for _ in range(4)]
+    A = np.random.default_rng(3).uniform(-1, 1, (4, 6)).astype(np.float32)
+    for s in range(2):
+        env.step(A)
+        x, _, _ = env.get_state()
+        for j in range(4):
+            orc[j].step(action=A[j], noise34=philox_ref.noise34(seed, off + j, 1 + s, scale))  # reset consumed counter 0
+            assert rel_err(x[j], orc[j].x) <= STEP_TOL * (s + 1), (s, j)
+    assert not np.allclose(x[0], x[1])  # different envs, different parameter draws
+    env.close()
+
+
+@pytest.mark.parametrize("role_warps", [1, 4])
+def test_termination_autoreset_and_stats(role_warps, weather0, params64):
+    """S6/S8 + SB3 VecEnv semantics: the step with timestep == N is terminal (episode length 5761,
+    tests/env_test.py:77-92); done envs keep their terminal observation and restart from init_state in the same call."""
+    B, N = 70, 5760
+    env = make_env(B, n_sub=300, role_warps=role_warps)
+    obs0 = env.reset()
+    x, u, k = env.get_state()
+    k[:] = N - 1
+    k[5] = 17          # one env elsewhere in its episode => the CTA is not in lock-step (no TMA staging)
+    env.set_state(timestep=k)
+    a = np.zeros((B, 6), dtype=np.float32)
+    obs, rew, done, infos = env.step(a)
+    assert not done.any()
+    obs, rew, done, infos = env.step(a)
+    assert done.sum() == B - 1 and not done[5]
+    x2, u2, k2 = env.get_state()
+    assert np.all(k2[done] == 0) and k2[5] == 19
+    assert np.array_equal(obs[done], np.tile(obs0[0], (B - 1, 1)))            # reset observation
+    assert rel_err(x2[done], x[0:1]) == 0.0 and np.all(u2[done] == 0)
+    term = infos[0]["terminal_observation"]
+    assert term.shape == (263,) and term[18] == N and "terminal_observation" not in infos[5]
+    o = ob.OracleEnv(weather0, params64, ob.default_cfg(n_sub=300))
+    o.e.timestep = N - 1
+    o.step(action=a[0]); oo, r, dn, _ = o.step(action=a[0])
+    assert dn and obs_close(term, oo)
+    st = env.episode_stats()
+    assert st["episodes"] == B - 1 and st["nonfinite"] == 0
+    env.close()
+
+
+def test_lockstep_and_scattered_blocks_agree(weather0):
+    """Weather rows come from the TMA-staged shared-memory tile when a CTA is in lock-step and straight from HBM
+    otherwise: both paths must give identical results for the same env."""
+    B = 64
+    rng = np.random.default_rng(2)
+    A = rng.uniform(-1, 1, (B, 6)).astype(np.float32)
+    res = []
+    for scatter in (False, True):
+        env = make_env(B, n_sub=300, role_warps=1)
+        env.reset()
+        x, u, k = env.get_state()
+        k[:] = 100
+        if scatter:
+            k[1::2] = 200
+        env.set_state(timestep=k)
+        obs, rew, done, _ = env.step(A)
+        res.append((obs.copy(), env.get_state()[0]))
+        env.close()
+    assert np.array_equal(res[0][0][0::2], res[1][0][0::2]) and np.array_equal(res[0][1][0::2], res[1][1][0::2])
+
+
+def test_multi_table_reset_and_start_days():
+    """Reset draws a weather table (start day) per env with Philox; day_of_year starts at the table's start day."""
+    from glgym.weather import load_weather_data
+    tabs = np.stack([load_weather_data(None, "Bleiswijk", "GL", 2009, sd, 60, 49, 900, 10) for sd in (0, 3, 11)])
+    env = make_env(512, n_sub=300, weather_tables=tabs, table_start_days=np.array([0.0, 3.0, 11.0]), seed=9)
+    obs = env.reset()
+    tb = env.table_t.cpu().numpy()
+    assert set(np.unique(tb)) == {0, 1, 2} and np.all(np.bincount(tb) > 100)
+    assert np.array_equal(np.array([philox_ref.rand_below(9, j, 0, 3) for j in range(16)]), tb[:16])
+    doy = env.time_t.cpu().numpy()[0]
+    assert np.array_equal(doy, np.array([0.0, 3.0, 11.0])[tb])
+    for j in (0, 1, 2):
+        i = int(np.nonzero(tb == j)[0][0])
+        assert np.array_equal(obs[i, 13:15], tabs[j, 0, 0:2].astype(np.float32))       # current weather
+        assert np.array_equal(obs[i, 23:28], tabs[j, 1, 0:5].astype(np.float32))       # first forecast row
+    env.close()
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_batch_properties_4096():
+    """BASELINE config 2 size (4096 envs): determinism, kernel A == kernel B, and shard independence
+    (an env's trajectory does not depend on which batch / GPU shard it sits in)."""
+    B = 4096
+    g = torch.Generator(device="cuda")
+    outs = {}
+    for tag, kw in (("A", dict(role_warps=1)), ("B", dict(role_warps=4)), ("B2", dict(role_warps=4))):
+        env = make_env(B, n_sub=600, **kw)
+        env.reset_tensor()
+        g.manual_seed(0)
+        for s in range(3):
+            a = torch.rand(B, 6, device="cuda", generator=g) * 2 - 1
+            obs, rew, done = env.step_tensor(a)
+        torch.cuda.synchronize()
+        outs[tag] = (env.state_t.cpu().numpy().T.copy(), obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), a.cpu().numpy())
+        env.close()
+    assert np.array_equal(outs["B"][0], outs["B2"][0]) and np.array_equal(outs["B"][1], outs["B2"][1])   # deterministic
+    assert rel_err(outs["A"][0], outs["B"][0]) <= 1e-12                                                 # same math, two kernels
+    assert np.isfinite(outs["A"][0]).all() and np.isfinite(outs["A"][2]).all()
+    # shard independence: replay envs 1000..1063 alone
+    env = make_env(64, n_sub=600, role_warps=4, env_id_offset=1000)
+    env.reset_tensor()
+    g.manual_seed(0)
+    for s in range(3):
+        a = torch.rand(B, 6, device="cuda", generator=g) * 2 - 1
+        env.step_tensor(a[1000:1064].contiguous())
+    torch.cuda.synchronize()
+    assert np.array_equal(env.state_t.cpu().numpy().T, outs["B"][0][1000:1064])
+    env.close()
+
+
+def test_free_running_episode_vs_oracle(weather0, params64):
+    """Episode gate: 4 envs, random-walk controls through S1, a full 5761-step season free-running on the GPU and in
+    the oracle; relative error at episode end <= 1e-6 per state; same episode return; auto-reset fires on step 5761."""
+    B, N = 4, 5760
+    rng = np.random.default_rng(123)
+    env = make_env(B, n_sub=600, role_warps=4)
+    env.reset()
+    orc = [ob.OracleEnv(weather0, params64) for _ in range(B)]
+    ret_gpu = np.zeros(B)
+    ret_orc = np.zeros(B)
+    actions = rng.uniform(-1, 1, (N + 1, B, 6)).astype(np.float32)
+
+    def run_oracle(b):
+        tot = 0.0
+        for s in range(N + 1):
+            o, r, dn, _ = orc[b].step(action=actions[s, b])
+            tot += r
+            if s == N - 1:
+                xs = orc[b].x.copy()
+        return tot, xs, dn
+    with cf.ThreadPoolExecutor(B) as ex:
+        fut = [ex.submit(run_oracle, b) for b in range(B)]
+        for s in range(N + 1):
+            obs, rew, done = env.step_tensor(torch.as_tensor(actions[s], device="cuda"))
+            ret_gpu += rew.cpu().numpy()
+            if s == N - 1:
+                x_gpu = env.state_t.cpu().numpy().T.copy()
+            assert bool(done.any().item()) == (s == N)
+        res = [f.result() for f in fut]
+    for b in range(B):
+        ret_orc[b], x_orc, dn = res[b]
+        assert dn
+        assert rel_err(x_gpu[b], x_orc) <= EPISODE_TOL, (b, rel_err(x_gpu[b], x_orc))
+    assert np.max(np.abs(ret_gpu - ret_orc)) <= 1e-6 * np.max(np.abs(ret_orc))
+    st = env.episode_stats()
+    assert st["episodes"] == B and abs(st["return_sum"] - ret_gpu.sum()) <= 1e-9 * abs(ret_gpu.sum()) and st["length_sum"] == B * (N + 1)
+    env.close()
+
+
+def test_handle_errors_are_loud(L):
+    from glgym import _lib
+    cfg = _lib.GlgConfig()
+    L.glg_default_config(C.byref(cfg))
+    cfg.num_envs = 8
+    h = C.c_void_p()
+    assert L.glg_create(C.byref(cfg), C.byref(h)) == 0
+    a = torch.zeros(8, 6, device="cuda")
+    assert L.glg_step(h, a.data_ptr(), 0, 0) == _lib.GLG_ERR_STATE and b"parameters not set" in L.glg_last_error(h)
+    assert L.glg_reset(h, 0, 0, 0) == _lib.GLG_ERR_STATE
+    p = np.zeros(208)
+    assert L.glg_set_params(h, p.ctypes.data) == 0
+    w = np.zeros((1, 100, 10))
+    assert L.glg_set_weather(h, w.ctypes.data, 1, 100, 0) == _lib.GLG_ERR_ARG  # rows < N + Np + 1
+    L.glg_destroy(h)
+    cfg.precision = 1
+    assert L.glg_create(C.byref(cfg), C.byref(h)) == _lib.GLG_ERR_ARG  # fp32 mode is not silently emulated
