@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- GreenLight env-steps/sec on B200 (BASELINE.json metric), fp64 parity mode.
+
+Workload (config.workload): BASELINE.json configs[1] -- "TomatoEnv 4096 batched envs fp64 parity mode, nominal
+parameters, fixed weather year": 4096 envs PER GPU (weak scaling: every rank owns its own 4096-env shard, no
+collective on the step path), Bleiswijk GL2009 weather table (start day 0), RK4 n_sub=600 substeps per 900 s control
+interval, U(-1,1) float32 actions through the rate-limited action->control map, observations (263 f32), reward,
+info, termination and auto-reset all inside the one fused kernel launch per step.
+
+One "step" = one vector env step (B env-steps per GPU).  `value` = whole-job env-steps/s with inputs resident in HBM
+(actions pre-generated on the device, CUDA-event timing per step, max over ranks).  `e2e` = the same metric through the
+numpy SB3-VecEnv call (`env.step(actions)`: host actions -> pinned -> device, kernel, obs/reward/done -> host), timed
+with the wall clock around K calls.  `roofline` is against the FP64 pipe (this path is FP64-bound by > 100x over
+HBM): achieved = env-steps/s x F_step(n_sub) algorithmic flop, peak = DFMA throughput measured live
+on the same GPU (glg_measure_fp64_peak; MEASURED_PEAKS.json carries no FP64 figure); the HBM view is reported
+beside it.  `cpu_baseline` = the CPU oracle (a port of the reference algorithm; the reference's CasADi/CVODES
+extension is not installable here) on all host cores over a bounded sample.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs B] [--n-sub S]
+    torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "greenlight-gym2_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "GreenLight env-steps/sec (fp64 parity)"
+UNIT = "env-steps/s"
+F_RHS, F_SUBSTEP_OVERHEAD, F_STEP_CONST = 880, 448, 529  # algorithmic flop model
+
+
+def flop_per_env_step(n_sub):
+    return (4 * F_RHS + F_SUBSTEP_OVERHEAD) * n_sub + F_STEP_CONST
+
+
+def algorithmic_bytes_per_env_step(obs_dim):
+    # read x,u,action,scalars ; write x,u,obs,reward,done,info (+ per-CTA weather tile, amortised)
+    return (224 + 48 + 24 + 16) + (224 + 48 + obs_dim * 4 + 8 + 1 + 88) + 16
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def load_inputs():
+    from glgym.params import init_default_params
+    from glgym.weather import load_weather_data
+    return init_default_params().astype(np.float64), load_weather_data(None, "Bleiswijk", "GL", 2009, 0, 60, 49, 900, 10)
+
+
+def cpu_rate(B, n_steps, n_sub, threads, warmup=0):
+    """env-steps/s of the CPU oracle batch (reference semantics, RK4 n_sub) on `threads` host threads."""
+    import oracle_binding as ob
+    p, W = load_inputs()
+    batch = ob.OracleBatch(W, p, B, ob.default_cfg(n_sub=n_sub), n_threads=threads)
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(-1, 1, (warmup + n_steps, B, 6)).astype(np.float32)
+    for s in range(warmup):
+        batch.step(acts[s])
+    t0 = time.perf_counter()
+    for s in range(n_steps):
+        batch.step(acts[warmup + s])
+    dt = time.perf_counter() - t0
+    batch.close()
+    return B * n_steps / dt, dt
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU implementation of the path.  CasADi/SUNDIALS cannot be installed in this
+    image (no wheel, no network), so this is the CPU oracle port with all host threads; rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 4 * cores  # envs per vector step: a bounded sample of the 4096-env workload
+    rate, dt = cpu_rate(sample, args.steps, args.n_sub, cores, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic actions; Bleiswijk GL2009 weather table shipped with the reference",
+        "config": {"workload": "TomatoEnv batched envs fp64, nominal parameters, fixed weather year (BASELINE configs[1])",
+                   "envs_per_step": sample, "n_sub": args.n_sub, "dt": 900, "integrator": "RK4 fixed step",
+                   "note": "CPU oracle port on host threads; the reference's CasADi CVODES extension is not installable here"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} envs x {args.steps} steps, {cores} threads"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local):
+    import ctypes as C
+    import torch
+    from glgym import _lib
+    from glgym.distributed import max_over_ranks
+    from glgym.vec_env import GreenLightVecEnv
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, K, Wm = args.envs, args.steps, args.warmup
+    env = GreenLightVecEnv(B, n_sub=args.n_sub, device=local, seed=0, env_id_offset=rank * B, role_warps=args.role_warps)
+    obs_dim = env.obs_dim
+    env.reset_tensor()
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    actions = torch.rand(Wm + K, B, 6, device=dev, generator=g) * 2 - 1
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident throughput: per-step CUDA events on the launching stream, L2 flushed between steps
+    for s in range(Wm):
+        env.step_tensor(actions[s])
+    sampler = ClockSampler(local)
+    launches0 = env.launch_count()
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for s in range(K):
+        flush.zero_()
+        ev[s][0].record()
+        env.step_tensor(actions[Wm + s])
+        ev[s][1].record()
+    barrier()
+    sampler.stop_flag = True
+    launches = env.launch_count() - launches0
+    dev_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = max_over_ranks(sum(dev_ms), dev)
+    value = world * B * K / (total_ms * 1e-3)
+    kernel_ms = float(np.mean(dev_ms))
+    finite = bool(torch.isfinite(env.state_t).all().item())
+
+    # ---- end to end through the numpy VecEnv API (host buffers, copies inside the timed region)
+    a_host = actions[Wm:].cpu().numpy()
+    for s in range(min(2, K)):
+        env.step(a_host[s])
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        obs, rew, done, infos = env.step(a_host[s])
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_s, dev)
+    e2e_value = world * B * K / e2e_s
+    sampler.join(timeout=1.0)
+
+    if rank == 0:
+        L = _lib.load()
+        pk = C.c_double()
+        L.glg_measure_fp64_peak(local, C.byref(pk))
+        peak_tf = pk.value / 1e12
+        per_gpu_rate = B / (kernel_ms * 1e-3)
+        achieved_tf = per_gpu_rate * flop_per_env_step(args.n_sub) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_gbs = per_gpu_rate * algorithmic_bytes_per_env_step(obs_dim) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        cores = os.cpu_count() or 1
+        cpu_B = 4 * cores
+        probe_rate, _ = cpu_rate(cpu_B, 2, args.n_sub, cores)           # size the sample for ~15 s of CPU work
+        cpu_steps = max(3, int(15.0 * probe_rate / cpu_B))
+        cpu_val, cpu_dt = cpu_rate(cpu_B, cpu_steps, args.n_sub, cores)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic actions; Bleiswijk GL2009 weather table shipped with the reference",
+            "config": {"workload": "TomatoEnv 4096 batched envs per GPU, fp64 parity mode, nominal parameters, fixed weather year "
+                                   "(BASELINE configs[1])",
+                       "envs_per_gpu": B, "n_sub": args.n_sub, "dt": 900, "integrator": "RK4 fixed step", "obs_dim": obs_dim,
+                       "kernel": "role-warps" if (args.role_warps == 4 or (args.role_warps == 0 and B <= 8192)) else "thread-per-env",
+                       "parallelism": f"env-shard x{world}, no collective on the step path",
+                       "l2": "flushed between timed steps (256 MiB memset outside the event pair)", "state_finite": finite},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 6 * 4,
+                    "d2h_bytes_per_step": B * obs_dim * 4 + B * 8 + B, "api": "GreenLightVecEnv.step(numpy) -> glg_step_host"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.result(),
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                         "peak_source": "glg_measure_fp64_peak: DFMA micro-benchmark measured live on this GPU "
+                                        "(MEASURED_PEAKS.json has no FP64 entry)",
+                         "flop_per_env_step": flop_per_env_step(args.n_sub), "kernel_ms": kernel_ms,
+                         "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                                 "bytes_per_env_step": algorithmic_bytes_per_env_step(obs_dim),
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"}},
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{cpu_B} envs x {cpu_steps} steps on {cores} threads ({cpu_dt:.1f} s), same n_sub / weather / "
+                                       "action distribution"},
+        }
+        print(json.dumps(line))
+    env.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--n-sub", type=int, default=600)
+    ap.add_argument("--role-warps", type=int, default=0)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        from glgym.distributed import init_from_env
+        import torch
+        torch.cuda.set_device(local)
+        init_from_env("nccl")
+    run_ours(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -712,3 +712,58 @@ long glgo_rollout(const glgo_env_cfg *c, const double *p_nom, const double *weat
     if (reward_sum_out) *reward_sum_out = rsum;
     return total;
 }
+
+struct glgo_batch {
+    glgo_env_cfg cfg;
+    double *p_nom, *weather;
+    int rows, B;
+    glgo_env *envs;
+    const float *actions;
+    float *obs_f32;
+    double *reward;
+    unsigned char *done;
+};
+glgo_batch *glgo_batch_create(const glgo_env_cfg *c, const double *p_nom, const double *weather, int rows, int B) {
+    glgo_batch *b = (glgo_batch *)calloc(1, sizeof *b);
+    int i;
+    b->cfg = *c;
+    b->rows = rows;
+    b->B = B;
+    b->p_nom = (double *)malloc(sizeof(double) * GLGO_NP);
+    memcpy(b->p_nom, p_nom, sizeof(double) * GLGO_NP);
+    b->weather = (double *)malloc(sizeof(double) * (size_t)rows * GLGO_ND);
+    memcpy(b->weather, weather, sizeof(double) * (size_t)rows * GLGO_ND);
+    b->envs = (glgo_env *)calloc((size_t)B, sizeof(glgo_env));
+    for (i = 0; i < B; ++i) glgo_env_reset(&b->envs[i], b->weather, rows, 0.0);
+    return b;
+}
+static void batch_item(void *vc, int i, int tid) {
+    glgo_batch *b = (glgo_batch *)vc;
+    const int nobs = GLGO_NOBS_FIXED + 5 * b->cfg.Np;
+    double obs[GLGO_NOBS_FIXED + 5 * 512], info[GLGO_NINFO], r;
+    int j, done;
+    (void)tid;
+    done = glgo_env_step(&b->cfg, &b->envs[i], b->p_nom, b->actions + (size_t)i * 6, 0, NULL, obs, &r, info);
+    if (done) {
+        glgo_env_reset(&b->envs[i], b->weather, b->rows, 0.0);
+        glgo_env_obs(&b->cfg, &b->envs[i], obs);
+    }
+    if (b->obs_f32)
+        for (j = 0; j < nobs; ++j) b->obs_f32[(size_t)i * nobs + j] = (float)obs[j];
+    if (b->reward) b->reward[i] = r;
+    if (b->done) b->done[i] = (unsigned char)done;
+}
+void glgo_batch_step(glgo_batch *b, const float *actions, float *obs_f32, double *reward, unsigned char *done, int n_threads) {
+    b->actions = actions;
+    b->obs_f32 = obs_f32;
+    b->reward = reward;
+    b->done = done;
+    glgo_parallel_for(batch_item, b, b->B, n_threads);
+}
+void glgo_batch_destroy(glgo_batch *b) {
+    if (!b) return;
+    free(b->p_nom);
+    free(b->weather);
+    free(b->envs);
+    free(b);
+}

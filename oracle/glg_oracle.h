@@ -83,6 +83,14 @@ int glgo_env_step(const glgo_env_cfg *c, glgo_env *e, const double *p_nom, const
 long glgo_rollout(const glgo_env_cfg *c, const double *p_nom, const double *weather, int rows, int B, int n_steps,
                   const float *actions, int n_threads, double *reward_sum_out);
 
+/* persistent batch of B reference-semantics envs stepped by n_threads host threads (auto-reset on termination):
+ * the CPU counterpart of the SubprocVecEnv-of-TomatoEnv stack, used as the measured CPU baseline. */
+typedef struct glgo_batch glgo_batch;
+glgo_batch *glgo_batch_create(const glgo_env_cfg *c, const double *p_nom, const double *weather, int rows, int B);
+/* actions float32 [B][6]; reward [B] doubles; done [B] bytes; obs_f32 may be NULL or float [B][23+5Np] */
+void glgo_batch_step(glgo_batch *b, const float *actions, float *obs_f32, double *reward, unsigned char *done, int n_threads);
+void glgo_batch_destroy(glgo_batch *b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,10 @@ def load():
         lib.glgo_rollout.argtypes = [C.POINTER(EnvCfg), _DP, _DP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                      C.c_int, _DP]
         lib.glgo_rollout.restype = C.c_long
+        lib.glgo_batch_create.argtypes = [C.POINTER(EnvCfg), _DP, _DP, C.c_int, C.c_int]
+        lib.glgo_batch_create.restype = C.c_void_p
+        lib.glgo_batch_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.glgo_batch_destroy.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
@@ -147,3 +151,28 @@ class OracleEnv:
     @property
     def u(self):
         return np.array(self.e.u[:])
+
+
+class OracleBatch:
+    """B reference-semantics envs stepped by host threads (the measured CPU baseline)."""
+
+    def __init__(self, weather, p_nom, B, cfg=None, n_threads=None):
+        self.cfg = cfg or default_cfg()
+        self.B, self.n_threads = int(B), int(n_threads or os.cpu_count() or 1)
+        self.W = np.ascontiguousarray(weather, dtype=np.float64)
+        self.p = np.ascontiguousarray(p_nom, dtype=np.float64)
+        self.h = load().glgo_batch_create(C.byref(self.cfg), P(self.p), P(self.W), self.W.shape[0], self.B)
+        self.reward = np.zeros(self.B)
+        self.done = np.zeros(self.B, dtype=np.uint8)
+        self.obs = np.zeros((self.B, 23 + 5 * self.cfg.Np), dtype=np.float32)
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        load().glgo_batch_step(self.h, a.ctypes.data, self.obs.ctypes.data, self.reward.ctypes.data, self.done.ctypes.data,
+                               self.n_threads)
+        return self.obs, self.reward, self.done
+
+    def close(self):
+        if self.h:
+            load().glgo_batch_destroy(self.h)
+            self.h = None
