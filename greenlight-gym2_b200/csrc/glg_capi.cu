@@ -25,7 +25,7 @@ static thread_local std::string g_create_error = "";
 
 struct glg_handle {
     glg_config cfg;
-    int B = 0, obs_dim = 0, nt = 64;
+    int B = 0, obs_dim = 0, nt = 64, role_lanes = 32;
     bool have_params = false, have_weather = false, general = false, is_reset = false;
     GlgUniform uni;
     // device buffers
@@ -137,6 +137,18 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     h->B = cfg->num_envs;
     h->obs_dim = GLG_NOBS_FIXED + 5 * cfg->Np;
     h->nt = 64;
+    {
+        // kernel B: choose envs-per-CTA so the batch fills the resident CTA slots (3 CTAs/SM at 168 registers) once
+        cudaDeviceProp prop;
+        int sms = 148;
+        if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) sms = prop.multiProcessorCount;
+        const int slots = sms * 3;
+        int lanes = (cfg->num_envs + slots - 1) / slots;
+        if (lanes < 8) lanes = 8;
+        if (lanes > 32) lanes = 32;
+        if (cfg->reserved >= 1 && cfg->reserved <= 32) lanes = cfg->reserved;  // test/tuning override
+        h->role_lanes = lanes;
+    }
     const size_t B = (size_t)h->B;
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e == cudaSuccess) e = dev_alloc(&h->x, GLG_NX * B);
@@ -233,6 +245,7 @@ static void fill_args(const glg_handle *h, GlgStepArgs *a) {
     a->fruit_price = c.fruit_price; a->dmfm = c.dmfm; a->fixed_costs = c.fixed_costs;
     a->uncertainty_scale = c.uncertainty_scale;
     a->seed = c.seed; a->env_id_offset = c.env_id_offset;
+    a->role_lanes = h->role_lanes;
     a->weather = h->weather; a->start_day = h->start_day; a->reset_tables = h->reset_tables;
     a->x = h->x; a->u = h->u; a->time = h->time; a->ep_return = h->ep_return; a->ep_info = h->ep_info;
     a->timestep = h->timestep; a->table = h->table; a->ep_len = h->ep_len; a->step_ctr = h->step_ctr;
@@ -284,7 +297,7 @@ static cudaError_t launch_step_roles(glg_handle *h, const GlgStepArgs &a, cudaSt
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    glg_step_roles_kernel<GENERAL, NOISY><<<(a.B + GLG_ROLE_LANES - 1) / GLG_ROLE_LANES, GLG_ROLE_THREADS, smem, s>>>(h->uni, a);
+    glg_step_roles_kernel<GENERAL, NOISY><<<(a.B + a.role_lanes - 1) / a.role_lanes, GLG_ROLE_THREADS, smem, s>>>(h->uni, a);
     return cudaGetLastError();
 }
 

@@ -34,6 +34,7 @@ struct GlgUniform {  // passed as a __grid_constant__ kernel parameter: lives in
 
 struct GlgStepArgs {
     int B, n_sub, N, Np, rows, n_tables, obs_dim, auto_reset, raw_control, n_reset_tables;
+    int role_lanes;  // kernel B: envs per CTA (<= 32); fewer envs per CTA = more CTAs = more resident warps for small batches
     double dt;
     double u_min[GLG_NU], u_max[GLG_NU];
     float delta_u_max_f32;

@@ -642,9 +642,9 @@ GLG_HD bool glg_params_nominal_structure(const P &p) {
 // three cube-root heat-exchange coefficients): an exchange would cost an extra block barrier per evaluation.
 //   role 0 RAD  : canopy extinction, PAR/NIR absorption, all FIR exchange, cover conduction/outside convection
 //   role 1 AIR  : roof ventilation, screen air flux, CO2 of the air compartments, sensible air/top/outside exchange,
-//                 screen and cover convection, air-borne vapour exchange
-//   role 2 VAP  : transpiration, condensation on screens/cover, pipe / grow-pipe / lamp / canopy / floor convection,
-//                 soil chain
+//                 air-borne vapour exchange, pipe / grow-pipe / lamp / canopy / floor convection, soil chain
+//   role 2 VAP  : the five cube-root heat-exchange coefficients (screens, cover) with their convective fluxes and the
+//                 condensation that shares them, transpiration
 //   role 3 CROP : photosynthesis, carbohydrate buffer and organ flows, harvest, canopy CO2 uptake, slow states
 // XV: x[i] -> stage state value.  PT: pt[i] = v stores role-local contribution for state i.
 // =========================================================================================================
@@ -652,9 +652,9 @@ GLG_HD bool glg_params_nominal_structure(const P &p) {
 
 // bit r set <=> role r contributes to state i
 GLG_HD constexpr unsigned glg_role_mask(int i) {
-    return i == 0 ? 0xAu : i == 1 ? 0x2u : i == 2 ? 0x7u : i == 3 ? 0x2u : i == 4 ? 0x5u : i == 5 ? 0x7u : i == 6 ? 0x1u
-         : i == 7 ? 0x7u : i == 8 ? 0x5u : i == 9 ? 0x5u : (i >= 10 && i <= 14) ? 0x4u : i == 15 ? 0x6u : i == 16 ? 0x6u
-         : i == 17 ? 0x5u : i == 18 ? 0x1u : i == 19 ? 0x5u : i == 20 ? 0x7u : 0x8u;
+    return i == 0 ? 0xAu : i == 1 ? 0x2u : i == 2 ? 0x7u : i == 3 ? 0x6u : i == 4 ? 0x7u : i == 5 ? 0x5u : i == 6 ? 0x1u
+         : i == 7 ? 0x5u : i == 8 ? 0x3u : i == 9 ? 0x3u : (i >= 10 && i <= 14) ? 0x2u : i == 15 ? 0x6u : i == 16 ? 0x6u
+         : i == 17 ? 0x3u : i == 18 ? 0x1u : i == 19 ? 0x3u : i == 20 ? 0x5u : 0x8u;
 }
 
 template <bool GENERAL, class KV, class CV, class HV, class P, class XV, class PT>
@@ -771,10 +771,10 @@ GLG_HD void glg_role_rad(const KV &K, const CV &C, const HV &H, const P &p, cons
     pt[20] = sBlScr;
 }
 
-template <class KV, class HV, class XV, class PT>
-GLG_HD void glg_role_air(const KV &K, const HV &H, const XV &x, PT &pt) {
-    const double co2Air = x[0], co2Top = x[1], tAir = x[2], tTop = x[3], tCovIn = x[5], tThScr = x[7];
-    const double vpAir = x[15], vpTop = x[16], tBlScr = x[20];
+template <class KV, class CV, class HV, class XV, class PT>
+GLG_HD void glg_role_air(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
+    const double co2Air = x[0], co2Top = x[1], tAir = x[2], tTop = x[3], tCan = x[4], tFlr = x[8], tPipe = x[9];
+    const double vpAir = x[15], vpTop = x[16], tLamp = x[17], tGroPipe = x[19];
     const double tOut = H[H_TOUT];
     const double tkAir = tAir + GLG_C2K, tkTop = tTop + GLG_C2K;
     const double rAir = glg_rcp(tkAir), rTop = glg_rcp(tkTop);
@@ -796,23 +796,7 @@ GLG_HD void glg_role_air(const KV &K, const HV &H, const XV &x, PT &pt) {
     pt[1] = mcAirTop - aVentRoof * (co2Top - H[H_CO2OUT]);
     pt[0] = H[H_MCEXT] - mcAirTop - H[H_FVENTSIDE_ABS] * (co2Air - H[H_CO2OUT]);
     const double hAirTop = fabs(K[K_RHOCP]) * aScr * (tAir - tTop);
-    double sAir = -(H[H_HEC_AIROUT] * (tAir - tOut) + hAirTop);
-    double sTop = hAirTop - fabs(K[K_RHOCP]) * aVentRoof * (tTop - tOut);
-    {
-        const double hec17Th = H[H_17TH], hec17Bl = H[H_17BL];
-        const double hAirThScr = fabs(hec17Th * glg_cbrt(fabs(tAir - tThScr + 1e-10))) * (tAir - tThScr);
-        const double hThScrTop = fabs(hec17Th * glg_cbrt(fabs(tThScr - tTop + 1e-10))) * (tThScr - tTop);
-        const double hAirBlScr = fabs(hec17Bl * glg_cbrt(fabs(tAir - tBlScr + 1e-10))) * (tAir - tBlScr);
-        const double hBlScrTop = fabs(hec17Bl * glg_cbrt(fabs(tBlScr - tTop + 1e-10))) * (tBlScr - tTop);
-        const double hTopCovIn = fabs(K[K_HECIN] * glg_cbrt(fabs(tTop - tCovIn + 1e-10))) * (tTop - tCovIn);
-        sAir -= hAirThScr + hAirBlScr;
-        sTop += hThScrTop + hBlScrTop - hTopCovIn;
-        pt[7] = hAirThScr - hThScrTop;
-        pt[20] = hAirBlScr - hBlScrTop;
-        pt[5] = hTopCovIn;
-    }
-    pt[2] = sAir;
-    pt[3] = sTop;
+    pt[3] = hAirTop - fabs(K[K_RHOCP]) * aVentRoof * (tTop - tOut);
     {
         const double rAirF = rAir - GLG_C2K_F32_DELTA * (rAir * rAir);
         const double rTopF = rTop - GLG_C2K_F32_DELTA * (rTop * rTop);
@@ -821,14 +805,6 @@ GLG_HD void glg_role_air(const KV &K, const HV &H, const XV &x, PT &pt) {
         pt[16] = (K[K_INVVPTOP] * tkTop) * (mvAirTop - 0.002165 * aVentRoof * (vTopT - H[H_VPOUT_T]));
         pt[15] = -(K[K_INVVPAIR] * tkAir) * (mvAirTop + H[H_MVAIROUT_C] * (vAirT - H[H_VPOUT_T]));
     }
-}
-
-template <class KV, class CV, class HV, class XV, class PT>
-GLG_HD void glg_role_vap(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
-    const double co2Air = x[0], tAir = x[2], tTop = x[3], tCan = x[4], tCovIn = x[5], tThScr = x[7], tFlr = x[8];
-    const double tPipe = x[9], vpAir = x[15], vpTop = x[16], tLamp = x[17], tGroPipe = x[19], tBlScr = x[20];
-    const double L = K[K_L];
-    const double lai = C[C_SLA] * x[23];
     // soil chain
     const double hFlrSo1 = K[K_HFLRSO1] * (tFlr - x[10]);
     {
@@ -847,29 +823,51 @@ GLG_HD void glg_role_vap(const KV &K, const CV &C, const HV &H, const XV &x, PT 
     const double hLampAir = K[K_HLAMPAIR] * (tLamp - tAir);
     const double hPipeAir = fabs(K[K_PIPEAIR]) * glg_pow(fabs(tPipe - tAir + 1e-10), 0.32) * (tPipe - tAir);
     const double hGroPipeAir = fabs(K[K_GROPIPEAIR]) * glg_pow(fabs(tGroPipe - tAir + 1e-10), 0.32) * (tGroPipe - tAir);
-    const double hCanAir = fabs(K[K_2ALFA] * lai) * (tCan - tAir);
+    const double hCanAir = fabs(K[K_2ALFA] * (C[C_SLA] * x[23])) * (tCan - tAir);
     const double hecFlr = (tFlr > tAir) ? 1.7 * glg_cbrt(fabs(tFlr - tAir + 1e-10))
                                         : 1.3 * glg_sqrt(glg_sqrt(fabs(tAir - tFlr + 1e-10) + 1e-300));
     const double hAirFlr = hecFlr * (tAir - tFlr);
-    pt[2] = hLampAir + hPipeAir + hGroPipeAir + hCanAir - hAirFlr;
+    pt[2] = hLampAir + hPipeAir + hGroPipeAir + hCanAir - hAirFlr - (H[H_HEC_AIROUT] * (tAir - tOut) + hAirTop);
+    pt[4] = -hCanAir;
     pt[8] = hAirFlr - hFlrSo1;
     pt[9] = -hPipeAir;
     pt[17] = -hLampAir;
     pt[19] = -hGroPipeAir;
-    // condensation (the cube-root HECs are recomputed here rather than exchanged with role AIR)
-    const double mvAirThScr = glg_cond(H[H_17TH] * glg_cbrt(fabs(tAir - tThScr + 1e-10)), vpAir, glg_satvp_f(tThScr));
-    const double mvAirBlScr = glg_cond(H[H_17BL] * glg_cbrt(fabs(tAir - tBlScr + 1e-10)), vpAir, glg_satvp_f(tBlScr));
-    const double mvTopCovIn = glg_cond(K[K_HECIN] * glg_cbrt(fabs(tTop - tCovIn + 1e-10)), vpTop, glg_satvp_f(tCovIn));
-    pt[7] = L * mvAirThScr;
-    pt[20] = L * mvAirBlScr;
-    pt[5] = L * mvTopCovIn;
+}
+
+template <class KV, class CV, class HV, class XV, class PT>
+GLG_HD void glg_role_vap(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
+    const double co2Air = x[0], tAir = x[2], tTop = x[3], tCan = x[4], tCovIn = x[5], tThScr = x[7];
+    const double vpAir = x[15], vpTop = x[16], tBlScr = x[20];
+    const double L = K[K_L];
+    const double hec17Th = H[H_17TH], hec17Bl = H[H_17BL];
+    // thermal screen: convection on both sides + condensation from the main air
+    const double hecAirTh = hec17Th * glg_cbrt(fabs(tAir - tThScr + 1e-10));
+    const double hAirThScr = fabs(hecAirTh) * (tAir - tThScr);
+    const double hThScrTop = fabs(hec17Th * glg_cbrt(fabs(tThScr - tTop + 1e-10))) * (tThScr - tTop);
+    const double mvAirThScr = glg_cond(hecAirTh, vpAir, glg_satvp_f(tThScr));
+    pt[7] = hAirThScr - hThScrTop + L * mvAirThScr;
+    // blackout screen
+    const double hecAirBl = hec17Bl * glg_cbrt(fabs(tAir - tBlScr + 1e-10));
+    const double hAirBlScr = fabs(hecAirBl) * (tAir - tBlScr);
+    const double hBlScrTop = fabs(hec17Bl * glg_cbrt(fabs(tBlScr - tTop + 1e-10))) * (tBlScr - tTop);
+    const double mvAirBlScr = glg_cond(hecAirBl, vpAir, glg_satvp_f(tBlScr));
+    pt[20] = hAirBlScr - hBlScrTop + L * mvAirBlScr;
+    // cover: convection from the top compartment + condensation
+    const double hecTopCov = K[K_HECIN] * glg_cbrt(fabs(tTop - tCovIn + 1e-10));
+    const double hTopCovIn = fabs(hecTopCov) * (tTop - tCovIn);
+    const double mvTopCovIn = glg_cond(hecTopCov, vpTop, glg_satvp_f(tCovIn));
+    pt[5] = hTopCovIn + L * mvTopCovIn;
+    pt[2] = -(hAirThScr + hAirBlScr);
+    pt[3] = hThScrTop + hBlScrTop - hTopCovIn;
     // transpiration
+    const double lai = C[C_SLA] * x[23];
     const double vpd = glg_satvp_f(tCan) - vpAir;
     const double rfCo2 = fmin(1.5, 1. + H[H_CEVAP3] * glg_sq(K[K_ETAMGPPM] * co2Air - 200));
     const double rfVp = fmin(5.8, 1. + H[H_CEVAP4] * (vpd * vpd));
     const double rS = H[H_RS] * rfCo2 * rfVp;
     const double mvCanAir = vpd * (K[K_VEC] * lai * glg_rcp(K[K_RB] + rS));
-    pt[4] = -hCanAir - L * mvCanAir;
+    pt[4] = -(L * mvCanAir);
     pt[15] = (K[K_INVVPAIR] * (tAir + GLG_C2K)) * (mvCanAir - mvAirThScr - mvAirBlScr);
     pt[16] = -(K[K_INVVPTOP] * (tTop + GLG_C2K)) * mvTopCovIn;
 }

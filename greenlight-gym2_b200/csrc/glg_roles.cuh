@@ -22,6 +22,9 @@
 
 #define GLG_ROLE_LANES 32
 #define GLG_ROLE_THREADS (GLG_ROLE_LANES * GLG_NROLES)
+#ifndef GLG_ROLE_MINBLOCKS
+#define GLG_ROLE_MINBLOCKS 4
+#endif
 
 // number of (role, state) pairs before (r, i) in role-major order = slot index of role r's contribution to state i
 __host__ __device__ constexpr int glg_part_slot(int r, int i) {
@@ -49,51 +52,69 @@ struct GlgPartCol {  // contribution slots of role R for this lane
 
 template <bool NOISY>
 struct GlgRoleSmem {
-    static constexpr int kColRows = GLG_NX + GLG_NPART + H_COUNT + (NOISY ? C_COUNT : 0);
+    static constexpr int kColRows = GLG_NX + (GLG_NPART + 2) + H_COUNT + (NOISY ? C_COUNT : 0);  // +zero slot, +canopy scale
     __host__ __device__ static size_t bytes(int Np) {
         return sizeof(double) * ((size_t)kColRows * GLG_ROLE_LANES + (size_t)(Np + 1) * GLG_ND) + 16 +
                sizeof(int) * (5 * GLG_ROLE_LANES + 4);
     }
 };
 
-// owner phase for warp W: states W, W+4, ..., W+24
-template <int W, class KV, class CV>
-__device__ __forceinline__ void glg_owner_update(const KV &K, const CV &C, double *xs_col, const double *part_col,
-                                                 double *xo, double *acc, int stage, double h, double can_scale) {
+// Owner phase.  ONE copy of the code for all four warps (the SM's instruction cache holds ~32 KB and the four role
+// streams already fill it: tools/ubench/icache2.cu): warp w owns states w, w+4, ..., w+24 and finds, per state, the
+// (up to three) contribution slots and the capacity-scale constant through small tables in the constant bank.
+struct GlgOwnerTable {
+    short slot[GLG_NX][3];  // contribution slots to add (GLG_NPART = an always-zero slot)
+    short scale_k[GLG_NX];  // index into K of the scale factor, -1: 1.0, -2: per-lane canopy scale from shared memory
+};
+__host__ __device__ constexpr GlgOwnerTable glg_make_owner_table() {
+    GlgOwnerTable t{};
+    for (int i = 0; i < GLG_NX; ++i) {
+        int n = 0;
+        for (int r = 0; r < GLG_NROLES; ++r)
+            if ((glg_role_mask(i) >> r) & 1u) t.slot[i][n++] = (short)glg_part_slot(r, i);
+        for (; n < 3; ++n) t.slot[i][n] = (short)GLG_NPART;
+        t.scale_k[i] = -1;
+    }
+    t.scale_k[0] = K_INVCAPCO2AIR; t.scale_k[1] = K_INVCAPCO2TOP; t.scale_k[2] = K_INVCAPAIR; t.scale_k[3] = K_INVCAPTOP;
+    t.scale_k[4] = -2; t.scale_k[5] = K_INVCAPCOV; t.scale_k[6] = K_INVCAPCOV; t.scale_k[7] = K_INVCAPTHSCR;
+    t.scale_k[8] = K_INVCAPFLR; t.scale_k[9] = K_INVCAPPIPE; t.scale_k[17] = K_INVCAPLAMP; t.scale_k[18] = K_INVCAPINTLAMP;
+    t.scale_k[19] = K_INVCAPGROPIPE; t.scale_k[20] = K_INVCAPBLSCR;
+    return t;
+}
+__constant__ GlgOwnerTable glg_owner_table = glg_make_owner_table();
+
+__device__ __forceinline__ void glg_owner_update(const double *Kc, int warp, double *xs_col, const double *part_col,
+                                                 const double *can_scale_col, double *xo, double *acc, int stage, double h) {
     const double w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
     const double c = (stage == 2) ? h : 0.5 * h;
+    const double c6 = h / 6.0;
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int i = W + 4 * j;  // compile-time after unrolling
-        double sum = 0.0;
-#pragma unroll
-        for (int r = 0; r < GLG_NROLES; ++r)
-            if ((glg_role_mask(i) >> r) & 1u) sum += part_col[glg_part_slot(r, i) * GLG_ROLE_LANES];
-        const double scale = (i == 4) ? can_scale : glg_state_scale(i, K, C, 0.0);
+        const int i = warp + 4 * j;
+        const double sum = part_col[glg_owner_table.slot[i][0] * GLG_ROLE_LANES] + part_col[glg_owner_table.slot[i][1] * GLG_ROLE_LANES] +
+                           part_col[glg_owner_table.slot[i][2] * GLG_ROLE_LANES];
+        const int sk = glg_owner_table.scale_k[i];
+        const double scale = sk >= 0 ? Kc[sk] : (sk == -1 ? 1.0 : *can_scale_col);
         const double k = scale * sum;
-        double xn;
-        if (stage == 3) {
-            xn = xo[j] + (h / 6.0) * (acc[j] + k);
-            xo[j] = xn;
-        } else {
-            acc[j] = (stage == 0) ? k : acc[j] + w * k;
-            xn = xo[j] + c * k;
-        }
+        // stage 0..2: acc = (stage ? acc : 0) + w k ; xs = x + c k      stage 3: x += h/6 (acc + k) ; xs = x
+        const double a_new = (stage == 0 ? 0.0 : acc[j]) + w * k;
+        const double x_fin = xo[j] + c6 * a_new;  // at stage 3 w = 1: acc + k
+        const double xn = (stage == 3) ? x_fin : xo[j] + c * k;
+        acc[j] = a_new;
+        if (stage == 3) xo[j] = x_fin;
         xs_col[i * GLG_ROLE_LANES] = xn;
     }
 }
 
 template <bool GENERAL, bool NOISY>
-__global__ void __launch_bounds__(GLG_ROLE_THREADS) glg_step_roles_kernel(const __grid_constant__ GlgUniform U,
+__global__ void __launch_bounds__(GLG_ROLE_THREADS, GLG_ROLE_MINBLOCKS) glg_step_roles_kernel(const __grid_constant__ GlgUniform U,
                                                                          const __grid_constant__ GlgStepArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NL = GLG_ROLE_LANES;
     double *s_wtile = reinterpret_cast<double *>(smem_raw);  // [(Np+1)][10]
     double *s_xs = s_wtile + (size_t)(A.Np + 1) * GLG_ND;     // [28][32]
     double *s_part = s_xs + GLG_NX * NL;                      // [GLG_NPART][32]
-    double *s_H = s_part + GLG_NPART * NL;                    // [H_COUNT][32]
+    double *s_H = s_part + (GLG_NPART + 2) * NL;              // [H_COUNT][32]; part slot GLG_NPART = 0, GLG_NPART+1 = canopy scale
     double *s_C = s_H + H_COUNT * NL;                         // [C_COUNT][32] (NOISY)
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_xs + (size_t)GlgRoleSmem<NOISY>::kColRows * NL);
     int *s_tbl = reinterpret_cast<int *>(s_bar + 2);
@@ -105,8 +126,10 @@ __global__ void __launch_bounds__(GLG_ROLE_THREADS) glg_step_roles_kernel(const 
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int e = blockIdx.x * NL + lane;
-    const bool active = e < A.B;
+    // a CTA owns A.role_lanes (<= 32) consecutive envs; the remaining lanes are padding (see glg_capi.cu: for small
+    // batches fewer envs per CTA means more CTAs, i.e. more warps to hide the FP64 dependency latency)
+    const int e = blockIdx.x * A.role_lanes + lane;
+    const bool active = lane < A.role_lanes && e < A.B;
     int k = 0, tbl = 0;
     if (active) {
         k = A.timestep[e];
@@ -146,9 +169,7 @@ __global__ void __launch_bounds__(GLG_ROLE_THREADS) glg_step_roles_kernel(const 
 #pragma unroll
         for (int i = 0; i < GLG_NX; ++i) s_xs[i * NL + lane] = x[i];
         s_bad[lane] = 0;
-    }
-    if (GENERAL && warp != 0) {
-        // the GENERAL extras of role RAD read raw controls; only warp 0 evaluates that role, nothing to do here
+        s_part[GLG_NPART * NL + lane] = 0.0;
     }
     __syncthreads();
 
@@ -169,19 +190,20 @@ __global__ void __launch_bounds__(GLG_ROLE_THREADS) glg_step_roles_kernel(const 
 #pragma unroll 1
     for (int ev = 0; ev < n_eval; ++ev) {
         const int stage = ev & 3;
-        double can_scale = 0.0;
         if (warp == 0) {
             GlgPartCol<0> pt{part_col};
+            // canopy heat capacity scale 1/(capLeaf*LAI) for state 4, from the stage value of cLeaf (before its owner moves it)
             if (NOISY) {
                 glg_role_rad<GENERAL>(Kv, Cc, Hc, Pv, u, X, pt);
-                can_scale = U.K[K_INVCAPLEAF] * glg_rcp(Cc[C_SLA] * X[23]);
+                part_col[(GLG_NPART + 1) * NL] = U.K[K_INVCAPLEAF] * glg_rcp(Cc[C_SLA] * X[23]);
             } else {
                 glg_role_rad<GENERAL>(Kv, GlgConstView{U.C}, Hc, Pv, u, X, pt);
-                can_scale = U.K[K_INVCAPLEAF] * glg_rcp(U.C[C_SLA] * X[23]);
+                part_col[(GLG_NPART + 1) * NL] = U.K[K_INVCAPLEAF] * glg_rcp(U.C[C_SLA] * X[23]);
             }
         } else if (warp == 1) {
             GlgPartCol<1> pt{part_col};
-            glg_role_air(Kv, Hc, X, pt);
+            if (NOISY) glg_role_air(Kv, Cc, Hc, X, pt);
+            else glg_role_air(Kv, GlgConstView{U.C}, Hc, X, pt);
         } else if (warp == 2) {
             GlgPartCol<2> pt{part_col};
             if (NOISY) glg_role_vap(Kv, Cc, Hc, X, pt);
@@ -192,10 +214,7 @@ __global__ void __launch_bounds__(GLG_ROLE_THREADS) glg_step_roles_kernel(const 
             else glg_role_crop<GENERAL>(Kv, GlgConstView{U.C}, Hc, X, pt);
         }
         __syncthreads();
-        if (warp == 0) glg_owner_update<0>(Kv, GlgConstView{U.C}, xs_col, part_col, xo, acc, stage, h, can_scale);
-        else if (warp == 1) glg_owner_update<1>(Kv, GlgConstView{U.C}, xs_col, part_col, xo, acc, stage, h, 0.0);
-        else if (warp == 2) glg_owner_update<2>(Kv, GlgConstView{U.C}, xs_col, part_col, xo, acc, stage, h, 0.0);
-        else glg_owner_update<3>(Kv, GlgConstView{U.C}, xs_col, part_col, xo, acc, stage, h, 0.0);
+        glg_owner_update(U.K, warp, xs_col, part_col, part_col + (GLG_NPART + 1) * NL, xo, acc, stage, h);
         __syncthreads();
     }
     {
@@ -226,5 +245,5 @@ __global__ void __launch_bounds__(GLG_ROLE_THREADS) glg_step_roles_kernel(const 
         glg_stats_reduce(A, active, bad, o);
     }
     __syncthreads();
-    glg_write_forecast(A, NL, s_tbl, s_k, s_tbl_t, s_k_t, s_wtile, uniform, bk, bt);
+    glg_write_forecast(A, A.role_lanes, s_tbl, s_k, s_tbl_t, s_k_t, s_wtile, uniform, bk, bt);
 }

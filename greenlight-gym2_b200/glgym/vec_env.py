@@ -66,7 +66,7 @@ class GreenLightVecEnv:
     def __init__(self, num_envs, reward_function="GreenhouseReward", observation_modules=None, constraints=None,
                  eval_options=None, reward_params=None, base_env_params=None, uncertainty_scale=0.0,
                  n_sub=600, device=0, seed=0, auto_reset=True, env_id_offset=0, weather_tables=None,
-                 table_start_days=None, params=None, info_mode=None, role_warps=0):
+                 table_start_days=None, params=None, info_mode=None, role_warps=0, role_lanes=0):
         if reward_function != "GreenhouseReward":
             raise ValueError("only GreenhouseReward exists in the reference (tomato_env.py:14)")
         mods = list(observation_modules or DEFAULT_OBSERVATION_MODULES)
@@ -162,6 +162,7 @@ class GreenLightVecEnv:
         cfg.uncertainty_scale = self.uncertainty_scale
         cfg.seed = int(seed) & (2**64 - 1)
         cfg.env_id_offset = int(env_id_offset)
+        cfg.reserved = int(role_lanes)    # kernel B envs-per-CTA override (0 = auto)
         cfg.role_warps = int(role_warps)  # 0 auto, 1 = one thread per env, 4 = warp-specialised RHS
         self.reward_params = rp
         self._seed = int(seed)

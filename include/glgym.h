@@ -64,7 +64,7 @@ typedef struct glg_config {
     uint64_t seed;           /* Philox key */
     int64_t env_id_offset;   /* global index of local env 0 (multi-GPU sharding; RNG streams follow the global id) */
     int32_t role_warps;      /* kernel variant: 0 = auto, 1 = one thread per env (kernel A), 4 = four role warps per 32 envs (kernel B) */
-    int32_t reserved;
+    int32_t reserved;        /* 0, or 1..32: override of kernel B's envs-per-CTA (tuning / tests) */
 } glg_config;
 
 /* Fills *cfg with the defaults of configs/envs/TomatoEnv.yml (dt 900, N 5760, Np 48, n_sub 600, ...). */

@@ -27,7 +27,7 @@ void hm_rhs_roles(const double *x, const double *u, const double *d, const doubl
     double *p0 = part[0], *p1 = part[1], *p2 = part[2], *p3 = part[3];
     if (general) glg_role_rad<true>(K, C, H, p, u, x, p0);
     else glg_role_rad<false>(K, C, H, p, u, x, p0);
-    glg_role_air(K, H, x, p1);
+    glg_role_air(K, C, H, x, p1);
     glg_role_vap(K, C, H, x, p2);
     if (general) glg_role_crop<true>(K, C, H, x, p3);
     else glg_role_crop<false>(K, C, H, x, p3);
