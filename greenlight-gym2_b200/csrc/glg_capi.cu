@@ -21,6 +21,10 @@
 #include "glg_kernels.cuh"
 #include "glg_roles.cuh"
 
+#ifndef GLG_AUTO_8WARP_MAX_ENVS
+#define GLG_AUTO_8WARP_MAX_ENVS 8192
+#endif
+
 static thread_local std::string g_create_error = "";
 
 struct glg_handle {
@@ -119,7 +123,7 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     }
     *out = nullptr;
     if (cfg->num_envs < 1 || cfg->n_sub < 1 || cfg->N < 0 || cfg->Np < 0 || !(cfg->dt > 0) || cfg->precision != 0 ||
-        (cfg->role_warps != 0 && cfg->role_warps != 1 && cfg->role_warps != 4)) {
+        (cfg->role_warps != 0 && cfg->role_warps != 1 && cfg->role_warps != 4 && cfg->role_warps != 8)) {
         g_create_error = cfg->precision != 0 ? "glg_create: precision=1 (fp32 throughput mode) is not built in this version"
                                              : "glg_create: invalid num_envs / n_sub / N / Np / dt";
         return GLG_ERR_ARG;
@@ -137,18 +141,9 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     h->B = cfg->num_envs;
     h->obs_dim = GLG_NOBS_FIXED + 5 * cfg->Np;
     h->nt = 64;
-    {
-        // kernel B: choose envs-per-CTA so the batch fills the resident CTA slots (3 CTAs/SM at 168 registers) once
-        cudaDeviceProp prop;
-        int sms = 148;
-        if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) sms = prop.multiProcessorCount;
-        const int slots = sms * 3;
-        int lanes = (cfg->num_envs + slots - 1) / slots;
-        if (lanes < 8) lanes = 8;
-        if (lanes > 32) lanes = 32;
-        if (cfg->reserved >= 1 && cfg->reserved <= 32) lanes = cfg->reserved;  // test/tuning override
-        h->role_lanes = lanes;
-    }
+    // kernel B: envs per CTA.  32 (full warps) is fastest at every batch size measured: a CTA's step time grows with the
+    // number of co-resident CTAs faster than under-filled warps could win back (profiles/r1_lane_sweep.txt).
+    h->role_lanes = (cfg->reserved >= 1 && cfg->reserved <= 32) ? cfg->reserved : 32;
     const size_t B = (size_t)h->B;
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e == cudaSuccess) e = dev_alloc(&h->x, GLG_NX * B);
@@ -288,25 +283,25 @@ static cudaError_t launch_step(glg_handle *h, const GlgStepArgs &a, cudaStream_t
     return cudaGetLastError();
 }
 
-template <bool GENERAL, bool NOISY>
+template <bool GENERAL, bool NOISY, int NR>
 static cudaError_t launch_step_roles(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
     const size_t smem = GlgRoleSmem<NOISY>::bytes(a.Np);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(glg_step_roles_kernel<GENERAL, NOISY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(glg_step_roles_kernel<GENERAL, NOISY, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    glg_step_roles_kernel<GENERAL, NOISY><<<(a.B + a.role_lanes - 1) / a.role_lanes, GLG_ROLE_THREADS, smem, s>>>(h->uni, a);
+    glg_step_roles_kernel<GENERAL, NOISY, NR><<<(a.B + a.role_lanes - 1) / a.role_lanes, 32 * NR, smem, s>>>(h->uni, a);
     return cudaGetLastError();
 }
 
-// kernel B (role warps) pays two CTA barriers per RHS evaluation but runs 4x the warps per env; it wins until
-// kernel A alone can keep every SM sub-partition busy.
-static bool use_role_kernel(const glg_handle *h) {
-    if (h->cfg.role_warps == 1) return false;
-    if (h->cfg.role_warps == 4) return true;
-    return h->B <= 8192;  // measured cross-over on B200 (profiles/): below ~2 waves of kernel A the role kernel wins
+// Kernel variant: 1 = kernel A (one thread per env), 4 / 8 = kernel B with 4 / 8 warps per 32 envs.
+// Measured on B200 (profiles/): B is latency-bound per CTA, so the 8-warp layout wins while the batch leaves SM
+// sub-partitions idle; the 4-warp layout (16 resident warps/SM, fewer barriers per env) wins once they are full.
+static int pick_role_warps(const glg_handle *h) {
+    if (h->cfg.role_warps != 0) return h->cfg.role_warps;
+    return h->B <= GLG_AUTO_8WARP_MAX_ENVS ? 8 : 4;
 }
 
 static int step_common(glg_handle *h, const float *actions_dev, const double *controls_dev, const double *noise_dev,
@@ -324,9 +319,13 @@ static int step_common(glg_handle *h, const float *actions_dev, const double *co
     const bool noisy = (h->cfg.uncertainty_scale != 0.0) || (noise_dev != nullptr);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
-    if (use_role_kernel(h)) {
-        if (h->general) e = noisy ? launch_step_roles<true, true>(h, a, s) : launch_step_roles<true, false>(h, a, s);
-        else e = noisy ? launch_step_roles<false, true>(h, a, s) : launch_step_roles<false, false>(h, a, s);
+    const int rw = pick_role_warps(h);
+    if (rw == 8) {
+        if (h->general) e = noisy ? launch_step_roles<true, true, 8>(h, a, s) : launch_step_roles<true, false, 8>(h, a, s);
+        else e = noisy ? launch_step_roles<false, true, 8>(h, a, s) : launch_step_roles<false, false, 8>(h, a, s);
+    } else if (rw == 4) {
+        if (h->general) e = noisy ? launch_step_roles<true, true, 4>(h, a, s) : launch_step_roles<true, false, 4>(h, a, s);
+        else e = noisy ? launch_step_roles<false, true, 4>(h, a, s) : launch_step_roles<false, false, 4>(h, a, s);
     } else {
         if (h->general) e = noisy ? launch_step<true, true>(h, a, s) : launch_step<true, false>(h, a, s);
         else e = noisy ? launch_step<false, true>(h, a, s) : launch_step<false, false>(h, a, s);

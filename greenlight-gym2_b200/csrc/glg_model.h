@@ -633,137 +633,168 @@ GLG_HD bool glg_params_nominal_structure(const P &p) {
 }
 
 // =========================================================================================================
-// Role-split form of the same right-hand side (used by the warp-specialised kernel, glg_roles.cuh).
+// Group-split form of the same right-hand side (used by the warp-specialised kernel, glg_roles.cuh).
 //
-// The RHS is cut into GLG_NROLES flux groups that share no intermediate value, so GLG_NROLES warps can evaluate
-// them concurrently for the same 32 envs.  Role r writes its contribution to state i's balance into PT[i]
-// (one slot per (role, state)); the state's owner adds the slots of the contributing roles (glg_role_mask) and
-// multiplies by glg_state_scale.  A few cheap values are recomputed instead of exchanged (canopy PAR factor,
-// three cube-root heat-exchange coefficients): an exchange would cost an extra block barrier per evaluation.
-//   role 0 RAD  : canopy extinction, PAR/NIR absorption, all FIR exchange, cover conduction/outside convection
-//   role 1 AIR  : roof ventilation, screen air flux, CO2 of the air compartments, sensible air/top/outside exchange,
-//                 air-borne vapour exchange, pipe / grow-pipe / lamp / canopy / floor convection, soil chain
-//   role 2 VAP  : the five cube-root heat-exchange coefficients (screens, cover) with their convective fluxes and the
-//                 condensation that shares them, transpiration
-//   role 3 CROP : photosynthesis, carbohydrate buffer and organ flows, harvest, canopy CO2 uptake, slow states
-// XV: x[i] -> stage state value.  PT: pt[i] = v stores role-local contribution for state i.
+// The RHS is cut into GLG_NGROUPS = 8 flux groups that share no intermediate value, so several warps can evaluate
+// them concurrently for the same 32 envs (8 warps x 1 group for small batches, 4 warps x 2 groups otherwise).
+// Group g writes its contribution to state i's balance into PT[i] (one slot per (group, state) pair); the state's
+// owner adds the slots of the contributing groups (glg_group_mask) and multiplies by the capacity scale.  Cheap
+// values are recomputed instead of exchanged (LAI exponentials): an exchange inside one evaluation would cost an
+// extra CTA barrier.  Sizes are balanced to ~130-240 SASS instructions per group.
+//   G0 rad      : canopy PAR/NIR extinction and absorption (:299-470), slow linear states 21,26,27, canopy capacity scale,
+//                 grow-pipe convection (:930)
+//   G1 fir      : all FIR exchange (:493-632), cover conduction and outside convection, boiler and lamp net input,
+//                 soil chain (:888-910)
+//   G2 airflow  : roof ventilation, screen air flux, CO2 of the air compartments, sensible air/top/outside exchange,
+//                 air-borne vapour exchange (:733-814, :1015-1024, :1201-1209)
+//   G3 conv     : lamp / pipe / canopy / floor convection with the main air (:824-935)
+//   G4 screens  : thermal + blackout screen convection towards the main air and condensation (:835-861, :999-1005)
+//   G5 cover    : top-compartment -> cover convection and condensation (:866, :1011), blackout screen -> top convection,
+//                 transpiration (:959-981)
+//   G6 photo    : canopy photosynthesis and buffer inflow (:1041-1097), maintenance respiration and harvest (:1161-1188)
+//   G7 flows    : carbohydrate flows buffer -> organs and growth respiration (:1103-1155)
+// XV: x[i] -> stage state value.  PT: pt[i] = v stores the group's contribution for state i.
 // =========================================================================================================
-#define GLG_NROLES 4
+#define GLG_NGROUPS 8
 
-// bit r set <=> role r contributes to state i
-GLG_HD constexpr unsigned glg_role_mask(int i) {
-    return i == 0 ? 0xAu : i == 1 ? 0x2u : i == 2 ? 0x7u : i == 3 ? 0x6u : i == 4 ? 0x7u : i == 5 ? 0x5u : i == 6 ? 0x1u
-         : i == 7 ? 0x5u : i == 8 ? 0x3u : i == 9 ? 0x3u : (i >= 10 && i <= 14) ? 0x2u : i == 15 ? 0x6u : i == 16 ? 0x6u
-         : i == 17 ? 0x3u : i == 18 ? 0x1u : i == 19 ? 0x3u : i == 20 ? 0x5u : 0x8u;
+// bit g set <=> group g contributes to state i
+GLG_HD constexpr unsigned glg_group_mask(int i) {
+    return i == 0 ? 0xC4u : i == 1 ? 0x04u : i == 2 ? 0x1Du : i == 3 ? 0x34u : i == 4 ? 0x2Bu : i == 5 ? 0x22u : i == 6 ? 0x02u
+         : i == 7 ? 0x12u : i == 8 ? 0x0Bu : i == 9 ? 0x0Au : (i >= 10 && i <= 14) ? 0x02u : i == 15 ? 0x34u : i == 16 ? 0x24u
+         : i == 17 ? 0x0Au : i == 18 ? 0x0Au : i == 19 ? 0x03u : i == 20 ? 0x32u : i == 21 ? 0x01u
+         : (i >= 22 && i <= 25) ? 0xC0u : 0x01u;
 }
 
+// G0: canopy PAR/NIR.  Also returns the canopy capacity scale K_INVCAPLEAF/LAI (state 4's owner needs the stage LAI).
+template <bool GENERAL, class KV, class CV, class HV, class XV, class PT>
+GLG_HD double glg_grp_rad(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
+    const double tCan = x[4];
+    pt[21] = (1. / 86400.) * (tCan - x[21]);
+    pt[26] = (1. / 86400.) * tCan;
+    pt[27] = 1. / 86400.;
+    const double lai = C[C_SLA] * x[23];
+    const double e32 = glg_exp(-K[K_K1PAR] * lai);
+    const double e33 = GENERAL ? glg_exp(-K[K_K2PAR] * lai) : e32;  // k1Par == k2Par in the nominal structure
+    const double e34 = glg_exp(-K[K_KNIR] * lai);
+    const double gPar = (1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33);
+    const double parLampCanW = H[H_PARLAMP_W] * gPar;
+    const double parLampFlrW = H[H_PARLAMPFLR_W] * e32;
+    const double rhoCovNir = H[H_RHOCOVNIR];
+    const double rhoHat = K[K_RHOCANNIR] * (1 - e34);
+    const double den1 = glg_rcp(1. - rhoCovNir * rhoHat);
+    const double tCC = H[H_TAUHATCOVNIR] * e34 * den1;
+    const double rUp = rhoCovNir + H[H_TAUHAT2] * rhoHat * den1;
+    const double rDn = rhoHat + e34 * e34 * rhoCovNir * den1;
+    const double den2 = glg_rcp(1. - rDn * K[K_RHOFLRNIR]);
+    const double aFlrNir = tCC * K[K_TAUHATFLRNIR] * den2;
+    const double rCCF = rUp + tCC * tCC * K[K_RHOFLRNIR] * den2;
+    const double aCanNir = 1 - aFlrNir - rCCF;
+    const double nirLampCan = H[H_NIRLAMPCAN] * (1 - e34), nirLampFlr = H[H_NIRLAMPFLR] * e34;
+    pt[4] = H[H_PARCAN_W] * gPar + H[H_NIRSUN] * aCanNir + nirLampCan;
+    pt[8] = H[H_PARFLR_W] * e32 + H[H_NIRSUN] * aFlrNir + nirLampFlr;
+    const double tAir = x[2], tGroPipe = x[19];
+    const double hGroPipeAir = fabs(K[K_GROPIPEAIR]) * glg_pow(fabs(tGroPipe - tAir + 1e-10), 0.32) * (tGroPipe - tAir);
+    pt[19] = -hGroPipeAir;
+    pt[2] = (H[H_LAMPRAD] - parLampCanW - nirLampCan - parLampFlrW - nirLampFlr) +
+            (H[H_GLOBAIR_A] + H[H_GLOBAIR_B] * (aCanNir + aFlrNir)) + hGroPipeAir;
+    return K[K_INVCAPLEAF] * glg_rcp(lai);
+}
+
+// G1: FIR exchange, cover conduction, cover-outside convection
 template <bool GENERAL, class KV, class CV, class HV, class P, class XV, class PT>
-GLG_HD void glg_role_rad(const KV &K, const CV &C, const HV &H, const P &p, const double *u, const XV &x, PT &pt) {
-    const double tAir = x[2], tCan = x[4], tCovIn = x[5], tCovE = x[6], tThScr = x[7], tFlr = x[8], tPipe = x[9];
+GLG_HD void glg_grp_fir(const KV &K, const CV &C, const HV &H, const P &p, const double *u, const XV &x, PT &pt) {
+    const double tCan = x[4], tCovIn = x[5], tCovE = x[6], tThScr = x[7], tFlr = x[8], tPipe = x[9];
     const double tLamp = x[17], tBlScr = x[20];
     const double lai = C[C_SLA] * x[23];
     const double e35 = glg_exp(-K[K_KFIR] * lai);
     const double aCan = 1 - e35;
-    double sCan, sFlr, sAir, sCovIn, sThScr, sBlScr, sPipe, sLamp, sCovE, sGroPipe = 0.0, sIntLamp = 0.0;
-    {
-        const double e32 = glg_exp(-K[K_K1PAR] * lai);
-        const double e33 = GENERAL ? glg_exp(-K[K_K2PAR] * lai) : e32;  // k1Par == k2Par in the nominal structure
-        const double e34 = glg_exp(-K[K_KNIR] * lai);
-        const double gPar = (1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33);
-        const double parLampCanW = H[H_PARLAMP_W] * gPar;
-        const double parLampFlrW = H[H_PARLAMPFLR_W] * e32;
-        const double rhoCovNir = H[H_RHOCOVNIR];
-        const double rhoHat = K[K_RHOCANNIR] * (1 - e34);
-        const double den1 = glg_rcp(1. - rhoCovNir * rhoHat);
-        const double tCC = H[H_TAUHATCOVNIR] * e34 * den1;
-        const double rUp = rhoCovNir + H[H_TAUHAT2] * rhoHat * den1;
-        const double rDn = rhoHat + e34 * e34 * rhoCovNir * den1;
-        const double den2 = glg_rcp(1. - rDn * K[K_RHOFLRNIR]);
-        const double aFlrNir = tCC * K[K_TAUHATFLRNIR] * den2;
-        const double rCCF = rUp + tCC * tCC * K[K_RHOFLRNIR] * den2;
-        const double aCanNir = 1 - aFlrNir - rCCF;
-        const double nirLampCan = H[H_NIRLAMPCAN] * (1 - e34), nirLampFlr = H[H_NIRLAMPFLR] * e34;
-        sCan = H[H_PARCAN_W] * gPar + H[H_NIRSUN] * aCanNir + nirLampCan;
-        sFlr = H[H_PARFLR_W] * e32 + H[H_NIRSUN] * aFlrNir + nirLampFlr;
-        sAir = (H[H_LAMPRAD] - parLampCanW - nirLampCan - parLampFlrW - nirLampFlr) +
-               (H[H_GLOBAIR_A] + H[H_GLOBAIR_B] * (aCanNir + aFlrNir));
-    }
-    {
-        const double q4Can = glg_sq(glg_sq(tCan + GLG_C2K)), q4CovIn = glg_sq(glg_sq(tCovIn + GLG_C2K));
-        const double q4ThScr = glg_sq(glg_sq(tThScr + GLG_C2K)), q4Flr = glg_sq(glg_sq(tFlr + GLG_C2K));
-        const double q4Pipe = glg_sq(glg_sq(tPipe + GLG_C2K)), q4Lamp = glg_sq(glg_sq(tLamp + GLG_C2K));
-        const double q4BlScr = glg_sq(glg_sq(tBlScr + GLG_C2K));
-        double f;
-        f = aCan * H[H_C84] * (q4Can - q4CovIn);   sCan -= f; sCovIn = f;
-        f = aCan * H[H_C86] * (q4Can - q4ThScr);   sCan -= f; sThScr = f;
-        f = aCan * K[K_C87] * (q4Can - q4Flr);     sCan -= f; sFlr += f;
-        f = aCan * H[H_C108] * (q4Can - q4BlScr);  sCan -= f; sBlScr = f;
-        f = aCan * K[K_C92] * (q4Pipe - q4Can);    sCan += f; sPipe = H[H_HBOIL] - f;
-        f = aCan * K[K_C101] * (q4Lamp - q4Can);   sCan += f; sLamp = H[H_LAMPNET] - f;
-        f = e35 * H[H_C88] * (q4Pipe - q4CovIn);   sPipe -= f; sCovIn += f;
-        f = e35 * H[H_C90] * (q4Pipe - q4ThScr);   sPipe -= f; sThScr += f;
-        f = e35 * H[H_C93] * (q4Flr - q4CovIn);    sFlr -= f; sCovIn += f;
-        f = e35 * H[H_C95] * (q4Flr - q4ThScr);    sFlr -= f; sThScr += f;
-        f = e35 * K[K_C99] * (q4Lamp - q4Flr);     sLamp -= f; sFlr += f;
-        f = e35 * K[K_C100] * (q4Lamp - q4Pipe);   sLamp -= f; sPipe += f;
-        f = e35 * H[H_C106] * (q4Flr - q4BlScr);   sFlr -= f; sBlScr += f;
-        f = e35 * H[H_C107] * (q4Pipe - q4BlScr);  sPipe -= f; sBlScr += f;
-        f = K[K_C91] * (q4Pipe - q4Flr);           sPipe -= f; sFlr += f;
-        f = H[H_C96] * (q4ThScr - q4CovIn);        sThScr -= f; sCovIn += f;
-        f = H[H_C102] * (q4Lamp - q4ThScr);        sLamp -= f; sThScr += f;
-        f = H[H_C103] * (q4Lamp - q4CovIn);        sLamp -= f; sCovIn += f;
-        f = H[H_C109] * (q4BlScr - q4ThScr);       sBlScr -= f; sThScr += f;
-        f = H[H_C110] * (q4BlScr - q4CovIn);       sBlScr -= f; sCovIn += f;
-        f = H[H_C112] * (q4Lamp - q4BlScr);        sLamp -= f; sBlScr += f;
-        sCovE = H[H_GLOBCOV] - K[K_C98] * (glg_sq(glg_sq(tCovE + GLG_C2K)) - H[H_TSKY4]);
-        if (GENERAL) {
-            const double sigma = p[2];
-            const double pi = 3.14159265358979323846;
-            const double thScr = u[2], blScr = u[5];
-            const double tauCovFir = p[70];
-            const double tauThFir = 1 - thScr * (1 - p[81]), tauBlFir = 1 - blScr * (1 - p[91]);
-            const double fPipe = 0.49 * pi * p[107] * p[105];
-            const double q4Sky = H[H_TSKY4];
-            const double tIntLamp = x[18];
-            const double q4Int = glg_sq(glg_sq(tIntLamp + GLG_C2K)), q4Gro = glg_sq(glg_sq(x[19] + GLG_C2K));
-            const double f85 = aCan * p[3] * p[4] * (p[178] * tauCovFir * tauThFir * tauBlFir) * sigma * (q4Can - q4Sky);
-            const double f89 = p[124] * p[104] * p[4] * (p[199] * p[178] * tauCovFir * tauThFir * 0.49 * e35) * sigma * (q4Pipe - q4Sky);
-            const double f94 = p[95] * p[4] * (p[199] * p[178] * tauCovFir * tauThFir * tauBlFir * (1 - fPipe) * e35) * sigma * (q4Flr - q4Sky);
-            const double f97 = p[74] * p[4] * (tauCovFir * thScr) * sigma * (q4ThScr - q4Sky);
-            const double f104 = p[181] * p[182] * p[4] * (tauCovFir * tauThFir * tauBlFir) * sigma * (q4Lamp - q4Sky);
-            const double f111 = blScr * p[85] * p[4] * (tauCovFir * tauThFir) * sigma * (q4BlScr - q4Sky);
-            const double f105 = p[169] * p[165] * p[3] * sigma * (q4Gro - q4Can);
-            const double upF = 1 - glg_exp(-p[203] * (1 - p[189]) * lai);
-            const double dnF = 1 - glg_exp(-p[203] * p[189] * lai);
-            const double ci = p[194] * p[195] * sigma;
-            const double f115 = ci * p[95] * ((1 - fPipe) * (1 - dnF)) * (q4Int - q4Flr);
-            const double f116 = ci * p[104] * (fPipe * (1 - dnF)) * (q4Int - q4Pipe);
-            const double f117 = ci * p[3] * (dnF + upF) * (q4Int - q4Can);
-            const double f118 = ci * p[183] * ((1 - upF) * p[181]) * (q4Int - q4Lamp);
-            const double f119 = ci * p[85] * (blScr * p[178] * (1 - upF)) * (q4Int - q4BlScr);
-            const double f120 = ci * p[74] * (thScr * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4ThScr);
-            const double f121 = ci * (1 - p[70] - p[67]) * (tauThFir * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4CovIn);
-            const double f122 = ci * p[4] * (tauCovFir * tauThFir * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4Sky);
-            const double hIntLampAir = fabs(p[198]) * (tIntLamp - tAir);
-            sAir += hIntLampAir;
-            sCan += -f85 + f105 + f117;
-            sCovIn += f121;
-            sThScr += -f97 + f120;
-            sFlr += -f94 + f115;
-            sPipe += -f89 + f116;
-            sLamp += -f104 + f118;
-            sIntLamp = -hIntLampAir - f122 - f121 - f120 - f116 - f119 - f115 - f117 - f118;
-            sGroPipe = -f105;
-            sBlScr += -f111 + f119;
-        }
+    double sCan, sFlr, sCovIn, sThScr, sBlScr, sPipe, sLamp, sCovE, sGroPipe = 0.0, sIntLamp = 0.0;
+    const double q4Can = glg_sq(glg_sq(tCan + GLG_C2K)), q4CovIn = glg_sq(glg_sq(tCovIn + GLG_C2K));
+    const double q4ThScr = glg_sq(glg_sq(tThScr + GLG_C2K)), q4Flr = glg_sq(glg_sq(tFlr + GLG_C2K));
+    const double q4Pipe = glg_sq(glg_sq(tPipe + GLG_C2K)), q4Lamp = glg_sq(glg_sq(tLamp + GLG_C2K));
+    const double q4BlScr = glg_sq(glg_sq(tBlScr + GLG_C2K));
+    double f;
+    f = aCan * H[H_C84] * (q4Can - q4CovIn);   sCan = -f; sCovIn = f;
+    f = aCan * H[H_C86] * (q4Can - q4ThScr);   sCan -= f; sThScr = f;
+    f = aCan * K[K_C87] * (q4Can - q4Flr);     sCan -= f; sFlr = f;
+    f = aCan * H[H_C108] * (q4Can - q4BlScr);  sCan -= f; sBlScr = f;
+    f = aCan * K[K_C92] * (q4Pipe - q4Can);    sCan += f; sPipe = H[H_HBOIL] - f;
+    f = aCan * K[K_C101] * (q4Lamp - q4Can);   sCan += f; sLamp = H[H_LAMPNET] - f;
+    f = e35 * H[H_C88] * (q4Pipe - q4CovIn);   sPipe -= f; sCovIn += f;
+    f = e35 * H[H_C90] * (q4Pipe - q4ThScr);   sPipe -= f; sThScr += f;
+    f = e35 * H[H_C93] * (q4Flr - q4CovIn);    sFlr -= f; sCovIn += f;
+    f = e35 * H[H_C95] * (q4Flr - q4ThScr);    sFlr -= f; sThScr += f;
+    f = e35 * K[K_C99] * (q4Lamp - q4Flr);     sLamp -= f; sFlr += f;
+    f = e35 * K[K_C100] * (q4Lamp - q4Pipe);   sLamp -= f; sPipe += f;
+    f = e35 * H[H_C106] * (q4Flr - q4BlScr);   sFlr -= f; sBlScr += f;
+    f = e35 * H[H_C107] * (q4Pipe - q4BlScr);  sPipe -= f; sBlScr += f;
+    f = K[K_C91] * (q4Pipe - q4Flr);           sPipe -= f; sFlr += f;
+    f = H[H_C96] * (q4ThScr - q4CovIn);        sThScr -= f; sCovIn += f;
+    f = H[H_C102] * (q4Lamp - q4ThScr);        sLamp -= f; sThScr += f;
+    f = H[H_C103] * (q4Lamp - q4CovIn);        sLamp -= f; sCovIn += f;
+    f = H[H_C109] * (q4BlScr - q4ThScr);       sBlScr -= f; sThScr += f;
+    f = H[H_C110] * (q4BlScr - q4CovIn);       sBlScr -= f; sCovIn += f;
+    f = H[H_C112] * (q4Lamp - q4BlScr);        sLamp -= f; sBlScr += f;
+    sCovE = H[H_GLOBCOV] - K[K_C98] * (glg_sq(glg_sq(tCovE + GLG_C2K)) - H[H_TSKY4]);
+    if (GENERAL) {
+        // Terms that are identically zero for the default table: sky FIR through the roof (tauRfFir p70),
+        // grow-pipe FIR (epsGroPipe p165), interlight FIR (p194,p195).  Written plainly.
+        const double sigma = p[2];
+        const double pi = 3.14159265358979323846;
+        const double thScr = u[2], blScr = u[5];
+        const double tauCovFir = p[70];
+        const double tauThFir = 1 - thScr * (1 - p[81]), tauBlFir = 1 - blScr * (1 - p[91]);
+        const double fPipe = 0.49 * pi * p[107] * p[105];
+        const double q4Sky = H[H_TSKY4];
+        const double q4Int = glg_sq(glg_sq(x[18] + GLG_C2K)), q4Gro = glg_sq(glg_sq(x[19] + GLG_C2K));
+        const double f85 = aCan * p[3] * p[4] * (p[178] * tauCovFir * tauThFir * tauBlFir) * sigma * (q4Can - q4Sky);
+        const double f89 = p[124] * p[104] * p[4] * (p[199] * p[178] * tauCovFir * tauThFir * 0.49 * e35) * sigma * (q4Pipe - q4Sky);
+        const double f94 = p[95] * p[4] * (p[199] * p[178] * tauCovFir * tauThFir * tauBlFir * (1 - fPipe) * e35) * sigma * (q4Flr - q4Sky);
+        const double f97 = p[74] * p[4] * (tauCovFir * thScr) * sigma * (q4ThScr - q4Sky);
+        const double f104 = p[181] * p[182] * p[4] * (tauCovFir * tauThFir * tauBlFir) * sigma * (q4Lamp - q4Sky);
+        const double f111 = blScr * p[85] * p[4] * (tauCovFir * tauThFir) * sigma * (q4BlScr - q4Sky);
+        const double f105 = p[169] * p[165] * p[3] * sigma * (q4Gro - q4Can);
+        const double upF = 1 - glg_exp(-p[203] * (1 - p[189]) * lai);
+        const double dnF = 1 - glg_exp(-p[203] * p[189] * lai);
+        const double ci = p[194] * p[195] * sigma;
+        const double f115 = ci * p[95] * ((1 - fPipe) * (1 - dnF)) * (q4Int - q4Flr);
+        const double f116 = ci * p[104] * (fPipe * (1 - dnF)) * (q4Int - q4Pipe);
+        const double f117 = ci * p[3] * (dnF + upF) * (q4Int - q4Can);
+        const double f118 = ci * p[183] * ((1 - upF) * p[181]) * (q4Int - q4Lamp);
+        const double f119 = ci * p[85] * (blScr * p[178] * (1 - upF)) * (q4Int - q4BlScr);
+        const double f120 = ci * p[74] * (thScr * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4ThScr);
+        const double f121 = ci * (1 - p[70] - p[67]) * (tauThFir * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4CovIn);
+        const double f122 = ci * p[4] * (tauCovFir * tauThFir * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4Sky);
+        sCan += -f85 + f105 + f117;
+        sCovIn += f121;
+        sThScr += -f97 + f120;
+        sFlr += -f94 + f115;
+        sPipe += -f89 + f116;
+        sLamp += -f104 + f118;
+        sIntLamp = -f122 - f121 - f120 - f116 - f119 - f115 - f117 - f118;
+        sGroPipe = -f105;
+        sBlScr += -f111 + f119;
     }
     const double hCovInCovE = K[K_HCOV] * (tCovIn - tCovE);
-    pt[2] = sAir;
+    // soil chain (:888-910)
+    const double hFlrSo1 = K[K_HFLRSO1] * (tFlr - x[10]);
+    {
+        const double hSo12 = K[K_HSO12] * (x[10] - x[11]);
+        const double hSo23 = K[K_HSO23] * (x[11] - x[12]);
+        const double hSo34 = K[K_HSO34] * (x[12] - x[13]);
+        const double hSo45 = K[K_HSO45] * (x[13] - x[14]);
+        const double hSo5Out = K[K_HSO5OUT] * (x[14] - H[H_TSOOUT]);
+        pt[10] = K[K_INVCAPSO1] * (hFlrSo1 - hSo12);
+        pt[11] = K[K_INVCAPSO2] * (hSo12 - hSo23);
+        pt[12] = K[K_INVCAPSO3] * (hSo23 - hSo34);
+        pt[13] = K[K_INVCAPSO4] * (hSo34 - hSo45);
+        pt[14] = K[K_INVCAPSO5] * (hSo45 - hSo5Out);
+    }
     pt[4] = sCan;
     pt[5] = sCovIn - hCovInCovE;
     pt[6] = sCovE + hCovInCovE - H[H_HEC_COVEOUT] * (tCovE - H[H_TOUT]);
     pt[7] = sThScr;
-    pt[8] = sFlr;
+    pt[8] = sFlr - hFlrSo1;
     pt[9] = sPipe;
     pt[17] = sLamp;
     pt[18] = sIntLamp;
@@ -771,10 +802,10 @@ GLG_HD void glg_role_rad(const KV &K, const CV &C, const HV &H, const P &p, cons
     pt[20] = sBlScr;
 }
 
-template <class KV, class CV, class HV, class XV, class PT>
-GLG_HD void glg_role_air(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
-    const double co2Air = x[0], co2Top = x[1], tAir = x[2], tTop = x[3], tCan = x[4], tFlr = x[8], tPipe = x[9];
-    const double vpAir = x[15], vpTop = x[16], tLamp = x[17], tGroPipe = x[19];
+// G2: ventilation, screen air flux, CO2 of the air compartments, sensible air/top/outside, air-borne vapour
+template <class KV, class HV, class XV, class PT>
+GLG_HD void glg_grp_airflow(const KV &K, const HV &H, const XV &x, PT &pt) {
+    const double co2Air = x[0], co2Top = x[1], tAir = x[2], tTop = x[3], vpAir = x[15], vpTop = x[16];
     const double tOut = H[H_TOUT];
     const double tkAir = tAir + GLG_C2K, tkTop = tTop + GLG_C2K;
     const double rAir = glg_rcp(tkAir), rTop = glg_rcp(tkTop);
@@ -796,71 +827,75 @@ GLG_HD void glg_role_air(const KV &K, const CV &C, const HV &H, const XV &x, PT 
     pt[1] = mcAirTop - aVentRoof * (co2Top - H[H_CO2OUT]);
     pt[0] = H[H_MCEXT] - mcAirTop - H[H_FVENTSIDE_ABS] * (co2Air - H[H_CO2OUT]);
     const double hAirTop = fabs(K[K_RHOCP]) * aScr * (tAir - tTop);
+    pt[2] = -(H[H_HEC_AIROUT] * (tAir - tOut) + hAirTop);
     pt[3] = hAirTop - fabs(K[K_RHOCP]) * aVentRoof * (tTop - tOut);
-    {
-        const double rAirF = rAir - GLG_C2K_F32_DELTA * (rAir * rAir);
-        const double rTopF = rTop - GLG_C2K_F32_DELTA * (rTop * rTop);
-        const double vAirT = vpAir * rAirF, vTopT = vpTop * rTopF;
-        const double mvAirTop = 0.002165 * aScr * (vAirT - vTopT);
-        pt[16] = (K[K_INVVPTOP] * tkTop) * (mvAirTop - 0.002165 * aVentRoof * (vTopT - H[H_VPOUT_T]));
-        pt[15] = -(K[K_INVVPAIR] * tkAir) * (mvAirTop + H[H_MVAIROUT_C] * (vAirT - H[H_VPOUT_T]));
-    }
-    // soil chain
-    const double hFlrSo1 = K[K_HFLRSO1] * (tFlr - x[10]);
-    {
-        const double hSo12 = K[K_HSO12] * (x[10] - x[11]);
-        const double hSo23 = K[K_HSO23] * (x[11] - x[12]);
-        const double hSo34 = K[K_HSO34] * (x[12] - x[13]);
-        const double hSo45 = K[K_HSO45] * (x[13] - x[14]);
-        const double hSo5Out = K[K_HSO5OUT] * (x[14] - H[H_TSOOUT]);
-        pt[10] = K[K_INVCAPSO1] * (hFlrSo1 - hSo12);
-        pt[11] = K[K_INVCAPSO2] * (hSo12 - hSo23);
-        pt[12] = K[K_INVCAPSO3] * (hSo23 - hSo34);
-        pt[13] = K[K_INVCAPSO4] * (hSo34 - hSo45);
-        pt[14] = K[K_INVCAPSO5] * (hSo45 - hSo5Out);
-    }
-    // convection of lamp, pipes, canopy, floor with the main air
+    const double rAirF = rAir - GLG_C2K_F32_DELTA * (rAir * rAir);  // 1/(tAir + 273.15f), aux_states.hpp:84
+    const double rTopF = rTop - GLG_C2K_F32_DELTA * (rTop * rTop);
+    const double vAirT = vpAir * rAirF, vTopT = vpTop * rTopF;
+    const double mvAirTop = 0.002165 * aScr * (vAirT - vTopT);
+    pt[16] = (K[K_INVVPTOP] * tkTop) * (mvAirTop - 0.002165 * aVentRoof * (vTopT - H[H_VPOUT_T]));
+    pt[15] = -(K[K_INVVPAIR] * tkAir) * (mvAirTop + H[H_MVAIROUT_C] * (vAirT - H[H_VPOUT_T]));
+}
+
+// G3: lamp / pipe / canopy / floor convection with the main air
+template <bool GENERAL, class KV, class CV, class HV, class P, class XV, class PT>
+GLG_HD void glg_grp_conv(const KV &K, const CV &C, const HV &H, const P &p, const XV &x, PT &pt) {
+    const double tAir = x[2], tCan = x[4], tFlr = x[8], tPipe = x[9], tLamp = x[17];
     const double hLampAir = K[K_HLAMPAIR] * (tLamp - tAir);
     const double hPipeAir = fabs(K[K_PIPEAIR]) * glg_pow(fabs(tPipe - tAir + 1e-10), 0.32) * (tPipe - tAir);
-    const double hGroPipeAir = fabs(K[K_GROPIPEAIR]) * glg_pow(fabs(tGroPipe - tAir + 1e-10), 0.32) * (tGroPipe - tAir);
     const double hCanAir = fabs(K[K_2ALFA] * (C[C_SLA] * x[23])) * (tCan - tAir);
     const double hecFlr = (tFlr > tAir) ? 1.7 * glg_cbrt(fabs(tFlr - tAir + 1e-10))
                                         : 1.3 * glg_sqrt(glg_sqrt(fabs(tAir - tFlr + 1e-10) + 1e-300));
     const double hAirFlr = hecFlr * (tAir - tFlr);
-    pt[2] = hLampAir + hPipeAir + hGroPipeAir + hCanAir - hAirFlr - (H[H_HEC_AIROUT] * (tAir - tOut) + hAirTop);
+    double sAir = hLampAir + hPipeAir + hCanAir - hAirFlr;
+    double sIntLamp = 0.0;
+    if (GENERAL) {
+        const double hIntLampAir = fabs(p[198]) * (x[18] - tAir);  // a167
+        sAir += hIntLampAir;
+        sIntLamp = -hIntLampAir;
+    }
+    pt[2] = sAir;
     pt[4] = -hCanAir;
-    pt[8] = hAirFlr - hFlrSo1;
+    pt[8] = hAirFlr;
     pt[9] = -hPipeAir;
     pt[17] = -hLampAir;
-    pt[19] = -hGroPipeAir;
+    pt[18] = sIntLamp;
 }
 
-template <class KV, class CV, class HV, class XV, class PT>
-GLG_HD void glg_role_vap(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
-    const double co2Air = x[0], tAir = x[2], tTop = x[3], tCan = x[4], tCovIn = x[5], tThScr = x[7];
-    const double vpAir = x[15], vpTop = x[16], tBlScr = x[20];
+// G4: thermal and blackout screen: convection on both sides + condensation from the main air
+template <class KV, class HV, class XV, class PT>
+GLG_HD void glg_grp_screens(const KV &K, const HV &H, const XV &x, PT &pt) {
+    const double tAir = x[2], tTop = x[3], tThScr = x[7], vpAir = x[15], tBlScr = x[20];
     const double L = K[K_L];
     const double hec17Th = H[H_17TH], hec17Bl = H[H_17BL];
-    // thermal screen: convection on both sides + condensation from the main air
     const double hecAirTh = hec17Th * glg_cbrt(fabs(tAir - tThScr + 1e-10));
     const double hAirThScr = fabs(hecAirTh) * (tAir - tThScr);
     const double hThScrTop = fabs(hec17Th * glg_cbrt(fabs(tThScr - tTop + 1e-10))) * (tThScr - tTop);
     const double mvAirThScr = glg_cond(hecAirTh, vpAir, glg_satvp_f(tThScr));
     pt[7] = hAirThScr - hThScrTop + L * mvAirThScr;
-    // blackout screen
     const double hecAirBl = hec17Bl * glg_cbrt(fabs(tAir - tBlScr + 1e-10));
     const double hAirBlScr = fabs(hecAirBl) * (tAir - tBlScr);
-    const double hBlScrTop = fabs(hec17Bl * glg_cbrt(fabs(tBlScr - tTop + 1e-10))) * (tBlScr - tTop);
     const double mvAirBlScr = glg_cond(hecAirBl, vpAir, glg_satvp_f(tBlScr));
-    pt[20] = hAirBlScr - hBlScrTop + L * mvAirBlScr;
-    // cover: convection from the top compartment + condensation
+    pt[20] = hAirBlScr + L * mvAirBlScr;
+    pt[2] = -(hAirThScr + hAirBlScr);
+    pt[3] = hThScrTop;
+    pt[15] = -(K[K_INVVPAIR] * (tAir + GLG_C2K)) * (mvAirThScr + mvAirBlScr);
+}
+
+// G5: cover (convection from the top compartment + condensation) and canopy transpiration
+template <class KV, class CV, class HV, class XV, class PT>
+GLG_HD void glg_grp_cover(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
+    const double co2Air = x[0], tAir = x[2], tTop = x[3], tCan = x[4], tCovIn = x[5], vpAir = x[15], vpTop = x[16];
+    const double L = K[K_L];
     const double hecTopCov = K[K_HECIN] * glg_cbrt(fabs(tTop - tCovIn + 1e-10));
     const double hTopCovIn = fabs(hecTopCov) * (tTop - tCovIn);
     const double mvTopCovIn = glg_cond(hecTopCov, vpTop, glg_satvp_f(tCovIn));
     pt[5] = hTopCovIn + L * mvTopCovIn;
-    pt[2] = -(hAirThScr + hAirBlScr);
-    pt[3] = hThScrTop + hBlScrTop - hTopCovIn;
-    // transpiration
+    const double tBlScr = x[20];
+    const double hBlScrTop = fabs(H[H_17BL] * glg_cbrt(fabs(tBlScr - tTop + 1e-10))) * (tBlScr - tTop);
+    pt[20] = -hBlScrTop;
+    pt[3] = hBlScrTop - hTopCovIn;
+    pt[16] = -(K[K_INVVPTOP] * (tTop + GLG_C2K)) * mvTopCovIn;
     const double lai = C[C_SLA] * x[23];
     const double vpd = glg_satvp_f(tCan) - vpAir;
     const double rfCo2 = fmin(1.5, 1. + H[H_CEVAP3] * glg_sq(K[K_ETAMGPPM] * co2Air - 200));
@@ -868,19 +903,15 @@ GLG_HD void glg_role_vap(const KV &K, const CV &C, const HV &H, const XV &x, PT 
     const double rS = H[H_RS] * rfCo2 * rfVp;
     const double mvCanAir = vpd * (K[K_VEC] * lai * glg_rcp(K[K_RB] + rS));
     pt[4] = -(L * mvCanAir);
-    pt[15] = (K[K_INVVPAIR] * (tAir + GLG_C2K)) * (mvCanAir - mvAirThScr - mvAirBlScr);
-    pt[16] = -(K[K_INVVPTOP] * (tTop + GLG_C2K)) * mvTopCovIn;
+    pt[15] = (K[K_INVVPAIR] * (tAir + GLG_C2K)) * mvCanAir;
 }
 
+// G6: canopy photosynthesis -> buffer inflow a200
 template <bool GENERAL, class KV, class CV, class HV, class XV, class PT>
-GLG_HD void glg_role_crop(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
-    const double co2Air = x[0], tAir = x[2], tCan = x[4], tCan24 = x[21], cBuf = x[22], cLeaf = x[23], cStem = x[24];
-    const double cFruit = x[25];
-    pt[21] = (1. / 86400.) * (tCan - tCan24);
-    pt[26] = (1. / 86400.) * tCan;
-    pt[27] = 1. / 86400.;
-    const double lai = C[C_SLA] * cLeaf;
-    // PAR absorbed by the canopy in umol (a191); the extinction factor is recomputed (role RAD has it too)
+GLG_HD void glg_grp_photo(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
+    const double co2Air = x[0], tAir = x[2], tCan = x[4], cBuf = x[22];
+    const double lai = C[C_SLA] * x[23];
+    // PAR absorbed by the canopy in umol (a191); the extinction factor is recomputed (G0 has it too)
     const double e32 = glg_exp(-K[K_K1PAR] * lai);
     const double e33 = GENERAL ? glg_exp(-K[K_K2PAR] * lai) : e32;
     const double parCan = H[H_PARUMOL] * ((1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33));
@@ -896,6 +927,24 @@ GLG_HD void glg_role_crop(const KV &K, const CV &C, const HV &H, const XV &x, PT
     const double phot = jE * (co2Stom - gamma) * glg_rcp(4 * (co2Stom + 2 * gamma));
     const double photNet = phot - phot * gamma * glg_rcp(co2Stom);
     const double mcAirBuf = C[C_MCH2O] * glg_inv1pexp(5e-4 * (cBuf - C[C_CBUFMAX])) * photNet;
+    // maintenance respiration (:1161-1178) and harvest (:75-79,1184,1188): additive pieces of the crop balances
+    const double cLeaf = x[23], cStem = x[24], cFruit = x[25];
+    const double maint = C[C_MAINT] * glg_exp(C[C_LNQ10X] * (x[21] - 25));
+    const double mcLeafAir = maint * cLeaf * C[C_MLEAF];
+    const double mcStemAir = maint * cStem * C[C_MSTEM];
+    const double mcFruitAir = maint * cFruit * C[C_MFRUIT];
+    const double kHar = 2.0 * 4.6052 / 1e4;  // smoothHar(v, cutoff, 1e4, 5e4) = 5e4/(1+exp(-kHar (v-cutoff)))
+    pt[22] = mcAirBuf;
+    pt[23] = -mcLeafAir - 5e4 * glg_inv1pexp(-kHar * (cLeaf - C[C_CLEAFMAX]));
+    pt[24] = -mcStemAir;
+    pt[25] = -mcFruitAir - 5e4 * glg_inv1pexp(-kHar * (cFruit - C[C_CFRUITMAX]));
+    pt[0] = -(C[C_CO2RATIO] * (mcAirBuf - (mcLeafAir + mcStemAir + mcFruitAir)));  // a216 without the growth-respiration part
+}
+
+// G7: carbohydrate flows buffer -> leaves / stem / fruit and the growth respiration that goes with them
+template <class KV, class CV, class XV, class PT>
+GLG_HD void glg_grp_flows(const KV &K, const CV &C, const XV &x, PT &pt) {
+    const double tCan = x[4], tCan24 = x[21], cBuf = x[22];
     const double gT24 = 0.047 * tCan24 + 0.06;
     const double hT24 = glg_rcp((1. + glg_exp(-1.1587 * (tCan24 - C[C_T24MIN]))) * (1. + glg_exp(1.3904 * (tCan24 - C[C_T24MAX]))));
     const double hTCan = glg_rcp((1. + glg_exp(-0.869 * (tCan - C[C_TCANMIN]))) * (1. + glg_exp(0.5793 * (tCan - C[C_TCANMAX]))));
@@ -907,38 +956,18 @@ GLG_HD void glg_role_crop(const KV &K, const CV &C, const HV &H, const XV &x, PT
     const double mcBufStem = flow * C[C_RGSTEM];
     const double mcBufFruit = flow * hTCan * hTSum * C[C_RGFRUIT];
     const double mcBufAir = C[C_GLEAF] * mcBufLeaf + C[C_GSTEM] * mcBufStem + C[C_GFRUIT] * mcBufFruit;
-    const double maint = C[C_MAINT] * glg_exp(C[C_LNQ10X] * (tCan24 - 25));
-    const double mcLeafAir = maint * cLeaf * C[C_MLEAF];
-    const double mcStemAir = maint * cStem * C[C_MSTEM];
-    const double mcFruitAir = maint * cFruit * C[C_MFRUIT];
-    const double kHar = 2.0 * 4.6052 / 1e4;
-    const double mcLeafHar = 5e4 * glg_inv1pexp(-kHar * (cLeaf - C[C_CLEAFMAX]));
-    const double mcFruitHar = 5e4 * glg_inv1pexp(-kHar * (cFruit - C[C_CFRUITMAX]));
-    pt[22] = mcAirBuf - mcBufFruit - mcBufLeaf - mcBufStem - mcBufAir;
-    pt[23] = mcBufLeaf - mcLeafAir - mcLeafHar;
-    pt[24] = mcBufStem - mcStemAir;
-    pt[25] = mcBufFruit - mcFruitAir - mcFruitHar;
-    pt[0] = -(C[C_CO2RATIO] * (mcAirBuf - mcBufAir - (mcLeafAir + mcStemAir + mcFruitAir)));
+    pt[22] = -mcBufFruit - mcBufLeaf - mcBufStem - mcBufAir;
+    pt[23] = mcBufLeaf;
+    pt[24] = mcBufStem;
+    pt[25] = mcBufFruit;
+    pt[0] = C[C_CO2RATIO] * mcBufAir;
 }
 
-// factor the owner of state i applies to the summed role contributions; xs23 = stage value of cLeaf
-template <class KV, class CV>
-GLG_HD double glg_state_scale(int i, const KV &K, const CV &C, double xs23) {
-    switch (i) {
-        case 0: return K[K_INVCAPCO2AIR];
-        case 1: return K[K_INVCAPCO2TOP];
-        case 2: return K[K_INVCAPAIR];
-        case 3: return K[K_INVCAPTOP];
-        case 4: return K[K_INVCAPLEAF] * glg_rcp(C[C_SLA] * xs23);
-        case 5: return K[K_INVCAPCOV];
-        case 6: return K[K_INVCAPCOV];
-        case 7: return K[K_INVCAPTHSCR];
-        case 8: return K[K_INVCAPFLR];
-        case 9: return K[K_INVCAPPIPE];
-        case 17: return K[K_INVCAPLAMP];
-        case 18: return K[K_INVCAPINTLAMP];
-        case 19: return K[K_INVCAPGROPIPE];
-        case 20: return K[K_INVCAPBLSCR];
-        default: return 1.0;
-    }
+// index into K of the capacity scale the owner applies to state i's summed contributions; -1: 1.0 (the groups
+// already wrote a derivative), -2: the per-lane canopy scale returned by G0
+GLG_HD constexpr int glg_state_scale_index(int i) {
+    return i == 0 ? (int)K_INVCAPCO2AIR : i == 1 ? (int)K_INVCAPCO2TOP : i == 2 ? (int)K_INVCAPAIR : i == 3 ? (int)K_INVCAPTOP
+         : i == 4 ? -2 : (i == 5 || i == 6) ? (int)K_INVCAPCOV : i == 7 ? (int)K_INVCAPTHSCR : i == 8 ? (int)K_INVCAPFLR
+         : i == 9 ? (int)K_INVCAPPIPE : i == 17 ? (int)K_INVCAPLAMP : i == 18 ? (int)K_INVCAPINTLAMP
+         : i == 19 ? (int)K_INVCAPGROPIPE : i == 20 ? (int)K_INVCAPBLSCR : -1;
 }

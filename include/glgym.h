@@ -63,7 +63,7 @@ typedef struct glg_config {
     double uncertainty_scale;/* tomato_env.py:34,118 ; 0 = nominal parameters */
     uint64_t seed;           /* Philox key */
     int64_t env_id_offset;   /* global index of local env 0 (multi-GPU sharding; RNG streams follow the global id) */
-    int32_t role_warps;      /* kernel variant: 0 = auto, 1 = one thread per env (kernel A), 4 = four role warps per 32 envs (kernel B) */
+    int32_t role_warps;      /* kernel variant: 0 = auto, 1 = one thread per env (kernel A), 4 / 8 = kernel B with 4 / 8 warps per 32 envs */
     int32_t reserved;        /* 0, or 1..32: override of kernel B's envs-per-CTA (tuning / tests) */
 } glg_config;
 

@@ -18,24 +18,36 @@ void hm_rhs(const double *x, const double *u, const double *d, const double *p, 
     else glg_rhs<false>(K, C, H, p, u, d, x, S);
 }
 
-// RHS assembled from the four role functions + owner-side summation/scaling (the warp-specialised kernel's data flow)
+// RHS assembled from the eight group functions + owner-side summation/scaling (the warp-specialised kernel's data flow)
 void hm_rhs_roles(const double *x, const double *u, const double *d, const double *p, int general, double *S) {
-    double K[K_COUNT], C[C_COUNT], H[H_COUNT], part[GLG_NROLES][GLG_NX] = {};
+    double K[K_COUNT], C[C_COUNT], H[H_COUNT], part[GLG_NGROUPS][GLG_NX] = {};
     glg_make_k(p, K);
     glg_make_c(p, C);
     glg_hoist(p, u, d, H);
-    double *p0 = part[0], *p1 = part[1], *p2 = part[2], *p3 = part[3];
-    if (general) glg_role_rad<true>(K, C, H, p, u, x, p0);
-    else glg_role_rad<false>(K, C, H, p, u, x, p0);
-    glg_role_air(K, C, H, x, p1);
-    glg_role_vap(K, C, H, x, p2);
-    if (general) glg_role_crop<true>(K, C, H, x, p3);
-    else glg_role_crop<false>(K, C, H, x, p3);
+    double *q[GLG_NGROUPS];
+    for (int g = 0; g < GLG_NGROUPS; ++g) q[g] = part[g];
+    double can_scale;
+    if (general) {
+        can_scale = glg_grp_rad<true>(K, C, H, x, q[0]);
+        glg_grp_fir<true>(K, C, H, p, u, x, q[1]);
+        glg_grp_conv<true>(K, C, H, p, x, q[3]);
+        glg_grp_photo<true>(K, C, H, x, q[6]);
+    } else {
+        can_scale = glg_grp_rad<false>(K, C, H, x, q[0]);
+        glg_grp_fir<false>(K, C, H, p, u, x, q[1]);
+        glg_grp_conv<false>(K, C, H, p, x, q[3]);
+        glg_grp_photo<false>(K, C, H, x, q[6]);
+    }
+    glg_grp_airflow(K, H, x, q[2]);
+    glg_grp_screens(K, H, x, q[4]);
+    glg_grp_cover(K, C, H, x, q[5]);
+    glg_grp_flows(K, C, x, q[7]);
     for (int i = 0; i < GLG_NX; ++i) {
         double sum = 0.0;
-        for (int r = 0; r < GLG_NROLES; ++r)
-            if (glg_role_mask(i) >> r & 1u) sum += part[r][i];
-        S[i] = glg_state_scale(i, K, C, x[23]) * sum;
+        for (int g = 0; g < GLG_NGROUPS; ++g)
+            if (glg_group_mask(i) >> g & 1u) sum += part[g][i];
+        const int sk = glg_state_scale_index(i);
+        S[i] = (sk >= 0 ? K[sk] : (sk == -1 ? 1.0 : can_scale)) * sum;
     }
 }
 
