@@ -129,6 +129,117 @@ GLG_HD double glg_exp(double x) {
     return glg_bits2d(glg_d2bits(p) + ((long long)ni << 52));
 }
 
+// ---- N independent exps with their dependency chains interleaved in SOURCE order.  The hardware issues in order and
+//      ptxas does not interleave independent Horner chains by itself (it emitted three back-to-back 11-deep DFMA chains
+//      in the photosynthesis group: each DFMA then waits the full 8-cycle latency).  Writing the steps "step-major"
+//      gives a lone warp N-way ILP at zero extra instructions.
+template <int N>
+GLG_HD void glg_exp_n(const double (&x)[N], double (&y)[N]) {
+    const double MAGIC = 6755399441055744.0;
+    double t[N], r[N], p[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = glg_fma(x[i], glg_kExp[10], MAGIC);
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = glg_fma(t[i] - MAGIC, glg_kExp[11], x[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = glg_fma(t[i] - MAGIC, glg_kExp[12], r[i]);
+    // even/odd split of the degree-11 polynomial: p = E(s) + r O(s), s = r^2 -- two independent 5-deep Horner chains per
+    // exp (2N-way ILP) for one extra multiply.  kExp[0..9] = c11..c2, c1 = c0 = 1.
+    double s2[N], pe[N], po[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) s2[i] = r[i] * r[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { po[i] = glg_fma(glg_kExp[0], s2[i], glg_kExp[2]); pe[i] = glg_fma(glg_kExp[1], s2[i], glg_kExp[3]); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { po[i] = glg_fma(po[i], s2[i], glg_kExp[4]); pe[i] = glg_fma(pe[i], s2[i], glg_kExp[5]); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { po[i] = glg_fma(po[i], s2[i], glg_kExp[6]); pe[i] = glg_fma(pe[i], s2[i], glg_kExp[7]); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { po[i] = glg_fma(po[i], s2[i], glg_kExp[8]); pe[i] = glg_fma(pe[i], s2[i], glg_kExp[9]); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { po[i] = glg_fma(po[i], s2[i], 1.0); pe[i] = glg_fma(pe[i], s2[i], 1.0); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = glg_fma(po[i], r[i], pe[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        int ni = (int)(uint32_t)(uint64_t)glg_d2bits(t[i]);
+        ni = ni < -1021 ? -1021 : (ni > 1023 ? 1023 : ni);
+        y[i] = glg_bits2d(glg_d2bits(p[i]) + ((long long)ni << 52));
+    }
+}
+// N independent reciprocals, interleaved the same way
+template <int N>
+GLG_HD void glg_rcp_n(const double (&x)[N], double (&y)[N]) {
+#if defined(__CUDA_ARCH__)
+    double r0[N], e[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0[i]) : "d"(x[i]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) e[i] = __fma_rn(-x[i], r0[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) e[i] = __fma_rn(e[i], e[i], e[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = __fma_rn(r0[i], e[i], r0[i]);
+#else
+    for (int i = 0; i < N; ++i) y[i] = 1.0 / x[i];
+#endif
+}
+
+// N independent square roots / cube roots, interleaved
+template <int N>
+GLG_HD void glg_sqrt_n(const double (&x)[N], double (&y)[N]) {
+#if defined(__CUDA_ARCH__)
+    double g[N], h[N], e[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(h[i]) : "d"(x[i]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) { g[i] = x[i] * h[i]; h[i] = 0.5 * h[i]; }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) e[i] = __fma_rn(-h[i], g[i], 0.5);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { g[i] = __fma_rn(g[i], e[i], g[i]); h[i] = __fma_rn(h[i], e[i], h[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) e[i] = __fma_rn(-g[i], g[i], x[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = __fma_rn(e[i], h[i], g[i]);
+#else
+    for (int i = 0; i < N; ++i) y[i] = sqrt(x[i]);
+#endif
+}
+template <int N>
+GLG_HD void glg_cbrt_n(const double (&x)[N], double (&y)[N]) {
+    const double third = 0x1.5555555555555p-2;
+    double r[N], e[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#if defined(__CUDA_ARCH__)
+        const float xf = fmaxf(__double2float_rn(x[i]), 1e-36f);
+        float lg, sd;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(-0.33333334f * lg));
+        r[i] = (double)sd;
+#else
+        r[i] = (double)(float)(1.0 / cbrt(fmax(x[i], 1e-36))) * (1.0 + 1e-7);
+#endif
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) e[i] = glg_fma(-x[i] * r[i], r[i] * r[i], 1.0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = glg_fma(r[i] * third, e[i], r[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = x[i] * (r[i] * r[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) e[i] = glg_fma(-y[i] * y[i], y[i], x[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = glg_fma(e[i], (r[i] * r[i]) * third, y[i]);
+}
+
 // ---- 1/(1+exp(z)) -- the model's ubiquitous sigmoid building block
 GLG_HD double glg_inv1pexp(double z) { return glg_rcp(1.0 + glg_exp(z)); }
 

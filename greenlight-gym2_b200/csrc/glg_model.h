@@ -647,11 +647,12 @@ GLG_HD bool glg_params_nominal_structure(const P &p) {
 //                 soil chain (:888-910)
 //   G2 airflow  : roof ventilation, screen air flux, CO2 of the air compartments, sensible air/top/outside exchange,
 //                 air-borne vapour exchange (:733-814, :1015-1024, :1201-1209)
-//   G3 conv     : lamp / pipe / canopy / floor convection with the main air (:824-935)
+//   G3 conv     : lamp / pipe / canopy / floor convection with the main air (:824-935), maintenance respiration and
+//                 harvest (:1161-1188)
 //   G4 screens  : thermal + blackout screen convection towards the main air and condensation (:835-861, :999-1005)
 //   G5 cover    : top-compartment -> cover convection and condensation (:866, :1011), blackout screen -> top convection,
 //                 transpiration (:959-981)
-//   G6 photo    : canopy photosynthesis and buffer inflow (:1041-1097), maintenance respiration and harvest (:1161-1188)
+//   G6 photo    : canopy photosynthesis and buffer inflow (:1041-1097)
 //   G7 flows    : carbohydrate flows buffer -> organs and growth respiration (:1103-1155)
 // XV: x[i] -> stage state value.  PT: pt[i] = v stores the group's contribution for state i.
 // =========================================================================================================
@@ -659,10 +660,10 @@ GLG_HD bool glg_params_nominal_structure(const P &p) {
 
 // bit g set <=> group g contributes to state i
 GLG_HD constexpr unsigned glg_group_mask(int i) {
-    return i == 0 ? 0xC4u : i == 1 ? 0x04u : i == 2 ? 0x1Du : i == 3 ? 0x34u : i == 4 ? 0x2Bu : i == 5 ? 0x22u : i == 6 ? 0x02u
+    return i == 0 ? 0xCCu : i == 1 ? 0x04u : i == 2 ? 0x1Du : i == 3 ? 0x34u : i == 4 ? 0x2Bu : i == 5 ? 0x22u : i == 6 ? 0x02u
          : i == 7 ? 0x12u : i == 8 ? 0x0Bu : i == 9 ? 0x0Au : (i >= 10 && i <= 14) ? 0x02u : i == 15 ? 0x34u : i == 16 ? 0x24u
-         : i == 17 ? 0x0Au : i == 18 ? 0x0Au : i == 19 ? 0x03u : i == 20 ? 0x32u : i == 21 ? 0x01u
-         : (i >= 22 && i <= 25) ? 0xC0u : 0x01u;
+         : i == 17 ? 0x0Au : i == 18 ? 0x0Au : i == 19 ? 0x03u : i == 20 ? 0x32u : i == 21 ? 0x01u : i == 22 ? 0xC0u
+         : (i >= 23 && i <= 25) ? 0x88u : 0x01u;
 }
 
 // G0: canopy PAR/NIR.  Also returns the canopy capacity scale K_INVCAPLEAF/LAI (state 4's owner needs the stage LAI).
@@ -673,9 +674,17 @@ GLG_HD double glg_grp_rad(const KV &K, const CV &C, const HV &H, const XV &x, PT
     pt[26] = (1. / 86400.) * tCan;
     pt[27] = 1. / 86400.;
     const double lai = C[C_SLA] * x[23];
-    const double e32 = glg_exp(-K[K_K1PAR] * lai);
-    const double e33 = GENERAL ? glg_exp(-K[K_K2PAR] * lai) : e32;  // k1Par == k2Par in the nominal structure
-    const double e34 = glg_exp(-K[K_KNIR] * lai);
+    const double ea[3] = {-K[K_K1PAR] * lai, -K[K_KNIR] * lai, -K[K_K2PAR] * lai};
+    double ey[3];
+    if (GENERAL) {
+        glg_exp_n<3>(ea, ey);
+    } else {  // k1Par == k2Par in the nominal structure
+        const double ea2[2] = {ea[0], ea[1]};
+        double ey2[2];
+        glg_exp_n<2>(ea2, ey2);
+        ey[0] = ey2[0]; ey[1] = ey2[1]; ey[2] = ey2[0];
+    }
+    const double e32 = ey[0], e34 = ey[1], e33 = ey[2];
     const double gPar = (1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33);
     const double parLampCanW = H[H_PARLAMP_W] * gPar;
     const double parLampFlrW = H[H_PARLAMPFLR_W] * e32;
@@ -808,10 +817,11 @@ GLG_HD void glg_grp_airflow(const KV &K, const HV &H, const XV &x, PT &pt) {
     const double co2Air = x[0], co2Top = x[1], tAir = x[2], tTop = x[3], vpAir = x[15], vpTop = x[16];
     const double tOut = H[H_TOUT];
     const double tkAir = tAir + GLG_C2K, tkTop = tTop + GLG_C2K;
-    const double rAir = glg_rcp(tkAir), rTop = glg_rcp(tkTop);
-    const double sVent = glg_sqrt(fabs(K[K_GHVENT] * (tAir - tOut) * glg_rcp(tAir + H[H_TOUT_2K]) + H[H_CW_WIND2]) + 1e-300);
-    const double aVentRoof = fabs(H[H_VR_A] * sVent + H[H_VR_B]);
-    double aScr;
+    const double ra[3] = {tkAir, tkTop, tAir + H[H_TOUT_2K]};
+    double ry[3];
+    glg_rcp_n<3>(ra, ry);
+    const double rAir = ry[0], rTop = ry[1];
+    double aScr, aVentRoof;
     {
         const double rhoTop = K[K_RHOC] * rTop, rhoAir = K[K_RHOC] * rAir;
         const double rhoMean = 0.5 * (rhoTop + rhoAir);
@@ -819,8 +829,13 @@ GLG_HD void glg_grp_airflow(const KV &K, const HV &H, const XV &x, PT &pt) {
         const double buoy = K[K_HALFG] * rhoMean * fabs(rhoAir - rhoTop);
         const double pw66 = glg_pow(fabs(tAir - tTop + 1e-10), 0.66);
         const double oneMTh = H[H_1MTH], oneMBl = H[H_1MBL];
-        const double fThScr = H[H_THK] * pw66 + (oneMTh * rMean) * glg_sqrt(buoy * oneMTh + 1e-10);
-        const double fBlScr = H[H_BLK] * pw66 + (oneMBl * rMean) * glg_sqrt(buoy * oneMBl + 1e-10);
+        const double sa[3] = {fabs(K[K_GHVENT] * (tAir - tOut) * ry[2] + H[H_CW_WIND2]) + 1e-300, buoy * oneMTh + 1e-10,
+                              buoy * oneMBl + 1e-10};
+        double sy[3];
+        glg_sqrt_n<3>(sa, sy);
+        aVentRoof = fabs(H[H_VR_A] * sy[0] + H[H_VR_B]);
+        const double fThScr = H[H_THK] * pw66 + (oneMTh * rMean) * sy[1];
+        const double fBlScr = H[H_BLK] * pw66 + (oneMBl * rMean) * sy[2];
         aScr = fabs(fmin(fThScr, fBlScr));
     }
     const double mcAirTop = aScr * (co2Air - co2Top);
@@ -860,6 +875,23 @@ GLG_HD void glg_grp_conv(const KV &K, const CV &C, const HV &H, const P &p, cons
     pt[9] = -hPipeAir;
     pt[17] = -hLampAir;
     pt[18] = sIntLamp;
+    // maintenance respiration (:1161-1178) and harvest (:75-79,1184,1188): additive pieces of the crop balances
+    const double cLeaf = x[23], cStem = x[24], cFruit = x[25];
+    const double kHar = 2.0 * 4.6052 / 1e4;  // smoothHar(v, cutoff, 1e4, 5e4) = 5e4/(1+exp(-kHar (v-cutoff)))
+    const double ea[3] = {C[C_LNQ10X] * (x[21] - 25), -kHar * (cLeaf - C[C_CLEAFMAX]), -kHar * (cFruit - C[C_CFRUITMAX])};
+    double ey[3];
+    glg_exp_n<3>(ea, ey);
+    const double ra[2] = {1.0 + ey[1], 1.0 + ey[2]};
+    double ry[2];
+    glg_rcp_n<2>(ra, ry);
+    const double maint = C[C_MAINT] * ey[0];
+    const double mcLeafAir = maint * cLeaf * C[C_MLEAF];
+    const double mcStemAir = maint * cStem * C[C_MSTEM];
+    const double mcFruitAir = maint * cFruit * C[C_MFRUIT];
+    pt[23] = -mcLeafAir - 5e4 * ry[0];
+    pt[24] = -mcStemAir;
+    pt[25] = -mcFruitAir - 5e4 * ry[1];
+    pt[0] = C[C_CO2RATIO] * (mcLeafAir + mcStemAir + mcFruitAir);  // maintenance part of -a216
 }
 
 // G4: thermal and blackout screen: convection on both sides + condensation from the main air
@@ -868,14 +900,31 @@ GLG_HD void glg_grp_screens(const KV &K, const HV &H, const XV &x, PT &pt) {
     const double tAir = x[2], tTop = x[3], tThScr = x[7], vpAir = x[15], tBlScr = x[20];
     const double L = K[K_L];
     const double hec17Th = H[H_17TH], hec17Bl = H[H_17BL];
-    const double hecAirTh = hec17Th * glg_cbrt(fabs(tAir - tThScr + 1e-10));
+    // three cube roots, two saturation pressures and two condensation sigmoids: independent chains, interleaved
+    const double ca[3] = {fabs(tAir - tThScr + 1e-10), fabs(tThScr - tTop + 1e-10), fabs(tAir - tBlScr + 1e-10)};
+    double cy[3];
+    glg_cbrt_n<3>(ca, cy);
+    const double ra[2] = {tThScr + 238.3, tBlScr + 238.3};
+    double ry[2];
+    glg_rcp_n<2>(ra, ry);
+    const double ea[2] = {17.2694 * (tThScr * ry[0]), 17.2694 * (tBlScr * ry[1])};
+    double ey[2];
+    glg_exp_n<2>(ea, ey);
+    const double dvTh = vpAir - 610.78 * ey[0], dvBl = vpAir - 610.78 * ey[1];
+    const double eb[2] = {-0.1 * dvTh, -0.1 * dvBl};
+    double ez[2];
+    glg_exp_n<2>(eb, ez);
+    const double rb[2] = {1.0 + ez[0], 1.0 + ez[1]};
+    double rz[2];
+    glg_rcp_n<2>(rb, rz);
+    const double hecAirTh = hec17Th * cy[0];
     const double hAirThScr = fabs(hecAirTh) * (tAir - tThScr);
-    const double hThScrTop = fabs(hec17Th * glg_cbrt(fabs(tThScr - tTop + 1e-10))) * (tThScr - tTop);
-    const double mvAirThScr = glg_cond(hecAirTh, vpAir, glg_satvp_f(tThScr));
+    const double hThScrTop = fabs(hec17Th * cy[1]) * (tThScr - tTop);
+    const double mvAirThScr = 6.4e-9 * hecAirTh * dvTh * rz[0];  // cond(), aux_states.hpp:60-63
     pt[7] = hAirThScr - hThScrTop + L * mvAirThScr;
-    const double hecAirBl = hec17Bl * glg_cbrt(fabs(tAir - tBlScr + 1e-10));
+    const double hecAirBl = hec17Bl * cy[2];
     const double hAirBlScr = fabs(hecAirBl) * (tAir - tBlScr);
-    const double mvAirBlScr = glg_cond(hecAirBl, vpAir, glg_satvp_f(tBlScr));
+    const double mvAirBlScr = 6.4e-9 * hecAirBl * dvBl * rz[1];
     pt[20] = hAirBlScr + L * mvAirBlScr;
     pt[2] = -(hAirThScr + hAirBlScr);
     pt[3] = hThScrTop;
@@ -887,21 +936,34 @@ template <class KV, class CV, class HV, class XV, class PT>
 GLG_HD void glg_grp_cover(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
     const double co2Air = x[0], tAir = x[2], tTop = x[3], tCan = x[4], tCovIn = x[5], vpAir = x[15], vpTop = x[16];
     const double L = K[K_L];
-    const double hecTopCov = K[K_HECIN] * glg_cbrt(fabs(tTop - tCovIn + 1e-10));
-    const double hTopCovIn = fabs(hecTopCov) * (tTop - tCovIn);
-    const double mvTopCovIn = glg_cond(hecTopCov, vpTop, glg_satvp_f(tCovIn));
-    pt[5] = hTopCovIn + L * mvTopCovIn;
     const double tBlScr = x[20];
-    const double hBlScrTop = fabs(H[H_17BL] * glg_cbrt(fabs(tBlScr - tTop + 1e-10))) * (tBlScr - tTop);
-    pt[20] = -hBlScrTop;
-    pt[3] = hBlScrTop - hTopCovIn;
-    pt[16] = -(K[K_INVVPTOP] * (tTop + GLG_C2K)) * mvTopCovIn;
+    const double ca[2] = {fabs(tTop - tCovIn + 1e-10), fabs(tBlScr - tTop + 1e-10)};
+    double cy[2];
+    glg_cbrt_n<2>(ca, cy);
+    const double ra[2] = {tCovIn + 238.3, tCan + 238.3};
+    double ry[2];
+    glg_rcp_n<2>(ra, ry);
+    const double ea[2] = {17.2694 * (tCovIn * ry[0]), 17.2694 * (tCan * ry[1])};
+    double ey[2];
+    glg_exp_n<2>(ea, ey);
+    const double hecTopCov = K[K_HECIN] * cy[0];
+    const double hTopCovIn = fabs(hecTopCov) * (tTop - tCovIn);
+    const double dvCov = vpTop - 610.78 * ey[0];
+    const double vpd = 610.78 * ey[1] - vpAir;
     const double lai = C[C_SLA] * x[23];
-    const double vpd = glg_satvp_f(tCan) - vpAir;
     const double rfCo2 = fmin(1.5, 1. + H[H_CEVAP3] * glg_sq(K[K_ETAMGPPM] * co2Air - 200));
     const double rfVp = fmin(5.8, 1. + H[H_CEVAP4] * (vpd * vpd));
     const double rS = H[H_RS] * rfCo2 * rfVp;
-    const double mvCanAir = vpd * (K[K_VEC] * lai * glg_rcp(K[K_RB] + rS));
+    const double rb[2] = {1.0 + glg_exp(-0.1 * dvCov), K[K_RB] + rS};
+    double rz[2];
+    glg_rcp_n<2>(rb, rz);
+    const double mvTopCovIn = 6.4e-9 * hecTopCov * dvCov * rz[0];  // cond(), aux_states.hpp:60-63
+    pt[5] = hTopCovIn + L * mvTopCovIn;
+    const double hBlScrTop = fabs(H[H_17BL] * cy[1]) * (tBlScr - tTop);
+    pt[20] = -hBlScrTop;
+    pt[3] = hBlScrTop - hTopCovIn;
+    pt[16] = -(K[K_INVVPTOP] * (tTop + GLG_C2K)) * mvTopCovIn;
+    const double mvCanAir = vpd * (K[K_VEC] * lai * rz[1]);
     pt[4] = -(L * mvCanAir);
     pt[15] = (K[K_INVVPAIR] * (tAir + GLG_C2K)) * mvCanAir;
 }
@@ -911,34 +973,39 @@ template <bool GENERAL, class KV, class CV, class HV, class XV, class PT>
 GLG_HD void glg_grp_photo(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
     const double co2Air = x[0], tAir = x[2], tCan = x[4], cBuf = x[22];
     const double lai = C[C_SLA] * x[23];
-    // PAR absorbed by the canopy in umol (a191); the extinction factor is recomputed (G0 has it too)
-    const double e32 = glg_exp(-K[K_K1PAR] * lai);
-    const double e33 = GENERAL ? glg_exp(-K[K_K2PAR] * lai) : e32;
-    const double parCan = H[H_PARUMOL] * ((1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33));
     const double j25 = lai * C[C_J25];
-    const double rj = C[C_J25] * glg_rcp(j25);
-    const double gamma = rj * C[C_CGAMMA] * tCan + C[C_20CGAMMA] * (1 - rj);
     const double co2Stom = C[C_ETASTOM] * (K[K_PPMC] * (tAir + GLG_C2K) * co2Air);
-    const double rCanK = glg_rcp(tCan + GLG_C2K);
-    const double jPot = j25 * glg_exp(C[C_ARR1] * (1 - C[C_T25K] * rCanK)) * C[C_JPOTNUM] *
-                        glg_inv1pexp(C[C_ARR2A] - C[C_ARR2B] * rCanK);
+    const double ra[3] = {j25, tCan + GLG_C2K, co2Stom};
+    double ry[3];
+    glg_rcp_n<3>(ra, ry);
+    const double rj = C[C_J25] * ry[0], rCanK = ry[1], rStom = ry[2];
+    // PAR absorbed by the canopy in umol (a191): the extinction factor is recomputed (G0 has it too); the four
+    // exponentials of this group are independent and evaluated interleaved
+    const double ea[5] = {-K[K_K1PAR] * lai, C[C_ARR1] * (1 - C[C_T25K] * rCanK), C[C_ARR2A] - C[C_ARR2B] * rCanK,
+                          5e-4 * (cBuf - C[C_CBUFMAX]), -K[K_K2PAR] * lai};
+    double ey[5];
+    if (GENERAL) {
+        glg_exp_n<5>(ea, ey);
+    } else {
+        const double ea4[4] = {ea[0], ea[1], ea[2], ea[3]};
+        double ey4[4];
+        glg_exp_n<4>(ea4, ey4);
+        ey[0] = ey4[0]; ey[1] = ey4[1]; ey[2] = ey4[2]; ey[3] = ey4[3]; ey[4] = ey4[0];
+    }
+    const double e32 = ey[0], e33 = ey[4];
+    const double parCan = H[H_PARUMOL] * ((1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33));
+    const double gamma = rj * C[C_CGAMMA] * tCan + C[C_20CGAMMA] * (1 - rj);
+    const double rb[3] = {1.0 + ey[2], 1.0 + ey[3], 4 * (co2Stom + 2 * gamma)};
+    double rz[3];
+    glg_rcp_n<3>(rb, rz);
+    const double jPot = j25 * ey[1] * C[C_JPOTNUM] * rz[0];
     const double jb = jPot + C[C_ALPHA] * parCan;
     const double jE = C[C_INV2THETA] * (jb - glg_sqrt(jb * jb - C[C_4THETAALPHA] * jPot * parCan + 1e-10));
-    const double phot = jE * (co2Stom - gamma) * glg_rcp(4 * (co2Stom + 2 * gamma));
-    const double photNet = phot - phot * gamma * glg_rcp(co2Stom);
-    const double mcAirBuf = C[C_MCH2O] * glg_inv1pexp(5e-4 * (cBuf - C[C_CBUFMAX])) * photNet;
-    // maintenance respiration (:1161-1178) and harvest (:75-79,1184,1188): additive pieces of the crop balances
-    const double cLeaf = x[23], cStem = x[24], cFruit = x[25];
-    const double maint = C[C_MAINT] * glg_exp(C[C_LNQ10X] * (x[21] - 25));
-    const double mcLeafAir = maint * cLeaf * C[C_MLEAF];
-    const double mcStemAir = maint * cStem * C[C_MSTEM];
-    const double mcFruitAir = maint * cFruit * C[C_MFRUIT];
-    const double kHar = 2.0 * 4.6052 / 1e4;  // smoothHar(v, cutoff, 1e4, 5e4) = 5e4/(1+exp(-kHar (v-cutoff)))
+    const double phot = jE * (co2Stom - gamma) * rz[2];
+    const double photNet = phot - phot * gamma * rStom;
+    const double mcAirBuf = C[C_MCH2O] * rz[1] * photNet;
     pt[22] = mcAirBuf;
-    pt[23] = -mcLeafAir - 5e4 * glg_inv1pexp(-kHar * (cLeaf - C[C_CLEAFMAX]));
-    pt[24] = -mcStemAir;
-    pt[25] = -mcFruitAir - 5e4 * glg_inv1pexp(-kHar * (cFruit - C[C_CFRUITMAX]));
-    pt[0] = -(C[C_CO2RATIO] * (mcAirBuf - (mcLeafAir + mcStemAir + mcFruitAir)));  // a216 without the growth-respiration part
+    pt[0] = -(C[C_CO2RATIO] * mcAirBuf);
 }
 
 // G7: carbohydrate flows buffer -> leaves / stem / fruit and the growth respiration that goes with them
@@ -946,12 +1013,18 @@ template <class KV, class CV, class XV, class PT>
 GLG_HD void glg_grp_flows(const KV &K, const CV &C, const XV &x, PT &pt) {
     const double tCan = x[4], tCan24 = x[21], cBuf = x[22];
     const double gT24 = 0.047 * tCan24 + 0.06;
-    const double hT24 = glg_rcp((1. + glg_exp(-1.1587 * (tCan24 - C[C_T24MIN]))) * (1. + glg_exp(1.3904 * (tCan24 - C[C_T24MAX]))));
-    const double hTCan = glg_rcp((1. + glg_exp(-0.869 * (tCan - C[C_TCANMIN]))) * (1. + glg_exp(0.5793 * (tCan - C[C_TCANMAX]))));
+    const double ea[5] = {-1.1587 * (tCan24 - C[C_T24MIN]), 1.3904 * (tCan24 - C[C_T24MAX]), -0.869 * (tCan - C[C_TCANMIN]),
+                          0.5793 * (tCan - C[C_TCANMAX]), -5e-3 * (cBuf - C[C_CBUFMIN])};
+    double ey[5];
+    glg_exp_n<5>(ea, ey);
+    const double ra[3] = {(1. + ey[0]) * (1. + ey[1]), (1. + ey[2]) * (1. + ey[3]), 1.0 + ey[4]};
+    double ry[3];
+    glg_rcp_n<3>(ra, ry);
+    const double hT24 = ry[0], hTCan = ry[1];
     const double sSum = x[26] * K[K_INVTENDSUM];
     const double sSum1 = sSum - 1.0;
     const double hTSum = 0.5 * (sSum + glg_sqrt(sSum * sSum + 1e-4)) - 0.5 * (sSum1 + glg_sqrt(sSum1 * sSum1 + 1e-4));
-    const double flow = glg_inv1pexp(-5e-3 * (cBuf - C[C_CBUFMIN])) * hT24 * gT24;
+    const double flow = ry[2] * hT24 * gT24;
     const double mcBufLeaf = flow * C[C_RGLEAF];
     const double mcBufStem = flow * C[C_RGSTEM];
     const double mcBufFruit = flow * hTCan * hTSum * C[C_RGFRUIT];

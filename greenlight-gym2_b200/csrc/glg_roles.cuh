@@ -71,37 +71,63 @@ __constant__ GlgOwnerTable glg_owner_table = glg_make_owner_table();
 
 template <bool NOISY>
 struct GlgRoleSmem {
-    static constexpr int kColRows = GLG_NX + (GLG_NPART + 2) + H_COUNT + (NOISY ? C_COUNT : 0);
+    static constexpr int kColRows = (GLG_NX + 1) + (GLG_NPART + 2) + H_COUNT + (NOISY ? C_COUNT : 0);  // +1: dummy state row
     __host__ __device__ static size_t bytes(int Np) {
         return sizeof(double) * ((size_t)kColRows * GLG_ROLE_LANES + (size_t)(Np + 1) * GLG_ND) + 16 +
                sizeof(int) * (5 * GLG_ROLE_LANES + 4);
     }
 };
 
-// owner phase: warp `warp` of NR owns states warp, warp+NR, ...
+// owner phase: warp `warp` of NR owns states warp, warp+NR, ...  The per-state table entries (shared-memory offsets of
+// the contribution slots, capacity scale) are loop invariants: they are fetched from the constant-bank table ONCE into
+// registers (GlgOwnerRegs) -- dynamic constant-bank indexing inside the loop cost ~600 cycles per evaluation.  The
+// update itself is branch-free straight-line code (warps with one state fewer update a dummy slot), so the NJ
+// load -> add -> scale -> RK4 chains of a warp overlap instead of running one after the other.
+constexpr int GLG_XS_ROWS = GLG_NX + 1;  // row GLG_NX is the dummy state slot
 template <int NR>
-__device__ __forceinline__ void glg_owner_update(const double *Kc, int warp, double *xs_col, const double *part_col,
-                                                 double *xo, double *acc, int stage, double h) {
-    constexpr int NJ = (GLG_NX + NR - 1) / NR;
-    const double w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
-    const double c = (stage == 2) ? h : 0.5 * h;
-    const double c6 = h / 6.0;
+struct GlgOwnerRegs {
+    static constexpr int NJ = (GLG_NX + NR - 1) / NR;
+    static constexpr int CAN_WARP = 4 % NR, CAN_J = 4 / NR;  // position of the canopy state (its scale changes per stage)
+    int off[NJ][GLG_MAXCONTRIB];  // element offsets of the contribution slots in this lane's column
+    double scale[NJ];             // capacity scale
+    int xs_off[NJ];               // element offset of the state in the xs column (dummy row for padding)
+};
+template <int NR>
+__device__ __forceinline__ void glg_owner_setup(const double *Kc, int warp, GlgOwnerRegs<NR> &o) {
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
+    for (int j = 0; j < GlgOwnerRegs<NR>::NJ; ++j) {
         const int i = warp + NR * j;
-        if (GLG_NX % NR != 0 && i >= GLG_NX) break;
-        double sum = part_col[glg_owner_table.slot[i][0] * GLG_ROLE_LANES] + part_col[glg_owner_table.slot[i][1] * GLG_ROLE_LANES];
-        sum += part_col[glg_owner_table.slot[i][2] * GLG_ROLE_LANES] + part_col[glg_owner_table.slot[i][3] * GLG_ROLE_LANES];
-        const int sk = glg_owner_table.scale_k[i];
-        const double scale = sk >= 0 ? Kc[sk] : (sk == -1 ? 1.0 : part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES]);
-        const double k = scale * sum;
-        // stage 0..2: acc = (stage ? acc : 0) + w k ; xs = x + c k      stage 3: x += h/6 (acc + k) ; xs = x
-        const double a_new = (stage == 0 ? 0.0 : acc[j]) + w * k;
-        const double x_fin = xo[j] + c6 * a_new;  // only used at stage 3, where w = 1: acc + k
-        const double xn = (stage == 3) ? x_fin : xo[j] + c * k;
+        const bool valid = i < GLG_NX;
+        const int ii = valid ? i : 0;
+#pragma unroll
+        for (int c = 0; c < GLG_MAXCONTRIB; ++c) o.off[j][c] = (valid ? glg_owner_table.slot[ii][c] : GLG_SLOT_ZERO) * GLG_ROLE_LANES;
+        const int sk = glg_owner_table.scale_k[ii];
+        o.scale[j] = (valid && sk >= 0) ? Kc[sk] : 1.0;
+        o.xs_off[j] = (valid ? i : GLG_NX) * GLG_ROLE_LANES;
+    }
+}
+template <int NR>
+__device__ __forceinline__ void glg_owner_update(const GlgOwnerRegs<NR> &o, int warp, double *xs_col, const double *part_col,
+                                                 double *xo, double *acc, int stage, double h) {
+    // stage 0..2: acc = (stage ? acc : 0) + w k ; xs = x + c k        stage 3: x += h/6 (acc + k) ; xs = x
+    const bool last = stage == 3;
+    const double w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
+    const double keep = stage == 0 ? 0.0 : 1.0;
+    const double m = last ? h / 6.0 : (stage == 2 ? h : 0.5 * h);
+    const double can_scale = part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES];
+    double sum[GlgOwnerRegs<NR>::NJ];
+#pragma unroll
+    for (int j = 0; j < GlgOwnerRegs<NR>::NJ; ++j)
+        sum[j] = (part_col[o.off[j][0]] + part_col[o.off[j][1]]) + (part_col[o.off[j][2]] + part_col[o.off[j][3]]);
+#pragma unroll
+    for (int j = 0; j < GlgOwnerRegs<NR>::NJ; ++j) {
+        const double sc = (j == GlgOwnerRegs<NR>::CAN_J && warp == GlgOwnerRegs<NR>::CAN_WARP) ? can_scale : o.scale[j];
+        const double k = sc * sum[j];
+        const double a_new = glg_fma(w, k, keep * acc[j]);
+        const double xn = glg_fma(m, last ? a_new : k, xo[j]);
         acc[j] = a_new;
-        if (stage == 3) xo[j] = x_fin;
-        xs_col[i * GLG_ROLE_LANES] = xn;
+        xo[j] = last ? xn : xo[j];
+        xs_col[o.xs_off[j]] = xn;
     }
 }
 
@@ -165,8 +191,8 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
     constexpr int NL = GLG_ROLE_LANES;
     constexpr int NJ = (GLG_NX + NR - 1) / NR;
     double *s_wtile = reinterpret_cast<double *>(smem_raw);  // [(Np+1)][10]
-    double *s_xs = s_wtile + (size_t)(A.Np + 1) * GLG_ND;     // [28][32]
-    double *s_part = s_xs + GLG_NX * NL;                      // [GLG_NPART + 2][32]
+    double *s_xs = s_wtile + (size_t)(A.Np + 1) * GLG_ND;     // [28 + 1 dummy][32]
+    double *s_part = s_xs + (GLG_NX + 1) * NL;                // [GLG_NPART + 2][32]
     double *s_H = s_part + (GLG_NPART + 2) * NL;              // [H_COUNT][32]
     double *s_C = s_H + H_COUNT * NL;                         // [C_COUNT][32] (NOISY)
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_xs + (size_t)GlgRoleSmem<NOISY>::kColRows * NL);
@@ -242,16 +268,42 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
         xo[j] = i < GLG_NX ? xs_col[i * NL] : 0.0;
         acc[j] = 0.0;
     }
+    GlgOwnerRegs<NR> own;
+    glg_owner_setup<NR>(U.K, warp, own);
     const double h = A.dt / (double)A.n_sub;
     const int n_eval = 4 * A.n_sub;
+#ifdef GLG_PROFILE_GROUPS
+    long long t_grp = 0, t_b1 = 0, t_own = 0, t_b2 = 0;
+#endif
 #pragma unroll 1
     for (int ev = 0; ev < n_eval; ++ev) {
+#ifdef GLG_PROFILE_GROUPS
+        const long long c0 = clock64();
+#endif
         if (NOISY) glg_run_warp_groups<GENERAL, NR>(warp, U, Cc, Hc, u, X, part_col);
         else glg_run_warp_groups<GENERAL, NR>(warp, U, GlgConstView{U.C}, Hc, u, X, part_col);
+#ifdef GLG_PROFILE_GROUPS
+        const long long c1 = clock64();
+#endif
         __syncthreads();
-        glg_owner_update<NR>(U.K, warp, xs_col, part_col, xo, acc, ev & 3, h);
+#ifdef GLG_PROFILE_GROUPS
+        const long long c2 = clock64();
+#endif
+        glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, ev & 3, h);
+#ifdef GLG_PROFILE_GROUPS
+        const long long c3 = clock64();
+#endif
         __syncthreads();
+#ifdef GLG_PROFILE_GROUPS
+        const long long c4 = clock64();
+        t_grp += c1 - c0; t_b1 += c2 - c1; t_own += c3 - c2; t_b2 += c4 - c3;
+#endif
     }
+#ifdef GLG_PROFILE_GROUPS
+    if (blockIdx.x == 0 && lane == 0)
+        printf("warp %d: group %lld  barrier1 %lld  owner %lld  barrier2 %lld  cycles/eval\n", warp, t_grp / n_eval, t_b1 / n_eval,
+               t_own / n_eval, t_b2 / n_eval);
+#endif
     {
         int bad = 0;
 #pragma unroll
