@@ -222,7 +222,8 @@ def run_ours(args, rank, world, local):
             "config": {"workload": "TomatoEnv 4096 batched envs per GPU, fp64 parity mode, nominal parameters, fixed weather year "
                                    "(BASELINE configs[1])",
                        "envs_per_gpu": B, "n_sub": args.n_sub, "dt": 900, "integrator": "RK4 fixed step", "obs_dim": obs_dim,
-                       "kernel": "role-warps" if (args.role_warps == 4 or (args.role_warps == 0 and B <= 8192)) else "thread-per-env",
+                       "kernel": {0: "glg_step_roles_kernel (auto: 8 warps per 32 envs up to 2*SMs*32 envs, else 4)", 1: "glg_step_kernel (thread per env)",
+                                  4: "glg_step_roles_kernel<4 warps>", 8: "glg_step_roles_kernel<8 warps>"}[args.role_warps],
                        "parallelism": f"env-shard x{world}, no collective on the step path",
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair)", "state_finite": finite},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 6 * 4,

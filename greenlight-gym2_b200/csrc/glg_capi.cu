@@ -21,15 +21,12 @@
 #include "glg_kernels.cuh"
 #include "glg_roles.cuh"
 
-#ifndef GLG_AUTO_8WARP_MAX_ENVS
-#define GLG_AUTO_8WARP_MAX_ENVS 8192
-#endif
 
 static thread_local std::string g_create_error = "";
 
 struct glg_handle {
     glg_config cfg;
-    int B = 0, obs_dim = 0, nt = 64, role_lanes = 32;
+    int B = 0, obs_dim = 0, nt = 64, role_lanes = 32, sms = 148;
     bool have_params = false, have_weather = false, general = false, is_reset = false;
     GlgUniform uni;
     // device buffers
@@ -122,10 +119,13 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
         return GLG_ERR_ARG;
     }
     *out = nullptr;
-    if (cfg->num_envs < 1 || cfg->n_sub < 1 || cfg->N < 0 || cfg->Np < 0 || !(cfg->dt > 0) || cfg->precision != 0 ||
-        (cfg->role_warps != 0 && cfg->role_warps != 1 && cfg->role_warps != 4 && cfg->role_warps != 8)) {
-        g_create_error = cfg->precision != 0 ? "glg_create: precision=1 (fp32 throughput mode) is not built in this version"
-                                             : "glg_create: invalid num_envs / n_sub / N / Np / dt";
+    if (cfg->num_envs < 1 || cfg->n_sub < 1 || cfg->N < 0 || cfg->Np < 0 || !(cfg->dt > 0) ||
+        (cfg->precision != 0 && cfg->precision != 1) ||
+        (cfg->role_warps != 0 && cfg->role_warps != 1 && cfg->role_warps != 4 && cfg->role_warps != 8) ||
+        (cfg->precision == 1 && cfg->role_warps == 1)) {
+        g_create_error = (cfg->precision == 1 && cfg->role_warps == 1)
+                             ? "glg_create: the fp32 throughput mode runs on kernel B only (role_warps 0, 4 or 8)"
+                             : "glg_create: invalid num_envs / n_sub / N / Np / dt / precision / role_warps";
         return GLG_ERR_ARG;
     }
     int ndev = 0;
@@ -144,6 +144,10 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     // kernel B: envs per CTA.  32 (full warps) is fastest at every batch size measured: a CTA's step time grows with the
     // number of co-resident CTAs faster than under-filled warps could win back (profiles/r1_lane_sweep.txt).
     h->role_lanes = (cfg->reserved >= 1 && cfg->reserved <= 32) ? cfg->reserved : 32;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->sms = prop.multiProcessorCount;
+    }
     const size_t B = (size_t)h->B;
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e == cudaSuccess) e = dev_alloc(&h->x, GLG_NX * B);
@@ -177,6 +181,8 @@ extern "C" int glg_set_params(glg_handle *h, const double *p_host) {
     for (int i = 0; i < GLG_NP; ++i) h->uni.P[i] = p_host[i];
     glg_make_k(p_host, h->uni.K);
     glg_make_c(p_host, h->uni.C);
+    for (int i = 0; i < K_COUNT; ++i) h->uni.Kf[i] = (float)h->uni.K[i];
+    for (int i = 0; i < C_COUNT; ++i) h->uni.Cf[i] = (float)h->uni.C[i];
     h->general = !glg_params_nominal_structure(p_host);
     h->have_params = true;
     return GLG_OK;
@@ -283,17 +289,23 @@ static cudaError_t launch_step(glg_handle *h, const GlgStepArgs &a, cudaStream_t
     return cudaGetLastError();
 }
 
-template <bool GENERAL, bool NOISY, int NR>
-static cudaError_t launch_step_roles(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
-    const size_t smem = GlgRoleSmem<NOISY>::bytes(a.Np);
+template <class T, bool GENERAL, bool NOISY, int NR>
+static cudaError_t launch_step_roles_t(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
+    const size_t smem = GlgRoleSmem<T, NOISY>::bytes(a.Np);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(glg_step_roles_kernel<GENERAL, NOISY, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(glg_step_roles_kernel<T, GENERAL, NOISY, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    glg_step_roles_kernel<GENERAL, NOISY, NR><<<(a.B + a.role_lanes - 1) / a.role_lanes, 32 * NR, smem, s>>>(h->uni, a);
+    glg_step_roles_kernel<T, GENERAL, NOISY, NR><<<(a.B + a.role_lanes - 1) / a.role_lanes, 32 * NR, smem, s>>>(h->uni, a);
     return cudaGetLastError();
+}
+template <bool GENERAL, bool NOISY, int NR>
+static cudaError_t launch_step_roles(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
+    // precision 0: fp64 parity mode ; 1: flux groups in fp32, RK4 state / stage sums / epilogue in fp64
+    return h->cfg.precision == 1 ? launch_step_roles_t<float, GENERAL, NOISY, NR>(h, a, s)
+                                 : launch_step_roles_t<double, GENERAL, NOISY, NR>(h, a, s);
 }
 
 // Kernel variant: 1 = kernel A (one thread per env), 4 / 8 = kernel B with 4 / 8 warps per 32 envs.
@@ -301,7 +313,8 @@ static cudaError_t launch_step_roles(glg_handle *h, const GlgStepArgs &a, cudaSt
 // sub-partitions idle; the 4-warp layout (16 resident warps/SM, fewer barriers per env) wins once they are full.
 static int pick_role_warps(const glg_handle *h) {
     if (h->cfg.role_warps != 0) return h->cfg.role_warps;
-    return h->B <= GLG_AUTO_8WARP_MAX_ENVS ? 8 : 4;
+    // 8-warp CTAs: 2 resident per SM (128 registers x 256 threads) => one wave holds 2 * SMs * 32 envs
+    return h->B <= 2 * h->sms * GLG_ROLE_LANES ? 8 : 4;
 }
 
 static int step_common(glg_handle *h, const float *actions_dev, const double *controls_dev, const double *noise_dev,
@@ -345,6 +358,15 @@ extern "C" int glg_step_raw_control(glg_handle *h, const double *controls_dev, c
     return step_common(h, nullptr, controls_dev, noise_dev, stream);
 }
 
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 extern "C" int glg_step_host(glg_handle *h, const float *actions_host, float *obs_host, double *reward_host,
                              uint8_t *done_host) {
     if (!h || !actions_host) return GLG_ERR_ARG;
@@ -357,17 +379,26 @@ extern "C" int glg_step_host(glg_handle *h, const float *actions_host, float *ob
         GLG_CUDA(h, cudaMallocHost((void **)&h->h_done, B));
     }
     cudaStream_t s = h->own_stream;
-    memcpy(h->h_actions, actions_host, GLG_NU * B * sizeof(float));
-    GLG_CUDA(h, cudaMemcpyAsync(h->actions, h->h_actions, GLG_NU * B * sizeof(float), cudaMemcpyHostToDevice, s));
+    // caller buffers that are page-locked are used directly; pageable ones are staged through the handle's pinned buffers
+    const bool a_pin = is_pinned(actions_host);
+    const bool o_pin = obs_host && is_pinned(obs_host), r_pin = reward_host && is_pinned(reward_host),
+               d_pin = done_host && is_pinned(done_host);
+    const float *a_src = actions_host;
+    if (!a_pin) {
+        memcpy(h->h_actions, actions_host, GLG_NU * B * sizeof(float));
+        a_src = h->h_actions;
+    }
+    GLG_CUDA(h, cudaMemcpyAsync(h->actions, a_src, GLG_NU * B * sizeof(float), cudaMemcpyHostToDevice, s));
     int rc = step_common(h, h->actions, nullptr, nullptr, s);
     if (rc) return rc;
-    if (obs_host) GLG_CUDA(h, cudaMemcpyAsync(h->h_obs, h->obs, (size_t)h->obs_dim * B * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (reward_host) GLG_CUDA(h, cudaMemcpyAsync(h->h_reward, h->reward, B * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (done_host) GLG_CUDA(h, cudaMemcpyAsync(h->h_done, h->done, B, cudaMemcpyDeviceToHost, s));
+    if (obs_host)
+        GLG_CUDA(h, cudaMemcpyAsync(o_pin ? obs_host : h->h_obs, h->obs, (size_t)h->obs_dim * B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (reward_host) GLG_CUDA(h, cudaMemcpyAsync(r_pin ? reward_host : h->h_reward, h->reward, B * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (done_host) GLG_CUDA(h, cudaMemcpyAsync(d_pin ? done_host : h->h_done, h->done, B, cudaMemcpyDeviceToHost, s));
     GLG_CUDA(h, cudaStreamSynchronize(s));
-    if (obs_host) memcpy(obs_host, h->h_obs, (size_t)h->obs_dim * B * sizeof(float));
-    if (reward_host) memcpy(reward_host, h->h_reward, B * sizeof(double));
-    if (done_host) memcpy(done_host, h->h_done, B);
+    if (obs_host && !o_pin) memcpy(obs_host, h->h_obs, (size_t)h->obs_dim * B * sizeof(float));
+    if (reward_host && !r_pin) memcpy(reward_host, h->h_reward, B * sizeof(double));
+    if (done_host && !d_pin) memcpy(done_host, h->h_done, B);
     return GLG_OK;
 }
 

@@ -30,6 +30,8 @@ struct GlgUniform {  // passed as a __grid_constant__ kernel parameter: lives in
     double P[GLG_NP];
     double K[K_COUNT];
     double C[C_COUNT];
+    float Kf[K_COUNT];  // fp32 copies for the throughput mode (precision = 1)
+    float Cf[C_COUNT];
 };
 
 struct GlgStepArgs {
@@ -75,6 +77,16 @@ struct GlgSmemStore {
 struct GlgConstView {  // read-only view of a constant-bank array
     const double *b;
     __device__ __forceinline__ double operator[](int i) const { return b[i]; }
+};
+struct GlgConstViewF {
+    const float *b;
+    __device__ __forceinline__ float operator[](int i) const { return b[i]; }
+};
+template <class T, int NT>
+struct GlgColT {  // shared-memory column of scalar type T
+    T *b;
+    __device__ __forceinline__ T &operator[](int i) { return b[i * NT]; }
+    __device__ __forceinline__ T operator[](int i) const { return b[i * NT]; }
 };
 
 // ---------------------------------------------------------------------------------------------------------

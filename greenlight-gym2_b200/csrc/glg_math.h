@@ -307,3 +307,90 @@ GLG_HD double glg_math_eval(int op, double v) {
         default: return v;
     }
 }
+
+// =========================================================================================================
+// fp32 versions (throughput mode, glg_config.precision = 1): the hardware's approximate MUFU functions are already at
+// fp32 accuracy (2^-22 .. 2^-23 relative), so each elementary function is 1-3 instructions and needs no interleaving.
+// inf/0 semantics are IEEE-like: exp saturates to +inf / 0, rcp(inf) = 0 -- cond()'s 1/(1+exp(big)) = 0 holds
+// (aux_states.hpp:60-63 overflows fp32 routinely).
+// =========================================================================================================
+GLG_HD float glg_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+GLG_HD float glg_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+GLG_HD float glg_exp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+#else
+    return expf(x);
+#endif
+}
+GLG_HD float glg_log(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.6931471805599453f;
+#else
+    return logf(x);
+#endif
+}
+GLG_HD float glg_pow(float b, float e) {
+#if defined(__CUDA_ARCH__)
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(b));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e * l));
+    return r;
+#else
+    return powf(b, e);
+#endif
+}
+GLG_HD float glg_cbrt(float x) {
+#if defined(__CUDA_ARCH__)
+    const float xc = fmaxf(x, 1e-36f);
+    float l, y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(xc));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(0.33333334f * l));
+    // one Newton step on y^3 = x:  y <- y - (y^3 - x) / (3 y^2)
+    const float y2 = y * y;
+    return x == 0.0f ? 0.0f : y - (y2 * y - x) * glg_rcp(3.0f * y2);
+#else
+    return cbrtf(x);
+#endif
+}
+GLG_HD float glg_inv1pexp(float z) { return glg_rcp(1.0f + glg_exp(z)); }
+template <int N>
+GLG_HD void glg_exp_n(const float (&x)[N], float (&y)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = glg_exp(x[i]);
+}
+template <int N>
+GLG_HD void glg_rcp_n(const float (&x)[N], float (&y)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = glg_rcp(x[i]);
+}
+template <int N>
+GLG_HD void glg_sqrt_n(const float (&x)[N], float (&y)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = glg_sqrt(x[i]);
+}
+template <int N>
+GLG_HD void glg_cbrt_n(const float (&x)[N], float (&y)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = glg_cbrt(x[i]);
+}

@@ -27,6 +27,9 @@
 #pragma once
 #include <math.h>
 
+#include <type_traits>
+#include <utility>
+
 #include "glg_math.h"
 
 #define GLG_NX 28
@@ -93,15 +96,18 @@ enum GlgH {  // per-env-step constants (depend on u, d and p)
 // (double)273.15f - 273.15 : the reference's airMv adds a float Kelvin offset (aux_states.hpp:84)
 #define GLG_C2K_F32_DELTA (273.149993896484375 - 273.15)
 
-GLG_HD double glg_sq(double v) { return v * v; }
+template <class T>
+GLG_HD T glg_sq(T v) { return v * v; }
 // exact-libm versions: used outside the substep loop (hoisting, observations), once per env-step
 GLG_HD double glg_satvp(double t) { return 610.78 * exp(17.2694 * t / (t + 238.3)); }  // aux_states.hpp:5-12
 // fast versions for the RHS (glg_math.h)
-GLG_HD double glg_satvp_f(double t) { return 610.78 * glg_exp(17.2694 * (t * glg_rcp(t + 238.3))); }
+template <class T>
+GLG_HD T glg_satvp_f(T t) { return T(610.78) * glg_exp(T(17.2694) * (t * glg_rcp(t + T(238.3)))); }
 // cond(): aux_states.hpp:60-63.  exp overflow -> 1/(1+huge) = 0, as with IEEE inf in the reference.
-GLG_HD double glg_cond(double hec, double vp1, double vp2) {
-    const double dv = vp1 - vp2;
-    return 6.4e-9 * hec * dv * glg_inv1pexp(-0.1 * dv);
+template <class T>
+GLG_HD T glg_cond(T hec, T vp1, T vp2) {
+    const T dv = vp1 - vp2;
+    return T(6.4e-9) * hec * dv * glg_inv1pexp(T(-0.1) * dv);
 }
 
 // two-layer optics (aux_states.hpp:25-41)
@@ -666,43 +672,49 @@ GLG_HD constexpr unsigned glg_group_mask(int i) {
          : (i >= 23 && i <= 25) ? 0x88u : 0x01u;
 }
 
+// scalar type of a constant set (double in parity mode, float in throughput mode); all sets passed to one group
+// function use the same type
+template <class V>
+using glg_scalar_t = typename std::remove_cv<typename std::remove_reference<decltype(std::declval<const V &>()[0])>::type>::type;
+
 // G0: canopy PAR/NIR.  Also returns the canopy capacity scale K_INVCAPLEAF/LAI (state 4's owner needs the stage LAI).
 template <bool GENERAL, class KV, class CV, class HV, class XV, class PT>
-GLG_HD double glg_grp_rad(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
-    const double tCan = x[4];
-    pt[21] = (1. / 86400.) * (tCan - x[21]);
-    pt[26] = (1. / 86400.) * tCan;
-    pt[27] = 1. / 86400.;
-    const double lai = C[C_SLA] * x[23];
-    const double ea[3] = {-K[K_K1PAR] * lai, -K[K_KNIR] * lai, -K[K_K2PAR] * lai};
-    double ey[3];
+GLG_HD glg_scalar_t<KV> glg_grp_rad(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
+    typedef glg_scalar_t<KV> T;
+    const T tCan = x[4];
+    pt[21] = (T(1.) / T(86400.)) * (tCan - x[21]);
+    pt[26] = (T(1.) / T(86400.)) * tCan;
+    pt[27] = T(1.) / T(86400.);
+    const T lai = C[C_SLA] * x[23];
+    const T ea[3] = {-K[K_K1PAR] * lai, -K[K_KNIR] * lai, -K[K_K2PAR] * lai};
+    T ey[3];
     if (GENERAL) {
         glg_exp_n<3>(ea, ey);
     } else {  // k1Par == k2Par in the nominal structure
-        const double ea2[2] = {ea[0], ea[1]};
-        double ey2[2];
+        const T ea2[2] = {ea[0], ea[1]};
+        T ey2[2];
         glg_exp_n<2>(ea2, ey2);
         ey[0] = ey2[0]; ey[1] = ey2[1]; ey[2] = ey2[0];
     }
-    const double e32 = ey[0], e34 = ey[1], e33 = ey[2];
-    const double gPar = (1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33);
-    const double parLampCanW = H[H_PARLAMP_W] * gPar;
-    const double parLampFlrW = H[H_PARLAMPFLR_W] * e32;
-    const double rhoCovNir = H[H_RHOCOVNIR];
-    const double rhoHat = K[K_RHOCANNIR] * (1 - e34);
-    const double den1 = glg_rcp(1. - rhoCovNir * rhoHat);
-    const double tCC = H[H_TAUHATCOVNIR] * e34 * den1;
-    const double rUp = rhoCovNir + H[H_TAUHAT2] * rhoHat * den1;
-    const double rDn = rhoHat + e34 * e34 * rhoCovNir * den1;
-    const double den2 = glg_rcp(1. - rDn * K[K_RHOFLRNIR]);
-    const double aFlrNir = tCC * K[K_TAUHATFLRNIR] * den2;
-    const double rCCF = rUp + tCC * tCC * K[K_RHOFLRNIR] * den2;
-    const double aCanNir = 1 - aFlrNir - rCCF;
-    const double nirLampCan = H[H_NIRLAMPCAN] * (1 - e34), nirLampFlr = H[H_NIRLAMPFLR] * e34;
+    const T e32 = ey[0], e34 = ey[1], e33 = ey[2];
+    const T gPar = (1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33);
+    const T parLampCanW = H[H_PARLAMP_W] * gPar;
+    const T parLampFlrW = H[H_PARLAMPFLR_W] * e32;
+    const T rhoCovNir = H[H_RHOCOVNIR];
+    const T rhoHat = K[K_RHOCANNIR] * (1 - e34);
+    const T den1 = glg_rcp(T(1.) - rhoCovNir * rhoHat);
+    const T tCC = H[H_TAUHATCOVNIR] * e34 * den1;
+    const T rUp = rhoCovNir + H[H_TAUHAT2] * rhoHat * den1;
+    const T rDn = rhoHat + e34 * e34 * rhoCovNir * den1;
+    const T den2 = glg_rcp(T(1.) - rDn * K[K_RHOFLRNIR]);
+    const T aFlrNir = tCC * K[K_TAUHATFLRNIR] * den2;
+    const T rCCF = rUp + tCC * tCC * K[K_RHOFLRNIR] * den2;
+    const T aCanNir = 1 - aFlrNir - rCCF;
+    const T nirLampCan = H[H_NIRLAMPCAN] * (1 - e34), nirLampFlr = H[H_NIRLAMPFLR] * e34;
     pt[4] = H[H_PARCAN_W] * gPar + H[H_NIRSUN] * aCanNir + nirLampCan;
     pt[8] = H[H_PARFLR_W] * e32 + H[H_NIRSUN] * aFlrNir + nirLampFlr;
-    const double tAir = x[2], tGroPipe = x[19];
-    const double hGroPipeAir = fabs(K[K_GROPIPEAIR]) * glg_pow(fabs(tGroPipe - tAir + 1e-10), 0.32) * (tGroPipe - tAir);
+    const T tAir = x[2], tGroPipe = x[19];
+    const T hGroPipeAir = fabs(K[K_GROPIPEAIR]) * glg_pow(fabs(tGroPipe - tAir + T(1e-10)), T(0.32)) * (tGroPipe - tAir);
     pt[19] = -hGroPipeAir;
     pt[2] = (H[H_LAMPRAD] - parLampCanW - nirLampCan - parLampFlrW - nirLampFlr) +
             (H[H_GLOBAIR_A] + H[H_GLOBAIR_B] * (aCanNir + aFlrNir)) + hGroPipeAir;
@@ -712,17 +724,18 @@ GLG_HD double glg_grp_rad(const KV &K, const CV &C, const HV &H, const XV &x, PT
 // G1: FIR exchange, cover conduction, cover-outside convection
 template <bool GENERAL, class KV, class CV, class HV, class P, class XV, class PT>
 GLG_HD void glg_grp_fir(const KV &K, const CV &C, const HV &H, const P &p, const double *u, const XV &x, PT &pt) {
-    const double tCan = x[4], tCovIn = x[5], tCovE = x[6], tThScr = x[7], tFlr = x[8], tPipe = x[9];
-    const double tLamp = x[17], tBlScr = x[20];
-    const double lai = C[C_SLA] * x[23];
-    const double e35 = glg_exp(-K[K_KFIR] * lai);
-    const double aCan = 1 - e35;
-    double sCan, sFlr, sCovIn, sThScr, sBlScr, sPipe, sLamp, sCovE, sGroPipe = 0.0, sIntLamp = 0.0;
-    const double q4Can = glg_sq(glg_sq(tCan + GLG_C2K)), q4CovIn = glg_sq(glg_sq(tCovIn + GLG_C2K));
-    const double q4ThScr = glg_sq(glg_sq(tThScr + GLG_C2K)), q4Flr = glg_sq(glg_sq(tFlr + GLG_C2K));
-    const double q4Pipe = glg_sq(glg_sq(tPipe + GLG_C2K)), q4Lamp = glg_sq(glg_sq(tLamp + GLG_C2K));
-    const double q4BlScr = glg_sq(glg_sq(tBlScr + GLG_C2K));
-    double f;
+    typedef glg_scalar_t<KV> T;
+    const T tCan = x[4], tCovIn = x[5], tCovE = x[6], tThScr = x[7], tFlr = x[8], tPipe = x[9];
+    const T tLamp = x[17], tBlScr = x[20];
+    const T lai = C[C_SLA] * x[23];
+    const T e35 = glg_exp(-K[K_KFIR] * lai);
+    const T aCan = 1 - e35;
+    T sCan, sFlr, sCovIn, sThScr, sBlScr, sPipe, sLamp, sCovE, sGroPipe = T(0.0), sIntLamp = T(0.0);
+    const T q4Can = glg_sq(glg_sq(tCan + T(GLG_C2K))), q4CovIn = glg_sq(glg_sq(tCovIn + T(GLG_C2K)));
+    const T q4ThScr = glg_sq(glg_sq(tThScr + T(GLG_C2K))), q4Flr = glg_sq(glg_sq(tFlr + T(GLG_C2K)));
+    const T q4Pipe = glg_sq(glg_sq(tPipe + T(GLG_C2K))), q4Lamp = glg_sq(glg_sq(tLamp + T(GLG_C2K)));
+    const T q4BlScr = glg_sq(glg_sq(tBlScr + T(GLG_C2K)));
+    T f;
     f = aCan * H[H_C84] * (q4Can - q4CovIn);   sCan = -f; sCovIn = f;
     f = aCan * H[H_C86] * (q4Can - q4ThScr);   sCan -= f; sThScr = f;
     f = aCan * K[K_C87] * (q4Can - q4Flr);     sCan -= f; sFlr = f;
@@ -744,36 +757,36 @@ GLG_HD void glg_grp_fir(const KV &K, const CV &C, const HV &H, const P &p, const
     f = H[H_C109] * (q4BlScr - q4ThScr);       sBlScr -= f; sThScr += f;
     f = H[H_C110] * (q4BlScr - q4CovIn);       sBlScr -= f; sCovIn += f;
     f = H[H_C112] * (q4Lamp - q4BlScr);        sLamp -= f; sBlScr += f;
-    sCovE = H[H_GLOBCOV] - K[K_C98] * (glg_sq(glg_sq(tCovE + GLG_C2K)) - H[H_TSKY4]);
+    sCovE = H[H_GLOBCOV] - K[K_C98] * (glg_sq(glg_sq(tCovE + T(GLG_C2K))) - H[H_TSKY4]);
     if (GENERAL) {
         // Terms that are identically zero for the default table: sky FIR through the roof (tauRfFir p70),
         // grow-pipe FIR (epsGroPipe p165), interlight FIR (p194,p195).  Written plainly.
-        const double sigma = p[2];
-        const double pi = 3.14159265358979323846;
-        const double thScr = u[2], blScr = u[5];
-        const double tauCovFir = p[70];
-        const double tauThFir = 1 - thScr * (1 - p[81]), tauBlFir = 1 - blScr * (1 - p[91]);
-        const double fPipe = 0.49 * pi * p[107] * p[105];
-        const double q4Sky = H[H_TSKY4];
-        const double q4Int = glg_sq(glg_sq(x[18] + GLG_C2K)), q4Gro = glg_sq(glg_sq(x[19] + GLG_C2K));
-        const double f85 = aCan * p[3] * p[4] * (p[178] * tauCovFir * tauThFir * tauBlFir) * sigma * (q4Can - q4Sky);
-        const double f89 = p[124] * p[104] * p[4] * (p[199] * p[178] * tauCovFir * tauThFir * 0.49 * e35) * sigma * (q4Pipe - q4Sky);
-        const double f94 = p[95] * p[4] * (p[199] * p[178] * tauCovFir * tauThFir * tauBlFir * (1 - fPipe) * e35) * sigma * (q4Flr - q4Sky);
-        const double f97 = p[74] * p[4] * (tauCovFir * thScr) * sigma * (q4ThScr - q4Sky);
-        const double f104 = p[181] * p[182] * p[4] * (tauCovFir * tauThFir * tauBlFir) * sigma * (q4Lamp - q4Sky);
-        const double f111 = blScr * p[85] * p[4] * (tauCovFir * tauThFir) * sigma * (q4BlScr - q4Sky);
-        const double f105 = p[169] * p[165] * p[3] * sigma * (q4Gro - q4Can);
-        const double upF = 1 - glg_exp(-p[203] * (1 - p[189]) * lai);
-        const double dnF = 1 - glg_exp(-p[203] * p[189] * lai);
-        const double ci = p[194] * p[195] * sigma;
-        const double f115 = ci * p[95] * ((1 - fPipe) * (1 - dnF)) * (q4Int - q4Flr);
-        const double f116 = ci * p[104] * (fPipe * (1 - dnF)) * (q4Int - q4Pipe);
-        const double f117 = ci * p[3] * (dnF + upF) * (q4Int - q4Can);
-        const double f118 = ci * p[183] * ((1 - upF) * p[181]) * (q4Int - q4Lamp);
-        const double f119 = ci * p[85] * (blScr * p[178] * (1 - upF)) * (q4Int - q4BlScr);
-        const double f120 = ci * p[74] * (thScr * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4ThScr);
-        const double f121 = ci * (1 - p[70] - p[67]) * (tauThFir * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4CovIn);
-        const double f122 = ci * p[4] * (tauCovFir * tauThFir * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4Sky);
+        const T sigma = p[2];
+        const T pi = T(3.14159265358979323846);
+        const T thScr = u[2], blScr = u[5];
+        const T tauCovFir = p[70];
+        const T tauThFir = 1 - thScr * (1 - p[81]), tauBlFir = 1 - blScr * (1 - p[91]);
+        const T fPipe = T(0.49) * pi * p[107] * p[105];
+        const T q4Sky = H[H_TSKY4];
+        const T q4Int = glg_sq(glg_sq(x[18] + T(GLG_C2K))), q4Gro = glg_sq(glg_sq(x[19] + T(GLG_C2K)));
+        const T f85 = aCan * p[3] * p[4] * (p[178] * tauCovFir * tauThFir * tauBlFir) * sigma * (q4Can - q4Sky);
+        const T f89 = p[124] * p[104] * p[4] * (p[199] * p[178] * tauCovFir * tauThFir * T(0.49) * e35) * sigma * (q4Pipe - q4Sky);
+        const T f94 = p[95] * p[4] * (p[199] * p[178] * tauCovFir * tauThFir * tauBlFir * (1 - fPipe) * e35) * sigma * (q4Flr - q4Sky);
+        const T f97 = p[74] * p[4] * (tauCovFir * thScr) * sigma * (q4ThScr - q4Sky);
+        const T f104 = p[181] * p[182] * p[4] * (tauCovFir * tauThFir * tauBlFir) * sigma * (q4Lamp - q4Sky);
+        const T f111 = blScr * p[85] * p[4] * (tauCovFir * tauThFir) * sigma * (q4BlScr - q4Sky);
+        const T f105 = p[169] * p[165] * p[3] * sigma * (q4Gro - q4Can);
+        const T upF = 1 - glg_exp(-p[203] * (1 - p[189]) * lai);
+        const T dnF = 1 - glg_exp(-p[203] * p[189] * lai);
+        const T ci = p[194] * p[195] * sigma;
+        const T f115 = ci * p[95] * ((1 - fPipe) * (1 - dnF)) * (q4Int - q4Flr);
+        const T f116 = ci * p[104] * (fPipe * (1 - dnF)) * (q4Int - q4Pipe);
+        const T f117 = ci * p[3] * (dnF + upF) * (q4Int - q4Can);
+        const T f118 = ci * p[183] * ((1 - upF) * p[181]) * (q4Int - q4Lamp);
+        const T f119 = ci * p[85] * (blScr * p[178] * (1 - upF)) * (q4Int - q4BlScr);
+        const T f120 = ci * p[74] * (thScr * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4ThScr);
+        const T f121 = ci * (1 - p[70] - p[67]) * (tauThFir * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4CovIn);
+        const T f122 = ci * p[4] * (tauCovFir * tauThFir * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4Sky);
         sCan += -f85 + f105 + f117;
         sCovIn += f121;
         sThScr += -f97 + f120;
@@ -784,15 +797,15 @@ GLG_HD void glg_grp_fir(const KV &K, const CV &C, const HV &H, const P &p, const
         sGroPipe = -f105;
         sBlScr += -f111 + f119;
     }
-    const double hCovInCovE = K[K_HCOV] * (tCovIn - tCovE);
+    const T hCovInCovE = K[K_HCOV] * (tCovIn - tCovE);
     // soil chain (:888-910)
-    const double hFlrSo1 = K[K_HFLRSO1] * (tFlr - x[10]);
+    const T hFlrSo1 = K[K_HFLRSO1] * (tFlr - x[10]);
     {
-        const double hSo12 = K[K_HSO12] * (x[10] - x[11]);
-        const double hSo23 = K[K_HSO23] * (x[11] - x[12]);
-        const double hSo34 = K[K_HSO34] * (x[12] - x[13]);
-        const double hSo45 = K[K_HSO45] * (x[13] - x[14]);
-        const double hSo5Out = K[K_HSO5OUT] * (x[14] - H[H_TSOOUT]);
+        const T hSo12 = K[K_HSO12] * (x[10] - x[11]);
+        const T hSo23 = K[K_HSO23] * (x[11] - x[12]);
+        const T hSo34 = K[K_HSO34] * (x[12] - x[13]);
+        const T hSo45 = K[K_HSO45] * (x[13] - x[14]);
+        const T hSo5Out = K[K_HSO5OUT] * (x[14] - H[H_TSOOUT]);
         pt[10] = K[K_INVCAPSO1] * (hFlrSo1 - hSo12);
         pt[11] = K[K_INVCAPSO2] * (hSo12 - hSo23);
         pt[12] = K[K_INVCAPSO3] * (hSo23 - hSo34);
@@ -814,58 +827,60 @@ GLG_HD void glg_grp_fir(const KV &K, const CV &C, const HV &H, const P &p, const
 // G2: ventilation, screen air flux, CO2 of the air compartments, sensible air/top/outside, air-borne vapour
 template <class KV, class HV, class XV, class PT>
 GLG_HD void glg_grp_airflow(const KV &K, const HV &H, const XV &x, PT &pt) {
-    const double co2Air = x[0], co2Top = x[1], tAir = x[2], tTop = x[3], vpAir = x[15], vpTop = x[16];
-    const double tOut = H[H_TOUT];
-    const double tkAir = tAir + GLG_C2K, tkTop = tTop + GLG_C2K;
-    const double ra[3] = {tkAir, tkTop, tAir + H[H_TOUT_2K]};
-    double ry[3];
+    typedef glg_scalar_t<KV> T;
+    const T co2Air = x[0], co2Top = x[1], tAir = x[2], tTop = x[3], vpAir = x[15], vpTop = x[16];
+    const T tOut = H[H_TOUT];
+    const T tkAir = tAir + T(GLG_C2K), tkTop = tTop + T(GLG_C2K);
+    const T ra[3] = {tkAir, tkTop, tAir + H[H_TOUT_2K]};
+    T ry[3];
     glg_rcp_n<3>(ra, ry);
-    const double rAir = ry[0], rTop = ry[1];
-    double aScr, aVentRoof;
+    const T rAir = ry[0], rTop = ry[1];
+    T aScr, aVentRoof;
     {
-        const double rhoTop = K[K_RHOC] * rTop, rhoAir = K[K_RHOC] * rAir;
-        const double rhoMean = 0.5 * (rhoTop + rhoAir);
-        const double rMean = glg_rcp(rhoMean);
-        const double buoy = K[K_HALFG] * rhoMean * fabs(rhoAir - rhoTop);
-        const double pw66 = glg_pow(fabs(tAir - tTop + 1e-10), 0.66);
-        const double oneMTh = H[H_1MTH], oneMBl = H[H_1MBL];
-        const double sa[3] = {fabs(K[K_GHVENT] * (tAir - tOut) * ry[2] + H[H_CW_WIND2]) + 1e-300, buoy * oneMTh + 1e-10,
-                              buoy * oneMBl + 1e-10};
-        double sy[3];
+        const T rhoTop = K[K_RHOC] * rTop, rhoAir = K[K_RHOC] * rAir;
+        const T rhoMean = T(0.5) * (rhoTop + rhoAir);
+        const T rMean = glg_rcp(rhoMean);
+        const T buoy = K[K_HALFG] * rhoMean * fabs(rhoAir - rhoTop);
+        const T pw66 = glg_pow(fabs(tAir - tTop + T(1e-10)), T(0.66));
+        const T oneMTh = H[H_1MTH], oneMBl = H[H_1MBL];
+        const T sa[3] = {fabs(K[K_GHVENT] * (tAir - tOut) * ry[2] + H[H_CW_WIND2]) + T(1e-300), buoy * oneMTh + T(1e-10),
+                              buoy * oneMBl + T(1e-10)};
+        T sy[3];
         glg_sqrt_n<3>(sa, sy);
         aVentRoof = fabs(H[H_VR_A] * sy[0] + H[H_VR_B]);
-        const double fThScr = H[H_THK] * pw66 + (oneMTh * rMean) * sy[1];
-        const double fBlScr = H[H_BLK] * pw66 + (oneMBl * rMean) * sy[2];
+        const T fThScr = H[H_THK] * pw66 + (oneMTh * rMean) * sy[1];
+        const T fBlScr = H[H_BLK] * pw66 + (oneMBl * rMean) * sy[2];
         aScr = fabs(fmin(fThScr, fBlScr));
     }
-    const double mcAirTop = aScr * (co2Air - co2Top);
+    const T mcAirTop = aScr * (co2Air - co2Top);
     pt[1] = mcAirTop - aVentRoof * (co2Top - H[H_CO2OUT]);
     pt[0] = H[H_MCEXT] - mcAirTop - H[H_FVENTSIDE_ABS] * (co2Air - H[H_CO2OUT]);
-    const double hAirTop = fabs(K[K_RHOCP]) * aScr * (tAir - tTop);
+    const T hAirTop = fabs(K[K_RHOCP]) * aScr * (tAir - tTop);
     pt[2] = -(H[H_HEC_AIROUT] * (tAir - tOut) + hAirTop);
     pt[3] = hAirTop - fabs(K[K_RHOCP]) * aVentRoof * (tTop - tOut);
-    const double rAirF = rAir - GLG_C2K_F32_DELTA * (rAir * rAir);  // 1/(tAir + 273.15f), aux_states.hpp:84
-    const double rTopF = rTop - GLG_C2K_F32_DELTA * (rTop * rTop);
-    const double vAirT = vpAir * rAirF, vTopT = vpTop * rTopF;
-    const double mvAirTop = 0.002165 * aScr * (vAirT - vTopT);
-    pt[16] = (K[K_INVVPTOP] * tkTop) * (mvAirTop - 0.002165 * aVentRoof * (vTopT - H[H_VPOUT_T]));
+    const T rAirF = rAir - T(GLG_C2K_F32_DELTA) * (rAir * rAir);  // 1/(tAir + 273.15f), aux_states.hpp:84
+    const T rTopF = rTop - T(GLG_C2K_F32_DELTA) * (rTop * rTop);
+    const T vAirT = vpAir * rAirF, vTopT = vpTop * rTopF;
+    const T mvAirTop = T(0.002165) * aScr * (vAirT - vTopT);
+    pt[16] = (K[K_INVVPTOP] * tkTop) * (mvAirTop - T(0.002165) * aVentRoof * (vTopT - H[H_VPOUT_T]));
     pt[15] = -(K[K_INVVPAIR] * tkAir) * (mvAirTop + H[H_MVAIROUT_C] * (vAirT - H[H_VPOUT_T]));
 }
 
 // G3: lamp / pipe / canopy / floor convection with the main air
 template <bool GENERAL, class KV, class CV, class HV, class P, class XV, class PT>
 GLG_HD void glg_grp_conv(const KV &K, const CV &C, const HV &H, const P &p, const XV &x, PT &pt) {
-    const double tAir = x[2], tCan = x[4], tFlr = x[8], tPipe = x[9], tLamp = x[17];
-    const double hLampAir = K[K_HLAMPAIR] * (tLamp - tAir);
-    const double hPipeAir = fabs(K[K_PIPEAIR]) * glg_pow(fabs(tPipe - tAir + 1e-10), 0.32) * (tPipe - tAir);
-    const double hCanAir = fabs(K[K_2ALFA] * (C[C_SLA] * x[23])) * (tCan - tAir);
-    const double hecFlr = (tFlr > tAir) ? 1.7 * glg_cbrt(fabs(tFlr - tAir + 1e-10))
-                                        : 1.3 * glg_sqrt(glg_sqrt(fabs(tAir - tFlr + 1e-10) + 1e-300));
-    const double hAirFlr = hecFlr * (tAir - tFlr);
-    double sAir = hLampAir + hPipeAir + hCanAir - hAirFlr;
-    double sIntLamp = 0.0;
+    typedef glg_scalar_t<KV> T;
+    const T tAir = x[2], tCan = x[4], tFlr = x[8], tPipe = x[9], tLamp = x[17];
+    const T hLampAir = K[K_HLAMPAIR] * (tLamp - tAir);
+    const T hPipeAir = fabs(K[K_PIPEAIR]) * glg_pow(fabs(tPipe - tAir + T(1e-10)), T(0.32)) * (tPipe - tAir);
+    const T hCanAir = fabs(K[K_2ALFA] * (C[C_SLA] * x[23])) * (tCan - tAir);
+    const T hecFlr = (tFlr > tAir) ? T(1.7) * glg_cbrt(fabs(tFlr - tAir + T(1e-10)))
+                                        : T(1.3) * glg_sqrt(glg_sqrt(fabs(tAir - tFlr + T(1e-10)) + T(1e-300)));
+    const T hAirFlr = hecFlr * (tAir - tFlr);
+    T sAir = hLampAir + hPipeAir + hCanAir - hAirFlr;
+    T sIntLamp = T(0.0);
     if (GENERAL) {
-        const double hIntLampAir = fabs(p[198]) * (x[18] - tAir);  // a167
+        const T hIntLampAir = fabs(p[198]) * (x[18] - tAir);  // a167
         sAir += hIntLampAir;
         sIntLamp = -hIntLampAir;
     }
@@ -876,134 +891,137 @@ GLG_HD void glg_grp_conv(const KV &K, const CV &C, const HV &H, const P &p, cons
     pt[17] = -hLampAir;
     pt[18] = sIntLamp;
     // maintenance respiration (:1161-1178) and harvest (:75-79,1184,1188): additive pieces of the crop balances
-    const double cLeaf = x[23], cStem = x[24], cFruit = x[25];
-    const double kHar = 2.0 * 4.6052 / 1e4;  // smoothHar(v, cutoff, 1e4, 5e4) = 5e4/(1+exp(-kHar (v-cutoff)))
-    const double ea[3] = {C[C_LNQ10X] * (x[21] - 25), -kHar * (cLeaf - C[C_CLEAFMAX]), -kHar * (cFruit - C[C_CFRUITMAX])};
-    double ey[3];
+    const T cLeaf = x[23], cStem = x[24], cFruit = x[25];
+    const T kHar = T(2.0) * T(4.6052) / T(1e4);  // smoothHar(v, cutoff, 1e4, 5e4) = 5e4/(1+exp(-kHar (v-cutoff)))
+    const T ea[3] = {C[C_LNQ10X] * (x[21] - 25), -kHar * (cLeaf - C[C_CLEAFMAX]), -kHar * (cFruit - C[C_CFRUITMAX])};
+    T ey[3];
     glg_exp_n<3>(ea, ey);
-    const double ra[2] = {1.0 + ey[1], 1.0 + ey[2]};
-    double ry[2];
+    const T ra[2] = {T(1.0) + ey[1], T(1.0) + ey[2]};
+    T ry[2];
     glg_rcp_n<2>(ra, ry);
-    const double maint = C[C_MAINT] * ey[0];
-    const double mcLeafAir = maint * cLeaf * C[C_MLEAF];
-    const double mcStemAir = maint * cStem * C[C_MSTEM];
-    const double mcFruitAir = maint * cFruit * C[C_MFRUIT];
-    pt[23] = -mcLeafAir - 5e4 * ry[0];
+    const T maint = C[C_MAINT] * ey[0];
+    const T mcLeafAir = maint * cLeaf * C[C_MLEAF];
+    const T mcStemAir = maint * cStem * C[C_MSTEM];
+    const T mcFruitAir = maint * cFruit * C[C_MFRUIT];
+    pt[23] = -mcLeafAir - T(5e4) * ry[0];
     pt[24] = -mcStemAir;
-    pt[25] = -mcFruitAir - 5e4 * ry[1];
+    pt[25] = -mcFruitAir - T(5e4) * ry[1];
     pt[0] = C[C_CO2RATIO] * (mcLeafAir + mcStemAir + mcFruitAir);  // maintenance part of -a216
 }
 
 // G4: thermal and blackout screen: convection on both sides + condensation from the main air
 template <class KV, class HV, class XV, class PT>
 GLG_HD void glg_grp_screens(const KV &K, const HV &H, const XV &x, PT &pt) {
-    const double tAir = x[2], tTop = x[3], tThScr = x[7], vpAir = x[15], tBlScr = x[20];
-    const double L = K[K_L];
-    const double hec17Th = H[H_17TH], hec17Bl = H[H_17BL];
+    typedef glg_scalar_t<KV> T;
+    const T tAir = x[2], tTop = x[3], tThScr = x[7], vpAir = x[15], tBlScr = x[20];
+    const T L = K[K_L];
+    const T hec17Th = H[H_17TH], hec17Bl = H[H_17BL];
     // three cube roots, two saturation pressures and two condensation sigmoids: independent chains, interleaved
-    const double ca[3] = {fabs(tAir - tThScr + 1e-10), fabs(tThScr - tTop + 1e-10), fabs(tAir - tBlScr + 1e-10)};
-    double cy[3];
+    const T ca[3] = {fabs(tAir - tThScr + T(1e-10)), fabs(tThScr - tTop + T(1e-10)), fabs(tAir - tBlScr + T(1e-10))};
+    T cy[3];
     glg_cbrt_n<3>(ca, cy);
-    const double ra[2] = {tThScr + 238.3, tBlScr + 238.3};
-    double ry[2];
+    const T ra[2] = {tThScr + T(238.3), tBlScr + T(238.3)};
+    T ry[2];
     glg_rcp_n<2>(ra, ry);
-    const double ea[2] = {17.2694 * (tThScr * ry[0]), 17.2694 * (tBlScr * ry[1])};
-    double ey[2];
+    const T ea[2] = {T(17.2694) * (tThScr * ry[0]), T(17.2694) * (tBlScr * ry[1])};
+    T ey[2];
     glg_exp_n<2>(ea, ey);
-    const double dvTh = vpAir - 610.78 * ey[0], dvBl = vpAir - 610.78 * ey[1];
-    const double eb[2] = {-0.1 * dvTh, -0.1 * dvBl};
-    double ez[2];
+    const T dvTh = vpAir - T(610.78) * ey[0], dvBl = vpAir - T(610.78) * ey[1];
+    const T eb[2] = {-T(0.1) * dvTh, -T(0.1) * dvBl};
+    T ez[2];
     glg_exp_n<2>(eb, ez);
-    const double rb[2] = {1.0 + ez[0], 1.0 + ez[1]};
-    double rz[2];
+    const T rb[2] = {T(1.0) + ez[0], T(1.0) + ez[1]};
+    T rz[2];
     glg_rcp_n<2>(rb, rz);
-    const double hecAirTh = hec17Th * cy[0];
-    const double hAirThScr = fabs(hecAirTh) * (tAir - tThScr);
-    const double hThScrTop = fabs(hec17Th * cy[1]) * (tThScr - tTop);
-    const double mvAirThScr = 6.4e-9 * hecAirTh * dvTh * rz[0];  // cond(), aux_states.hpp:60-63
+    const T hecAirTh = hec17Th * cy[0];
+    const T hAirThScr = fabs(hecAirTh) * (tAir - tThScr);
+    const T hThScrTop = fabs(hec17Th * cy[1]) * (tThScr - tTop);
+    const T mvAirThScr = T(6.4e-9) * hecAirTh * dvTh * rz[0];  // cond(), aux_states.hpp:60-63
     pt[7] = hAirThScr - hThScrTop + L * mvAirThScr;
-    const double hecAirBl = hec17Bl * cy[2];
-    const double hAirBlScr = fabs(hecAirBl) * (tAir - tBlScr);
-    const double mvAirBlScr = 6.4e-9 * hecAirBl * dvBl * rz[1];
+    const T hecAirBl = hec17Bl * cy[2];
+    const T hAirBlScr = fabs(hecAirBl) * (tAir - tBlScr);
+    const T mvAirBlScr = T(6.4e-9) * hecAirBl * dvBl * rz[1];
     pt[20] = hAirBlScr + L * mvAirBlScr;
     pt[2] = -(hAirThScr + hAirBlScr);
     pt[3] = hThScrTop;
-    pt[15] = -(K[K_INVVPAIR] * (tAir + GLG_C2K)) * (mvAirThScr + mvAirBlScr);
+    pt[15] = -(K[K_INVVPAIR] * (tAir + T(GLG_C2K))) * (mvAirThScr + mvAirBlScr);
 }
 
 // G5: cover (convection from the top compartment + condensation) and canopy transpiration
 template <class KV, class CV, class HV, class XV, class PT>
 GLG_HD void glg_grp_cover(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
-    const double co2Air = x[0], tAir = x[2], tTop = x[3], tCan = x[4], tCovIn = x[5], vpAir = x[15], vpTop = x[16];
-    const double L = K[K_L];
-    const double tBlScr = x[20];
-    const double ca[2] = {fabs(tTop - tCovIn + 1e-10), fabs(tBlScr - tTop + 1e-10)};
-    double cy[2];
+    typedef glg_scalar_t<KV> T;
+    const T co2Air = x[0], tAir = x[2], tTop = x[3], tCan = x[4], tCovIn = x[5], vpAir = x[15], vpTop = x[16];
+    const T L = K[K_L];
+    const T tBlScr = x[20];
+    const T ca[2] = {fabs(tTop - tCovIn + T(1e-10)), fabs(tBlScr - tTop + T(1e-10))};
+    T cy[2];
     glg_cbrt_n<2>(ca, cy);
-    const double ra[2] = {tCovIn + 238.3, tCan + 238.3};
-    double ry[2];
+    const T ra[2] = {tCovIn + T(238.3), tCan + T(238.3)};
+    T ry[2];
     glg_rcp_n<2>(ra, ry);
-    const double ea[2] = {17.2694 * (tCovIn * ry[0]), 17.2694 * (tCan * ry[1])};
-    double ey[2];
+    const T ea[2] = {T(17.2694) * (tCovIn * ry[0]), T(17.2694) * (tCan * ry[1])};
+    T ey[2];
     glg_exp_n<2>(ea, ey);
-    const double hecTopCov = K[K_HECIN] * cy[0];
-    const double hTopCovIn = fabs(hecTopCov) * (tTop - tCovIn);
-    const double dvCov = vpTop - 610.78 * ey[0];
-    const double vpd = 610.78 * ey[1] - vpAir;
-    const double lai = C[C_SLA] * x[23];
-    const double rfCo2 = fmin(1.5, 1. + H[H_CEVAP3] * glg_sq(K[K_ETAMGPPM] * co2Air - 200));
-    const double rfVp = fmin(5.8, 1. + H[H_CEVAP4] * (vpd * vpd));
-    const double rS = H[H_RS] * rfCo2 * rfVp;
-    const double rb[2] = {1.0 + glg_exp(-0.1 * dvCov), K[K_RB] + rS};
-    double rz[2];
+    const T hecTopCov = K[K_HECIN] * cy[0];
+    const T hTopCovIn = fabs(hecTopCov) * (tTop - tCovIn);
+    const T dvCov = vpTop - T(610.78) * ey[0];
+    const T vpd = T(610.78) * ey[1] - vpAir;
+    const T lai = C[C_SLA] * x[23];
+    const T rfCo2 = fmin(T(1.5), T(1.) + H[H_CEVAP3] * glg_sq(K[K_ETAMGPPM] * co2Air - 200));
+    const T rfVp = fmin(T(5.8), T(1.) + H[H_CEVAP4] * (vpd * vpd));
+    const T rS = H[H_RS] * rfCo2 * rfVp;
+    const T rb[2] = {T(1.0) + glg_exp(-T(0.1) * dvCov), K[K_RB] + rS};
+    T rz[2];
     glg_rcp_n<2>(rb, rz);
-    const double mvTopCovIn = 6.4e-9 * hecTopCov * dvCov * rz[0];  // cond(), aux_states.hpp:60-63
+    const T mvTopCovIn = T(6.4e-9) * hecTopCov * dvCov * rz[0];  // cond(), aux_states.hpp:60-63
     pt[5] = hTopCovIn + L * mvTopCovIn;
-    const double hBlScrTop = fabs(H[H_17BL] * cy[1]) * (tBlScr - tTop);
+    const T hBlScrTop = fabs(H[H_17BL] * cy[1]) * (tBlScr - tTop);
     pt[20] = -hBlScrTop;
     pt[3] = hBlScrTop - hTopCovIn;
-    pt[16] = -(K[K_INVVPTOP] * (tTop + GLG_C2K)) * mvTopCovIn;
-    const double mvCanAir = vpd * (K[K_VEC] * lai * rz[1]);
+    pt[16] = -(K[K_INVVPTOP] * (tTop + T(GLG_C2K))) * mvTopCovIn;
+    const T mvCanAir = vpd * (K[K_VEC] * lai * rz[1]);
     pt[4] = -(L * mvCanAir);
-    pt[15] = (K[K_INVVPAIR] * (tAir + GLG_C2K)) * mvCanAir;
+    pt[15] = (K[K_INVVPAIR] * (tAir + T(GLG_C2K))) * mvCanAir;
 }
 
 // G6: canopy photosynthesis -> buffer inflow a200
 template <bool GENERAL, class KV, class CV, class HV, class XV, class PT>
 GLG_HD void glg_grp_photo(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
-    const double co2Air = x[0], tAir = x[2], tCan = x[4], cBuf = x[22];
-    const double lai = C[C_SLA] * x[23];
-    const double j25 = lai * C[C_J25];
-    const double co2Stom = C[C_ETASTOM] * (K[K_PPMC] * (tAir + GLG_C2K) * co2Air);
-    const double ra[3] = {j25, tCan + GLG_C2K, co2Stom};
-    double ry[3];
+    typedef glg_scalar_t<KV> T;
+    const T co2Air = x[0], tAir = x[2], tCan = x[4], cBuf = x[22];
+    const T lai = C[C_SLA] * x[23];
+    const T j25 = lai * C[C_J25];
+    const T co2Stom = C[C_ETASTOM] * (K[K_PPMC] * (tAir + T(GLG_C2K)) * co2Air);
+    const T ra[3] = {j25, tCan + T(GLG_C2K), co2Stom};
+    T ry[3];
     glg_rcp_n<3>(ra, ry);
-    const double rj = C[C_J25] * ry[0], rCanK = ry[1], rStom = ry[2];
+    const T rj = C[C_J25] * ry[0], rCanK = ry[1], rStom = ry[2];
     // PAR absorbed by the canopy in umol (a191): the extinction factor is recomputed (G0 has it too); the four
     // exponentials of this group are independent and evaluated interleaved
-    const double ea[5] = {-K[K_K1PAR] * lai, C[C_ARR1] * (1 - C[C_T25K] * rCanK), C[C_ARR2A] - C[C_ARR2B] * rCanK,
-                          5e-4 * (cBuf - C[C_CBUFMAX]), -K[K_K2PAR] * lai};
-    double ey[5];
+    const T ea[5] = {-K[K_K1PAR] * lai, C[C_ARR1] * (1 - C[C_T25K] * rCanK), C[C_ARR2A] - C[C_ARR2B] * rCanK,
+                          T(5e-4) * (cBuf - C[C_CBUFMAX]), -K[K_K2PAR] * lai};
+    T ey[5];
     if (GENERAL) {
         glg_exp_n<5>(ea, ey);
     } else {
-        const double ea4[4] = {ea[0], ea[1], ea[2], ea[3]};
-        double ey4[4];
+        const T ea4[4] = {ea[0], ea[1], ea[2], ea[3]};
+        T ey4[4];
         glg_exp_n<4>(ea4, ey4);
         ey[0] = ey4[0]; ey[1] = ey4[1]; ey[2] = ey4[2]; ey[3] = ey4[3]; ey[4] = ey4[0];
     }
-    const double e32 = ey[0], e33 = ey[4];
-    const double parCan = H[H_PARUMOL] * ((1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33));
-    const double gamma = rj * C[C_CGAMMA] * tCan + C[C_20CGAMMA] * (1 - rj);
-    const double rb[3] = {1.0 + ey[2], 1.0 + ey[3], 4 * (co2Stom + 2 * gamma)};
-    double rz[3];
+    const T e32 = ey[0], e33 = ey[4];
+    const T parCan = H[H_PARUMOL] * ((1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33));
+    const T gamma = rj * C[C_CGAMMA] * tCan + C[C_20CGAMMA] * (1 - rj);
+    const T rb[3] = {T(1.0) + ey[2], T(1.0) + ey[3], 4 * (co2Stom + 2 * gamma)};
+    T rz[3];
     glg_rcp_n<3>(rb, rz);
-    const double jPot = j25 * ey[1] * C[C_JPOTNUM] * rz[0];
-    const double jb = jPot + C[C_ALPHA] * parCan;
-    const double jE = C[C_INV2THETA] * (jb - glg_sqrt(jb * jb - C[C_4THETAALPHA] * jPot * parCan + 1e-10));
-    const double phot = jE * (co2Stom - gamma) * rz[2];
-    const double photNet = phot - phot * gamma * rStom;
-    const double mcAirBuf = C[C_MCH2O] * rz[1] * photNet;
+    const T jPot = j25 * ey[1] * C[C_JPOTNUM] * rz[0];
+    const T jb = jPot + C[C_ALPHA] * parCan;
+    const T jE = C[C_INV2THETA] * (jb - glg_sqrt(jb * jb - C[C_4THETAALPHA] * jPot * parCan + T(1e-10)));
+    const T phot = jE * (co2Stom - gamma) * rz[2];
+    const T photNet = phot - phot * gamma * rStom;
+    const T mcAirBuf = C[C_MCH2O] * rz[1] * photNet;
     pt[22] = mcAirBuf;
     pt[0] = -(C[C_CO2RATIO] * mcAirBuf);
 }
@@ -1011,24 +1029,25 @@ GLG_HD void glg_grp_photo(const KV &K, const CV &C, const HV &H, const XV &x, PT
 // G7: carbohydrate flows buffer -> leaves / stem / fruit and the growth respiration that goes with them
 template <class KV, class CV, class XV, class PT>
 GLG_HD void glg_grp_flows(const KV &K, const CV &C, const XV &x, PT &pt) {
-    const double tCan = x[4], tCan24 = x[21], cBuf = x[22];
-    const double gT24 = 0.047 * tCan24 + 0.06;
-    const double ea[5] = {-1.1587 * (tCan24 - C[C_T24MIN]), 1.3904 * (tCan24 - C[C_T24MAX]), -0.869 * (tCan - C[C_TCANMIN]),
-                          0.5793 * (tCan - C[C_TCANMAX]), -5e-3 * (cBuf - C[C_CBUFMIN])};
-    double ey[5];
+    typedef glg_scalar_t<KV> T;
+    const T tCan = x[4], tCan24 = x[21], cBuf = x[22];
+    const T gT24 = T(0.047) * tCan24 + T(0.06);
+    const T ea[5] = {-T(1.1587) * (tCan24 - C[C_T24MIN]), T(1.3904) * (tCan24 - C[C_T24MAX]), -T(0.869) * (tCan - C[C_TCANMIN]),
+                          T(0.5793) * (tCan - C[C_TCANMAX]), -T(5e-3) * (cBuf - C[C_CBUFMIN])};
+    T ey[5];
     glg_exp_n<5>(ea, ey);
-    const double ra[3] = {(1. + ey[0]) * (1. + ey[1]), (1. + ey[2]) * (1. + ey[3]), 1.0 + ey[4]};
-    double ry[3];
+    const T ra[3] = {(T(1.) + ey[0]) * (T(1.) + ey[1]), (T(1.) + ey[2]) * (T(1.) + ey[3]), T(1.0) + ey[4]};
+    T ry[3];
     glg_rcp_n<3>(ra, ry);
-    const double hT24 = ry[0], hTCan = ry[1];
-    const double sSum = x[26] * K[K_INVTENDSUM];
-    const double sSum1 = sSum - 1.0;
-    const double hTSum = 0.5 * (sSum + glg_sqrt(sSum * sSum + 1e-4)) - 0.5 * (sSum1 + glg_sqrt(sSum1 * sSum1 + 1e-4));
-    const double flow = ry[2] * hT24 * gT24;
-    const double mcBufLeaf = flow * C[C_RGLEAF];
-    const double mcBufStem = flow * C[C_RGSTEM];
-    const double mcBufFruit = flow * hTCan * hTSum * C[C_RGFRUIT];
-    const double mcBufAir = C[C_GLEAF] * mcBufLeaf + C[C_GSTEM] * mcBufStem + C[C_GFRUIT] * mcBufFruit;
+    const T hT24 = ry[0], hTCan = ry[1];
+    const T sSum = x[26] * K[K_INVTENDSUM];
+    const T sSum1 = sSum - T(1.0);
+    const T hTSum = T(0.5) * (sSum + glg_sqrt(sSum * sSum + T(1e-4))) - T(0.5) * (sSum1 + glg_sqrt(sSum1 * sSum1 + T(1e-4)));
+    const T flow = ry[2] * hT24 * gT24;
+    const T mcBufLeaf = flow * C[C_RGLEAF];
+    const T mcBufStem = flow * C[C_RGSTEM];
+    const T mcBufFruit = flow * hTCan * hTSum * C[C_RGFRUIT];
+    const T mcBufAir = C[C_GLEAF] * mcBufLeaf + C[C_GSTEM] * mcBufStem + C[C_GFRUIT] * mcBufFruit;
     pt[22] = -mcBufFruit - mcBufLeaf - mcBufStem - mcBufAir;
     pt[23] = mcBufLeaf;
     pt[24] = mcBufStem;

@@ -38,16 +38,17 @@ constexpr int GLG_SLOT_ZERO = GLG_NPART;          // always 0.0
 constexpr int GLG_SLOT_CANSCALE = GLG_NPART + 1;  // canopy capacity scale of the current stage (written by G0's warp)
 constexpr int GLG_MAXCONTRIB = 4;
 
+template <class T>
 struct GlgXsCol {  // stage-state column of this lane
-    const double *b;
-    __device__ __forceinline__ double operator[](int i) const { return b[i * GLG_ROLE_LANES]; }
+    const T *b;
+    __device__ __forceinline__ T operator[](int i) const { return b[i * GLG_ROLE_LANES]; }
 };
-template <int G>
+template <int G, class T>
 struct GlgPartCol {  // contribution slots of group G for this lane
-    double *b;
+    T *b;
     struct Ref {
-        double *p;
-        __device__ __forceinline__ void operator=(double v) { *p = v; }
+        T *p;
+        __device__ __forceinline__ void operator=(T v) { *p = v; }
     };
     __device__ __forceinline__ Ref operator[](int i) { return Ref{b + glg_part_slot(G, i) * GLG_ROLE_LANES}; }
 };
@@ -69,11 +70,13 @@ __host__ __device__ constexpr GlgOwnerTable glg_make_owner_table() {
 }
 __constant__ GlgOwnerTable glg_owner_table = glg_make_owner_table();
 
-template <bool NOISY>
+template <class T, bool NOISY>
 struct GlgRoleSmem {
     static constexpr int kColRows = (GLG_NX + 1) + (GLG_NPART + 2) + H_COUNT + (NOISY ? C_COUNT : 0);  // +1: dummy state row
+    // weather tile (f64) | final state (f64 [28][32]) | T columns | mbarrier | ints
+    __host__ __device__ static size_t col_bytes() { return (sizeof(T) * (size_t)kColRows * GLG_ROLE_LANES + 15) / 16 * 16; }
     __host__ __device__ static size_t bytes(int Np) {
-        return sizeof(double) * ((size_t)kColRows * GLG_ROLE_LANES + (size_t)(Np + 1) * GLG_ND) + 16 +
+        return sizeof(double) * ((size_t)(Np + 1) * GLG_ND + (size_t)GLG_NX * GLG_ROLE_LANES) + col_bytes() + 16 +
                sizeof(int) * (5 * GLG_ROLE_LANES + 4);
     }
 };
@@ -106,19 +109,20 @@ __device__ __forceinline__ void glg_owner_setup(const double *Kc, int warp, GlgO
         o.xs_off[j] = (valid ? i : GLG_NX) * GLG_ROLE_LANES;
     }
 }
-template <int NR>
-__device__ __forceinline__ void glg_owner_update(const GlgOwnerRegs<NR> &o, int warp, double *xs_col, const double *part_col,
+template <int NR, class T>
+__device__ __forceinline__ void glg_owner_update(const GlgOwnerRegs<NR> &o, int warp, T *xs_col, const T *part_col,
                                                  double *xo, double *acc, int stage, double h) {
     // stage 0..2: acc = (stage ? acc : 0) + w k ; xs = x + c k        stage 3: x += h/6 (acc + k) ; xs = x
     const bool last = stage == 3;
     const double w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
     const double keep = stage == 0 ? 0.0 : 1.0;
     const double m = last ? h / 6.0 : (stage == 2 ? h : 0.5 * h);
-    const double can_scale = part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES];
+    const double can_scale = (double)part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES];
     double sum[GlgOwnerRegs<NR>::NJ];
 #pragma unroll
     for (int j = 0; j < GlgOwnerRegs<NR>::NJ; ++j)
-        sum[j] = (part_col[o.off[j][0]] + part_col[o.off[j][1]]) + (part_col[o.off[j][2]] + part_col[o.off[j][3]]);
+        sum[j] = ((double)part_col[o.off[j][0]] + (double)part_col[o.off[j][1]]) +
+                 ((double)part_col[o.off[j][2]] + (double)part_col[o.off[j][3]]);
 #pragma unroll
     for (int j = 0; j < GlgOwnerRegs<NR>::NJ; ++j) {
         const double sc = (j == GlgOwnerRegs<NR>::CAN_J && warp == GlgOwnerRegs<NR>::CAN_WARP) ? can_scale : o.scale[j];
@@ -127,17 +131,32 @@ __device__ __forceinline__ void glg_owner_update(const GlgOwnerRegs<NR> &o, int 
         const double xn = glg_fma(m, last ? a_new : k, xo[j]);
         acc[j] = a_new;
         xo[j] = last ? xn : xo[j];
-        xs_col[o.xs_off[j]] = xn;
+        xs_col[o.xs_off[j]] = (T)xn;
     }
 }
 
 // evaluates flux group G for this lane
-template <int G, bool GENERAL, class CV, class HV>
-__device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv, const HV &Hc, const double *u, const GlgXsCol &X,
-                                              double *part_col) {
-    const GlgConstView Kv{U.K};
+template <class T>
+struct GlgKView;
+template <>
+struct GlgKView<double> {
+    typedef GlgConstView type;
+    __device__ __forceinline__ static type k(const GlgUniform &U) { return type{U.K}; }
+    __device__ __forceinline__ static type c(const GlgUniform &U) { return type{U.C}; }
+};
+template <>
+struct GlgKView<float> {
+    typedef GlgConstViewF type;
+    __device__ __forceinline__ static type k(const GlgUniform &U) { return type{U.Kf}; }
+    __device__ __forceinline__ static type c(const GlgUniform &U) { return type{U.Cf}; }
+};
+
+template <int G, bool GENERAL, class T, class CV, class HV>
+__device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv, const HV &Hc, const double *u, const GlgXsCol<T> &X,
+                                              T *part_col) {
+    const typename GlgKView<T>::type Kv = GlgKView<T>::k(U);
     const GlgConstView Pv{U.P};
-    GlgPartCol<G> pt{part_col};
+    GlgPartCol<G, T> pt{part_col};
     if (G == 0) part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES] = glg_grp_rad<GENERAL>(Kv, Cv, Hc, X, pt);
     else if (G == 1) glg_grp_fir<GENERAL>(Kv, Cv, Hc, Pv, u, X, pt);
     else if (G == 2) glg_grp_airflow(Kv, Hc, X, pt);
@@ -148,9 +167,9 @@ __device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv,
     else glg_grp_flows(Kv, Cv, X, pt);
 }
 
-template <bool GENERAL, int NR, class CV, class HV>
+template <bool GENERAL, int NR, class T, class CV, class HV>
 __device__ __forceinline__ void glg_run_warp_groups(int warp, const GlgUniform &U, const CV &Cv, const HV &Hc, const double *u,
-                                                    const GlgXsCol &X, double *part_col) {
+                                                    const GlgXsCol<T> &X, T *part_col) {
     if (NR == 8) {
         switch (warp) {
             case 0: glg_run_group<0, GENERAL>(U, Cv, Hc, u, X, part_col); break;
@@ -184,18 +203,19 @@ __device__ __forceinline__ void glg_run_warp_groups(int warp, const GlgUniform &
     }
 }
 
-template <bool GENERAL, bool NOISY, int NR>
+template <class T, bool GENERAL, bool NOISY, int NR>
 __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const __grid_constant__ GlgUniform U,
                                                                           const __grid_constant__ GlgStepArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NL = GLG_ROLE_LANES;
     constexpr int NJ = (GLG_NX + NR - 1) / NR;
-    double *s_wtile = reinterpret_cast<double *>(smem_raw);  // [(Np+1)][10]
-    double *s_xs = s_wtile + (size_t)(A.Np + 1) * GLG_ND;     // [28 + 1 dummy][32]
-    double *s_part = s_xs + (GLG_NX + 1) * NL;                // [GLG_NPART + 2][32]
-    double *s_H = s_part + (GLG_NPART + 2) * NL;              // [H_COUNT][32]
-    double *s_C = s_H + H_COUNT * NL;                         // [C_COUNT][32] (NOISY)
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_xs + (size_t)GlgRoleSmem<NOISY>::kColRows * NL);
+    double *s_wtile = reinterpret_cast<double *>(smem_raw);  // [(Np+1)][10] f64
+    double *s_xfin = s_wtile + (size_t)(A.Np + 1) * GLG_ND;   // [28][32] f64: state in / final state out (owners <-> warp 0)
+    T *s_xs = reinterpret_cast<T *>(s_xfin + GLG_NX * NL);    // [28 + 1 dummy][32] stage state in the groups' precision
+    T *s_part = s_xs + (GLG_NX + 1) * NL;                     // [GLG_NPART + 2][32]: contributions, zero slot, canopy scale
+    T *s_H = s_part + (GLG_NPART + 2) * NL;                   // [H_COUNT][32]
+    T *s_C = s_H + H_COUNT * NL;                              // [C_COUNT][32] (NOISY)
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_xs) + GlgRoleSmem<T, NOISY>::col_bytes());
     int *s_tbl = reinterpret_cast<int *>(s_bar + 2);
     int *s_k = s_tbl + NL;
     int *s_tbl_t = s_k + NL;
@@ -224,8 +244,8 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
     for (int i = 0; i < GLG_NU; ++i) u[i] = 0.0;
     double fruit_prev = 0.0;
     unsigned int ctr = 0;
-    GlgCol<NL> Hc{s_H + lane};
-    GlgCol<NL> Cc{s_C + lane};
+    GlgColT<T, NL> Hc{s_H + lane};
+    GlgColT<T, NL> Cc{s_C + lane};
     if (warp == 0) {
         double x[GLG_NX];
         if (active) {
@@ -240,14 +260,17 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
             glg_init_state(d0, x);
             if (NOISY) {
 #pragma unroll
-                for (int i = 0; i < C_COUNT; ++i) Cc[i] = U.C[i];
+                for (int i = 0; i < C_COUNT; ++i) Cc[i] = (T)U.C[i];
             }
             glg_hoist(GlgConstView{U.P}, u, d0, Hc);
         }
 #pragma unroll
-        for (int i = 0; i < GLG_NX; ++i) s_xs[i * NL + lane] = x[i];
+        for (int i = 0; i < GLG_NX; ++i) {
+            s_xs[i * NL + lane] = (T)x[i];
+            s_xfin[i * NL + lane] = x[i];
+        }
         s_bad[lane] = 0;
-        s_part[GLG_SLOT_ZERO * NL + lane] = 0.0;
+        s_part[GLG_SLOT_ZERO * NL + lane] = (T)0;
     }
     __syncthreads();
     if (GENERAL && warp == 1 && active) {
@@ -258,14 +281,14 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
     }
 
     // ---- integration: group phase / owner phase
-    double *xs_col = s_xs + lane;
-    double *part_col = s_part + lane;
-    const GlgXsCol X{xs_col};
-    double xo[NJ], acc[NJ];
+    T *xs_col = s_xs + lane;
+    T *part_col = s_part + lane;
+    const GlgXsCol<T> X{xs_col};
+    double xo[NJ], acc[NJ];  // the RK4 state and stage sum stay fp64 in both precisions
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int i = warp + NR * j;
-        xo[j] = i < GLG_NX ? xs_col[i * NL] : 0.0;
+        xo[j] = i < GLG_NX ? s_xfin[i * NL + lane] : 0.0;
         acc[j] = 0.0;
     }
     GlgOwnerRegs<NR> own;
@@ -281,7 +304,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
         const long long c0 = clock64();
 #endif
         if (NOISY) glg_run_warp_groups<GENERAL, NR>(warp, U, Cc, Hc, u, X, part_col);
-        else glg_run_warp_groups<GENERAL, NR>(warp, U, GlgConstView{U.C}, Hc, u, X, part_col);
+        else glg_run_warp_groups<GENERAL, NR>(warp, U, GlgKView<T>::c(U), Hc, u, X, part_col);
 #ifdef GLG_PROFILE_GROUPS
         const long long c1 = clock64();
 #endif
@@ -307,7 +330,11 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
     {
         int bad = 0;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) bad |= !(fabs(xo[j]) <= 1.79769313486231570e308);
+        for (int j = 0; j < NJ; ++j) {
+            const int i = warp + NR * j;
+            bad |= !(fabs(xo[j]) <= 1.79769313486231570e308);
+            if (i < GLG_NX) s_xfin[i * NL + lane] = xo[j];
+        }
         if (bad) s_bad[lane] = 1;  // benign race: every writer stores 1
     }
     __syncthreads();
@@ -322,7 +349,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
         if (active) {
             double x[GLG_NX];
 #pragma unroll
-            for (int i = 0; i < GLG_NX; ++i) x[i] = xs_col[i * NL];
+            for (int i = 0; i < GLG_NX; ++i) x[i] = s_xfin[i * NL + lane];
             glg_env_epilogue(U, A, e, k, kw, tbl, wrow, x, fruit_prev, bad, ctr, o);
         }
         s_tbl[lane] = o.tbl_obs;

@@ -66,7 +66,7 @@ class GreenLightVecEnv:
     def __init__(self, num_envs, reward_function="GreenhouseReward", observation_modules=None, constraints=None,
                  eval_options=None, reward_params=None, base_env_params=None, uncertainty_scale=0.0,
                  n_sub=600, device=0, seed=0, auto_reset=True, env_id_offset=0, weather_tables=None,
-                 table_start_days=None, params=None, info_mode=None, role_warps=0, role_lanes=0):
+                 table_start_days=None, params=None, info_mode=None, role_warps=0, role_lanes=0, precision="fp64"):
         if reward_function != "GreenhouseReward":
             raise ValueError("only GreenhouseReward exists in the reference (tomato_env.py:14)")
         mods = list(observation_modules or DEFAULT_OBSERVATION_MODULES)
@@ -148,7 +148,10 @@ class GreenLightVecEnv:
         self._lib.glg_default_config(C.byref(cfg))
         cfg.num_envs, cfg.device, cfg.dt, cfg.n_sub, cfg.N, cfg.Np = self.num_envs, self.device_index, float(self.dt), \
             self.n_sub, self.N, self.Np
-        cfg.precision = 0
+        if precision not in ("fp64", "fp32"):
+            raise ValueError("precision must be 'fp64' (parity mode) or 'fp32' (throughput mode)")
+        self.precision = precision
+        cfg.precision = 0 if precision == "fp64" else 1
         cfg.auto_reset = 1 if auto_reset else 0
         for i in range(self.nu):
             cfg.u_min[i], cfg.u_max[i] = float(self.u_min[i]), float(self.u_max[i])
@@ -187,9 +190,10 @@ class GreenLightVecEnv:
         self.time_t = view(L.glg_time_dev(self._h), (2, B), "<f8")
         self.stats_t = view(L.glg_stats_dev(self._h), (_lib.NSTATS,), "<f8")
         self._actions = None
-        self._obs_host = np.empty((B, self.obs_dim), dtype=np.float32)
-        self._rew_host = np.empty(B, dtype=np.float64)
-        self._done_host = np.empty(B, dtype=np.uint8)
+        # page-locked result buffers: glg_step_host copies device -> these directly (no staging copy)
+        self._pin = [torch.empty((B, self.obs_dim), dtype=torch.float32).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory(),
+                     torch.empty(B, dtype=torch.uint8).pin_memory(), torch.empty((B, self.nu), dtype=torch.float32).pin_memory()]
+        self._obs_host, self._rew_host, self._done_host, self._act_host = (t.numpy() for t in self._pin)
 
     # ------------------------------------------------------------------ tensor fast path
     def _stream(self):
@@ -224,7 +228,8 @@ class GreenLightVecEnv:
         return self.obs_t.cpu().numpy()
 
     def step_async(self, actions):
-        self._actions = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, self.nu)
+        np.copyto(self._act_host, np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.nu))
+        self._actions = self._act_host
 
     def step_wait(self):
         _lib.check(self._lib.glg_step_host(self._h, self._actions.ctypes.data, self._obs_host.ctypes.data,

@@ -51,6 +51,38 @@ void hm_rhs_roles(const double *x, const double *u, const double *d, const doubl
     }
 }
 
+// the same group functions instantiated in float (throughput mode): contributions in fp32, owner-side sum/scale in fp64
+struct HmF32View { const float *b; float operator[](int i) const { return b[i]; } };
+void hm_rhs_roles_f32(const double *x, const double *u, const double *d, const double *p, double *S) {
+    double Kd[K_COUNT], Cd[C_COUNT], Hd[H_COUNT];
+    glg_make_k(p, Kd);
+    glg_make_c(p, Cd);
+    glg_hoist(p, u, d, Hd);
+    float Kf[K_COUNT], Cf[C_COUNT], Hf[H_COUNT], xf[GLG_NX], part[GLG_NGROUPS][GLG_NX] = {};
+    for (int i = 0; i < K_COUNT; ++i) Kf[i] = (float)Kd[i];
+    for (int i = 0; i < C_COUNT; ++i) Cf[i] = (float)Cd[i];
+    for (int i = 0; i < H_COUNT; ++i) Hf[i] = (float)Hd[i];
+    for (int i = 0; i < GLG_NX; ++i) xf[i] = (float)x[i];
+    HmF32View K{Kf}, C{Cf}, H{Hf}, X{xf};
+    float *q[GLG_NGROUPS];
+    for (int g = 0; g < GLG_NGROUPS; ++g) q[g] = part[g];
+    const float can_scale = glg_grp_rad<false>(K, C, H, X, q[0]);
+    glg_grp_fir<false>(K, C, H, p, u, X, q[1]);
+    glg_grp_airflow(K, H, X, q[2]);
+    glg_grp_conv<false>(K, C, H, p, X, q[3]);
+    glg_grp_screens(K, H, X, q[4]);
+    glg_grp_cover(K, C, H, X, q[5]);
+    glg_grp_photo<false>(K, C, H, X, q[6]);
+    glg_grp_flows(K, C, X, q[7]);
+    for (int i = 0; i < GLG_NX; ++i) {
+        double sum = 0.0;
+        for (int g = 0; g < GLG_NGROUPS; ++g)
+            if (glg_group_mask(i) >> g & 1u) sum += (double)part[g][i];
+        const int sk = glg_state_scale_index(i);
+        S[i] = (sk >= 0 ? Kd[sk] : (sk == -1 ? 1.0 : (double)can_scale)) * sum;
+    }
+}
+
 int hm_evalf(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub, int general,
              double *x_next) {
     double K[K_COUNT], C[C_COUNT], H[H_COUNT], xc[GLG_NX];

@@ -11,8 +11,8 @@ __global__ void k_group(const __grid_constant__ GlgUniform U, double *xs, double
     for (int i = threadIdx.x; i < 28 * 32; i += blockDim.x) s_xs[i] = xs[i];
     for (int i = threadIdx.x; i < H_COUNT * 32; i += blockDim.x) s_H[i] = Hs[i];
     __syncthreads();
-    GlgCol<32> Hc{s_H + lane};
-    const GlgXsCol X{s_xs + lane};
+    GlgColT<double, 32> Hc{s_H + lane};
+    const GlgXsCol<double> X{s_xs + lane};
     part = s_part;
     for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) s_part[i] = 0.0;
     double u[6] = {0.5, 0.5, 0.5, 0.5, 0.5, 0.5};
