@@ -628,6 +628,24 @@ GLG_HD void glg_rhs(const KV &K, const CV &C, const HV &H, const P &p, const dou
     }
 }
 
+// Harvest-stiffness guard (same rule as the oracle's glgo_micro_steps): number of equal micro-steps a nominal RK4 substep
+// of length h is split into, from the rate constant lambda of the harvest sigmoids at the substep's start.
+#define GLG_MAX_MICRO 64
+template <class T>
+GLG_HD T glg_harvest_lambda(T sigLeaf, T sigFruit) {  // sig = 1/(1+exp(-k (c - cMax)))
+    return T(5e4 * (2.0 * 4.6052 / 1e4)) * fmax(sigLeaf * (T(1) - sigLeaf), sigFruit * (T(1) - sigFruit));
+}
+GLG_HD int glg_micro_steps_from_lambda(double lam, double h) {
+    const int m = 1 + (int)floor(2.0 * h * lam);
+    return m > GLG_MAX_MICRO ? GLG_MAX_MICRO : (m < 1 ? 1 : m);  // m < 1 only for a NaN lambda (diverged env)
+}
+template <class CV>
+GLG_HD int glg_micro_steps(const CV &C, double cLeaf, double cFruit, double h) {
+    const double k = 2.0 * 4.6052 / 1e4;
+    const double sL = glg_inv1pexp(-k * (cLeaf - (double)C[C_CLEAFMAX])), sF = glg_inv1pexp(-k * (cFruit - (double)C[C_CFRUITMAX]));
+    return glg_micro_steps_from_lambda(glg_harvest_lambda(sL, sF), h);
+}
+
 // True when the default-structure (GENERAL=false) variant is exact for this parameter table.
 template <class P>
 GLG_HD bool glg_params_nominal_structure(const P &p) {
@@ -868,7 +886,7 @@ GLG_HD void glg_grp_airflow(const KV &K, const HV &H, const XV &x, PT &pt) {
 
 // G3: lamp / pipe / canopy / floor convection with the main air
 template <bool GENERAL, class KV, class CV, class HV, class P, class XV, class PT>
-GLG_HD void glg_grp_conv(const KV &K, const CV &C, const HV &H, const P &p, const XV &x, PT &pt) {
+GLG_HD glg_scalar_t<KV> glg_grp_conv(const KV &K, const CV &C, const HV &H, const P &p, const XV &x, PT &pt) {
     typedef glg_scalar_t<KV> T;
     const T tAir = x[2], tCan = x[4], tFlr = x[8], tPipe = x[9], tLamp = x[17];
     const T hLampAir = K[K_HLAMPAIR] * (tLamp - tAir);
@@ -907,6 +925,7 @@ GLG_HD void glg_grp_conv(const KV &K, const CV &C, const HV &H, const P &p, cons
     pt[24] = -mcStemAir;
     pt[25] = -mcFruitAir - T(5e4) * ry[1];
     pt[0] = C[C_CO2RATIO] * (mcLeafAir + mcStemAir + mcFruitAir);  // maintenance part of -a216
+    return glg_harvest_lambda(ry[0], ry[1]);                        // rate constant of the harvest switches (micro-step guard)
 }
 
 // G4: thermal and blackout screen: convection on both sides + condensation from the main air
@@ -1018,7 +1037,15 @@ GLG_HD void glg_grp_photo(const KV &K, const CV &C, const HV &H, const XV &x, PT
     glg_rcp_n<3>(rb, rz);
     const T jPot = j25 * ey[1] * C[C_JPOTNUM] * rz[0];
     const T jb = jPot + C[C_ALPHA] * parCan;
-    const T jE = C[C_INV2THETA] * (jb - glg_sqrt(jb * jb - C[C_4THETAALPHA] * jPot * parCan + T(1e-10)));
+    // smaller root of theta J^2 - jb J + jPot alpha par = 0 (:1076-1077) in its cancellation-free form
+    //   (jb - sqrt(D)) / (2 theta) = (jb^2 - D) / (2 theta (jb + sqrt(D))),  D = jb^2 - 4 theta alpha jPot par + 1e-10
+    // (the reference's form loses all fp32 digits when a perturbed t25k makes jPot >> alpha*par)
+    // Used in fp32 only; in fp64 the reference's own form is accurate to ~1e-12 and keeps a reciprocal off this group's
+    // critical path.
+    const T fourTc = C[C_4THETAALPHA] * jPot * parCan;
+    const T sqD = glg_sqrt(jb * jb - fourTc + T(1e-10));
+    const T jE = std::is_same<T, float>::value ? C[C_INV2THETA] * (fourTc - T(1e-10)) * glg_rcp(jb + sqD)
+                                               : C[C_INV2THETA] * (jb - sqD);
     const T phot = jE * (co2Stom - gamma) * rz[2];
     const T photNet = phot - phot * gamma * rStom;
     const T mcAirBuf = C[C_MCH2O] * rz[1] * photNet;

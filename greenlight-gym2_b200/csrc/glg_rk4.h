@@ -21,34 +21,39 @@ struct GlgLocalStore {  // host / local-memory policy
 template <bool GENERAL, class KV, class CV, class HV, class P, class STORE>
 GLG_HD int glg_rk4_step(const KV &K, const CV &C, const HV &H, const P &p, const double *u, const double *d,
                         double *xc, double dt, int n_sub, STORE &st) {
-    const double h = dt / (double)n_sub;
+    const double h_nom = dt / (double)n_sub;
     double xs[GLG_NX], k[GLG_NX];
 #pragma unroll
     for (int i = 0; i < GLG_NX; ++i) {
         xs[i] = xc[i];
         st.x(i) = xc[i];
     }
-    const int n_eval = 4 * n_sub;
 #pragma unroll 1
-    for (int e = 0; e < n_eval; ++e) {
-        const int stage = e & 3;
-        glg_rhs<GENERAL>(K, C, H, p, u, d, xs, k);
-        // stage weights: acc = k1 + 2k2 + 2k3 (+k4 at the end); next stage point x + c*k
-        const double w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
-        const double c = (stage == 2) ? h : 0.5 * h;
-        if (stage == 3) {
+    for (int s = 0; s < n_sub; ++s) {
+        // harvest-stiffness guard (glg_model.h): m equal micro-steps inside this nominal substep, m = 1 normally
+        const int m = glg_micro_steps(C, xs[23], xs[25], h_nom);
+        const double h = h_nom / (double)m;
+#pragma unroll 1
+        for (int e = 0; e < 4 * m; ++e) {
+            const int stage = e & 3;
+            glg_rhs<GENERAL>(K, C, H, p, u, d, xs, k);
+            // stage weights: acc = k1 + 2k2 + 2k3 (+k4 at the end); next stage point x + c*k
+            const double w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
+            const double c = (stage == 2) ? h : 0.5 * h;
+            if (stage == 3) {
 #pragma unroll
-            for (int i = 0; i < GLG_NX; ++i) {
-                const double xn = st.x(i) + (h / 6.0) * (st.acc(i) + k[i]);
-                st.x(i) = xn;
-                xs[i] = xn;
-            }
-        } else {
+                for (int i = 0; i < GLG_NX; ++i) {
+                    const double xn = st.x(i) + (h / 6.0) * (st.acc(i) + k[i]);
+                    st.x(i) = xn;
+                    xs[i] = xn;
+                }
+            } else {
 #pragma unroll
-            for (int i = 0; i < GLG_NX; ++i) {
-                const double a = (stage == 0) ? k[i] : st.acc(i) + w * k[i];
-                st.acc(i) = a;
-                xs[i] = st.x(i) + c * k[i];
+                for (int i = 0; i < GLG_NX; ++i) {
+                    const double a = (stage == 0) ? k[i] : st.acc(i) + w * k[i];
+                    st.acc(i) = a;
+                    xs[i] = st.x(i) + c * k[i];
+                }
             }
         }
     }

@@ -36,6 +36,8 @@ __host__ __device__ constexpr int glg_part_slot(int g, int i) {
 constexpr int GLG_NPART = glg_part_slot(GLG_NGROUPS, 0);
 constexpr int GLG_SLOT_ZERO = GLG_NPART;          // always 0.0
 constexpr int GLG_SLOT_CANSCALE = GLG_NPART + 1;  // canopy capacity scale of the current stage (written by G0's warp)
+constexpr int GLG_SLOT_LAMBDA = GLG_NPART + 2;    // harvest rate constant of the current stage state (written by G3's warp)
+constexpr int GLG_NSLOTS = GLG_NPART + 3;
 constexpr int GLG_MAXCONTRIB = 4;
 
 template <class T>
@@ -72,7 +74,7 @@ __constant__ GlgOwnerTable glg_owner_table = glg_make_owner_table();
 
 template <class T, bool NOISY>
 struct GlgRoleSmem {
-    static constexpr int kColRows = (GLG_NX + 1) + (GLG_NPART + 2) + H_COUNT + (NOISY ? C_COUNT : 0);  // +1: dummy state row
+    static constexpr int kColRows = (GLG_NX + 1) + GLG_NSLOTS + H_COUNT + (NOISY ? C_COUNT : 0);  // +1: dummy state row
     // weather tile (f64) | final state (f64 [28][32]) | T columns | mbarrier | ints
     __host__ __device__ static size_t col_bytes() { return (sizeof(T) * (size_t)kColRows * GLG_ROLE_LANES + 15) / 16 * 16; }
     __host__ __device__ static size_t bytes(int Np) {
@@ -160,7 +162,7 @@ __device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv,
     if (G == 0) part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES] = glg_grp_rad<GENERAL>(Kv, Cv, Hc, X, pt);
     else if (G == 1) glg_grp_fir<GENERAL>(Kv, Cv, Hc, Pv, u, X, pt);
     else if (G == 2) glg_grp_airflow(Kv, Hc, X, pt);
-    else if (G == 3) glg_grp_conv<GENERAL>(Kv, Cv, Hc, Pv, X, pt);
+    else if (G == 3) part_col[GLG_SLOT_LAMBDA * GLG_ROLE_LANES] = glg_grp_conv<GENERAL>(Kv, Cv, Hc, Pv, X, pt);
     else if (G == 4) glg_grp_screens(Kv, Hc, X, pt);
     else if (G == 5) glg_grp_cover(Kv, Cv, Hc, X, pt);
     else if (G == 6) glg_grp_photo<GENERAL>(Kv, Cv, Hc, X, pt);
@@ -212,8 +214,8 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
     double *s_wtile = reinterpret_cast<double *>(smem_raw);  // [(Np+1)][10] f64
     double *s_xfin = s_wtile + (size_t)(A.Np + 1) * GLG_ND;   // [28][32] f64: state in / final state out (owners <-> warp 0)
     T *s_xs = reinterpret_cast<T *>(s_xfin + GLG_NX * NL);    // [28 + 1 dummy][32] stage state in the groups' precision
-    T *s_part = s_xs + (GLG_NX + 1) * NL;                     // [GLG_NPART + 2][32]: contributions, zero slot, canopy scale
-    T *s_H = s_part + (GLG_NPART + 2) * NL;                   // [H_COUNT][32]
+    T *s_part = s_xs + (GLG_NX + 1) * NL;                     // [GLG_NSLOTS][32]: contributions, zero slot, canopy scale, lambda
+    T *s_H = s_part + GLG_NSLOTS * NL;                        // [H_COUNT][32]
     T *s_C = s_H + H_COUNT * NL;                              // [C_COUNT][32] (NOISY)
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_xs) + GlgRoleSmem<T, NOISY>::col_bytes());
     int *s_tbl = reinterpret_cast<int *>(s_bar + 2);
@@ -293,39 +295,69 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
     }
     GlgOwnerRegs<NR> own;
     glg_owner_setup<NR>(U.K, warp, own);
-    const double h = A.dt / (double)A.n_sub;
-    const int n_eval = 4 * A.n_sub;
+    const double h_nom = A.dt / (double)A.n_sub;
 #ifdef GLG_PROFILE_GROUPS
     long long t_grp = 0, t_b1 = 0, t_own = 0, t_b2 = 0;
 #endif
+    if (!NOISY) {
+        // nominal parameters: plain fixed-step loop (the harvest guard cannot trigger: the crop approaches cLeafMax from
+        // below and lambda stays ~1e-5 1/s; the guarded loop's extra state costs ~8 % at B = 4096)
+        const int n_eval = 4 * A.n_sub;
 #pragma unroll 1
-    for (int ev = 0; ev < n_eval; ++ev) {
+        for (int ev = 0; ev < n_eval; ++ev) {
 #ifdef GLG_PROFILE_GROUPS
-        const long long c0 = clock64();
+            const long long c0 = clock64();
 #endif
-        if (NOISY) glg_run_warp_groups<GENERAL, NR>(warp, U, Cc, Hc, u, X, part_col);
-        else glg_run_warp_groups<GENERAL, NR>(warp, U, GlgKView<T>::c(U), Hc, u, X, part_col);
+            glg_run_warp_groups<GENERAL, NR>(warp, U, GlgKView<T>::c(U), Hc, u, X, part_col);
 #ifdef GLG_PROFILE_GROUPS
-        const long long c1 = clock64();
+            const long long c1 = clock64();
 #endif
-        __syncthreads();
+            __syncthreads();
 #ifdef GLG_PROFILE_GROUPS
-        const long long c2 = clock64();
+            const long long c2 = clock64();
 #endif
-        glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, ev & 3, h);
+            glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, ev & 3, h_nom);
 #ifdef GLG_PROFILE_GROUPS
-        const long long c3 = clock64();
+            const long long c3 = clock64();
 #endif
-        __syncthreads();
+            __syncthreads();
 #ifdef GLG_PROFILE_GROUPS
-        const long long c4 = clock64();
-        t_grp += c1 - c0; t_b1 += c2 - c1; t_own += c3 - c2; t_b2 += c4 - c3;
+            const long long c4 = clock64();
+            t_grp += c1 - c0; t_b1 += c2 - c1; t_own += c3 - c2; t_b2 += c4 - c3;
 #endif
+        }
+    } else {
+        // Parametric uncertainty: one nominal RK4 substep = m micro-steps of h_nom/m, m per env from the harvest-stiffness
+        // guard (glg_model.h; m = 1 unless an organ sits inside its harvest window).  Lanes with a smaller m idle with
+        // h = 0 for the remaining micro-steps of the CTA, so an env's result never depends on its CTA mates.
+        int sub = 0, q = 0, stage = 0, m_lane = 1, m_cta = 1;
+        double h_lane = h_nom;
+#pragma unroll 1
+        while (sub < A.n_sub) {
+            glg_run_warp_groups<GENERAL, NR>(warp, U, Cc, Hc, u, X, part_col);
+            __syncthreads();
+            if (stage == 0) {
+                if (q == 0) {
+                    m_lane = glg_micro_steps_from_lambda((double)part_col[GLG_SLOT_LAMBDA * NL], h_nom);
+                    m_cta = __reduce_max_sync(0xffffffffu, m_lane);  // every warp sees the same 32 envs
+                }
+                h_lane = q < m_lane ? h_nom / (double)m_lane : 0.0;
+            }
+            glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, stage, h_lane);
+            __syncthreads();
+            if (++stage == 4) {
+                stage = 0;
+                if (++q >= m_cta) {
+                    q = 0;
+                    ++sub;
+                }
+            }
+        }
     }
 #ifdef GLG_PROFILE_GROUPS
     if (blockIdx.x == 0 && lane == 0)
-        printf("warp %d: group %lld  barrier1 %lld  owner %lld  barrier2 %lld  cycles/eval\n", warp, t_grp / n_eval, t_b1 / n_eval,
-               t_own / n_eval, t_b2 / n_eval);
+        printf("warp %d: group %lld  barrier1 %lld  owner %lld  barrier2 %lld  cycles/eval\n", warp, t_grp / (4 * A.n_sub),
+               t_b1 / (4 * A.n_sub), t_own / (4 * A.n_sub), t_b2 / (4 * A.n_sub));
 #endif
     {
         int bad = 0;

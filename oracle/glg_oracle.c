@@ -452,24 +452,44 @@ void glgo_rhs(const double *x, const double *u, const double *d, const double *p
     glgo_aux_rhs(x, u, d, p, NULL, dxdt);
 }
 
-/* Classical RK4, n_sub equal substeps over [0,dt], inputs held constant (greenlight_model.cpp:59-63 passes
- * p=[u;d;p] as integrator parameters => zero-order hold).  Stage layout (the GPU kernel uses the same):
+/* Harvest-stiffness guard.  smoothHar (aux_states.hpp:75-79) removes leaf / fruit mass with a rate constant of up to
+ * R*k/4 = 11.5 1/s when the organ mass sits inside the 1e4 mg window around its maximum -- which the per-step redraw
+ * of cLeafMax = laiMax/sla under parametric uncertainty (noise.py:16-22) can cause at any step.  A nominal substep of
+ * h = 1.5 s would overshoot by tens of grams.  Rule (identical in the CUDA kernels): at the start of every nominal
+ * substep, lambda = R*k*max(sL(1-sL), sF(1-sF)) from the current state, m = 1 + floor(2*h*lambda) (capped at 64) equal
+ * micro-steps of h/m.  With the default parameters lambda ~ 1e-5 1/s, so m = 1 and nothing changes. */
+#define GLGO_MAX_MICRO 64
+static int glgo_micro_steps(const double *x, const double *p, double h) {
+    const double k = 2.0 * 4.6052 / 1e4, R = 5e4;
+    const double sL = 1.0 / (1.0 + exp(-k * (x[23] - p[144])));
+    const double sF = 1.0 / (1.0 + exp(-k * (x[25] - p[145])));
+    const double lam = R * k * fmax(sL * (1.0 - sL), sF * (1.0 - sF));
+    int m = 1 + (int)floor(2.0 * h * lam);
+    return m > GLGO_MAX_MICRO ? GLGO_MAX_MICRO : m;
+}
+
+/* Classical RK4, n_sub equal nominal substeps over [0,dt] (each split into m micro-steps by the guard above), inputs
+ * held constant (greenlight_model.cpp:59-63 passes p=[u;d;p] as integrator parameters => zero-order hold).
  *   k1=f(x) ; k2=f(x+h/2 k1) ; k3=f(x+h/2 k2) ; k4=f(x+h k3) ; x += h/6 (k1+2k2+2k3+k4)                   */
 int glgo_evalf(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub,
                double *x_next) {
     double xc[GLGO_NX], xs[GLGO_NX], k[GLGO_NX], acc[GLGO_NX];
-    const double h = dt / (double)n_sub;
-    int s, i, bad = 0;
+    const double h_nom = dt / (double)n_sub;
+    int s, q, i, bad = 0;
     memcpy(xc, x, sizeof xc);
     for (s = 0; s < n_sub; ++s) {
-        glgo_rhs(xc, u, d, p, k);
-        for (i = 0; i < GLGO_NX; ++i) { acc[i] = k[i]; xs[i] = xc[i] + (0.5 * h) * k[i]; }
-        glgo_rhs(xs, u, d, p, k);
-        for (i = 0; i < GLGO_NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = xc[i] + (0.5 * h) * k[i]; }
-        glgo_rhs(xs, u, d, p, k);
-        for (i = 0; i < GLGO_NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = xc[i] + h * k[i]; }
-        glgo_rhs(xs, u, d, p, k);
-        for (i = 0; i < GLGO_NX; ++i) xc[i] = xc[i] + (h / 6.0) * (acc[i] + k[i]);
+        const int m = glgo_micro_steps(xc, p, h_nom);
+        const double h = h_nom / (double)m;
+        for (q = 0; q < m; ++q) {
+            glgo_rhs(xc, u, d, p, k);
+            for (i = 0; i < GLGO_NX; ++i) { acc[i] = k[i]; xs[i] = xc[i] + (0.5 * h) * k[i]; }
+            glgo_rhs(xs, u, d, p, k);
+            for (i = 0; i < GLGO_NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = xc[i] + (0.5 * h) * k[i]; }
+            glgo_rhs(xs, u, d, p, k);
+            for (i = 0; i < GLGO_NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = xc[i] + h * k[i]; }
+            glgo_rhs(xs, u, d, p, k);
+            for (i = 0; i < GLGO_NX; ++i) xc[i] = xc[i] + (h / 6.0) * (acc[i] + k[i]);
+        }
     }
     for (i = 0; i < GLGO_NX; ++i) {
         x_next[i] = xc[i];

@@ -196,6 +196,20 @@ def test_parametric_noise_external_and_philox(shell_trace, weather0, params64):
             assert rel_err(x[j], orc[j].x) <= STEP_TOL * (s + 1), (s, j)
     assert not np.allclose(x[0], x[1])  # different envs, different parameter draws
     env.close()
+    # (c) harvest-stiffness guard: external noise that drops cLeafMax below the leaf mass in env 1 only
+    n = np.zeros((3, 34))
+    n[1, 141 - 128], n[1, 142 - 128] = -0.15, 0.15
+    for rw in (4, 8, 1):
+        env = make_env(3, n_sub=600, uncertainty_scale=0.3, role_warps=rw)
+        env.reset()
+        env.step_tensor(torch.zeros(3, 6, device="cuda"), noise=torch.as_tensor(n, device="cuda"))
+        x, _, _ = env.get_state()
+        for j in range(3):
+            o = ob.OracleEnv(weather0, params64)
+            o.step(action=np.zeros(6, dtype=np.float32), noise34=n[j])
+            assert rel_err(x[j], o.x) <= 1e-8, (rw, j, rel_err(x[j], o.x))  # micro-stepped env included
+        assert x[1, 23] < x[0, 23] - 5e3 and np.array_equal(x[0], x[2])  # env 1 pruned; its CTA mates are unaffected
+        env.close()
 
 
 @pytest.mark.parametrize("role_warps", [1, 4])

@@ -126,3 +126,29 @@ def test_batch_evalf_threads_agree(rhs_golden, params64):
     y4 = ob.evalf_batch(x, u, d, params64, n_sub=300, n_threads=4)
     assert np.array_equal(y1, y4)
     assert np.array_equal(y1[3], ob.evalf(x[3], u[3], d[3], params64, 900.0, 300)[0])
+
+
+def test_harvest_stiffness_guard(weather0, params64):
+    """Perturbed cLeafMax below the current leaf mass (noise.py:16-22 can do that at uncertainty 0.3): the harvest sigmoid's
+    rate constant reaches ~10 1/s.  With the micro-step guard RK4(600) stays close to a 40x finer integration; the guard
+    is inert (m = 1) for the nominal table, where results equal the unguarded scheme bit for bit."""
+    from glgym.weather import init_state
+    lib = ob.load()
+    x0, d = init_state(weather0[0]), weather0[0].copy()
+    n34 = np.zeros(34)
+    n34[141 - 128], n34[142 - 128] = -0.15, 0.15  # laiMax down, sla up => cLeafMax' = 83.4e3 < cLeaf = 95.3e3
+    p = np.zeros(208)
+    lib.glgo_param_noise(ob.P(params64), ob.P(n34), ob.P(p))
+    assert p[144] < x0[23] - 5e3
+    y600, bad = ob.evalf(x0, np.zeros(6), d, p, 900.0, 600)
+    yfine, _ = ob.evalf(x0, np.zeros(6), d, p, 900.0, 24000)
+    assert not bad and rel_err(y600, yfine) <= 2e-4, rel_err(y600, yfine)
+    assert abs(y600[23] - p[144]) < 2.0e4 and y600[23] < x0[23]  # pruned towards the new maximum, no overshoot to ~2e4
+    # nominal table: the guard never splits a substep => identical to plain RK4 written out here
+    x, h = x0.copy(), 900.0 / 300
+    for _ in range(300):
+        k1 = ob.rhs(x, np.zeros(6), d, params64); k2 = ob.rhs(x + 0.5 * h * k1, np.zeros(6), d, params64)
+        k3 = ob.rhs(x + 0.5 * h * k2, np.zeros(6), d, params64); k4 = ob.rhs(x + h * k3, np.zeros(6), d, params64)
+        acc = k1.copy(); acc += 2.0 * k2; acc += 2.0 * k3
+        x = x + (h / 6.0) * (acc + k4)
+    assert np.array_equal(x, ob.evalf(x0, np.zeros(6), d, params64, 900.0, 300)[0])
