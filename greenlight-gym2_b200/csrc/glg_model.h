@@ -629,11 +629,11 @@ GLG_HD void glg_rhs(const KV &K, const CV &C, const HV &H, const P &p, const dou
 }
 
 // Harvest-stiffness guard (same rule as the oracle's glgo_micro_steps): number of equal micro-steps a nominal RK4 substep
-// of length h is split into, from the rate constant lambda of the harvest sigmoids at the substep's start.
-#define GLG_MAX_MICRO 64
+// of length h is split into, so that harvest moves an organ at most half a sigmoid window-width per micro-step.
+#define GLG_MAX_MICRO 512
 template <class T>
 GLG_HD T glg_harvest_lambda(T sigLeaf, T sigFruit) {  // sig = 1/(1+exp(-k (c - cMax)))
-    return T(5e4 * (2.0 * 4.6052 / 1e4)) * fmax(sigLeaf * (T(1) - sigLeaf), sigFruit * (T(1) - sigFruit));
+    return T(5e4 * (2.0 * 4.6052 / 1e4)) * fmax(sigLeaf, sigFruit);  // harvest speed in window-widths per second
 }
 GLG_HD int glg_micro_steps_from_lambda(double lam, double h) {
     const int m = 1 + (int)floor(2.0 * h * lam);

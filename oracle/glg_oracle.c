@@ -452,18 +452,20 @@ void glgo_rhs(const double *x, const double *u, const double *d, const double *p
     glgo_aux_rhs(x, u, d, p, NULL, dxdt);
 }
 
-/* Harvest-stiffness guard.  smoothHar (aux_states.hpp:75-79) removes leaf / fruit mass with a rate constant of up to
- * R*k/4 = 11.5 1/s when the organ mass sits inside the 1e4 mg window around its maximum -- which the per-step redraw
- * of cLeafMax = laiMax/sla under parametric uncertainty (noise.py:16-22) can cause at any step.  A nominal substep of
- * h = 1.5 s would overshoot by tens of grams.  Rule (identical in the CUDA kernels): at the start of every nominal
- * substep, lambda = R*k*max(sL(1-sL), sF(1-sF)) from the current state, m = 1 + floor(2*h*lambda) (capped at 64) equal
- * micro-steps of h/m.  With the default parameters lambda ~ 1e-5 1/s, so m = 1 and nothing changes. */
-#define GLGO_MAX_MICRO 64
+/* Harvest-stiffness guard.  smoothHar (aux_states.hpp:75-79) removes leaf / fruit mass at up to R = 5e4 mg m-2 s-1 once the
+ * organ mass is above its maximum, switching off over a window of ~1/k = 1086 mg -- a speed of R*k = 46 window-widths per
+ * second.  The per-step redraw of cLeafMax = laiMax/sla under parametric uncertainty (noise.py:16-22) can put the leaf
+ * mass thousands of mg above the new maximum at any step; a nominal substep of h = 1.5 s would then remove 7.5e4 mg and
+ * land far below the window.  Rule (identical in the CUDA kernels): at the start of every nominal substep,
+ * lambda = R*k*max(sL, sF) (sigmoid values at the current state), m = 1 + floor(2*h*lambda) (capped at 512) equal
+ * micro-steps of h/m, i.e. at most half a window-width of harvest per micro-step.  With the default parameters
+ * sL ~ 1e-7, so m = 1 and nothing changes. */
+#define GLGO_MAX_MICRO 512
 static int glgo_micro_steps(const double *x, const double *p, double h) {
     const double k = 2.0 * 4.6052 / 1e4, R = 5e4;
     const double sL = 1.0 / (1.0 + exp(-k * (x[23] - p[144])));
     const double sF = 1.0 / (1.0 + exp(-k * (x[25] - p[145])));
-    const double lam = R * k * fmax(sL * (1.0 - sL), sF * (1.0 - sF));
+    const double lam = R * k * fmax(sL, sF);
     int m = 1 + (int)floor(2.0 * h * lam);
     return m > GLGO_MAX_MICRO ? GLGO_MAX_MICRO : m;
 }
