@@ -298,6 +298,12 @@ static cudaError_t launch_step_roles_t(glg_handle *h, const GlgStepArgs &a, cuda
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+#ifdef GLG_PROFILE_GROUPS
+    if (const char *m = getenv("GLG_PROF_MASK")) {
+        const int mask = (int)strtol(m, nullptr, 0);
+        cudaMemcpyToSymbol(glg_prof_mask_dev, &mask, sizeof(int));
+    }
+#endif
     glg_step_roles_kernel<T, GENERAL, NOISY, NR><<<(a.B + a.role_lanes - 1) / a.role_lanes, 32 * NR, smem, s>>>(h->uni, a);
     return cudaGetLastError();
 }

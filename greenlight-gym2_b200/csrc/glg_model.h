@@ -671,23 +671,23 @@ GLG_HD bool glg_params_nominal_structure(const P &p) {
 //                 soil chain (:888-910)
 //   G2 airflow  : roof ventilation, screen air flux, CO2 of the air compartments, sensible air/top/outside exchange,
 //                 air-borne vapour exchange (:733-814, :1015-1024, :1201-1209)
-//   G3 conv     : lamp / pipe / canopy / floor convection with the main air (:824-935), maintenance respiration and
-//                 harvest (:1161-1188)
+//   G3 conv     : lamp / pipe / canopy / floor convection with the main air (:824-935)
 //   G4 screens  : thermal + blackout screen convection towards the main air and condensation (:835-861, :999-1005)
 //   G5 cover    : top-compartment -> cover convection and condensation (:866, :1011), blackout screen -> top convection,
 //                 transpiration (:959-981)
 //   G6 photo    : canopy photosynthesis and buffer inflow (:1041-1097)
-//   G7 flows    : carbohydrate flows buffer -> organs and growth respiration (:1103-1155)
+//   G7 flows    : carbohydrate flows buffer -> organs and growth respiration (:1103-1155), maintenance respiration and
+//                 harvest (:1161-1188)
 // XV: x[i] -> stage state value.  PT: pt[i] = v stores the group's contribution for state i.
 // =========================================================================================================
 #define GLG_NGROUPS 8
 
 // bit g set <=> group g contributes to state i
 GLG_HD constexpr unsigned glg_group_mask(int i) {
-    return i == 0 ? 0xCCu : i == 1 ? 0x04u : i == 2 ? 0x1Du : i == 3 ? 0x34u : i == 4 ? 0x2Bu : i == 5 ? 0x22u : i == 6 ? 0x02u
+    return i == 0 ? 0xC4u : i == 1 ? 0x04u : i == 2 ? 0x1Du : i == 3 ? 0x34u : i == 4 ? 0x2Bu : i == 5 ? 0x22u : i == 6 ? 0x02u
          : i == 7 ? 0x12u : i == 8 ? 0x0Bu : i == 9 ? 0x0Au : (i >= 10 && i <= 14) ? 0x02u : i == 15 ? 0x34u : i == 16 ? 0x24u
          : i == 17 ? 0x0Au : i == 18 ? 0x0Au : i == 19 ? 0x03u : i == 20 ? 0x32u : i == 21 ? 0x01u : i == 22 ? 0xC0u
-         : (i >= 23 && i <= 25) ? 0x88u : 0x01u;
+         : (i >= 23 && i <= 25) ? 0x80u : 0x01u;
 }
 
 // scalar type of a constant set (double in parity mode, float in throughput mode); all sets passed to one group
@@ -886,7 +886,7 @@ GLG_HD void glg_grp_airflow(const KV &K, const HV &H, const XV &x, PT &pt) {
 
 // G3: lamp / pipe / canopy / floor convection with the main air
 template <bool GENERAL, class KV, class CV, class HV, class P, class XV, class PT>
-GLG_HD glg_scalar_t<KV> glg_grp_conv(const KV &K, const CV &C, const HV &H, const P &p, const XV &x, PT &pt) {
+GLG_HD void glg_grp_conv(const KV &K, const CV &C, const HV &H, const P &p, const XV &x, PT &pt) {
     typedef glg_scalar_t<KV> T;
     const T tAir = x[2], tCan = x[4], tFlr = x[8], tPipe = x[9], tLamp = x[17];
     const T hLampAir = K[K_HLAMPAIR] * (tLamp - tAir);
@@ -908,24 +908,6 @@ GLG_HD glg_scalar_t<KV> glg_grp_conv(const KV &K, const CV &C, const HV &H, cons
     pt[9] = -hPipeAir;
     pt[17] = -hLampAir;
     pt[18] = sIntLamp;
-    // maintenance respiration (:1161-1178) and harvest (:75-79,1184,1188): additive pieces of the crop balances
-    const T cLeaf = x[23], cStem = x[24], cFruit = x[25];
-    const T kHar = T(2.0) * T(4.6052) / T(1e4);  // smoothHar(v, cutoff, 1e4, 5e4) = 5e4/(1+exp(-kHar (v-cutoff)))
-    const T ea[3] = {C[C_LNQ10X] * (x[21] - 25), -kHar * (cLeaf - C[C_CLEAFMAX]), -kHar * (cFruit - C[C_CFRUITMAX])};
-    T ey[3];
-    glg_exp_n<3>(ea, ey);
-    const T ra[2] = {T(1.0) + ey[1], T(1.0) + ey[2]};
-    T ry[2];
-    glg_rcp_n<2>(ra, ry);
-    const T maint = C[C_MAINT] * ey[0];
-    const T mcLeafAir = maint * cLeaf * C[C_MLEAF];
-    const T mcStemAir = maint * cStem * C[C_MSTEM];
-    const T mcFruitAir = maint * cFruit * C[C_MFRUIT];
-    pt[23] = -mcLeafAir - T(5e4) * ry[0];
-    pt[24] = -mcStemAir;
-    pt[25] = -mcFruitAir - T(5e4) * ry[1];
-    pt[0] = C[C_CO2RATIO] * (mcLeafAir + mcStemAir + mcFruitAir);  // maintenance part of -a216
-    return glg_harvest_lambda(ry[0], ry[1]);                        // rate constant of the harvest switches (micro-step guard)
 }
 
 // G4: thermal and blackout screen: convection on both sides + condensation from the main air
@@ -1053,19 +1035,35 @@ GLG_HD void glg_grp_photo(const KV &K, const CV &C, const HV &H, const XV &x, PT
     pt[0] = -(C[C_CO2RATIO] * mcAirBuf);
 }
 
-// G7: carbohydrate flows buffer -> leaves / stem / fruit and the growth respiration that goes with them
+// G7: carbohydrate flows buffer -> leaves / stem / fruit with their growth respiration (:1103-1155), maintenance
+// respiration (:1161-1178) and harvest (:75-79,1184,1188).  Returns the harvest speed for the micro-step guard.
 template <class KV, class CV, class XV, class PT>
-GLG_HD void glg_grp_flows(const KV &K, const CV &C, const XV &x, PT &pt) {
+GLG_HD glg_scalar_t<KV> glg_grp_flows(const KV &K, const CV &C, const XV &x, PT &pt) {
     typedef glg_scalar_t<KV> T;
     const T tCan = x[4], tCan24 = x[21], cBuf = x[22];
+    const T cLeaf = x[23], cStem = x[24], cFruit = x[25];
     const T gT24 = T(0.047) * tCan24 + T(0.06);
-    const T ea[5] = {-T(1.1587) * (tCan24 - C[C_T24MIN]), T(1.3904) * (tCan24 - C[C_T24MAX]), -T(0.869) * (tCan - C[C_TCANMIN]),
-                          T(0.5793) * (tCan - C[C_TCANMAX]), -T(5e-3) * (cBuf - C[C_CBUFMIN])};
-    T ey[5];
-    glg_exp_n<5>(ea, ey);
-    const T ra[3] = {(T(1.) + ey[0]) * (T(1.) + ey[1]), (T(1.) + ey[2]) * (T(1.) + ey[3]), T(1.0) + ey[4]};
-    T ry[3];
-    glg_rcp_n<3>(ra, ry);
+    const T kHar = T(2.0) * T(4.6052) / T(1e4);  // smoothHar(v, cutoff, 1e4, 5e4) = 5e4/(1+exp(-kHar (v-cutoff)))
+    // eight independent exponentials (two interleaved batches of four: eight at once spill), then five reciprocals
+    const T ea[4] = {-T(1.1587) * (tCan24 - C[C_T24MIN]), T(1.3904) * (tCan24 - C[C_T24MAX]), -T(0.869) * (tCan - C[C_TCANMIN]),
+                     T(0.5793) * (tCan - C[C_TCANMAX])};
+    const T eb[4] = {-T(5e-3) * (cBuf - C[C_CBUFMIN]), C[C_LNQ10X] * (tCan24 - 25), -kHar * (cLeaf - C[C_CLEAFMAX]),
+                     -kHar * (cFruit - C[C_CFRUITMAX])};
+    T ey[8];
+    {
+        T ya[4], yb[4];
+        glg_exp_n<4>(ea, ya);
+        glg_exp_n<4>(eb, yb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ey[i] = ya[i];
+            ey[4 + i] = yb[i];
+        }
+    }
+    const T ra[5] = {(T(1.) + ey[0]) * (T(1.) + ey[1]), (T(1.) + ey[2]) * (T(1.) + ey[3]), T(1.0) + ey[4], T(1.0) + ey[6],
+                     T(1.0) + ey[7]};
+    T ry[5];
+    glg_rcp_n<5>(ra, ry);
     const T hT24 = ry[0], hTCan = ry[1];
     const T sSum = x[26] * K[K_INVTENDSUM];
     const T sSum1 = sSum - T(1.0);
@@ -1075,11 +1073,16 @@ GLG_HD void glg_grp_flows(const KV &K, const CV &C, const XV &x, PT &pt) {
     const T mcBufStem = flow * C[C_RGSTEM];
     const T mcBufFruit = flow * hTCan * hTSum * C[C_RGFRUIT];
     const T mcBufAir = C[C_GLEAF] * mcBufLeaf + C[C_GSTEM] * mcBufStem + C[C_GFRUIT] * mcBufFruit;
+    const T maint = C[C_MAINT] * ey[5];
+    const T mcLeafAir = maint * cLeaf * C[C_MLEAF];
+    const T mcStemAir = maint * cStem * C[C_MSTEM];
+    const T mcFruitAir = maint * cFruit * C[C_MFRUIT];
     pt[22] = -mcBufFruit - mcBufLeaf - mcBufStem - mcBufAir;
-    pt[23] = mcBufLeaf;
-    pt[24] = mcBufStem;
-    pt[25] = mcBufFruit;
-    pt[0] = C[C_CO2RATIO] * mcBufAir;
+    pt[23] = (mcBufLeaf - mcLeafAir) - T(5e4) * ry[3];
+    pt[24] = mcBufStem - mcStemAir;
+    pt[25] = (mcBufFruit - mcFruitAir) - T(5e4) * ry[4];
+    pt[0] = C[C_CO2RATIO] * (mcBufAir + (mcLeafAir + mcStemAir + mcFruitAir));
+    return glg_harvest_lambda(ry[3], ry[4]);
 }
 
 // index into K of the capacity scale the owner applies to state i's summed contributions; -1: 1.0 (the groups

@@ -36,7 +36,7 @@ __host__ __device__ constexpr int glg_part_slot(int g, int i) {
 constexpr int GLG_NPART = glg_part_slot(GLG_NGROUPS, 0);
 constexpr int GLG_SLOT_ZERO = GLG_NPART;          // always 0.0
 constexpr int GLG_SLOT_CANSCALE = GLG_NPART + 1;  // canopy capacity scale of the current stage (written by G0's warp)
-constexpr int GLG_SLOT_LAMBDA = GLG_NPART + 2;    // harvest rate constant of the current stage state (written by G3's warp)
+constexpr int GLG_SLOT_LAMBDA = GLG_NPART + 2;    // harvest rate constant of the current stage state (written by G7's warp)
 constexpr int GLG_NSLOTS = GLG_NPART + 3;
 constexpr int GLG_MAXCONTRIB = 4;
 
@@ -55,10 +55,23 @@ struct GlgPartCol {  // contribution slots of group G for this lane
     __device__ __forceinline__ Ref operator[](int i) { return Ref{b + glg_part_slot(G, i) * GLG_ROLE_LANES}; }
 };
 
+// Owner plan.  States are sorted by their number of contributing groups (descending) and dealt round-robin to the NR
+// owner warps: row j of warp w is state order[j * NR + w].  All warps run ONE copy of straight-line owner code, so row j
+// loads as many slots as its hungriest state needs (the row's first entry): 4+2+1+1 = 8 shared-memory loads per warp
+// with 8 warps (4+3+2+2+1+1+1 = 14 with 4) instead of 4 per state -- the owner phase is bound by shared-memory
+// bandwidth (128 B/clk: one 32-lane fp64 load = 2 cycles), and padding loads of the zero slot were half of it.
+constexpr int GLG_PLAN_ROWS = 32;
 struct GlgOwnerTable {
     short slot[GLG_NX][GLG_MAXCONTRIB];  // contribution slots to add (GLG_SLOT_ZERO pads)
     short scale_k[GLG_NX];               // glg_state_scale_index
+    short order[GLG_PLAN_ROWS];          // states by contribution count, descending; -1 pads
+    short count[GLG_PLAN_ROWS];
 };
+__host__ __device__ constexpr int glg_popcount8(unsigned m) {
+    int n = 0;
+    for (int g = 0; g < GLG_NGROUPS; ++g) n += (int)((m >> g) & 1u);
+    return n;
+}
 __host__ __device__ constexpr GlgOwnerTable glg_make_owner_table() {
     GlgOwnerTable t{};
     for (int i = 0; i < GLG_NX; ++i) {
@@ -68,9 +81,46 @@ __host__ __device__ constexpr GlgOwnerTable glg_make_owner_table() {
         for (; n < GLG_MAXCONTRIB; ++n) t.slot[i][n] = (short)GLG_SLOT_ZERO;
         t.scale_k[i] = (short)glg_state_scale_index(i);
     }
+    int n = 0;
+    for (int c = GLG_MAXCONTRIB; c >= 1; --c)
+        for (int i = 0; i < GLG_NX; ++i)
+            if (glg_popcount8(glg_group_mask(i)) == c) {
+                t.order[n] = (short)i;
+                t.count[n] = (short)c;
+                ++n;
+            }
+    for (; n < GLG_PLAN_ROWS; ++n) {
+        t.order[n] = -1;
+        t.count[n] = 1;
+    }
     return t;
 }
 __constant__ GlgOwnerTable glg_owner_table = glg_make_owner_table();
+template <int NR, int J>
+struct GlgRowSlots {  // slots row J loads (compile-time)
+    static constexpr int value = glg_make_owner_table().count[J * NR];
+};
+template <int NR>
+struct GlgCanopyPos {  // (warp, row) of the canopy state 4, whose capacity scale changes with the stage LAI
+    static constexpr int find() {
+        const GlgOwnerTable t = glg_make_owner_table();
+        for (int n = 0; n < GLG_PLAN_ROWS; ++n)
+            if (t.order[n] == 4) return n;
+        return -1;
+    }
+    static constexpr int warp = find() % NR, row = find() / NR;
+};
+template <int I>
+struct GlgInt {
+    static constexpr int value = I;
+};
+template <int I, int N, class F>
+__device__ __forceinline__ void glg_static_for(F &&f) {
+    if constexpr (I < N) {
+        f(GlgInt<I>{});
+        glg_static_for<I + 1, N>(f);
+    }
+}
 
 template <class T, bool NOISY>
 struct GlgRoleSmem {
@@ -83,33 +133,32 @@ struct GlgRoleSmem {
     }
 };
 
-// owner phase: warp `warp` of NR owns states warp, warp+NR, ...  The per-state table entries (shared-memory offsets of
-// the contribution slots, capacity scale) are loop invariants: they are fetched from the constant-bank table ONCE into
-// registers (GlgOwnerRegs) -- dynamic constant-bank indexing inside the loop cost ~600 cycles per evaluation.  The
-// update itself is branch-free straight-line code (warps with one state fewer update a dummy slot), so the NJ
-// load -> add -> scale -> RK4 chains of a warp overlap instead of running one after the other.
+// owner phase: the per-state table entries (shared-memory offsets of the contribution slots, capacity scale) are loop
+// invariants: they are fetched from the constant-bank table ONCE into registers (GlgOwnerRegs) -- dynamic constant-bank
+// indexing inside the loop cost ~600 cycles per evaluation.  The update itself is branch-free straight-line code (rows
+// without a state update a dummy slot), so the NJ load -> add -> scale -> RK4 chains of a warp overlap.
 constexpr int GLG_XS_ROWS = GLG_NX + 1;  // row GLG_NX is the dummy state slot
 template <int NR>
 struct GlgOwnerRegs {
     static constexpr int NJ = (GLG_NX + NR - 1) / NR;
-    static constexpr int CAN_WARP = 4 % NR, CAN_J = 4 / NR;  // position of the canopy state (its scale changes per stage)
-    int off[NJ][GLG_MAXCONTRIB];  // element offsets of the contribution slots in this lane's column
+    int off[NJ][GLG_MAXCONTRIB];  // element offsets of the contribution slots in this lane's column (first GlgRowSlots used)
     double scale[NJ];             // capacity scale
     int xs_off[NJ];               // element offset of the state in the xs column (dummy row for padding)
 };
 template <int NR>
 __device__ __forceinline__ void glg_owner_setup(const double *Kc, int warp, GlgOwnerRegs<NR> &o) {
-#pragma unroll
-    for (int j = 0; j < GlgOwnerRegs<NR>::NJ; ++j) {
-        const int i = warp + NR * j;
-        const bool valid = i < GLG_NX;
+    glg_static_for<0, GlgOwnerRegs<NR>::NJ>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const int i = glg_owner_table.order[j * NR + warp];
+        const bool valid = i >= 0;
         const int ii = valid ? i : 0;
 #pragma unroll
-        for (int c = 0; c < GLG_MAXCONTRIB; ++c) o.off[j][c] = (valid ? glg_owner_table.slot[ii][c] : GLG_SLOT_ZERO) * GLG_ROLE_LANES;
+        for (int c = 0; c < GlgRowSlots<NR, j>::value; ++c)
+            o.off[j][c] = (valid ? glg_owner_table.slot[ii][c] : GLG_SLOT_ZERO) * GLG_ROLE_LANES;
         const int sk = glg_owner_table.scale_k[ii];
         o.scale[j] = (valid && sk >= 0) ? Kc[sk] : 1.0;
         o.xs_off[j] = (valid ? i : GLG_NX) * GLG_ROLE_LANES;
-    }
+    });
 }
 template <int NR, class T>
 __device__ __forceinline__ void glg_owner_update(const GlgOwnerRegs<NR> &o, int warp, T *xs_col, const T *part_col,
@@ -121,13 +170,18 @@ __device__ __forceinline__ void glg_owner_update(const GlgOwnerRegs<NR> &o, int 
     const double m = last ? h / 6.0 : (stage == 2 ? h : 0.5 * h);
     const double can_scale = (double)part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES];
     double sum[GlgOwnerRegs<NR>::NJ];
-#pragma unroll
-    for (int j = 0; j < GlgOwnerRegs<NR>::NJ; ++j)
-        sum[j] = ((double)part_col[o.off[j][0]] + (double)part_col[o.off[j][1]]) +
-                 ((double)part_col[o.off[j][2]] + (double)part_col[o.off[j][3]]);
+    glg_static_for<0, GlgOwnerRegs<NR>::NJ>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        constexpr int n = GlgRowSlots<NR, j>::value;
+        const double a = (double)part_col[o.off[j][0]];
+        if constexpr (n == 1) sum[j] = a;
+        else if constexpr (n == 2) sum[j] = a + (double)part_col[o.off[j][1]];
+        else if constexpr (n == 3) sum[j] = (a + (double)part_col[o.off[j][1]]) + (double)part_col[o.off[j][2]];
+        else sum[j] = (a + (double)part_col[o.off[j][1]]) + ((double)part_col[o.off[j][2]] + (double)part_col[o.off[j][3]]);
+    });
 #pragma unroll
     for (int j = 0; j < GlgOwnerRegs<NR>::NJ; ++j) {
-        const double sc = (j == GlgOwnerRegs<NR>::CAN_J && warp == GlgOwnerRegs<NR>::CAN_WARP) ? can_scale : o.scale[j];
+        const double sc = (j == GlgCanopyPos<NR>::row && warp == GlgCanopyPos<NR>::warp) ? can_scale : o.scale[j];
         const double k = sc * sum[j];
         const double a_new = glg_fma(w, k, keep * acc[j]);
         const double xn = glg_fma(m, last ? a_new : k, xo[j]);
@@ -153,20 +207,26 @@ struct GlgKView<float> {
     __device__ __forceinline__ static type c(const GlgUniform &U) { return type{U.Cf}; }
 };
 
+#ifdef GLG_PROFILE_GROUPS
+__device__ int glg_prof_mask_dev = 0x1FF;  // bits 0..7: run group g ; bit 8: run the owner phase (timing experiments only)
+#endif
 template <int G, bool GENERAL, class T, class CV, class HV>
 __device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv, const HV &Hc, const double *u, const GlgXsCol<T> &X,
                                               T *part_col) {
+#ifdef GLG_PROFILE_GROUPS
+    if (!((glg_prof_mask_dev >> G) & 1)) return;
+#endif
     const typename GlgKView<T>::type Kv = GlgKView<T>::k(U);
     const GlgConstView Pv{U.P};
     GlgPartCol<G, T> pt{part_col};
     if (G == 0) part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES] = glg_grp_rad<GENERAL>(Kv, Cv, Hc, X, pt);
     else if (G == 1) glg_grp_fir<GENERAL>(Kv, Cv, Hc, Pv, u, X, pt);
     else if (G == 2) glg_grp_airflow(Kv, Hc, X, pt);
-    else if (G == 3) part_col[GLG_SLOT_LAMBDA * GLG_ROLE_LANES] = glg_grp_conv<GENERAL>(Kv, Cv, Hc, Pv, X, pt);
+    else if (G == 3) glg_grp_conv<GENERAL>(Kv, Cv, Hc, Pv, X, pt);
     else if (G == 4) glg_grp_screens(Kv, Hc, X, pt);
     else if (G == 5) glg_grp_cover(Kv, Cv, Hc, X, pt);
     else if (G == 6) glg_grp_photo<GENERAL>(Kv, Cv, Hc, X, pt);
-    else glg_grp_flows(Kv, Cv, X, pt);
+    else part_col[GLG_SLOT_LAMBDA * GLG_ROLE_LANES] = glg_grp_flows(Kv, Cv, X, pt);
 }
 
 template <bool GENERAL, int NR, class T, class CV, class HV>
@@ -288,13 +348,14 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
     const GlgXsCol<T> X{xs_col};
     double xo[NJ], acc[NJ];  // the RK4 state and stage sum stay fp64 in both precisions
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const int i = warp + NR * j;
-        xo[j] = i < GLG_NX ? s_xfin[i * NL + lane] : 0.0;
-        acc[j] = 0.0;
-    }
     GlgOwnerRegs<NR> own;
     glg_owner_setup<NR>(U.K, warp, own);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int i = glg_owner_table.order[j * NR + warp];
+        xo[j] = i >= 0 ? s_xfin[i * NL + lane] : 0.0;
+        acc[j] = 0.0;
+    }
     const double h_nom = A.dt / (double)A.n_sub;
 #ifdef GLG_PROFILE_GROUPS
     long long t_grp = 0, t_b1 = 0, t_own = 0, t_b2 = 0;
@@ -315,6 +376,9 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
             __syncthreads();
 #ifdef GLG_PROFILE_GROUPS
             const long long c2 = clock64();
+#endif
+#ifdef GLG_PROFILE_GROUPS
+            if ((glg_prof_mask_dev >> 8) & 1)
 #endif
             glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, ev & 3, h_nom);
 #ifdef GLG_PROFILE_GROUPS
@@ -363,9 +427,9 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
         int bad = 0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            const int i = warp + NR * j;
             bad |= !(fabs(xo[j]) <= 1.79769313486231570e308);
-            if (i < GLG_NX) s_xfin[i * NL + lane] = xo[j];
+            const int i = glg_owner_table.order[j * NR + warp];
+            if (i >= 0) s_xfin[i * NL + lane] = xo[j];
         }
         if (bad) s_bad[lane] = 1;  // benign race: every writer stores 1
     }
