@@ -298,7 +298,7 @@ static cudaError_t launch_step_roles_t(glg_handle *h, const GlgStepArgs &a, cuda
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-#ifdef GLG_PROFILE_GROUPS
+#if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
     if (const char *m = getenv("GLG_PROF_MASK")) {
         const int mask = (int)strtol(m, nullptr, 0);
         cudaMemcpyToSymbol(glg_prof_mask_dev, &mask, sizeof(int));

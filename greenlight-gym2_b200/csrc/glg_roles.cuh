@@ -207,13 +207,13 @@ struct GlgKView<float> {
     __device__ __forceinline__ static type c(const GlgUniform &U) { return type{U.Cf}; }
 };
 
-#ifdef GLG_PROFILE_GROUPS
+#if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
 __device__ int glg_prof_mask_dev = 0x1FF;  // bits 0..7: run group g ; bit 8: run the owner phase (timing experiments only)
 #endif
 template <int G, bool GENERAL, class T, class CV, class HV>
 __device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv, const HV &Hc, const double *u, const GlgXsCol<T> &X,
                                               T *part_col) {
-#ifdef GLG_PROFILE_GROUPS
+#if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
     if (!((glg_prof_mask_dev >> G) & 1)) return;
 #endif
     const typename GlgKView<T>::type Kv = GlgKView<T>::k(U);
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
 #ifdef GLG_PROFILE_GROUPS
             const long long c2 = clock64();
 #endif
-#ifdef GLG_PROFILE_GROUPS
+#if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
             if ((glg_prof_mask_dev >> 8) & 1)
 #endif
             glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, ev & 3, h_nom);

@@ -697,6 +697,57 @@ int glgo_env_step(const glgo_env_cfg *c, glgo_env *e, const double *p_nom, const
     return e->terminated;
 }
 
+/* ---- rule-based controller: environments/baseline.py:68-227 (proportional_control :226-227) ---- */
+static double prop_ctrl(double pv, double sp, double pb, double minv, double maxv) {
+    return minv + (maxv - minv) * (1.0 / (1.0 + exp(-2.0 / pb * log(100.0) * (pv - sp - pb / 2.0))));
+}
+static int window01(double lo, double hi, double v) { /* :76-77, :85-86: 1 inside the (possibly wrapping) open interval */
+    return (lo <= hi) * (lo < v && v < hi) + (1 - (lo <= hi)) * (lo < v || v < hi);
+}
+void glgo_rule_control(const double *s, const double *x, const double *d, double hod, double doy, double *u) {
+    const double lamps_on = s[0], lamps_off = s[1], day_start = s[2], day_stop = s[3], off_sun = s[4], rad_limit = s[5];
+    const double tsp_day = s[6], tsp_night = s[7], heat_corr = s[8], heat_dead = s[9], co2_day = s[10], vent_heat_pb = s[11];
+    const double rh_max = s[12], mech_pb = s[13], vent_rh_pb = s[14], t_vent_off = s[15], vent_cold_pb = s[16];
+    const double th_sp_day = s[17], th_sp_night = s[18], th_pb = s[19], th_dead = s[20], th_rh = s[21], th_rh_pb = s[22];
+    const double lamp_extra_heat = s[23], bl_extra_rh = s[24], rhMax = s[25], t_heat_band = s[26], co2_band = s[27];
+    const double use_bl = s[28];
+    const int lamp_tod = window01(lamps_on, lamps_off, hod);
+    const int lamp_doy = window01(day_start, day_stop, doy);
+    const double lamp_no_cons = (double)((d[0] < off_sun) * (d[7] < rad_limit) * lamp_tod * lamp_doy);                 /* :98 */
+    const double sw_on = fmax(0.0, fmin(1.0, hod - lamps_on + 1));                                                      /* :107 */
+    const double sw_off = fmax(0.0, fmin(1.0, lamps_off - hod + 1));                                                    /* :113 */
+    const double both = (lamps_on != lamps_off) *
+                        ((lamps_on < lamps_off) * fmin(sw_on, sw_off) + (1 - (lamps_on < lamps_off)) * fmax(sw_on, sw_off)); /* :119 */
+    const double smooth_lamp = both * (d[7] < rad_limit) * lamp_doy;                                                    /* :128 */
+    const double is_day = fmax(smooth_lamp, d[8]);                                                                      /* :133 */
+    const double heat_sp = is_day * tsp_day + (1 - is_day) * tsp_night + heat_corr * lamp_no_cons;                      /* :136 */
+    const double heat_max = heat_sp + heat_dead;
+    const double co2_sp = is_day * co2_day;
+    const double co2_ppm = dens2ppm(x[2], 1e-6 * x[0]);
+    const double vent_heat = prop_ctrl(x[2], heat_max, vent_heat_pb, 0, 1);
+    const double rh_in = 100 * x[15] / sat_vp(x[2]);
+    const double vent_rh = prop_ctrl(rh_in, rh_max + 0 * mech_pb, vent_rh_pb, 0, 1);
+    const double vent_cold = prop_ctrl(x[2], heat_sp - t_vent_off, vent_cold_pb, 1, 0);
+    const double th_sp = d[8] * th_sp_day + (1 - d[8]) * th_sp_night;
+    const double th_cold = prop_ctrl(d[1], th_sp, th_pb, 0, 1);
+    const double th_heat = prop_ctrl(x[2], heat_sp + th_dead, -th_pb, 1, 0);
+    const double th_rhv = fmax(prop_ctrl(rh_in, rhMax + th_rh, th_rh_pb, 1, 0), 1 - vent_cold);
+    const double lamp_on = lamp_no_cons * prop_ctrl(x[2], heat_max + lamp_extra_heat, -0.5, 0, 1) * (d[9] + (1 - d[9])) *
+                           fmax(prop_ctrl(rh_in, rhMax + bl_extra_rh, -0.5, 0, 1), 1 - vent_cold);                      /* :187-189 */
+    u[0] = prop_ctrl(x[2], heat_sp, t_heat_band, 0, 1);
+    u[1] = prop_ctrl(co2_ppm, co2_sp, co2_band, 0, 1);
+    u[2] = fmin(th_cold, fmax(th_heat, th_rhv));
+    u[3] = fmin(vent_cold, fmax(vent_heat, vent_rh));
+    u[4] = lamp_on;
+    u[5] = use_bl * (1 - d[9]) * lamp_on;
+}
+int glgo_env_step_rule(const glgo_env_cfg *c, glgo_env *e, const double *p_nom, const double *ctrl29, const double *noise34,
+                       double *obs, double *reward, double *info) {
+    double u[6];
+    glgo_rule_control(ctrl29, e->x, e->weather + (size_t)e->timestep * GLGO_ND, e->hour_of_day, e->day_of_year, u);
+    return glgo_env_step(c, e, p_nom, u, 1, noise34, obs, reward, info);
+}
+
 typedef struct rollout_ctx {
     const glgo_env_cfg *c;
     const double *p_nom, *weather;

@@ -85,6 +85,19 @@ long glgo_rollout(const glgo_env_cfg *c, const double *p_nom, const double *weat
 
 /* persistent batch of B reference-semantics envs stepped by n_threads host threads (auto-reset on termination):
  * the CPU counterpart of the SubprocVecEnv-of-TomatoEnv stack, used as the measured CPU baseline. */
+/* Rule-based controller: environments/baseline.py:68-227, settings configs/agents/rule_based.yml.
+ * s[29] in the order of GLGO_CTRL_NAMES below; x = state before the step, d = weather row of the current timestep
+ * (all 10 columns), hod / doy = env clock before the step (experiments/evaluate_baseline.py:21-23). */
+#define GLGO_NCTRL 29
+/* lamps_on, lamps_off, lamps_day_start, lamps_day_stop, lamps_off_sun, lamp_rad_sum_limit, temp_setpoint_day,
+ * temp_setpoint_night, heat_correction, heat_deadzone, co2_day, vent_heat_Pband, rh_max, mech_dehumid_Pband,
+ * vent_rh_Pband, t_vent_off, vent_cold_Pband, thScrSpDay, thScrSpNight, thScrPband, thScrDeadZone, thScrRh,
+ * thScrRhPband, lampExtraHeat, blScrExtraRh, rhMax, tHeatBand, co2Band, useBlScr */
+void glgo_rule_control(const double *s, const double *x, const double *d, double hod, double doy, double *u);
+/* one env step with the controller in the loop: u = rule_control(x, weather[k], clock) ; step_raw_control(u) */
+int glgo_env_step_rule(const glgo_env_cfg *c, glgo_env *e, const double *p_nom, const double *ctrl29, const double *noise34,
+                       double *obs, double *reward, double *info);
+
 typedef struct glgo_batch glgo_batch;
 glgo_batch *glgo_batch_create(const glgo_env_cfg *c, const double *p_nom, const double *weather, int rows, int B);
 /* actions float32 [B][6]; reward [B] doubles; done [B] bytes; obs_f32 may be NULL or float [B][23+5Np] */

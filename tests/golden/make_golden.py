@@ -243,6 +243,35 @@ def main():
     tr.update(noise_actions=np.array(na), noise_obs=np.array(no), noise_reward=np.array(nr), noise_x=np.array(nx),
               noise_draws=np.array([n for n, _ in recorded]), noise_params=np.array([q for _, q in recorded]))
     np.savez_compressed(os.path.join(HERE, "shell_trace.npz"), **tr)
+
+    # rule-based controller known-answer vectors: the reference's RuleBasedController.predict (baseline.py:68-227) on
+    # random (x, d, clock) points, for the shipped settings and for variants that exercise the wrapping lamp window,
+    # the day-of-year window and the lamps_on == lamps_off case
+    import types
+    base = yaml.safe_load(open("/root/reference/gl_gym/configs/agents/rule_based.yml"))["TomatoEnv"]
+    names = list(base.keys())
+    variants = [dict(base), dict(base, lamps_on=20, lamps_off=6), dict(base, lamps_day_start=300, lamps_day_stop=60),
+                dict(base, lamps_on=7, lamps_off=7), dict(base, lamps_on=2, lamps_off=20, heat_correction=1.5, useBlScr=0,
+                                                          lamp_rad_sum_limit=4, lamps_off_sun=150)]
+    krng = np.random.default_rng(2024)
+    K = 160
+    ks, kx, kd, kh, kdoy, ku = [], [], [], [], [], []
+    for vi, var in enumerate(variants):
+        ctrl_v = RuleBasedController(**var)
+        for _ in range(K):
+            x = np.array(tr["rb_x"][krng.integers(0, 40)])
+            x[0] = krng.uniform(400, 2500); x[2] = krng.uniform(5, 35); x[15] = krng.uniform(300, 3500)
+            d = np.array([krng.choice([0.0, krng.uniform(0, 800)]), krng.uniform(-10, 30), krng.uniform(200, 2000),
+                          krng.uniform(700, 800), krng.uniform(0, 15), krng.uniform(-30, 15), krng.uniform(5, 15),
+                          krng.uniform(0, 20), krng.choice([0.0, 1.0, krng.uniform(0, 1)]), krng.choice([0.0, 1.0, krng.uniform(0, 1)])])
+            fake = types.SimpleNamespace(nu=6, hour_of_day=float(krng.choice([krng.uniform(0, 24), float(krng.integers(0, 24))])),
+                                         day_of_year=float(krng.uniform(0, 365)))
+            with np.errstate(all="ignore"):
+                u = ctrl_v.predict(x, d, fake)
+            ks.append([float(var[n]) for n in names]); kx.append(x); kd.append(d); kh.append(fake.hour_of_day)
+            kdoy.append(fake.day_of_year); ku.append(np.asarray(u, dtype=np.float64))
+    np.savez_compressed(os.path.join(HERE, "ctrl_golden.npz"), names=np.array(names), settings=np.array(ks), x=np.array(kx),
+                        d=np.array(kd), hod=np.array(kh), doy=np.array(kdoy), u=np.array(ku))
     print("golden fixtures written:", sorted(f for f in os.listdir(HERE) if f.endswith((".npz", ".npy"))))
 
 

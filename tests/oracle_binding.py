@@ -53,6 +53,9 @@ def load():
         lib.glgo_env_obs.argtypes = [C.POINTER(EnvCfg), C.POINTER(Env), _DP]
         lib.glgo_env_step.argtypes = [C.POINTER(EnvCfg), C.POINTER(Env), _DP, C.c_void_p, C.c_int, _DP, _DP, _DP, _DP]
         lib.glgo_env_step.restype = C.c_int
+        lib.glgo_rule_control.argtypes = [_DP, _DP, _DP, C.c_double, C.c_double, _DP]
+        lib.glgo_env_step_rule.argtypes = [C.POINTER(EnvCfg), C.POINTER(Env), _DP, _DP, _DP, _DP, _DP, _DP]
+        lib.glgo_env_step_rule.restype = C.c_int
         lib.glgo_rollout.argtypes = [C.POINTER(EnvCfg), _DP, _DP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                      C.c_int, _DP]
         lib.glgo_rollout.restype = C.c_long
@@ -113,6 +116,13 @@ def evalf_batch(x, u, d, p, dt=900.0, n_sub=600, n_threads=0):
     return y
 
 
+def rule_control(settings29, x, d, hod, doy):
+    u = np.zeros(6)
+    load().glgo_rule_control(P(np.ascontiguousarray(settings29, dtype=np.float64)), P(np.ascontiguousarray(x, dtype=np.float64)),
+                             P(np.ascontiguousarray(d, dtype=np.float64)), float(hod), float(doy), P(u))
+    return u
+
+
 class OracleEnv:
     """One reference-semantics env stepped by the C oracle."""
 
@@ -142,6 +152,15 @@ class OracleEnv:
         n = None if noise34 is None else P(np.ascontiguousarray(noise34, dtype=np.float64))
         done = load().glgo_env_step(C.byref(self.cfg), C.byref(self.e), P(self.p), a.ctypes.data, raw, n, P(obs),
                                     C.cast(C.byref(r), _DP), P(info))
+        return obs, r.value, bool(done), info
+
+    def step_rule(self, settings29, noise34=None):
+        """controller in the loop: u = glgo_rule_control(x, weather[k], clock); step_raw_control(u)"""
+        obs, r, info = np.zeros(self.nobs), C.c_double(0.0), np.zeros(11)
+        s29 = np.ascontiguousarray(settings29, dtype=np.float64)
+        n = None if noise34 is None else P(np.ascontiguousarray(noise34, dtype=np.float64))
+        done = load().glgo_env_step_rule(C.byref(self.cfg), C.byref(self.e), P(self.p), P(s29), n, P(obs),
+                                         C.cast(C.byref(r), _DP), P(info))
         return obs, r.value, bool(done), info
 
     @property
