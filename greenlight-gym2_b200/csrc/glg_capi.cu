@@ -45,8 +45,11 @@ struct glg_handle {
     unsigned char *h_done = nullptr;
     cudaStream_t own_stream = nullptr;
     long long launches = 0;
+    double ctrl[GLG_NCTRL];  // rule-based controller settings (defaults: configs/agents/rule_based.yml)
     std::string err;
 };
+static const double kDefaultCtrl[GLG_NCTRL] = {0, 18, -1, 366, 400, 10, 19.5, 16.5, 0, 5, 800, 4, 85, 2, 5, 1, -1, 5, 10, -1, 4, -2,
+                                               2, 2, 100, 85, -1, -100, 1};
 
 #define GLG_CUDA(h, call)                                                                            \
     do {                                                                                             \
@@ -138,6 +141,7 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     glg_handle *h = new (std::nothrow) glg_handle();
     if (!h) return GLG_ERR_ALLOC;
     h->cfg = *cfg;
+    for (int i = 0; i < GLG_NCTRL; ++i) h->ctrl[i] = kDefaultCtrl[i];
     h->B = cfg->num_envs;
     h->obs_dim = GLG_NOBS_FIXED + 5 * cfg->Np;
     h->nt = 64;
@@ -324,7 +328,7 @@ static int pick_role_warps(const glg_handle *h) {
 }
 
 static int step_common(glg_handle *h, const float *actions_dev, const double *controls_dev, const double *noise_dev,
-                       void *stream) {
+                       void *stream, bool rule_based = false) {
     int rc = check_ready(h);
     if (rc) return rc;
     if (!h->is_reset) return fail(h, GLG_ERR_STATE, "step before reset");
@@ -333,7 +337,8 @@ static int step_common(glg_handle *h, const float *actions_dev, const double *co
     fill_args(h, &a);
     a.actions = actions_dev;
     a.controls = controls_dev;
-    a.raw_control = controls_dev ? 1 : 0;
+    a.raw_control = rule_based ? 2 : (controls_dev ? 1 : 0);
+    for (int i = 0; i < GLG_NCTRL; ++i) a.ctrl[i] = h->ctrl[i];
     a.noise = noise_dev;
     const bool noisy = (h->cfg.uncertainty_scale != 0.0) || (noise_dev != nullptr);
     cudaStream_t s = (cudaStream_t)stream;
@@ -362,6 +367,49 @@ extern "C" int glg_step(glg_handle *h, const float *actions_dev, const double *n
 extern "C" int glg_step_raw_control(glg_handle *h, const double *controls_dev, const double *noise_dev, void *stream) {
     if (!h || !controls_dev) return GLG_ERR_ARG;
     return step_common(h, nullptr, controls_dev, noise_dev, stream);
+}
+
+extern "C" int glg_set_rule_controller(glg_handle *h, const double *settings29) {
+    if (!h) return GLG_ERR_ARG;
+    for (int i = 0; i < GLG_NCTRL; ++i) h->ctrl[i] = settings29 ? settings29[i] : kDefaultCtrl[i];
+    return GLG_OK;
+}
+
+extern "C" int glg_step_rule_based(glg_handle *h, const double *noise_dev, void *stream) {
+    if (!h) return GLG_ERR_ARG;
+    return step_common(h, nullptr, nullptr, noise_dev, stream, true);
+}
+
+// known-answer entry for the controller alone: one thread per point
+__global__ void glg_rule_control_kernel(GlgStepArgs A, const double *x, const double *d, const double *hod, const double *doy,
+                                        double *u, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double xl[GLG_NX], dl[GLG_ND], ul[GLG_NU];
+    for (int j = 0; j < GLG_NX; ++j) xl[j] = x[(size_t)i * GLG_NX + j];
+    for (int j = 0; j < GLG_ND; ++j) dl[j] = d[(size_t)i * GLG_ND + j];
+    glg_rule_control(A.ctrl, xl, dl, hod[i], doy[i], ul);
+    for (int j = 0; j < GLG_NU; ++j) u[(size_t)i * GLG_NU + j] = ul[j];
+}
+extern "C" int glg_rule_control_batch(const double *settings29, const double *x_dev, const double *d_dev, const double *hod_dev,
+                                      const double *doy_dev, double *u_dev, int32_t n, int32_t device, void *stream) {
+    if (!x_dev || !d_dev || !hod_dev || !doy_dev || !u_dev || n < 1) {
+        g_create_error = "glg_rule_control_batch: invalid argument";
+        return GLG_ERR_ARG;
+    }
+    GlgStepArgs a;
+    memset(&a, 0, sizeof a);
+    for (int i = 0; i < GLG_NCTRL; ++i) a.ctrl[i] = settings29 ? settings29[i] : kDefaultCtrl[i];
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) {
+        glg_rule_control_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, x_dev, d_dev, hod_dev, doy_dev, u_dev, n);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        g_create_error = std::string("glg_rule_control_batch: ") + cudaGetErrorString(e);
+        return GLG_ERR_CUDA;
+    }
+    return GLG_OK;
 }
 
 static bool is_pinned(const void *p) {

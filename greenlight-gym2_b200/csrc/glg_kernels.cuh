@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "glg_controller.h"
 #include "glg_model.h"
 #include "glg_philox.h"
 #include "glg_rk4.h"
@@ -37,6 +38,8 @@ struct GlgUniform {  // passed as a __grid_constant__ kernel parameter: lives in
 struct GlgStepArgs {
     int B, n_sub, N, Np, rows, n_tables, obs_dim, auto_reset, raw_control, n_reset_tables;
     int role_lanes;  // kernel B: envs per CTA (<= 32); fewer envs per CTA = more CTAs = more resident warps for small batches
+    // raw_control: 0 = actions through S1, 1 = caller's controls as-is, 2 = rule-based controller evaluated in the prologue
+    double ctrl[GLG_NCTRL];  // rule-based controller settings (glg_controller.h)
     double dt;
     double u_min[GLG_NU], u_max[GLG_NU];
     float delta_u_max_f32;
@@ -229,7 +232,16 @@ __device__ __forceinline__ void glg_env_prologue(const GlgUniform &U, const GlgS
 #pragma unroll
     for (int i = 0; i < 7; ++i) d[i] = wrow[i];
     // S1: tomato_env.py:109-113 (float32 action * float32 delta, then float64 add and clip) or raw control :148-149
-    if (A.raw_control) {
+    if (A.raw_control == 2) {
+        // baseline.py:68-227 on the state before the step, the full weather row and the pre-step clock
+        // (experiments/evaluate_baseline.py:21-23), then used as-is like step_raw_control
+        double xc[GLG_NX], dc[GLG_ND];
+#pragma unroll
+        for (int i = 0; i < GLG_NX; ++i) xc[i] = (i == 0 || i == 2 || i == 15) ? A.x[(size_t)i * B + e] : 0.0;
+#pragma unroll
+        for (int i = 0; i < GLG_ND; ++i) dc[i] = wrow[i];
+        glg_rule_control(A.ctrl, xc, dc, A.time[(size_t)B + e], A.time[e], u);
+    } else if (A.raw_control) {
 #pragma unroll
         for (int i = 0; i < GLG_NU; ++i) u[i] = A.controls[(size_t)e * GLG_NU + i];
     } else {

@@ -43,6 +43,9 @@ SIGNATURES = {
     "glg_reset": (C.c_int, [C.c_void_p, _U8P, _IP, _VP]),
     "glg_step": (C.c_int, [C.c_void_p, _FP, _DP, _VP]),
     "glg_step_raw_control": (C.c_int, [C.c_void_p, _DP, _DP, _VP]),
+    "glg_set_rule_controller": (C.c_int, [C.c_void_p, _DP]),
+    "glg_step_rule_based": (C.c_int, [C.c_void_p, _DP, _VP]),
+    "glg_rule_control_batch": (C.c_int, [_DP, _DP, _DP, _DP, _DP, _DP, C.c_int32, C.c_int32, _VP]),
     "glg_step_host": (C.c_int, [C.c_void_p, _FP, _FP, _DP, _U8P]),
     "glg_obs_dim": (C.c_int32, [C.c_void_p]),
     "glg_obs_dev": (C.c_void_p, [C.c_void_p]),

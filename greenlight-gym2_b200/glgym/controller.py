@@ -3,7 +3,8 @@
 Same contract as the reference's `RuleBasedController.predict(x, d, env) -> u[6]`
 (gl_gym/environments/baseline.py:68-227, settings gl_gym/configs/agents/rule_based.yml), but for a batch:
 `predict(x[B,28], d[B,10], hour_of_day[B], day_of_year[B]) -> u[B,6]`; used with `step_raw_control`
-(experiments/evaluate_baseline.py:12-37).  SURVEY.md 8f ranks a device-side version as the next row.
+(experiments/evaluate_baseline.py:12-37).  The device-side version is csrc/glg_controller.h: `predict_device` here,
+`GreenLightVecEnv.step_rule_based*` for the fused controller-in-the-loop step.
 """
 import numpy as np
 
@@ -28,6 +29,27 @@ class RuleBasedController:
         cfg = dict(DEFAULT_SETTINGS)
         cfg.update(settings)
         self.__dict__.update(cfg)
+
+    def settings_vector(self):
+        """float64[29] in the order of rule_based.yml -- what `glg_set_rule_controller` / `glg_rule_control_batch` take."""
+        return np.array([float(getattr(self, k)) for k in DEFAULT_SETTINGS], dtype=np.float64)
+
+    def predict_device(self, x, d, hour_of_day, day_of_year, device=0):
+        """Same as `predict`, evaluated by the CUDA controller (glg_rule_control_batch); inputs/outputs are torch CUDA
+        or numpy arrays [n,28], [n,10], [n], [n] -> [n,6] (torch, float64, on `device`)."""
+        import torch
+        from . import _lib
+        dev = torch.device("cuda", device)
+        t = lambda a, shape: torch.as_tensor(a, dtype=torch.float64, device=dev).reshape(shape).contiguous()
+        x = t(x, (-1, 28))
+        n = x.shape[0]
+        d, hod, doy = t(d, (n, 10)), t(hour_of_day, (n,)), t(day_of_year, (n,))
+        u = torch.empty((n, 6), dtype=torch.float64, device=dev)
+        s = np.ascontiguousarray(self.settings_vector())
+        _lib.check(_lib.load().glg_rule_control_batch(s.ctypes.data, x.data_ptr(), d.data_ptr(), hod.data_ptr(), doy.data_ptr(),
+                                                      u.data_ptr(), n, device, torch.cuda.current_stream(dev).cuda_stream),
+                   None, "glg_rule_control_batch")
+        return u
 
     def _window(self, lo, hi, v):
         """1 inside the (possibly wrapping) interval (lo, hi), else 0 (baseline.py:76-86)."""

@@ -220,6 +220,31 @@ class GreenLightVecEnv:
         _lib.check(self._lib.glg_step_raw_control(self._h, u.data_ptr(), n, self._stream()), self._h, "glg_step_raw_control")
         return self.obs_t, self.reward_t, self.done_t
 
+    def set_rule_controller(self, controller=None):
+        """Settings of the on-device rule-based controller: a `glgym.controller.RuleBasedController`, a dict of
+        rule_based.yml keys, or None for the shipped values."""
+        from .controller import RuleBasedController
+        if controller is None:
+            vec = None
+        else:
+            c = controller if isinstance(controller, RuleBasedController) else RuleBasedController(**controller)
+            vec = np.ascontiguousarray(c.settings_vector())
+        _lib.check(self._lib.glg_set_rule_controller(self._h, None if vec is None else vec.ctypes.data), self._h,
+                   "glg_set_rule_controller")
+
+    def step_rule_based_tensor(self, noise=None):
+        """One step with RuleBasedController.predict (baseline.py:68-227) evaluated on the device from each env's own
+        state, weather row and clock, then applied like step_raw_control (evaluate_baseline.py:21-23) -- no host round trip."""
+        n = 0 if noise is None else noise.to(device=self.device, dtype=torch.float64).contiguous().data_ptr()
+        _lib.check(self._lib.glg_step_rule_based(self._h, n, self._stream()), self._h, "glg_step_rule_based")
+        return self.obs_t, self.reward_t, self.done_t
+
+    def step_rule_based(self):
+        self.step_rule_based_tensor()
+        torch.cuda.synchronize(self.device)
+        dones = self.done_t.cpu().numpy().astype(bool)
+        return self.obs_t.cpu().numpy(), self.reward_t.cpu().numpy(), dones, self._make_infos(dones)
+
     # ------------------------------------------------------------------ SB3 VecEnv protocol (numpy)
     def reset(self):
         self.reset_tensor()

@@ -97,6 +97,21 @@ int glg_step(glg_handle *h, const float *actions_dev, const double *noise_dev, v
 /* step_raw_control(): tomato_env.py:148-173.  controls_dev: double [B][6], used as-is (no clip / rate limit). */
 int glg_step_raw_control(glg_handle *h, const double *controls_dev, const double *noise_dev, void *stream);
 
+/* Rule-based controller in the loop: RuleBasedController.predict, environments/baseline.py:68-227, evaluated
+ * on the device from each env's state, the weather row of its current timestep and its clock, then stepped like
+ * step_raw_control -- replaces the host loop of experiments/evaluate_baseline.py:21-23.
+ *   settings29 : host double[29] in the order of configs/agents/rule_based.yml (lamps_on, lamps_off, lamps_day_start,
+ *                lamps_day_stop, lamps_off_sun, lamp_rad_sum_limit, temp_setpoint_day, temp_setpoint_night,
+ *                heat_correction, heat_deadzone, co2_day, vent_heat_Pband, rh_max, mech_dehumid_Pband, vent_rh_Pband,
+ *                t_vent_off, vent_cold_Pband, thScrSpDay, thScrSpNight, thScrPband, thScrDeadZone, thScrRh, thScrRhPband,
+ *                lampExtraHeat, blScrExtraRh, rhMax, tHeatBand, co2Band, useBlScr); NULL = the shipped YAML values. */
+int glg_set_rule_controller(glg_handle *h, const double *settings29);
+int glg_step_rule_based(glg_handle *h, const double *noise_dev, void *stream);
+/* Known-answer entry for the controller alone: x_dev double [n][28], d_dev double [n][10], hod_dev / doy_dev double [n]
+ * -> u_dev double [n][6]. */
+int glg_rule_control_batch(const double *settings29, const double *x_dev, const double *d_dev, const double *hod_dev,
+                           const double *doy_dev, double *u_dev, int32_t n, int32_t device, void *stream);
+
 /* End-to-end convenience for host callers (the SB3 VecEnv numpy path): copies actions host->device, runs
  * glg_step on the handle's own stream, copies obs/reward/done device->host and synchronises.  Any output may be
  * NULL.  obs_host float32 [B][obs_dim], reward_host double [B], done_host uint8 [B]. */

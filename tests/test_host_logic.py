@@ -65,6 +65,41 @@ def test_rule_based_controller_matches_reference(shell_trace, weather0):
     assert np.array_equal(U[1], c.predict(X[1], weather0[31], 7.75, 0.32)[0])
 
 
+def test_rule_based_controller_known_answers():
+    """Oracle restatement and host port of RuleBasedController.predict against 800 known-answer vectors produced by the
+    reference's own class (tests/golden/make_golden.py: shipped settings, wrapping lamp window, day-of-year window,
+    lamps_on == lamps_off, non-default thresholds)."""
+    import oracle_binding as ob
+    from glgym.controller import RuleBasedController, DEFAULT_SETTINGS
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ctrl_golden.npz"))
+    names = [str(n) for n in z["names"]]
+    assert names == list(DEFAULT_SETTINGS)  # the settings-vector order of the C-ABI
+    assert (z["u"][:, 4] > 0).sum() > 50 and (z["u"][:, 5] > 0).sum() > 20  # lamps / blackout screen exercised
+    worst = 0.0
+    for i in range(z["u"].shape[0]):
+        u = ob.rule_control(z["settings"][i], z["x"][i], z["d"][i], z["hod"][i], z["doy"][i])
+        worst = max(worst, np.abs(u - z["u"][i]).max())
+        c = RuleBasedController(**dict(zip(names, z["settings"][i])))
+        assert np.array_equal(c.settings_vector(), z["settings"][i])
+        with np.errstate(all="ignore"):
+            assert np.array_equal(c.predict(z["x"][i], z["d"][i], z["hod"][i], z["doy"][i])[0], z["u"][i]), i
+    assert worst <= 4e-16  # glibc exp vs numpy exp: one rounding of a value in [0, 1]
+
+
+def test_oracle_rule_based_step_matches_reference_trace(shell_trace, weather0, params64):
+    """Controller in the loop (glgo_env_step_rule) reproduces the reference's rule-based episode prefix."""
+    import oracle_binding as ob
+    from glgym.controller import RuleBasedController
+    t = shell_trace
+    env = ob.OracleEnv(weather0, params64, ob.default_cfg(n_sub=int(t["n_sub"])))
+    s29 = RuleBasedController().settings_vector()
+    for s in range(t["rb_u"].shape[0]):
+        obs, r, done, info = env.step_rule(s29)
+        assert np.abs(env.u - t["rb_u"][s]).max() <= 1e-11, s  # closed loop: 1e-15 state differences times the sigmoid gains
+        assert abs(r - t["rb_reward"][s]) <= 1e-9
+    assert np.max(np.abs(env.x - t["rb_x"][-1]) / np.maximum(np.abs(t["rb_x"][-1]), 1e-3)) <= 1e-9
+
+
 def test_kernel_math_restructuring_matches_oracle(hm, rhs_golden):
     """The hoisted / streaming RHS of csrc/glg_model.h (host build) and its role-split form against the oracle."""
     g = rhs_golden
