@@ -66,7 +66,8 @@ class GreenLightVecEnv:
     def __init__(self, num_envs, reward_function="GreenhouseReward", observation_modules=None, constraints=None,
                  eval_options=None, reward_params=None, base_env_params=None, uncertainty_scale=0.0,
                  n_sub=600, device=0, seed=0, auto_reset=True, env_id_offset=0, weather_tables=None,
-                 table_start_days=None, params=None, info_mode=None, role_warps=0, role_lanes=0, precision="fp64"):
+                 table_start_days=None, params=None, info_mode=None, role_warps=0, role_lanes=0, precision="fp64",
+                 reuse_output_buffers=False):
         if reward_function != "GreenhouseReward":
             raise ValueError("only GreenhouseReward exists in the reference (tomato_env.py:14)")
         mods = list(observation_modules or DEFAULT_OBSERVATION_MODULES)
@@ -194,6 +195,15 @@ class GreenLightVecEnv:
         self._pin = [torch.empty((B, self.obs_dim), dtype=torch.float32).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory(),
                      torch.empty(B, dtype=torch.uint8).pin_memory(), torch.empty((B, self.nu), dtype=torch.float32).pin_memory()]
         self._obs_host, self._rew_host, self._done_host, self._act_host = (t.numpy() for t in self._pin)
+        # reuse_output_buffers: `step()` returns views of two alternating page-locked observation buffers instead of a fresh
+        # copy (saves a 263*4*B-byte host memcpy per step).  An array returned by step k is overwritten by step k+2 -- safe
+        # for SB3's collect loop (it copies `new_obs` into its rollout buffer before the next step); off by default because
+        # the reference returns fresh arrays.
+        self.reuse_output_buffers = bool(reuse_output_buffers)
+        if self.reuse_output_buffers:
+            self._pin.append(torch.empty((B, self.obs_dim), dtype=torch.float32).pin_memory())
+            self._obs_ring = [self._obs_host, self._pin[-1].numpy()]
+            self._obs_turn = 0
 
     # ------------------------------------------------------------------ tensor fast path
     def _stream(self):
@@ -257,10 +267,16 @@ class GreenLightVecEnv:
         self._actions = self._act_host
 
     def step_wait(self):
-        _lib.check(self._lib.glg_step_host(self._h, self._actions.ctypes.data, self._obs_host.ctypes.data,
+        if self.reuse_output_buffers:
+            self._obs_turn ^= 1
+            obs_buf = self._obs_ring[self._obs_turn]
+        else:
+            obs_buf = self._obs_host
+        _lib.check(self._lib.glg_step_host(self._h, self._actions.ctypes.data, obs_buf.ctypes.data,
                                            self._rew_host.ctypes.data, self._done_host.ctypes.data), self._h, "glg_step_host")
         dones = self._done_host.astype(bool)
-        return self._obs_host.copy(), self._rew_host.astype(np.float32), dones, self._make_infos(dones)
+        obs = obs_buf if self.reuse_output_buffers else obs_buf.copy()
+        return obs, self._rew_host.astype(np.float32), dones, self._make_infos(dones)
 
     def step(self, actions):
         self.step_async(actions)
