@@ -45,11 +45,18 @@ struct glg_handle {
     unsigned char *h_done = nullptr;
     cudaStream_t own_stream = nullptr;
     long long launches = 0;
+    unsigned long long uni_version = 0;  // bumped by glg_set_params; compared with the resident copy's version
     double ctrl[GLG_NCTRL];  // rule-based controller settings (defaults: configs/agents/rule_based.yml)
     std::string err;
 };
 static const double kDefaultCtrl[GLG_NCTRL] = {0, 18, -1, 366, 400, 10, 19.5, 16.5, 0, 5, 800, 4, 85, 2, 5, 1, -1, 5, 10, -1, 4, -2,
                                                2, 2, 100, 85, -1, -100, 1};
+
+// owner of the device's __constant__ glg_uni_c copy (kernel B's group functions read their constants from it)
+#include <mutex>
+static std::mutex g_uni_mutex;
+static const void *g_uni_owner[64] = {};  // per device ordinal: handle whose table is resident
+static unsigned long long g_uni_version[64] = {};
 
 #define GLG_CUDA(h, call)                                                                            \
     do {                                                                                             \
@@ -113,6 +120,10 @@ extern "C" void glg_destroy(glg_handle *h) {
     if (h->h_reward) cudaFreeHost(h->h_reward);
     if (h->h_done) cudaFreeHost(h->h_done);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    {
+        std::lock_guard<std::mutex> lk(g_uni_mutex);
+        if (h->cfg.device >= 0 && h->cfg.device < 64 && g_uni_owner[h->cfg.device] == h) g_uni_owner[h->cfg.device] = nullptr;
+    }
     delete h;
 }
 
@@ -188,6 +199,11 @@ extern "C" int glg_set_params(glg_handle *h, const double *p_host) {
     for (int i = 0; i < K_COUNT; ++i) h->uni.Kf[i] = (float)h->uni.K[i];
     for (int i = 0; i < C_COUNT; ++i) h->uni.Cf[i] = (float)h->uni.C[i];
     h->general = !glg_params_nominal_structure(p_host);
+    static unsigned long long next_version = 1;
+    {
+        std::lock_guard<std::mutex> lk(g_uni_mutex);
+        h->uni_version = next_version++;
+    }
     h->have_params = true;
     return GLG_OK;
 }
@@ -293,8 +309,30 @@ static cudaError_t launch_step(glg_handle *h, const GlgStepArgs &a, cudaStream_t
     return cudaGetLastError();
 }
 
+// Makes this handle's constant table the resident __constant__ copy of its device.  Switching owners waits for the
+// device first: a kernel of the previous owner may still be reading the copy on another stream.
+[[maybe_unused]] static cudaError_t bind_uniform(glg_handle *h) {
+    const int d = h->cfg.device;
+    if (d < 0 || d >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(g_uni_mutex);
+    if (g_uni_owner[d] == h && g_uni_version[d] == h->uni_version) return cudaSuccess;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(glg_uni_c, &h->uni, sizeof(GlgUniform));
+    if (e == cudaSuccess) {
+        g_uni_owner[d] = h;
+        g_uni_version[d] = h->uni_version;
+    }
+    return e;
+}
+
 template <class T, bool GENERAL, bool NOISY, int NR>
 static cudaError_t launch_step_roles_t(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
+#if GLG_NOINLINE_MASK
+    {
+        cudaError_t e = bind_uniform(h);
+        if (e != cudaSuccess) return e;
+    }
+#endif
     const size_t smem = GlgRoleSmem<T, NOISY>::bytes(a.Np);
     static bool attr_set = false;
     if (!attr_set) {

@@ -229,40 +229,75 @@ __device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv,
     else part_col[GLG_SLOT_LAMBDA * GLG_ROLE_LANES] = glg_grp_flows(Kv, Cv, X, pt);
 }
 
-template <bool GENERAL, int NR, class T, class CV, class HV>
-__device__ __forceinline__ void glg_run_warp_groups(int warp, const GlgUniform &U, const CV &Cv, const HV &Hc, const double *u,
-                                                    const GlgXsCol<T> &X, T *part_col) {
+// Each flux group is a separate (__noinline__) device function.  Inlined into the kernel, ptxas serialises the hand-
+// interleaved chains of the math routines once the function holds all eight groups (FP64 producer distance <= 2 for 40 %
+// of the instructions vs 10 % when a group is compiled on its own -- tools/ubench/sched_probe.cu, tools/sass_dep_all.py),
+// which doubled the latency of the long groups.  A callee cannot see the kernel's __grid_constant__ parameter, so kernel
+// B's group functions read the constants from this __constant__ copy (direct c[3][imm] operands, like the kernel
+// parameter was).  There is ONE copy per device: the host uploads a handle's table before launching when another handle
+// used it last (glg_capi.cu: bind_uniform), after a device synchronise -- alternating handles on one device serialises.
+__constant__ GlgUniform glg_uni_c;
+
+template <int G, bool GENERAL, bool NOISY, class T>
+__device__ __noinline__ void glg_group_call(const T *xs_col, T *part_col, T *h_col, T *c_col, double thScr, double blScr) {
+    const GlgUniform &U = glg_uni_c;
+    const GlgColT<T, GLG_ROLE_LANES> Hc{h_col};
+    const GlgXsCol<T> X{xs_col};
+    const double u[GLG_NU] = {0.0, 0.0, thScr, 0.0, 0.0, blScr};  // only G1's GENERAL terms read the raw screen controls
+    if (NOISY) {
+        const GlgColT<T, GLG_ROLE_LANES> Cc{c_col};
+        glg_run_group<G, GENERAL>(U, Cc, Hc, u, X, part_col);
+    } else {
+        glg_run_group<G, GENERAL>(U, GlgKView<T>::c(U), Hc, u, X, part_col);
+    }
+}
+
+// GLG_NOINLINE_MASK: bit g set = group g runs as a __noinline__ call, else inlined into the kernel (default: all
+// inlined).  Measured on B200, B = 4096 (profiles/r1_noinline_groups.txt): in-kernel latency of a group running alone,
+// cycles -- inlined G0 693, G1 464, G2 723, G3 643, G4 722, G5 895, G6 1058, G7 1010; as calls G0 968, G4 564, G5 600,
+// G6 546, G7 680.  The calls keep the interleaved order and halve the long groups' latency, but the step gets SLOWER
+// (2.02 ms all inlined, 2.24 ms all calls, 2.39 ms calls for G4..G7 only): two warps share each SM sub-partition's FP64
+// pipe (1148 DFMA-class instructions per evaluation = 631 cycles per sub-partition at 2.2 cycles each), and once both
+// have ILP they queue on it.  Kept as an experiment switch for the round-2 work on group balance.
+#ifndef GLG_NOINLINE_MASK
+#define GLG_NOINLINE_MASK 0x00
+#endif
+template <int G, bool GENERAL, bool NOISY, class T, class CV>
+__device__ __forceinline__ void glg_dispatch_group(const GlgUniform &U, const CV &Cv, const T *xs_col, T *part_col, T *h_col,
+                                                   T *c_col, const double *u) {
+    if ((GLG_NOINLINE_MASK >> G) & 1) {
+        glg_group_call<G, GENERAL, NOISY, T>(xs_col, part_col, h_col, c_col, u[2], u[5]);
+    } else {
+        const GlgColT<T, GLG_ROLE_LANES> Hc{h_col};
+        const GlgXsCol<T> X{xs_col};
+        glg_run_group<G, GENERAL>(U, Cv, Hc, u, X, part_col);
+    }
+}
+
+template <bool GENERAL, bool NOISY, int NR, class T, class CV>
+__device__ __forceinline__ void glg_run_warp_groups(int warp, const GlgUniform &U, const CV &Cv, const T *xs_col, T *part_col,
+                                                    T *h_col, T *c_col, const double *u) {
+#define GLG_CALL(G) glg_dispatch_group<G, GENERAL, NOISY, T>(U, Cv, xs_col, part_col, h_col, c_col, u)
     if (NR == 8) {
         switch (warp) {
-            case 0: glg_run_group<0, GENERAL>(U, Cv, Hc, u, X, part_col); break;
-            case 1: glg_run_group<1, GENERAL>(U, Cv, Hc, u, X, part_col); break;
-            case 2: glg_run_group<2, GENERAL>(U, Cv, Hc, u, X, part_col); break;
-            case 3: glg_run_group<3, GENERAL>(U, Cv, Hc, u, X, part_col); break;
-            case 4: glg_run_group<4, GENERAL>(U, Cv, Hc, u, X, part_col); break;
-            case 5: glg_run_group<5, GENERAL>(U, Cv, Hc, u, X, part_col); break;
-            case 6: glg_run_group<6, GENERAL>(U, Cv, Hc, u, X, part_col); break;
-            default: glg_run_group<7, GENERAL>(U, Cv, Hc, u, X, part_col); break;
+            case 0: GLG_CALL(0); break;
+            case 1: GLG_CALL(1); break;
+            case 2: GLG_CALL(2); break;
+            case 3: GLG_CALL(3); break;
+            case 4: GLG_CALL(4); break;
+            case 5: GLG_CALL(5); break;
+            case 6: GLG_CALL(6); break;
+            default: GLG_CALL(7); break;
         }
-    } else {  // NR == 4: pairs balanced by SASS size (rad+airflow, fir+conv, screens+cover, photo+flows)
+    } else {  // NR == 4: pairs balanced by measured latency (rad+airflow, fir+conv, screens+cover, photo+flows)
         switch (warp) {
-            case 0:
-                glg_run_group<0, GENERAL>(U, Cv, Hc, u, X, part_col);
-                glg_run_group<2, GENERAL>(U, Cv, Hc, u, X, part_col);
-                break;
-            case 1:
-                glg_run_group<1, GENERAL>(U, Cv, Hc, u, X, part_col);
-                glg_run_group<3, GENERAL>(U, Cv, Hc, u, X, part_col);
-                break;
-            case 2:
-                glg_run_group<4, GENERAL>(U, Cv, Hc, u, X, part_col);
-                glg_run_group<5, GENERAL>(U, Cv, Hc, u, X, part_col);
-                break;
-            default:
-                glg_run_group<6, GENERAL>(U, Cv, Hc, u, X, part_col);
-                glg_run_group<7, GENERAL>(U, Cv, Hc, u, X, part_col);
-                break;
+            case 0: GLG_CALL(0); GLG_CALL(2); break;
+            case 1: GLG_CALL(1); GLG_CALL(3); break;
+            case 2: GLG_CALL(4); GLG_CALL(5); break;
+            default: GLG_CALL(6); GLG_CALL(7); break;
         }
     }
+#undef GLG_CALL
 }
 
 template <class T, bool GENERAL, bool NOISY, int NR>
@@ -369,7 +404,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
 #ifdef GLG_PROFILE_GROUPS
             const long long c0 = clock64();
 #endif
-            glg_run_warp_groups<GENERAL, NR>(warp, U, GlgKView<T>::c(U), Hc, u, X, part_col);
+            glg_run_warp_groups<GENERAL, NOISY, NR, T>(warp, U, GlgKView<T>::c(U), xs_col, part_col, s_H + lane, s_C + lane, u);
 #ifdef GLG_PROFILE_GROUPS
             const long long c1 = clock64();
 #endif
@@ -398,7 +433,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
         double h_lane = h_nom;
 #pragma unroll 1
         while (sub < A.n_sub) {
-            glg_run_warp_groups<GENERAL, NR>(warp, U, Cc, Hc, u, X, part_col);
+            glg_run_warp_groups<GENERAL, NOISY, NR, T>(warp, U, Cc, xs_col, part_col, s_H + lane, s_C + lane, u);
             __syncthreads();
             if (stage == 0) {
                 if (q == 0) {
