@@ -34,10 +34,34 @@
 #else
 #define GLG_COEF static const
 #endif
-GLG_COEF double glg_kExp[13] = {
-    0x1.af631d0059becp-26, 0x1.28b4057f44145p-22, 0x1.71ddf5749d126p-19, 0x1.a01991ac8730ap-16, 0x1.a01a01b14378fp-13,
-    0x1.6c16c187fbe02p-10, 0x1.111111110f225p-7,  0x1.555555554f0cfp-5,  0x1.555555555555ap-3,  0x1.0000000000011p-1,
-    0x1.71547652b82fep+0 /*log2(e)*/, -0x1.62e42fee00000p-1 /*-ln2_hi*/, -0x1.a39ef35793c76p-33 /*-ln2_lo*/};
+// Table-driven exp: x = (64 m + j) ln2/64 + r, |r| <= ln2/128; exp(x) = 2^m T[j] (1 + expm1(r)) with a degree-5 Taylor
+// polynomial (remainder r^6/720 < 4e-17).  10 FP64 instructions per exp instead of 17 -- exp is 43 % of the FP64
+// instruction stream of the RHS.  T[j] = 2^(j/64) is per-lane indexed: it lives in global memory and is read through the
+// L1 (4 cache lines; the load is issued right after the reduction and consumed by the last FMA).
+GLG_COEF double glg_kExpT[7] = {0x1.71547652b82fep+6 /*64/ln2*/, -0x1.62e42fef00000p-7 /*-(ln2/64)_hi, 34 bits*/,
+                                -0x1.473de6af278edp-40 /*-(ln2/64)_lo*/, 0x1.1111111111111p-7 /*1/120*/,
+                                0x1.5555555555555p-5 /*1/24*/, 0x1.5555555555555p-3 /*1/6*/, 0x1.0000000000000p-1};
+#define GLG_EXP_TABLE_VALUES \
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0, \
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0, \
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0, \
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0, \
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0, \
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0, \
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0, \
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0, \
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0, \
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0, \
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0, \
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0, \
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0, \
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0, \
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0, \
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0
+#if defined(__CUDACC__)
+__device__ const double glg_exp_tbl_dev[64] = {GLG_EXP_TABLE_VALUES};
+#endif
+static const double glg_exp_tbl_host[64] = {GLG_EXP_TABLE_VALUES};
 GLG_COEF double glg_kLog[9] = {
     0x1.2b584aae78a57p-3, 0x1.39fe606542ddep-3, 0x1.7462b4ab2ef6bp-3, 0x1.c71c62e5800a1p-3, 0x1.2492492df148dp-2,
     0x1.99999999952e2p-2, 0x1.5555555555558p-1, 0x1.62e42fee00000p-1 /*ln2_hi*/, 0x1.a39ef35793c76p-33 /*ln2_lo*/};
@@ -101,70 +125,67 @@ GLG_HD double glg_sqrt(double x) {
 #endif
 }
 
-// ---- exp: Cody-Waite reduction r = x - n ln2, |r| <= ln2/2; degree-11 near-minimax polynomial (4e-18);
-//      scaling by 2^n through the exponent field, n clamped so the result stays a normal number.
+// ---- exp (table-driven, see glg_kExpT).  2^m goes through the exponent field; m is clamped on the integer pipe so the
+//      result stays a normal number and the function saturates (~1e-308 / ~1e308) instead of wrapping for |x| > 708.
+GLG_HD double glg_exp_tbl(int j) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(glg_exp_tbl_dev + j);
+#else
+    return glg_exp_tbl_host[j];
+#endif
+}
 GLG_HD double glg_exp(double x) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to nearest integer in the low word
-    const double t = glg_fma(x, glg_kExp[10], MAGIC);
-    const double n = t - MAGIC;
-    double r = glg_fma(n, glg_kExp[11], x);
-    r = glg_fma(n, glg_kExp[12], r);
-    double p = glg_kExp[0];
-    p = glg_fma(p, r, glg_kExp[1]);
-    p = glg_fma(p, r, glg_kExp[2]);
-    p = glg_fma(p, r, glg_kExp[3]);
-    p = glg_fma(p, r, glg_kExp[4]);
-    p = glg_fma(p, r, glg_kExp[5]);
-    p = glg_fma(p, r, glg_kExp[6]);
-    p = glg_fma(p, r, glg_kExp[7]);
-    p = glg_fma(p, r, glg_kExp[8]);
-    p = glg_fma(p, r, glg_kExp[9]);
-    p = glg_fma(p, r, 1.0);
-    p = glg_fma(p, r, 1.0);
-    // 2^n: n sits in the low 32 bits of t (two's complement, valid for |x| < 2^30); add it to the exponent field
-    // of p.  p is in [0.70, 1.42]; clamping n to [-1021, 1023] on the integer pipe keeps the result a normal
-    // number and makes the function saturate (~1e-308 / ~1e308) instead of wrapping for |x| > 708.
-    int ni = (int)(uint32_t)(uint64_t)glg_d2bits(t);
-    ni = ni < -1021 ? -1021 : (ni > 1023 ? 1023 : ni);
-    return glg_bits2d(glg_d2bits(p) + ((long long)ni << 52));
+    const double t = glg_fma(x, glg_kExpT[0], MAGIC);
+    const double kf = t - MAGIC;
+    const int k = (int)(uint32_t)(uint64_t)glg_d2bits(t);  // two's complement in the low word, valid for |x| < 2^24
+    const double T = glg_exp_tbl(k & 63);
+    double r = glg_fma(kf, glg_kExpT[1], x);
+    r = glg_fma(kf, glg_kExpT[2], r);
+    const double r2 = r * r;
+    double q = glg_fma(r, glg_kExpT[3], glg_kExpT[4]);
+    q = glg_fma(r, q, glg_kExpT[5]);
+    q = glg_fma(r, q, glg_kExpT[6]);
+    const double p = glg_fma(r2, q, r);  // expm1(r)
+    const double y = glg_fma(T, p, T);   // in [1, 2)
+    int m = k >> 6;
+    m = m < -1021 ? -1021 : (m > 1023 ? 1023 : m);
+    return glg_bits2d(glg_d2bits(y) + ((long long)m << 52));
 }
 
 // ---- N independent exps with their dependency chains interleaved in SOURCE order.  The hardware issues in order and
-//      ptxas does not interleave independent Horner chains by itself (it emitted three back-to-back 11-deep DFMA chains
-//      in the photosynthesis group: each DFMA then waits the full 8-cycle latency).  Writing the steps "step-major"
-//      gives a lone warp N-way ILP at zero extra instructions.
+//      ptxas does not interleave independent chains by itself; writing the steps "step-major" gives a lone warp N-way
+//      ILP at zero extra instructions.
 template <int N>
 GLG_HD void glg_exp_n(const double (&x)[N], double (&y)[N]) {
     const double MAGIC = 6755399441055744.0;
-    double t[N], r[N], p[N];
+    double t[N], r[N], T[N], r2[N], q[N];
+    int k[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) t[i] = glg_fma(x[i], glg_kExp[10], MAGIC);
-#pragma unroll
-    for (int i = 0; i < N; ++i) r[i] = glg_fma(t[i] - MAGIC, glg_kExp[11], x[i]);
-#pragma unroll
-    for (int i = 0; i < N; ++i) r[i] = glg_fma(t[i] - MAGIC, glg_kExp[12], r[i]);
-    // even/odd split of the degree-11 polynomial: p = E(s) + r O(s), s = r^2 -- two independent 5-deep Horner chains per
-    // exp (2N-way ILP) for one extra multiply.  kExp[0..9] = c11..c2, c1 = c0 = 1.
-    double s2[N], pe[N], po[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) s2[i] = r[i] * r[i];
-#pragma unroll
-    for (int i = 0; i < N; ++i) { po[i] = glg_fma(glg_kExp[0], s2[i], glg_kExp[2]); pe[i] = glg_fma(glg_kExp[1], s2[i], glg_kExp[3]); }
-#pragma unroll
-    for (int i = 0; i < N; ++i) { po[i] = glg_fma(po[i], s2[i], glg_kExp[4]); pe[i] = glg_fma(pe[i], s2[i], glg_kExp[5]); }
-#pragma unroll
-    for (int i = 0; i < N; ++i) { po[i] = glg_fma(po[i], s2[i], glg_kExp[6]); pe[i] = glg_fma(pe[i], s2[i], glg_kExp[7]); }
-#pragma unroll
-    for (int i = 0; i < N; ++i) { po[i] = glg_fma(po[i], s2[i], glg_kExp[8]); pe[i] = glg_fma(pe[i], s2[i], glg_kExp[9]); }
-#pragma unroll
-    for (int i = 0; i < N; ++i) { po[i] = glg_fma(po[i], s2[i], 1.0); pe[i] = glg_fma(pe[i], s2[i], 1.0); }
-#pragma unroll
-    for (int i = 0; i < N; ++i) p[i] = glg_fma(po[i], r[i], pe[i]);
+    for (int i = 0; i < N; ++i) t[i] = glg_fma(x[i], glg_kExpT[0], MAGIC);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        int ni = (int)(uint32_t)(uint64_t)glg_d2bits(t[i]);
-        ni = ni < -1021 ? -1021 : (ni > 1023 ? 1023 : ni);
-        y[i] = glg_bits2d(glg_d2bits(p[i]) + ((long long)ni << 52));
+        k[i] = (int)(uint32_t)(uint64_t)glg_d2bits(t[i]);
+        T[i] = glg_exp_tbl(k[i] & 63);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = glg_fma(t[i] - MAGIC, glg_kExpT[1], x[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = glg_fma(t[i] - MAGIC, glg_kExpT[2], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { r2[i] = r[i] * r[i]; q[i] = glg_fma(r[i], glg_kExpT[3], glg_kExpT[4]); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = glg_fma(r[i], q[i], glg_kExpT[5]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = glg_fma(r[i], q[i], glg_kExpT[6]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = glg_fma(r2[i], q[i], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double v = glg_fma(T[i], q[i], T[i]);
+        int m = k[i] >> 6;
+        m = m < -1021 ? -1021 : (m > 1023 ? 1023 : m);
+        y[i] = glg_bits2d(glg_d2bits(v) + ((long long)m << 52));
     }
 }
 // N independent reciprocals, interleaved the same way
