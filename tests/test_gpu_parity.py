@@ -210,6 +210,33 @@ def test_device_rule_based_controller(shell_trace, weather0, params64):
         env.close()
 
 
+def test_evaluation_outputs_match_reference_layout(tmp_path, weather0, params64):
+    """the device-recorded evaluation array equals the oracle's controller-in-the-loop episode prefix in the
+    column layout of experiments/evaluate_baseline.py:63-67, and round-trips through the Results CSV."""
+    import pandas as pd
+    from glgym.controller import RuleBasedController
+    from glgym.evaluation import evaluate_rule_based, result_columns, save_results
+    env = make_env(3, n_sub=600)
+    T = 12
+    data = evaluate_rule_based(env, None, n_steps=T)
+    assert data.shape == (3, T, 32)
+    orc = ob.OracleEnv(weather0, params64, ob.default_cfg())
+    s29 = RuleBasedController().settings_vector()
+    for t in range(T):
+        o, r, dn, info = orc.step_rule(s29)
+        assert obs_close(data[1, t, :23], o[:23]) and abs(data[1, t, 23] - r) <= 1e-9
+        ref = np.array([info[0], info[1], info[5], info[4], info[6], info[7], info[8], info[9]])
+        assert np.abs(data[2, t, 24:] - ref).max() <= 1e-9, t
+    cols = result_columns(env)
+    assert cols[:3] == ["co2_air", "temp_air", "rh_air"] and cols[23:] == ["Rewards", "EPI", "Revenue", "Heat costs", "CO2 costs",
+        "Elec costs", "temp_violation", "co2_violation", "rh_violation", "episode"]
+    save_results(data, cols, tmp_path / "rb.csv")
+    df = pd.read_csv(tmp_path / "rb.csv")
+    assert df.shape == (3 * T, 33) and df["episode"].tolist() == sorted([0.0, 1.0, 2.0] * T)
+    assert np.allclose(df["Rewards"].to_numpy()[T:2 * T], data[1, :, 23])
+    env.close()
+
+
 def test_parametric_noise_external_and_philox(shell_trace, weather0, params64):
     """S2: (a) external multipliers = the reference env's numpy draws (golden) reproduce its trajectory;
     (b) the device Philox stream equals its numpy restatement and is keyed by the GLOBAL env id."""
