@@ -122,6 +122,9 @@ __device__ __forceinline__ void glg_static_for(F &&f) {
     }
 }
 
+// per-warp copy of the owner tables in shared memory (used by the call build, where registers do not survive the calls)
+constexpr int GLG_OWNER_TAB_WORDS = 52;
+constexpr int GLG_OWNER_TAB_BYTES = 8 * GLG_OWNER_TAB_WORDS * 4;
 template <class T, bool NOISY>
 struct GlgRoleSmem {
     static constexpr int kColRows = (GLG_NX + 1) + GLG_NSLOTS + H_COUNT + (NOISY ? C_COUNT : 0);  // +1: dummy state row
@@ -129,7 +132,7 @@ struct GlgRoleSmem {
     __host__ __device__ static size_t col_bytes() { return (sizeof(T) * (size_t)kColRows * GLG_ROLE_LANES + 15) / 16 * 16; }
     __host__ __device__ static size_t bytes(int Np) {
         return sizeof(double) * ((size_t)(Np + 1) * GLG_ND + (size_t)GLG_NX * GLG_ROLE_LANES) + col_bytes() + 16 +
-               sizeof(int) * (5 * GLG_ROLE_LANES + 4);
+               sizeof(int) * (5 * GLG_ROLE_LANES + 4) + GLG_OWNER_TAB_BYTES;
     }
 };
 
@@ -158,6 +161,29 @@ __device__ __forceinline__ void glg_owner_setup(const double *Kc, int warp, GlgO
         const int sk = glg_owner_table.scale_k[ii];
         o.scale[j] = (valid && sk >= 0) ? Kc[sk] : 1.0;
         o.xs_off[j] = (valid ? i : GLG_NX) * GLG_ROLE_LANES;
+    });
+}
+// shared-memory image of GlgOwnerRegs: words [0,NJ*4) slot offsets, [NJ*4, NJ*5) xs offsets, then NJ doubles (8-byte aligned)
+template <int NR>
+__device__ __forceinline__ void glg_owner_store(const GlgOwnerRegs<NR> &o, int *tab) {
+    constexpr int NJ = GlgOwnerRegs<NR>::NJ;
+    glg_static_for<0, NJ>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+#pragma unroll
+        for (int c = 0; c < GlgRowSlots<NR, j>::value; ++c) tab[j * 4 + c] = o.off[j][c];
+        tab[NJ * 4 + j] = o.xs_off[j];
+        reinterpret_cast<double *>(tab + 36)[j] = o.scale[j];
+    });
+}
+template <int NR>
+__device__ __forceinline__ void glg_owner_fetch(GlgOwnerRegs<NR> &o, const int *tab) {
+    constexpr int NJ = GlgOwnerRegs<NR>::NJ;
+    glg_static_for<0, NJ>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+#pragma unroll
+        for (int c = 0; c < GlgRowSlots<NR, j>::value; ++c) o.off[j][c] = tab[j * 4 + c];
+        o.xs_off[j] = tab[NJ * 4 + j];
+        o.scale[j] = reinterpret_cast<const double *>(tab + 36)[j];
     });
 }
 template <int NR, class T>
@@ -319,6 +345,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
     int *s_k_t = s_tbl_t + NL;
     int *s_bad = s_k_t + NL;
     int *s_misc = s_bad + NL;
+    int *s_owntab = s_misc + 4;  // [NR][GLG_OWNER_TAB_WORDS]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -382,9 +409,12 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
     T *part_col = s_part + lane;
     const GlgXsCol<T> X{xs_col};
     double xo[NJ], acc[NJ];  // the RK4 state and stage sum stay fp64 in both precisions
-#pragma unroll
     GlgOwnerRegs<NR> own;
     glg_owner_setup<NR>(U.K, warp, own);
+#if GLG_NOINLINE_MASK
+    if (lane == 0) glg_owner_store<NR>(own, s_owntab + warp * GLG_OWNER_TAB_WORDS);
+    __syncwarp();
+#endif
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int i = glg_owner_table.order[j * NR + warp];
@@ -405,6 +435,9 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
             const long long c0 = clock64();
 #endif
             glg_run_warp_groups<GENERAL, NOISY, NR, T>(warp, U, GlgKView<T>::c(U), xs_col, part_col, s_H + lane, s_C + lane, u);
+#if GLG_NOINLINE_MASK
+            glg_owner_fetch<NR>(own, s_owntab + warp * GLG_OWNER_TAB_WORDS);
+#endif
 #ifdef GLG_PROFILE_GROUPS
             const long long c1 = clock64();
 #endif
@@ -434,6 +467,9 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
 #pragma unroll 1
         while (sub < A.n_sub) {
             glg_run_warp_groups<GENERAL, NOISY, NR, T>(warp, U, Cc, xs_col, part_col, s_H + lane, s_C + lane, u);
+#if GLG_NOINLINE_MASK
+            glg_owner_fetch<NR>(own, s_owntab + warp * GLG_OWNER_TAB_WORDS);
+#endif
             __syncthreads();
             if (stage == 0) {
                 if (q == 0) {
