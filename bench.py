@@ -108,6 +108,13 @@ def cpu_rate(B, n_steps, n_sub, threads, warmup=0):
     return B * n_steps / dt, dt
 
 
+def workload_config(args):
+    """The `config` both arms report: the workload is the same, only how a step is sampled differs."""
+    return {"workload": f"TomatoEnv {args.envs} batched envs per GPU, fp64 parity mode, nominal parameters, fixed weather year "
+                        "(BASELINE configs[1])",
+            "envs_per_gpu": args.envs, "n_sub": args.n_sub, "dt": 900, "integrator": "RK4 fixed step", "obs_dim": 263}
+
+
 def run_reference(args, rank, world):
     """`--impl reference`: the reference's CPU implementation of the path.  CasADi/SUNDIALS cannot be installed in this
     image (no wheel, no network), so this is the CPU oracle port with all host threads; rank 0 only."""
@@ -120,9 +127,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic actions; Bleiswijk GL2009 weather table shipped with the reference",
-        "config": {"workload": "TomatoEnv batched envs fp64, nominal parameters, fixed weather year (BASELINE configs[1])",
-                   "envs_per_step": sample, "n_sub": args.n_sub, "dt": 900, "integrator": "RK4 fixed step",
-                   "note": "CPU oracle port on host threads; the reference's CasADi CVODES extension is not installable here"},
+        "config": dict(workload_config(args), reference_sample=f"each step advances a bounded sample of {sample} of the "
+                       f"{args.envs} envs on {cores} host threads",
+                       note="CPU oracle port; the reference's CasADi CVODES extension is not installable here"),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} envs x {args.steps} steps, {cores} threads"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,13 +227,11 @@ def run_ours(args, rank, world, local):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic actions; Bleiswijk GL2009 weather table shipped with the reference",
-            "config": {"workload": "TomatoEnv 4096 batched envs per GPU, fp64 parity mode, nominal parameters, fixed weather year "
-                                   "(BASELINE configs[1])",
-                       "envs_per_gpu": B, "n_sub": args.n_sub, "dt": 900, "integrator": "RK4 fixed step", "obs_dim": obs_dim,
-                       "kernel": {0: "glg_step_roles_kernel (auto: 8 warps per 32 envs up to 2*SMs*32 envs, else 4)", 1: "glg_step_kernel (thread per env)",
+            "config": dict(workload_config(args),
+                       kernel= {0: "glg_step_roles_kernel (auto: 8 warps per 32 envs up to 2*SMs*32 envs, else 4)", 1: "glg_step_kernel (thread per env)",
                                   4: "glg_step_roles_kernel<4 warps>", 8: "glg_step_roles_kernel<8 warps>"}[args.role_warps],
-                       "parallelism": f"env-shard x{world}, no collective on the step path",
-                       "l2": "flushed between timed steps (256 MiB memset outside the event pair)", "state_finite": finite},
+                       parallelism=f"env-shard x{world}, no collective on the step path",
+                       l2="flushed between timed steps (256 MiB memset outside the event pair)", state_finite=finite),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 6 * 4,
                     "d2h_bytes_per_step": B * obs_dim * 4 + B * 8 + B, "api": "GreenLightVecEnv(reuse_output_buffers=True).step(numpy) -> glg_step_host; obs returned as views of "
                            "two alternating pinned buffers"},
