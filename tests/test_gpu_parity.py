@@ -108,7 +108,7 @@ def test_evalf_nonfinite_raises_like_reference(weather0, params64):
 
 
 # ------------------------------------------------------------------------------------------------ fused step
-@pytest.mark.parametrize("role_warps", [1, 4])
+@pytest.mark.parametrize("role_warps", [1, 4, 8])
 def test_step_matches_reference_env_trace(role_warps, shell_trace, weather0):
     """GPU step() against the trace of the reference's own TomatoEnv (golden, n_sub=300): obs, reward, info, state."""
     t = shell_trace
@@ -129,7 +129,7 @@ def test_step_matches_reference_env_trace(role_warps, shell_trace, weather0):
     env.close()
 
 
-@pytest.mark.parametrize("role_warps", [1, 4])
+@pytest.mark.parametrize("role_warps", [1, 4, 8])
 def test_step_teacher_forced_vs_oracle(role_warps, weather0, params64):
     """Per-step gate: identical (x,u,d,p) into GPU and oracle each step, 96 envs with different actions
     (one full + one partial CTA for kernel A, three CTAs for kernel B), n_sub=600."""
@@ -153,6 +153,47 @@ def test_step_teacher_forced_vs_oracle(role_warps, weather0, params64):
             # teacher forcing: continue both from the oracle's state
         env.set_state(x=np.stack([o_.x for o_ in orc]))
     env.close()
+
+
+@pytest.mark.parametrize("role_warps", [1, 4, 8])
+def test_step_general_parameter_structure(role_warps, weather0, params64):
+    """A parameter table that switches on the terms the default table zeroes (sky FIR through the roof p70, interlights
+    p194/p195/p198, grow-pipe FIR p165, k1Par != k2Par): `glg_set_params` must select the GENERAL kernel variants and the step
+    must still match the oracle, with nominal parameters and with per-env uncertainty (external multipliers)."""
+    pp = params64.copy()
+    pp[70], pp[194], pp[195], pp[165], pp[198], pp[33] = 0.05, 0.03, 0.9, 0.5, 2.0, 0.65
+    pp = pp.astype(np.float32).astype(np.float64)  # the env keeps the table in float32 like the reference
+    rng = np.random.default_rng(5)
+    B = 40
+    for scale in (0.0, 0.2):
+        env = make_env(B, n_sub=600, role_warps=role_warps, params=pp, uncertainty_scale=scale)
+        env.reset()
+        orc = [ob.OracleEnv(weather0, pp) for _ in range(B)]
+        for s in range(3):
+            A = rng.uniform(-1, 1, (B, 6)).astype(np.float32)
+            noise = rng.uniform(-scale / 2, scale / 2, (B, 34)) if scale else None
+            nt = None if noise is None else torch.as_tensor(noise, device="cuda")
+            env.step_tensor(torch.as_tensor(A, device="cuda"), noise=nt)
+            x, u, k = env.get_state()
+            r64 = env.reward_t.cpu().numpy()
+            for b in range(0, B, 3):
+                o, r, dn, info = orc[b].step(action=A[b], noise34=None if noise is None else noise[b])
+                assert rel_err(x[b], orc[b].x) <= STEP_TOL, (scale, s, b)
+                assert abs(r64[b] - r) <= 1e-9
+            xs = x.copy()
+            for b in range(0, B, 3):
+                xs[b] = orc[b].x
+            env.set_state(x=xs)
+        env.close()
+    if role_warps != 1:
+        e64 = make_env(B, n_sub=600, role_warps=role_warps, params=pp)
+        e32 = make_env(B, n_sub=600, role_warps=role_warps, params=pp, precision="fp32")
+        e64.reset_tensor(); e32.reset_tensor()
+        for s in range(20):
+            A = torch.as_tensor(rng.uniform(-1, 1, (B, 6)).astype(np.float32), device="cuda")
+            e64.step_tensor(A); e32.step_tensor(A)
+        assert rel_err(e32.state_t.cpu().numpy(), e64.state_t.cpu().numpy()) <= 1e-4
+        e64.close(); e32.close()
 
 
 def test_raw_control_and_rule_based_trace(shell_trace):
@@ -282,7 +323,7 @@ def test_parametric_noise_external_and_philox(shell_trace, weather0, params64):
         env.close()
 
 
-@pytest.mark.parametrize("role_warps", [1, 4])
+@pytest.mark.parametrize("role_warps", [1, 4, 8])
 def test_termination_autoreset_and_stats(role_warps, weather0, params64):
     """S6/S8 + SB3 VecEnv semantics: the step with timestep == N is terminal (episode length 5761,
     tests/env_test.py:77-92); done envs keep their terminal observation and restart from init_state in the same call."""
