@@ -299,11 +299,12 @@ template <bool GENERAL, bool NOISY>
 static cudaError_t launch_step(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
     constexpr int NT = 64;
     const size_t smem = GlgStepSmem<NT, NOISY>::bytes(a.Np);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static size_t attr_smem_dev[64] = {};  // largest size opted into so far, per device (the attribute is per context)
+    size_t &attr_smem = attr_smem_dev[h->cfg.device & 63];
+    if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(glg_step_kernel<GENERAL, NOISY, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_smem = smem;
     }
     glg_step_kernel<GENERAL, NOISY, NT><<<(a.B + NT - 1) / NT, NT, smem, s>>>(h->uni, a);
     return cudaGetLastError();
@@ -334,11 +335,12 @@ static cudaError_t launch_step_roles_t(glg_handle *h, const GlgStepArgs &a, cuda
     }
 #endif
     const size_t smem = GlgRoleSmem<T, NOISY>::bytes(a.Np);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static size_t attr_smem_dev[64] = {};  // largest size opted into so far, per device (the attribute is per context)
+    size_t &attr_smem = attr_smem_dev[h->cfg.device & 63];
+    if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(glg_step_roles_kernel<T, GENERAL, NOISY, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_smem = smem;
     }
 #if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
     if (const char *m = getenv("GLG_PROF_MASK")) {
@@ -588,7 +590,7 @@ extern "C" int glg_evalf_batch(const double *x_dev, const double *u_dev, const d
     }
     cudaError_t e = cudaSetDevice(device);
     cudaStream_t s = (cudaStream_t)stream;
-    static GlgUniform uni;  // only read by the shared-p variants
+    GlgUniform uni{};  // only read by the shared-p variants (passed to the kernel by value)
     if (e == cudaSuccess) {
         if (p_stride == 0) {
             double ph[GLG_NP];

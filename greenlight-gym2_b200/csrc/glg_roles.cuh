@@ -122,9 +122,12 @@ __device__ __forceinline__ void glg_static_for(F &&f) {
     }
 }
 
+#ifndef GLG_NOINLINE_MASK
+#define GLG_NOINLINE_MASK 0x00  // see glg_dispatch_group
+#endif
 // per-warp copy of the owner tables in shared memory (used by the call build, where registers do not survive the calls)
 constexpr int GLG_OWNER_TAB_WORDS = 52;
-constexpr int GLG_OWNER_TAB_BYTES = 8 * GLG_OWNER_TAB_WORDS * 4;
+constexpr int GLG_OWNER_TAB_BYTES = GLG_NOINLINE_MASK ? 8 * GLG_OWNER_TAB_WORDS * 4 : 0;
 template <class T, bool NOISY>
 struct GlgRoleSmem {
     static constexpr int kColRows = (GLG_NX + 1) + GLG_NSLOTS + H_COUNT + (NOISY ? C_COUNT : 0);  // +1: dummy state row
@@ -285,9 +288,7 @@ __device__ __noinline__ void glg_group_call(const T *xs_col, T *part_col, T *h_c
 // (2.02 ms all inlined, 2.24 ms all calls, 2.39 ms calls for G4..G7 only): two warps share each SM sub-partition's FP64
 // pipe (1148 DFMA-class instructions per evaluation = 631 cycles per sub-partition at 2.2 cycles each), and once both
 // have ILP they queue on it.  Kept as an experiment switch for the round-2 work on group balance.
-#ifndef GLG_NOINLINE_MASK
-#define GLG_NOINLINE_MASK 0x00
-#endif
+
 template <int G, bool GENERAL, bool NOISY, class T, class CV>
 __device__ __forceinline__ void glg_dispatch_group(const GlgUniform &U, const CV &Cv, const T *xs_col, T *part_col, T *h_col,
                                                    T *c_col, const double *u) {
