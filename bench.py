@@ -110,7 +110,8 @@ def cpu_rate(B, n_steps, n_sub, threads, warmup=0):
 
 def workload_config(args):
     """The `config` both arms report: the workload is the same, only how a step is sampled differs."""
-    return {"workload": f"TomatoEnv {args.envs} batched envs per GPU, fp64 parity mode, nominal parameters, fixed weather year "
+    mode = "fp64 parity mode" if getattr(args, "precision", "fp64") == "fp64" else "fp32 throughput mode"
+    return {"workload": f"TomatoEnv {args.envs} batched envs per GPU, {mode}, nominal parameters, fixed weather year "
                         "(BASELINE configs[1])",
             "envs_per_gpu": args.envs, "n_sub": args.n_sub, "dt": 900, "integrator": "RK4 fixed step", "obs_dim": 263}
 
@@ -150,7 +151,7 @@ def run_ours(args, rank, world, local):
     dev = torch.device("cuda", local)
     B, K, Wm = args.envs, args.steps, args.warmup
     env = GreenLightVecEnv(B, n_sub=args.n_sub, device=local, seed=0, env_id_offset=rank * B, role_warps=args.role_warps,
-                           reuse_output_buffers=True)
+                           reuse_output_buffers=True, precision=args.precision)
     obs_dim = env.obs_dim
     env.reset_tensor()
     g = torch.Generator(device=dev)
@@ -202,7 +203,7 @@ def run_ours(args, rank, world, local):
     if rank == 0:
         L = _lib.load()
         pk = C.c_double()
-        L.glg_measure_fp64_peak(local, C.byref(pk))
+        (L.glg_measure_fp64_peak if args.precision == "fp64" else L.glg_measure_fp32_peak)(local, C.byref(pk))
         peak_tf = pk.value / 1e12
         per_gpu_rate = B / (kernel_ms * 1e-3)
         achieved_tf = per_gpu_rate * flop_per_env_step(args.n_sub) / 1e12
@@ -213,9 +214,13 @@ def run_ours(args, rank, world, local):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_gbs = per_gpu_rate * algorithmic_bytes_per_env_step(obs_dim) / 1e9
-        traffic = None
+        traffic, ncu_info = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get("dram_bytes_per_launch")
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if args.precision == "fp64" and B == prof.get("B") and args.n_sub == prof.get("n_sub"):
+                traffic = prof.get("dram_bytes_per_launch")
+                ncu_info = {"fp64_pipe_active_pct": prof.get("fp64_pipe_active_pct"), "issue_active_pct": prof.get("issue_active_pct"),
+                            "source": prof.get("source")}
         except Exception:
             pass
         cores = os.cpu_count() or 1
@@ -224,9 +229,11 @@ def run_ours(args, rank, world, local):
         cpu_steps = max(3, int(15.0 * probe_rate / cpu_B))
         cpu_val, cpu_dt = cpu_rate(cpu_B, cpu_steps, args.n_sub, cores)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "metric": METRIC if args.precision == "fp64" else "GreenLight env-steps/sec (fp32 throughput mode)",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic actions; Bleiswijk GL2009 weather table shipped with the reference",
+            "dtype": "f64" if args.precision == "fp64" else "f32 (RK4 state f64)",
+            "data": "synthetic actions; Bleiswijk GL2009 weather table shipped with the reference",
             "config": dict(workload_config(args),
                        kernel= {0: "glg_step_roles_kernel (auto: 8 warps per 32 envs up to 2*SMs*32 envs, else 4)", 1: "glg_step_kernel (thread per env)",
                                   4: "glg_step_roles_kernel<4 warps>", 8: "glg_step_roles_kernel<8 warps>"}[args.role_warps],
@@ -237,11 +244,11 @@ def run_ours(args, rank, world, local):
                            "two alternating pinned buffers"},
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "roofline": {"bound": args.precision, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                         "peak_source": "glg_measure_fp64_peak: DFMA micro-benchmark measured live on this GPU "
-                                        "(MEASURED_PEAKS.json has no FP64 entry)",
-                         "flop_per_env_step": flop_per_env_step(args.n_sub), "kernel_ms": kernel_ms,
+                         "peak_source": ("glg_measure_fp64_peak: DFMA" if args.precision == "fp64" else "glg_measure_fp32_peak: FFMA")
+                                        + " micro-benchmark measured live on this GPU (MEASURED_PEAKS.json has no FP64/FP32 pipe entry)",
+                         "flop_per_env_step": flop_per_env_step(args.n_sub), "kernel_ms": kernel_ms, "ncu": ncu_info,
                          "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                                  "bytes_per_env_step": algorithmic_bytes_per_env_step(obs_dim),
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"}},
@@ -262,6 +269,8 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--n-sub", type=int, default=600)
     ap.add_argument("--role-warps", type=int, default=0)
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
+                    help="fp64 = parity mode (the BASELINE metric); fp32 = throughput mode (flux groups in fp32, RK4 state in fp64)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
