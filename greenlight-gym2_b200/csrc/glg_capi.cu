@@ -136,10 +136,11 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     if (cfg->num_envs < 1 || cfg->n_sub < 1 || cfg->N < 0 || cfg->Np < 0 || !(cfg->dt > 0) ||
         (cfg->precision != 0 && cfg->precision != 1) ||
         (cfg->role_warps != 0 && cfg->role_warps != 1 && cfg->role_warps != 4 && cfg->role_warps != 8) ||
-        (cfg->precision == 1 && cfg->role_warps == 1)) {
-        g_create_error = (cfg->precision == 1 && cfg->role_warps == 1)
-                             ? "glg_create: the fp32 throughput mode runs on kernel B only (role_warps 0, 4 or 8)"
-                             : "glg_create: invalid num_envs / n_sub / N / Np / dt / precision / role_warps";
+        (cfg->integrator != 0 && cfg->integrator != 1) ||
+        ((cfg->precision == 1 || cfg->integrator == 1) && cfg->role_warps == 1)) {
+        g_create_error = ((cfg->precision == 1 || cfg->integrator == 1) && cfg->role_warps == 1)
+                             ? "glg_create: the fp32 throughput mode and the graded integrator run on kernel B only (role_warps 0, 4 or 8)"
+                             : "glg_create: invalid num_envs / n_sub / N / Np / dt / precision / role_warps / integrator";
         return GLG_ERR_ARG;
     }
     int ndev = 0;
@@ -267,6 +268,7 @@ static void fill_args(const glg_handle *h, GlgStepArgs *a) {
     a->uncertainty_scale = c.uncertainty_scale;
     a->seed = c.seed; a->env_id_offset = c.env_id_offset;
     a->role_lanes = h->role_lanes;
+    a->integrator = c.integrator;
     a->weather = h->weather; a->start_day = h->start_day; a->reset_tables = h->reset_tables;
     a->x = h->x; a->u = h->u; a->time = h->time; a->ep_return = h->ep_return; a->ep_info = h->ep_info;
     a->timestep = h->timestep; a->table = h->table; a->ep_len = h->ep_len; a->step_ctr = h->step_ctr;
@@ -380,7 +382,9 @@ static int step_common(glg_handle *h, const float *actions_dev, const double *co
     a.raw_control = rule_based ? 2 : (controls_dev ? 1 : 0);
     for (int i = 0; i < GLG_NCTRL; ++i) a.ctrl[i] = h->ctrl[i];
     a.noise = noise_dev;
-    const bool noisy = (h->cfg.uncertainty_scale != 0.0) || (noise_dev != nullptr);
+    // kernel B compiles its guarded (micro-stepping) loop into the parametric-uncertainty variants; the graded integrator uses
+    // them too (scale 0 leaves the float32 parameter table unchanged)
+    const bool noisy = (h->cfg.uncertainty_scale != 0.0) || (noise_dev != nullptr) || (h->cfg.integrator == 1);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
     const int rw = pick_role_warps(h);

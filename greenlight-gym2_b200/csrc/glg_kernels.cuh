@@ -37,6 +37,7 @@ struct GlgUniform {  // passed as a __grid_constant__ kernel parameter: lives in
 
 struct GlgStepArgs {
     int B, n_sub, N, Np, rows, n_tables, obs_dim, auto_reset, raw_control, n_reset_tables;
+    int integrator;  // 0 fixed-step, 1 graded (kernel B's guarded loop)
     int role_lanes;  // kernel B: envs per CTA (<= 32); fewer envs per CTA = more CTAs = more resident warps for small batches
     // raw_control: 0 = actions through S1, 1 = caller's controls as-is, 2 = rule-based controller evaluated in the prologue
     double ctrl[GLG_NCTRL];  // rule-based controller settings (glg_controller.h)

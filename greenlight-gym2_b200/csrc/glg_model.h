@@ -631,6 +631,11 @@ GLG_HD void glg_rhs(const KV &K, const CV &C, const HV &H, const P &p, const dou
 // Harvest-stiffness guard (same rule as the oracle's glgo_micro_steps): number of equal micro-steps a nominal RK4 substep
 // of length h is split into, so that harvest moves an organ at most half a sigmoid window-width per micro-step.
 #define GLG_MAX_MICRO 512
+// graded integrator (integrator = 1): the first GLG_GRADED_SUBSTEPS nominal substeps of a control interval are split in
+// GLG_GRADED_M; any nominal substep is split in 1 + floor(h lambda_est / GLG_STIFF_CFL) (RK4's real-axis limit is 2.785)
+#define GLG_GRADED_SUBSTEPS 5
+#define GLG_GRADED_M 4
+#define GLG_STIFF_CFL 2.5
 template <class T>
 GLG_HD T glg_harvest_lambda(T sigLeaf, T sigFruit) {  // sig = 1/(1+exp(-k (c - cMax)))
     return T(5e4 * (2.0 * 4.6052 / 1e4)) * fmax(sigLeaf, sigFruit);  // harvest speed in window-widths per second
@@ -843,8 +848,9 @@ GLG_HD void glg_grp_fir(const KV &K, const CV &C, const HV &H, const P &p, const
 }
 
 // G2: ventilation, screen air flux, CO2 of the air compartments, sensible air/top/outside, air-borne vapour
+// Returns the transient-stiffness estimate lambda_est [1/s] of the graded integrator (same rule as the oracle's glgo_stiffness).
 template <class KV, class HV, class XV, class PT>
-GLG_HD void glg_grp_airflow(const KV &K, const HV &H, const XV &x, PT &pt) {
+GLG_HD glg_scalar_t<KV> glg_grp_airflow(const KV &K, const HV &H, const XV &x, PT &pt) {
     typedef glg_scalar_t<KV> T;
     const T co2Air = x[0], co2Top = x[1], tAir = x[2], tTop = x[3], vpAir = x[15], vpTop = x[16];
     const T tOut = H[H_TOUT];
@@ -882,6 +888,10 @@ GLG_HD void glg_grp_airflow(const KV &K, const HV &H, const XV &x, PT &pt) {
     const T mvAirTop = T(0.002165) * aScr * (vAirT - vTopT);
     pt[16] = (K[K_INVVPTOP] * tkTop) * (mvAirTop - T(0.002165) * aVentRoof * (vTopT - H[H_VPOUT_T]));
     pt[15] = -(K[K_INVVPAIR] * tkAir) * (mvAirTop + H[H_MVAIROUT_C] * (vAirT - H[H_VPOUT_T]));
+    const T lamCov = T(2.0) * K[K_HCOV] * K[K_INVCAPCOV];
+    const T lamTop = fabs(K[K_RHOCP]) * K[K_INVCAPTOP] * (T(1.5) * aScr + aVentRoof);
+    const T lamGas = (aScr + aVentRoof) * K[K_INVCAPCO2TOP];
+    return T(1.07) * fmax(lamCov, fmax(lamTop, lamGas));
 }
 
 // G3: lamp / pipe / canopy / floor convection with the main air

@@ -37,7 +37,8 @@ constexpr int GLG_NPART = glg_part_slot(GLG_NGROUPS, 0);
 constexpr int GLG_SLOT_ZERO = GLG_NPART;          // always 0.0
 constexpr int GLG_SLOT_CANSCALE = GLG_NPART + 1;  // canopy capacity scale of the current stage (written by G0's warp)
 constexpr int GLG_SLOT_LAMBDA = GLG_NPART + 2;    // harvest rate constant of the current stage state (written by G7's warp)
-constexpr int GLG_NSLOTS = GLG_NPART + 3;
+constexpr int GLG_SLOT_STIFF = GLG_NPART + 3;     // transient-stiffness estimate of the current stage state (written by G2's warp)
+constexpr int GLG_NSLOTS = GLG_NPART + 4;
 constexpr int GLG_MAXCONTRIB = 4;
 
 template <class T>
@@ -239,7 +240,7 @@ struct GlgKView<float> {
 #if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
 __device__ int glg_prof_mask_dev = 0x1FF;  // bits 0..7: run group g ; bit 8: run the owner phase (timing experiments only)
 #endif
-template <int G, bool GENERAL, class T, class CV, class HV>
+template <int G, bool GENERAL, bool GUARD = true, class T, class CV, class HV>
 __device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv, const HV &Hc, const double *u, const GlgXsCol<T> &X,
                                               T *part_col) {
 #if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
@@ -250,7 +251,10 @@ __device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv,
     GlgPartCol<G, T> pt{part_col};
     if (G == 0) part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES] = glg_grp_rad<GENERAL>(Kv, Cv, Hc, X, pt);
     else if (G == 1) glg_grp_fir<GENERAL>(Kv, Cv, Hc, Pv, u, X, pt);
-    else if (G == 2) glg_grp_airflow(Kv, Hc, X, pt);
+    else if (G == 2) {  // the stiffness estimate is only consumed by the guarded loop
+        const T lam = glg_grp_airflow(Kv, Hc, X, pt);
+        if (GUARD) part_col[GLG_SLOT_STIFF * GLG_ROLE_LANES] = lam;
+    }
     else if (G == 3) glg_grp_conv<GENERAL>(Kv, Cv, Hc, Pv, X, pt);
     else if (G == 4) glg_grp_screens(Kv, Hc, X, pt);
     else if (G == 5) glg_grp_cover(Kv, Cv, Hc, X, pt);
@@ -275,9 +279,9 @@ __device__ __noinline__ void glg_group_call(const T *xs_col, T *part_col, T *h_c
     const double u[GLG_NU] = {0.0, 0.0, thScr, 0.0, 0.0, blScr};  // only G1's GENERAL terms read the raw screen controls
     if (NOISY) {
         const GlgColT<T, GLG_ROLE_LANES> Cc{c_col};
-        glg_run_group<G, GENERAL>(U, Cc, Hc, u, X, part_col);
+        glg_run_group<G, GENERAL, NOISY>(U, Cc, Hc, u, X, part_col);
     } else {
-        glg_run_group<G, GENERAL>(U, GlgKView<T>::c(U), Hc, u, X, part_col);
+        glg_run_group<G, GENERAL, NOISY>(U, GlgKView<T>::c(U), Hc, u, X, part_col);
     }
 }
 
@@ -297,7 +301,7 @@ __device__ __forceinline__ void glg_dispatch_group(const GlgUniform &U, const CV
     } else {
         const GlgColT<T, GLG_ROLE_LANES> Hc{h_col};
         const GlgXsCol<T> X{xs_col};
-        glg_run_group<G, GENERAL>(U, Cv, Hc, u, X, part_col);
+        glg_run_group<G, GENERAL, NOISY>(U, Cv, Hc, u, X, part_col);
     }
 }
 
@@ -423,6 +427,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
         acc[j] = 0.0;
     }
     const double h_nom = A.dt / (double)A.n_sub;
+    int n_micro = 0;  // RK4 micro-steps this env executed (guarded loop only)
 #ifdef GLG_PROFILE_GROUPS
     long long t_grp = 0, t_b1 = 0, t_own = 0, t_b2 = 0;
 #endif
@@ -460,9 +465,10 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
 #endif
         }
     } else {
-        // Parametric uncertainty: one nominal RK4 substep = m micro-steps of h_nom/m, m per env from the harvest-stiffness
-        // guard (glg_model.h; m = 1 unless an organ sits inside its harvest window).  Lanes with a smaller m idle with
-        // h = 0 for the remaining micro-steps of the CTA, so an env's result never depends on its CTA mates.
+        // Guarded loop (parametric uncertainty and / or the graded integrator): one nominal RK4 substep = m micro-steps of
+        // h_nom/m, m per env = max of the harvest-stiffness guard (glg_model.h; 1 unless an organ sits inside its harvest
+        // window) and, with integrator = 1, the graded start of the interval and the transient-stiffness rule.  Lanes with a
+        // smaller m idle with h = 0 for the remaining micro-steps of the CTA, so an env's result never depends on its CTA mates.
         int sub = 0, q = 0, stage = 0, m_lane = 1, m_cta = 1;
         double h_lane = h_nom;
 #pragma unroll 1
@@ -475,6 +481,13 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
             if (stage == 0) {
                 if (q == 0) {
                     m_lane = glg_micro_steps_from_lambda((double)part_col[GLG_SLOT_LAMBDA * NL], h_nom);
+                    if (A.integrator == 1) {
+                        int ms = 1 + (int)floor(h_nom * (double)part_col[GLG_SLOT_STIFF * NL] * (1.0 / GLG_STIFF_CFL));
+                        ms = ms > GLG_MAX_MICRO ? GLG_MAX_MICRO : (ms < 1 ? 1 : ms);  // ms < 1 only for a NaN estimate
+                        if (sub < GLG_GRADED_SUBSTEPS && ms < GLG_GRADED_M) ms = GLG_GRADED_M;
+                        m_lane = max(m_lane, ms);
+                    }
+                    n_micro += m_lane;
                     m_cta = __reduce_max_sync(0xffffffffu, m_lane);  // every warp sees the same 32 envs
                 }
                 h_lane = q < m_lane ? h_nom / (double)m_lane : 0.0;
@@ -525,6 +538,10 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
         s_tbl_t[lane] = o.tbl_term;
         s_k_t[lane] = o.k_term;
         glg_stats_reduce(A, active, bad, o);
+        if (NOISY) {
+            const int tot = __reduce_add_sync(0xffffffffu, active ? n_micro : 0);
+            if (lane == 0 && tot > 0) atomicAdd(&A.stats[15], (double)tot);
+        }
     }
     __syncthreads();
     glg_write_forecast(A, A.role_lanes, s_tbl, s_k, s_tbl_t, s_k_t, s_wtile, uniform, bk, bt);

@@ -26,7 +26,7 @@ class GlgConfig(C.Structure):
         ("elec_price", C.c_double), ("heating_price", C.c_double), ("co2_price", C.c_double),
         ("fruit_price", C.c_double), ("dmfm", C.c_double), ("fixed_costs", C.c_double),
         ("uncertainty_scale", C.c_double), ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
-        ("role_warps", C.c_int32), ("reserved", C.c_int32),
+        ("role_warps", C.c_int32), ("reserved", C.c_int32), ("integrator", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

@@ -65,9 +65,9 @@ class GreenLightVecEnv:
 
     def __init__(self, num_envs, reward_function="GreenhouseReward", observation_modules=None, constraints=None,
                  eval_options=None, reward_params=None, base_env_params=None, uncertainty_scale=0.0,
-                 n_sub=600, device=0, seed=0, auto_reset=True, env_id_offset=0, weather_tables=None,
+                 n_sub=None, device=0, seed=0, auto_reset=True, env_id_offset=0, weather_tables=None,
                  table_start_days=None, params=None, info_mode=None, role_warps=0, role_lanes=0, precision="fp64",
-                 reuse_output_buffers=False):
+                 reuse_output_buffers=False, integrator="fixed"):
         if reward_function != "GreenhouseReward":
             raise ValueError("only GreenhouseReward exists in the reference (tomato_env.py:14)")
         mods = list(observation_modules or DEFAULT_OBSERVATION_MODULES)
@@ -101,7 +101,12 @@ class GreenLightVecEnv:
         self.training = bp["training"]
         self.train_years = list(range(bp["start_train_year"], bp["end_train_year"] + 1))
         self.train_days = list(range(bp["start_train_day"], bp["end_train_day"] + 1))
-        self.n_sub = int(n_sub)
+        # integrator: "fixed" = n_sub equal RK4 substeps (default 600, the parity contract); "graded" = RK4 with a refined
+        # start of every control interval and a transient-stiffness rule (default n_sub 300; DESIGN.md "Graded integrator")
+        if integrator not in ("fixed", "graded"):
+            raise ValueError("integrator must be 'fixed' or 'graded'")
+        self.integrator = integrator
+        self.n_sub = int(n_sub) if n_sub is not None else (600 if integrator == "fixed" else 300)
         self.observation_modules = mods
         self.obs_dim = 23 + 5 * self.Np
         # spaces: tomato_env.py:83-98 / observations.py observation_space() of each module
@@ -166,6 +171,7 @@ class GreenLightVecEnv:
         cfg.uncertainty_scale = self.uncertainty_scale
         cfg.seed = int(seed) & (2**64 - 1)
         cfg.env_id_offset = int(env_id_offset)
+        cfg.integrator = 0 if integrator == "fixed" else 1
         cfg.reserved = int(role_lanes)    # kernel B envs-per-CTA override (0 = auto)
         cfg.role_warps = int(role_warps)  # 0 auto, 1 = one thread per env, 4 = warp-specialised RHS
         self.reward_params = rp

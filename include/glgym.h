@@ -65,6 +65,12 @@ typedef struct glg_config {
     int64_t env_id_offset;   /* global index of local env 0 (multi-GPU sharding; RNG streams follow the global id) */
     int32_t role_warps;      /* kernel variant: 0 = auto, 1 = one thread per env (kernel A), 4 / 8 = kernel B with 4 / 8 warps per 32 envs */
     int32_t reserved;        /* 0, or 1..32: override of kernel B's envs-per-CTA (tuning / tests) */
+    int32_t integrator;      /* 0 = fixed-step RK4, n_sub equal substeps (the parity contract);
+                                1 = graded RK4: the first 5 nominal substeps of every control interval are split in 4 (the
+                                    controls just changed: fast transients) and any nominal substep is split further while the
+                                    top-compartment / cover stiffness estimate asks for it (DESIGN.md "Graded integrator");
+                                    meant for n_sub = 300.  Kernel B only. */
+    int32_t reserved2;
 } glg_config;
 
 /* Fills *cfg with the defaults of configs/envs/TomatoEnv.yml (dt 900, N 5760, Np 48, n_sub 600, ...). */
@@ -132,7 +138,8 @@ int32_t *glg_timestep_dev(glg_handle *h);          /* int32 [B] */
 int32_t *glg_table_dev(glg_handle *h);             /* int32 [B] weather table of each env */
 double *glg_time_dev(glg_handle *h);               /* double [2][B]: day_of_year, hour_of_day */
 /* Finished-episode statistics (sums since the last clear): [0] episodes, [1] sum return, [2] sum length,
- * [3..13] sums of the 11 info entries, [14] non-finite terminations, [15] reserved. */
+ * [3..13] sums of the 11 info entries, [14] non-finite terminations, [15] RK4 micro-steps executed, summed over envs
+ * (counted by kernel B's guarded loop, i.e. with parametric uncertainty or the graded integrator; 0 otherwise). */
 double *glg_stats_dev(glg_handle *h);
 int glg_clear_stats(glg_handle *h, void *stream);
 

@@ -473,17 +473,56 @@ static int glgo_micro_steps(const double *x, const double *p, double h) {
 /* Classical RK4, n_sub equal nominal substeps over [0,dt] (each split into m micro-steps by the guard above), inputs
  * held constant (greenlight_model.cpp:59-63 passes p=[u;d;p] as integrator parameters => zero-order hold).
  *   k1=f(x) ; k2=f(x+h/2 k1) ; k3=f(x+h/2 k2) ; k4=f(x+h k3) ; x += h/6 (k1+2k2+2k3+k4)                   */
-int glgo_evalf(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub,
-               double *x_next) {
-    double xc[GLGO_NX], xs[GLGO_NX], k[GLGO_NX], acc[GLGO_NX];
+/* Transient-stiffness estimate (opt-in): the fast modes of the model are the cover pair {tCovIn, tCovE}
+ * (conduction 2 hCov/capCov = 0.653 1/s, parameter-only) and the thin top compartment, whose exchange rate grows with the
+ * screen air flux fScr (~ sqrt of the air/top density difference) and the roof ventilation fVentRoof.  Measured over 1750
+ * points (rule-based and random-action trajectories, adversarial air/top temperature differences up to 30 K, wind to 20 m/s;
+ * numpy eigenvalues of the finite-difference Jacobian, all real): max|Re lambda| = (rho cp / capTop) (1.5 fScr + fVentRoof)
+ * x [0.95, 1.05] whenever it exceeds the cover mode.  lambda_est = 1.07 max(cover mode, that expression, CO2/vapour mode). */
+static double glgo_stiffness(const double *p, const double *a) {
+    const double fScr = fabs(a[144]), fVent = fabs(a[136]);
+    const double capCov = a[33] < a[34] ? a[33] : a[34];
+    const double lam_cov = 2.0 * fabs(1. / (p[73] / p[71])) / capCov;
+    const double lam_top = (p[111] * p[23] / p[120]) * (1.5 * fScr + fVent);
+    const double lam_gas = (fScr + fVent) / p[123];
+    double l = lam_cov > lam_top ? lam_cov : lam_top;
+    if (lam_gas > l) l = lam_gas;
+    return 1.07 * l;
+}
+#define GLGO_STIFF_CFL 2.5 /* RK4's real-axis stability limit is 2.785 */
+#ifndef GLGO_GRADED_SUBSTEPS
+#define GLGO_GRADED_SUBSTEPS 5
+#define GLGO_GRADED_M 4
+#endif
+
+/* Classical RK4, n_sub equal nominal substeps over [0,dt] (each split into m micro-steps by the guards above), inputs
+ * held constant (greenlight_model.cpp:59-63 passes p=[u;d;p] as integrator parameters => zero-order hold).
+ *   k1=f(x) ; k2=f(x+h/2 k1) ; k3=f(x+h/2 k2) ; k4=f(x+h k3) ; x += h/6 (k1+2k2+2k3+k4)
+ * stiff_guard != 0 adds the transient-stiffness rule m >= 1 + floor(h lambda_est / 2.5), evaluated from the auxiliaries of the
+ * first k1 of every nominal substep (no extra evaluation). */
+int glgo_evalf_ex(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub, int stiff_guard,
+                  double *x_next, long *n_micro) {
+    double xc[GLGO_NX], xs[GLGO_NX], k[GLGO_NX], acc[GLGO_NX], a[GLGO_NA];
     const double h_nom = dt / (double)n_sub;
     int s, q, i, bad = 0;
+    long total = 0;
     memcpy(xc, x, sizeof xc);
     for (s = 0; s < n_sub; ++s) {
-        const int m = glgo_micro_steps(xc, p, h_nom);
-        const double h = h_nom / (double)m;
+        int m = glgo_micro_steps(xc, p, h_nom);
+        double h;
+        glgo_aux_rhs(xc, u, d, p, a, k); /* k1 of the first micro-step */
+        if ((stiff_guard & 2) && s < GLGO_GRADED_SUBSTEPS && m < GLGO_GRADED_M) m = GLGO_GRADED_M;
+        if (stiff_guard & 1) {
+            const double ls = glgo_stiffness(p, a);
+            int ms = 1 + (int)floor(h_nom * ls / GLGO_STIFF_CFL);
+            if (!(ms >= 1)) ms = 1; /* NaN */
+            if (ms > GLGO_MAX_MICRO) ms = GLGO_MAX_MICRO;
+            if (ms > m) m = ms;
+        }
+        h = h_nom / (double)m;
+        total += m;
         for (q = 0; q < m; ++q) {
-            glgo_rhs(xc, u, d, p, k);
+            if (q > 0) glgo_rhs(xc, u, d, p, k);
             for (i = 0; i < GLGO_NX; ++i) { acc[i] = k[i]; xs[i] = xc[i] + (0.5 * h) * k[i]; }
             glgo_rhs(xs, u, d, p, k);
             for (i = 0; i < GLGO_NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = xc[i] + (0.5 * h) * k[i]; }
@@ -497,7 +536,12 @@ int glgo_evalf(const double *x, const double *u, const double *d, const double *
         x_next[i] = xc[i];
         if (!isfinite(xc[i])) bad = 1;
     }
+    if (n_micro) *n_micro = total;
     return bad;
+}
+int glgo_evalf(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub,
+               double *x_next) {
+    return glgo_evalf_ex(x, u, d, p, dt, n_sub, 0, x_next, NULL);
 }
 
 /* tiny fork-join helper: n_threads pthreads, thread t handles items t, t+n, t+2n, ... */
@@ -648,7 +692,8 @@ int glgo_env_step(const glgo_env_cfg *c, glgo_env *e, const double *p_nom, const
         glgo_param_noise(p_nom, noise34, p_step);
         pp = p_step;
     }
-    bad = glgo_evalf(e->x, e->u, e->weather + (size_t)e->timestep * GLGO_ND, pp, c->dt, c->n_sub, x_next);
+    bad = glgo_evalf_ex(e->x, e->u, e->weather + (size_t)e->timestep * GLGO_ND, pp, c->dt, c->n_sub, c->stiff_guard, x_next,
+                        &e->n_micro);
     memcpy(e->x, x_next, sizeof x_next);
     if (bad) e->terminated = 1; /* mirrors the bare except -> terminated (tomato_env.py:121-123) */
 

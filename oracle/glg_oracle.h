@@ -36,6 +36,10 @@ extern "C" {
 void glgo_aux_rhs(const double *x, const double *u, const double *d, const double *p, double *a, double *dxdt);
 /* R2: ODE() */
 void glgo_rhs(const double *x, const double *u, const double *d, const double *p, double *dxdt);
+/* glgo_evalf with options: stiff_guard != 0 adds the transient-stiffness micro-step rule; n_micro (may be NULL) receives the
+ * number of RK4 micro-steps executed. */
+int glgo_evalf_ex(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub, int stiff_guard,
+                  double *x_next, long *n_micro);
 /* R3/R4: x_next = RK4^n_sub(x; u,d,p const).  returns 0, or 1 if the result is not finite */
 int glgo_evalf(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub,
                double *x_next);
@@ -55,6 +59,7 @@ typedef struct glgo_env_cfg {
     double elec_price, heating_price, co2_price, fruit_price, dmfm;
     double uncertainty_scale;
     double fixed_costs;     /* rewards.py:69-70,154: yearly/365/(86400//dt); reported in info only */
+    int stiff_guard;        /* opt-in transient-stiffness micro-step rule (glgo_evalf_ex); 0 = the fixed-step contract */
 } glgo_env_cfg;
 
 typedef struct glgo_env {
@@ -64,6 +69,7 @@ typedef struct glgo_env {
     int terminated;
     const double *weather; /* [rows][10] */
     int weather_rows;
+    long n_micro;          /* RK4 micro-steps executed by the last step */
 } glgo_env;
 
 void glgo_init_state(const double *d0, double *x);                                   /* utils.py:13-46 */

@@ -18,13 +18,13 @@ class EnvCfg(C.Structure):
                 ("con_low", C.c_double * 3), ("con_high", C.c_double * 3),
                 ("elec_price", C.c_double), ("heating_price", C.c_double), ("co2_price", C.c_double),
                 ("fruit_price", C.c_double), ("dmfm", C.c_double), ("uncertainty_scale", C.c_double),
-                ("fixed_costs", C.c_double)]
+                ("fixed_costs", C.c_double), ("stiff_guard", C.c_int)]
 
 
 class Env(C.Structure):
     _fields_ = [("x", C.c_double * 28), ("x_prev", C.c_double * 28), ("u", C.c_double * 6),
                 ("day_of_year", C.c_double), ("hour_of_day", C.c_double), ("timestep", C.c_int),
-                ("terminated", C.c_int), ("weather", _DP), ("weather_rows", C.c_int)]
+                ("terminated", C.c_int), ("weather", _DP), ("weather_rows", C.c_int), ("n_micro", C.c_long)]
 
 
 def build():
@@ -45,6 +45,8 @@ def load():
         lib.glgo_rhs.argtypes = [_DP] * 5
         lib.glgo_evalf.argtypes = [_DP, _DP, _DP, _DP, C.c_double, C.c_int, _DP]
         lib.glgo_evalf.restype = C.c_int
+        lib.glgo_evalf_ex.argtypes = [_DP, _DP, _DP, _DP, C.c_double, C.c_int, C.c_int, _DP, C.POINTER(C.c_long)]
+        lib.glgo_evalf_ex.restype = C.c_int
         lib.glgo_evalf_batch.argtypes = [_DP, _DP, _DP, _DP, C.c_int, C.c_double, C.c_int, _DP, C.c_int, C.c_int]
         lib.glgo_evalf_batch.restype = C.c_int
         lib.glgo_init_state.argtypes = [_DP, _DP]
@@ -104,6 +106,15 @@ def evalf(x, u, d, p, dt=900.0, n_sub=600):
                             P(np.ascontiguousarray(d, dtype=np.float64)), P(np.ascontiguousarray(p, dtype=np.float64)),
                             dt, n_sub, P(y))
     return y, bad
+
+
+def evalf_ex(x, u, d, p, dt=900.0, n_sub=600, stiff_guard=0):
+    """-> (x_next, bad, RK4 micro-steps executed)"""
+    y, n = np.zeros(28), C.c_long(0)
+    bad = load().glgo_evalf_ex(P(np.ascontiguousarray(x, dtype=np.float64)), P(np.ascontiguousarray(u, dtype=np.float64)),
+                               P(np.ascontiguousarray(d, dtype=np.float64)), P(np.ascontiguousarray(p, dtype=np.float64)),
+                               float(dt), int(n_sub), int(stiff_guard), P(y), C.byref(n))
+    return y, bool(bad), n.value
 
 
 def evalf_batch(x, u, d, p, dt=900.0, n_sub=600, n_threads=0):

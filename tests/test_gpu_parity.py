@@ -559,6 +559,68 @@ def test_config3_full_size_properties():
     assert rel_err(xs.cpu().numpy(), x64.cpu().numpy()) <= 1e-4
 
 
+@pytest.mark.parametrize("role_warps", [4, 8])
+def test_graded_integrator_matches_oracle(role_warps, weather0, params64):
+    """integrator="graded" (n_sub 300, graded start + transient-stiffness rule): teacher-forced parity with the oracle's
+    glgo_evalf_ex(stiff_guard=3) under the rule-based controller through the B.6 transient steps, the executed-micro-step
+    counter (stats[15]) against the oracle's count, and the errors glg_create must raise."""
+    from glgym.controller import RuleBasedController
+    from glgym import _lib
+    B = 33
+    env = make_env(B, integrator="graded", role_warps=role_warps)
+    assert env.n_sub == 300
+    env.reset()
+    cfg = ob.default_cfg(n_sub=300)
+    cfg.stiff_guard = 3
+    orc = ob.OracleEnv(weather0, params64, cfg)
+    s29 = RuleBasedController().settings_vector()
+    env.episode_stats(clear=True)
+    total = 0
+    for s in range(350):
+        obs, rew, done, _ = env.step_rule_based()
+        o, r, dn, info = orc.step_rule(s29)
+        total += orc.e.n_micro
+        x, u, k = env.get_state()
+        assert rel_err(x[32], orc.x) <= STEP_TOL and np.abs(u[0] - orc.u).max() <= 1e-11, s
+        assert abs(rew[1] - r) <= 1e-9
+        env.set_state(x=np.tile(orc.x, (B, 1)))
+    assert env.stats_t[15].item() == B * total and total >= 350 * 315
+    env.close()
+    # the transient-stiffness rule itself: open screens and vents, 18 m/s wind, top compartment 25 K below the air
+    Wx = weather0.copy()
+    Wx[:, 4] = 18.0
+    env = make_env(B, integrator="graded", role_warps=role_warps, weather_tables=Wx)
+    env.reset()
+    orc = ob.OracleEnv(Wx, params64, cfg)
+    x0 = orc.x.copy()
+    x0[3] = x0[2] - 25.0
+    orc.e.x[:] = list(x0)
+    env.set_state(x=np.tile(x0, (B, 1)))
+    env.episode_stats(clear=True)
+    uc = np.array([0.0, 0.0, 0.0, 1.0, 0.0, 0.0])
+    extra = 0
+    for s in range(3):
+        env.step_raw_control(np.tile(uc, (B, 1)))
+        orc.step(control=uc)
+        extra += orc.e.n_micro - 315
+        x, u, k = env.get_state()
+        assert rel_err(x[5], orc.x) <= STEP_TOL, s
+        env.set_state(x=np.tile(orc.x, (B, 1)))
+    assert extra > 0 and env.stats_t[15].item() == B * (3 * 315 + extra)
+    env.close()
+    with pytest.raises(_lib.GlgError):
+        make_env(4, integrator="graded", role_warps=1)
+    # free-running season prefix in fp32 + graded stays close to fp64 + graded
+    e64, e32 = make_env(64, integrator="graded"), make_env(64, integrator="graded", precision="fp32")
+    e64.reset_tensor(); e32.reset_tensor()
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    for s in range(100):
+        a = torch.rand(64, 6, device="cuda", generator=g) * 2 - 1
+        e64.step_tensor(a); e32.step_tensor(a)
+    assert rel_err(e32.state_t.cpu().numpy(), e64.state_t.cpu().numpy()) <= 1e-4
+    e64.close(); e32.close()
+
+
 def test_fp32_mode_full_episode():
     B, N = 8, 5760
     e64, e32 = make_env(B, n_sub=600, precision="fp64"), make_env(B, n_sub=600, precision="fp32")

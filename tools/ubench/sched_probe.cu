@@ -89,3 +89,31 @@ __global__ void __launch_bounds__(256, 2) k_probe(const __grid_constant__ GlgUni
     for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) Hs[H_COUNT * 32 + i] = s_part[i];
 }
 #endif
+#if VARIANT >= 10  // VARIANT = 10 + n: the first n groups inlined behind a switch (where does ptxas stop interleaving?)
+__global__ void __launch_bounds__(256, 2) k_probe(const __grid_constant__ GlgUniform U, double *xs, double *Hs, int n) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ double s_xs[29 * 32], s_H[H_COUNT * 32], s_part[80 * 32];
+    for (int i = threadIdx.x; i < 28 * 32; i += blockDim.x) s_xs[i] = xs[i];
+    for (int i = threadIdx.x; i < H_COUNT * 32; i += blockDim.x) s_H[i] = Hs[i];
+    __syncthreads();
+    GlgColT<double, 32> Hc{s_H + lane};
+    const GlgXsCol<double> X{s_xs + lane};
+    double u[6] = {0.5, 0.5, 0.5, 0.5, 0.5, 0.5};
+    constexpr int NG = VARIANT - 10;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        switch (warp) {
+            case 0: if (NG > 0) glg_run_group<6, false>(U, GlgConstView{U.C}, Hc, u, X, s_part + lane); break;
+            case 1: if (NG > 1) glg_run_group<7, false>(U, GlgConstView{U.C}, Hc, u, X, s_part + lane); break;
+            case 2: if (NG > 2) glg_run_group<5, false>(U, GlgConstView{U.C}, Hc, u, X, s_part + lane); break;
+            case 3: if (NG > 3) glg_run_group<4, false>(U, GlgConstView{U.C}, Hc, u, X, s_part + lane); break;
+            case 4: if (NG > 4) glg_run_group<2, false>(U, GlgConstView{U.C}, Hc, u, X, s_part + lane); break;
+            case 5: if (NG > 5) glg_run_group<0, false>(U, GlgConstView{U.C}, Hc, u, X, s_part + lane); break;
+            case 6: if (NG > 6) glg_run_group<3, false>(U, GlgConstView{U.C}, Hc, u, X, s_part + lane); break;
+            default: if (NG > 7) glg_run_group<1, false>(U, GlgConstView{U.C}, Hc, u, X, s_part + lane); break;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) Hs[H_COUNT * 32 + i] = s_part[i];
+}
+#endif
