@@ -328,7 +328,7 @@ static cudaError_t launch_step(glg_handle *h, const GlgStepArgs &a, cudaStream_t
     return e;
 }
 
-template <class T, bool GENERAL, bool NOISY, int NR>
+template <class T, bool GENERAL, bool NOISY, int NR, bool GRADED>
 static cudaError_t launch_step_roles_t(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
 #if GLG_NOINLINE_MASK
     {
@@ -340,7 +340,7 @@ static cudaError_t launch_step_roles_t(glg_handle *h, const GlgStepArgs &a, cuda
     static size_t attr_smem_dev[64] = {};  // largest size opted into so far, per device (the attribute is per context)
     size_t &attr_smem = attr_smem_dev[h->cfg.device & 63];
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(glg_step_roles_kernel<T, GENERAL, NOISY, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(glg_step_roles_kernel<T, GENERAL, NOISY, NR, GRADED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_smem = smem;
     }
@@ -350,14 +350,18 @@ static cudaError_t launch_step_roles_t(glg_handle *h, const GlgStepArgs &a, cuda
         cudaMemcpyToSymbol(glg_prof_mask_dev, &mask, sizeof(int));
     }
 #endif
-    glg_step_roles_kernel<T, GENERAL, NOISY, NR><<<(a.B + a.role_lanes - 1) / a.role_lanes, 32 * NR, smem, s>>>(h->uni, a);
+    glg_step_roles_kernel<T, GENERAL, NOISY, NR, GRADED><<<(a.B + a.role_lanes - 1) / a.role_lanes, 32 * NR, smem, s>>>(h->uni, a);
     return cudaGetLastError();
 }
 template <bool GENERAL, bool NOISY, int NR>
 static cudaError_t launch_step_roles(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
     // precision 0: fp64 parity mode ; 1: flux groups in fp32, RK4 state / stage sums / epilogue in fp64
-    return h->cfg.precision == 1 ? launch_step_roles_t<float, GENERAL, NOISY, NR>(h, a, s)
-                                 : launch_step_roles_t<double, GENERAL, NOISY, NR>(h, a, s);
+    // the guarded loop is part of every NOISY variant; with nominal parameters the graded integrator has its own variant
+    if (!NOISY && h->cfg.integrator == 1)
+        return h->cfg.precision == 1 ? launch_step_roles_t<float, GENERAL, false, NR, true>(h, a, s)
+                                     : launch_step_roles_t<double, GENERAL, false, NR, true>(h, a, s);
+    return h->cfg.precision == 1 ? launch_step_roles_t<float, GENERAL, NOISY, NR, false>(h, a, s)
+                                 : launch_step_roles_t<double, GENERAL, NOISY, NR, false>(h, a, s);
 }
 
 // Kernel variant: 1 = kernel A (one thread per env), 4 / 8 = kernel B with 4 / 8 warps per 32 envs.
@@ -382,9 +386,7 @@ static int step_common(glg_handle *h, const float *actions_dev, const double *co
     a.raw_control = rule_based ? 2 : (controls_dev ? 1 : 0);
     for (int i = 0; i < GLG_NCTRL; ++i) a.ctrl[i] = h->ctrl[i];
     a.noise = noise_dev;
-    // kernel B compiles its guarded (micro-stepping) loop into the parametric-uncertainty variants; the graded integrator uses
-    // them too (scale 0 leaves the float32 parameter table unchanged)
-    const bool noisy = (h->cfg.uncertainty_scale != 0.0) || (noise_dev != nullptr) || (h->cfg.integrator == 1);
+    const bool noisy = (h->cfg.uncertainty_scale != 0.0) || (noise_dev != nullptr);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
     const int rw = pick_role_warps(h);

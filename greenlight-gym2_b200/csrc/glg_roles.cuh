@@ -192,12 +192,13 @@ __device__ __forceinline__ void glg_owner_fetch(GlgOwnerRegs<NR> &o, const int *
 }
 template <int NR, class T>
 __device__ __forceinline__ void glg_owner_update(const GlgOwnerRegs<NR> &o, int warp, T *xs_col, const T *part_col,
-                                                 double *xo, double *acc, int stage, double h) {
+                                                 double *xo, double *acc, int stage, double h, double h_sixth) {
     // stage 0..2: acc = (stage ? acc : 0) + w k ; xs = x + c k        stage 3: x += h/6 (acc + k) ; xs = x
+    // h_sixth = h / 6.0 is passed in: the division is done once per (micro-)step size, not once per evaluation
     const bool last = stage == 3;
     const double w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
     const double keep = stage == 0 ? 0.0 : 1.0;
-    const double m = last ? h / 6.0 : (stage == 2 ? h : 0.5 * h);
+    const double m = last ? h_sixth : (stage == 2 ? h : 0.5 * h);
     const double can_scale = (double)part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES];
     double sum[GlgOwnerRegs<NR>::NJ];
     glg_static_for<0, GlgOwnerRegs<NR>::NJ>([&](auto jc) {
@@ -271,7 +272,7 @@ __device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv,
 // used it last (glg_capi.cu: bind_uniform), after a device synchronise -- alternating handles on one device serialises.
 __constant__ GlgUniform glg_uni_c;
 
-template <int G, bool GENERAL, bool NOISY, class T>
+template <int G, bool GENERAL, bool NOISY, bool GUARD, class T>
 __device__ __noinline__ void glg_group_call(const T *xs_col, T *part_col, T *h_col, T *c_col, double thScr, double blScr) {
     const GlgUniform &U = glg_uni_c;
     const GlgColT<T, GLG_ROLE_LANES> Hc{h_col};
@@ -279,9 +280,9 @@ __device__ __noinline__ void glg_group_call(const T *xs_col, T *part_col, T *h_c
     const double u[GLG_NU] = {0.0, 0.0, thScr, 0.0, 0.0, blScr};  // only G1's GENERAL terms read the raw screen controls
     if (NOISY) {
         const GlgColT<T, GLG_ROLE_LANES> Cc{c_col};
-        glg_run_group<G, GENERAL, NOISY>(U, Cc, Hc, u, X, part_col);
+        glg_run_group<G, GENERAL, GUARD>(U, Cc, Hc, u, X, part_col);
     } else {
-        glg_run_group<G, GENERAL, NOISY>(U, GlgKView<T>::c(U), Hc, u, X, part_col);
+        glg_run_group<G, GENERAL, GUARD>(U, GlgKView<T>::c(U), Hc, u, X, part_col);
     }
 }
 
@@ -293,22 +294,22 @@ __device__ __noinline__ void glg_group_call(const T *xs_col, T *part_col, T *h_c
 // pipe (1148 DFMA-class instructions per evaluation = 631 cycles per sub-partition at 2.2 cycles each), and once both
 // have ILP they queue on it.  Kept as an experiment switch for the round-2 work on group balance.
 
-template <int G, bool GENERAL, bool NOISY, class T, class CV>
+template <int G, bool GENERAL, bool NOISY, bool GUARD, class T, class CV>
 __device__ __forceinline__ void glg_dispatch_group(const GlgUniform &U, const CV &Cv, const T *xs_col, T *part_col, T *h_col,
                                                    T *c_col, const double *u) {
     if ((GLG_NOINLINE_MASK >> G) & 1) {
-        glg_group_call<G, GENERAL, NOISY, T>(xs_col, part_col, h_col, c_col, u[2], u[5]);
+        glg_group_call<G, GENERAL, NOISY, GUARD, T>(xs_col, part_col, h_col, c_col, u[2], u[5]);
     } else {
         const GlgColT<T, GLG_ROLE_LANES> Hc{h_col};
         const GlgXsCol<T> X{xs_col};
-        glg_run_group<G, GENERAL, NOISY>(U, Cv, Hc, u, X, part_col);
+        glg_run_group<G, GENERAL, GUARD>(U, Cv, Hc, u, X, part_col);
     }
 }
 
-template <bool GENERAL, bool NOISY, int NR, class T, class CV>
+template <bool GENERAL, bool NOISY, bool GUARD, int NR, class T, class CV>
 __device__ __forceinline__ void glg_run_warp_groups(int warp, const GlgUniform &U, const CV &Cv, const T *xs_col, T *part_col,
                                                     T *h_col, T *c_col, const double *u) {
-#define GLG_CALL(G) glg_dispatch_group<G, GENERAL, NOISY, T>(U, Cv, xs_col, part_col, h_col, c_col, u)
+#define GLG_CALL(G) glg_dispatch_group<G, GENERAL, NOISY, GUARD, T>(U, Cv, xs_col, part_col, h_col, c_col, u)
     if (NR == 8) {
         switch (warp) {
             case 0: GLG_CALL(0); break;
@@ -331,7 +332,8 @@ __device__ __forceinline__ void glg_run_warp_groups(int warp, const GlgUniform &
 #undef GLG_CALL
 }
 
-template <class T, bool GENERAL, bool NOISY, int NR>
+// GRADED: compile the guarded (micro-stepping) loop although the parameters are nominal (NOISY variants always have it).
+template <class T, bool GENERAL, bool NOISY, int NR, bool GRADED = false>
 __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const __grid_constant__ GlgUniform U,
                                                                           const __grid_constant__ GlgStepArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -427,12 +429,14 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
         acc[j] = 0.0;
     }
     const double h_nom = A.dt / (double)A.n_sub;
+    const double h_nom_sixth = h_nom / 6.0;
     int n_micro = 0;  // RK4 micro-steps this env executed (guarded loop only)
 #ifdef GLG_PROFILE_GROUPS
     long long t_grp = 0, t_b1 = 0, t_own = 0, t_b2 = 0;
 #endif
-    if (!NOISY) {
-        // nominal parameters: plain fixed-step loop (the harvest guard cannot trigger: the crop approaches cLeafMax from
+    constexpr bool GUARDED = NOISY || GRADED;
+    if (!GUARDED) {
+        // nominal parameters, fixed-step integrator: plain loop (the harvest guard cannot trigger: the crop approaches cLeafMax from
         // below and lambda stays ~1e-5 1/s; the guarded loop's extra state costs ~8 % at B = 4096)
         const int n_eval = 4 * A.n_sub;
 #pragma unroll 1
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
 #ifdef GLG_PROFILE_GROUPS
             const long long c0 = clock64();
 #endif
-            glg_run_warp_groups<GENERAL, NOISY, NR, T>(warp, U, GlgKView<T>::c(U), xs_col, part_col, s_H + lane, s_C + lane, u);
+            glg_run_warp_groups<GENERAL, NOISY, false, NR, T>(warp, U, GlgKView<T>::c(U), xs_col, part_col, s_H + lane, s_C + lane, u);
 #if GLG_NOINLINE_MASK
             glg_owner_fetch<NR>(own, s_owntab + warp * GLG_OWNER_TAB_WORDS);
 #endif
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
 #if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
             if ((glg_prof_mask_dev >> 8) & 1)
 #endif
-            glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, ev & 3, h_nom);
+            glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, ev & 3, h_nom, h_nom_sixth);
 #ifdef GLG_PROFILE_GROUPS
             const long long c3 = clock64();
 #endif
@@ -470,10 +474,11 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
         // window) and, with integrator = 1, the graded start of the interval and the transient-stiffness rule.  Lanes with a
         // smaller m idle with h = 0 for the remaining micro-steps of the CTA, so an env's result never depends on its CTA mates.
         int sub = 0, q = 0, stage = 0, m_lane = 1, m_cta = 1;
-        double h_lane = h_nom;
+        double h_lane = h_nom, h_sixth = h_nom_sixth;
 #pragma unroll 1
         while (sub < A.n_sub) {
-            glg_run_warp_groups<GENERAL, NOISY, NR, T>(warp, U, Cc, xs_col, part_col, s_H + lane, s_C + lane, u);
+            if (NOISY) glg_run_warp_groups<GENERAL, true, true, NR, T>(warp, U, Cc, xs_col, part_col, s_H + lane, s_C + lane, u);
+            else glg_run_warp_groups<GENERAL, false, true, NR, T>(warp, U, GlgKView<T>::c(U), xs_col, part_col, s_H + lane, s_C + lane, u);
 #if GLG_NOINLINE_MASK
             glg_owner_fetch<NR>(own, s_owntab + warp * GLG_OWNER_TAB_WORDS);
 #endif
@@ -482,17 +487,18 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
                 if (q == 0) {
                     m_lane = glg_micro_steps_from_lambda((double)part_col[GLG_SLOT_LAMBDA * NL], h_nom);
                     if (A.integrator == 1) {
-                        int ms = 1 + (int)floor(h_nom * (double)part_col[GLG_SLOT_STIFF * NL] * (1.0 / GLG_STIFF_CFL));
+                        int ms = 1 + (int)floor(h_nom * (double)part_col[GLG_SLOT_STIFF * NL] / GLG_STIFF_CFL);
                         ms = ms > GLG_MAX_MICRO ? GLG_MAX_MICRO : (ms < 1 ? 1 : ms);  // ms < 1 only for a NaN estimate
                         if (sub < GLG_GRADED_SUBSTEPS && ms < GLG_GRADED_M) ms = GLG_GRADED_M;
                         m_lane = max(m_lane, ms);
                     }
                     n_micro += m_lane;
                     m_cta = __reduce_max_sync(0xffffffffu, m_lane);  // every warp sees the same 32 envs
+                    h_lane = h_nom / (double)m_lane;
+                    h_sixth = h_lane / 6.0;
                 }
-                h_lane = q < m_lane ? h_nom / (double)m_lane : 0.0;
             }
-            glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, stage, h_lane);
+            glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, stage, q < m_lane ? h_lane : 0.0, q < m_lane ? h_sixth : 0.0);
             __syncthreads();
             if (++stage == 4) {
                 stage = 0;
@@ -538,7 +544,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
         s_tbl_t[lane] = o.tbl_term;
         s_k_t[lane] = o.k_term;
         glg_stats_reduce(A, active, bad, o);
-        if (NOISY) {
+        if (GUARDED) {
             const int tot = __reduce_add_sync(0xffffffffu, active ? n_micro : 0);
             if (lane == 0 && tot > 0) atomicAdd(&A.stats[15], (double)tot);
         }
