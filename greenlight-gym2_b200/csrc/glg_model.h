@@ -636,6 +636,7 @@ GLG_HD void glg_rhs(const KV &K, const CV &C, const HV &H, const P &p, const dou
 #define GLG_GRADED_SUBSTEPS 5
 #define GLG_GRADED_M 4
 #define GLG_STIFF_CFL 2.5
+#define GLG_STIFF_INV_CFL 0.4  // the rule multiplies by this constant (oracle and kernels alike)
 template <class T>
 GLG_HD T glg_harvest_lambda(T sigLeaf, T sigFruit) {  // sig = 1/(1+exp(-k (c - cMax)))
     return T(5e4 * (2.0 * 4.6052 / 1e4)) * fmax(sigLeaf, sigFruit);  // harvest speed in window-widths per second

@@ -487,15 +487,17 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
                 if (q == 0) {
                     m_lane = glg_micro_steps_from_lambda((double)part_col[GLG_SLOT_LAMBDA * NL], h_nom);
                     if (A.integrator == 1) {
-                        int ms = 1 + (int)floor(h_nom * (double)part_col[GLG_SLOT_STIFF * NL] / GLG_STIFF_CFL);
+                        int ms = 1 + (int)floor(h_nom * (double)part_col[GLG_SLOT_STIFF * NL] * GLG_STIFF_INV_CFL);
                         ms = ms > GLG_MAX_MICRO ? GLG_MAX_MICRO : (ms < 1 ? 1 : ms);  // ms < 1 only for a NaN estimate
                         if (sub < GLG_GRADED_SUBSTEPS && ms < GLG_GRADED_M) ms = GLG_GRADED_M;
                         m_lane = max(m_lane, ms);
                     }
                     n_micro += m_lane;
                     m_cta = __reduce_max_sync(0xffffffffu, m_lane);  // every warp sees the same 32 envs
-                    h_lane = h_nom / (double)m_lane;
-                    h_sixth = h_lane / 6.0;
+                    // reciprocal + multiply instead of IEEE divisions: three of them (with their slow paths) pushed the loop
+                    // body past the 32 KB instruction cache; the step size differs from h_nom/m by at most 1 ulp
+                    h_lane = h_nom * glg_rcp((double)m_lane);
+                    h_sixth = h_lane * (1.0 / 6.0);
                 }
             }
             glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, stage, q < m_lane ? h_lane : 0.0, q < m_lane ? h_sixth : 0.0);

@@ -489,7 +489,7 @@ static double glgo_stiffness(const double *p, const double *a) {
     if (lam_gas > l) l = lam_gas;
     return 1.07 * l;
 }
-#define GLGO_STIFF_CFL 2.5 /* RK4's real-axis stability limit is 2.785 */
+#define GLGO_STIFF_INV_CFL 0.4 /* 1/2.5; RK4's real-axis stability limit is 2.785 */
 #ifndef GLGO_GRADED_SUBSTEPS
 #define GLGO_GRADED_SUBSTEPS 5
 #define GLGO_GRADED_M 4
@@ -498,7 +498,8 @@ static double glgo_stiffness(const double *p, const double *a) {
 /* Classical RK4, n_sub equal nominal substeps over [0,dt] (each split into m micro-steps by the guards above), inputs
  * held constant (greenlight_model.cpp:59-63 passes p=[u;d;p] as integrator parameters => zero-order hold).
  *   k1=f(x) ; k2=f(x+h/2 k1) ; k3=f(x+h/2 k2) ; k4=f(x+h k3) ; x += h/6 (k1+2k2+2k3+k4)
- * stiff_guard != 0 adds the transient-stiffness rule m >= 1 + floor(h lambda_est / 2.5), evaluated from the auxiliaries of the
+ * stiff_guard bit 0 adds the transient-stiffness rule m >= 1 + floor(h lambda_est * 0.4), bit 1 the graded start of the
+ * interval (first 5 nominal substeps split in 4), evaluated from the auxiliaries of the
  * first k1 of every nominal substep (no extra evaluation). */
 int glgo_evalf_ex(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub, int stiff_guard,
                   double *x_next, long *n_micro) {
@@ -514,7 +515,7 @@ int glgo_evalf_ex(const double *x, const double *u, const double *d, const doubl
         if ((stiff_guard & 2) && s < GLGO_GRADED_SUBSTEPS && m < GLGO_GRADED_M) m = GLGO_GRADED_M;
         if (stiff_guard & 1) {
             const double ls = glgo_stiffness(p, a);
-            int ms = 1 + (int)floor(h_nom * ls / GLGO_STIFF_CFL);
+            int ms = 1 + (int)floor(h_nom * ls * GLGO_STIFF_INV_CFL);
             if (!(ms >= 1)) ms = 1; /* NaN */
             if (ms > GLGO_MAX_MICRO) ms = GLGO_MAX_MICRO;
             if (ms > m) m = ms;
