@@ -464,6 +464,43 @@ def test_free_running_episode_vs_oracle(weather0, params64):
     env.close()
 
 
+def test_free_running_season_graded_integrator(weather0, params64):
+    """The same episode gate for integrator="graded": a full free-running season (random-walk controls) on the GPU against
+    the oracle's graded RK4 (glgo_evalf_ex, stiff_guard = 3), <= 1e-6 per state at episode end, same return, and the executed
+    RK4 steps counted by the kernel equal the oracle's."""
+    B, N = 2, 5760
+    rng = np.random.default_rng(321)
+    env = make_env(B, integrator="graded", role_warps=8)
+    env.reset()
+    cfg = ob.default_cfg(n_sub=300)
+    cfg.stiff_guard = 3
+    orc = [ob.OracleEnv(weather0, params64, cfg) for _ in range(B)]
+    actions = rng.uniform(-1, 1, (N, B, 6)).astype(np.float32)
+
+    def run_oracle(b):
+        tot, micro = 0.0, 0
+        for s in range(N):
+            o, r, dn, _ = orc[b].step(action=actions[s, b])
+            tot += r
+            micro += orc[b].e.n_micro
+        return tot, micro
+    env.episode_stats(clear=True)
+    ret_gpu = torch.zeros(B, dtype=torch.float64, device="cuda")
+    with cf.ThreadPoolExecutor(B) as ex:
+        fut = [ex.submit(run_oracle, b) for b in range(B)]
+        a_dev = torch.as_tensor(actions, device="cuda")
+        for s in range(N):
+            obs, rew, done = env.step_tensor(a_dev[s])
+            ret_gpu += rew
+        res = [f.result() for f in fut]
+    x_gpu = env.state_t.cpu().numpy().T
+    for b in range(B):
+        assert rel_err(x_gpu[b], orc[b].x) <= EPISODE_TOL, (b, rel_err(x_gpu[b], orc[b].x))
+        assert abs(ret_gpu[b].item() - res[b][0]) <= 1e-6 * abs(res[b][0])
+    assert env.stats_t[15].item() == sum(r[1] for r in res)
+    env.close()
+
+
 def test_handle_errors_are_loud(L):
     from glgym import _lib
     cfg = _lib.GlgConfig()
