@@ -136,10 +136,9 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     if (cfg->num_envs < 1 || cfg->n_sub < 1 || cfg->N < 0 || cfg->Np < 0 || !(cfg->dt > 0) ||
         (cfg->precision != 0 && cfg->precision != 1) ||
         (cfg->role_warps != 0 && cfg->role_warps != 1 && cfg->role_warps != 4 && cfg->role_warps != 8) ||
-        (cfg->integrator != 0 && cfg->integrator != 1) ||
-        ((cfg->precision == 1 || cfg->integrator == 1) && cfg->role_warps == 1)) {
-        g_create_error = ((cfg->precision == 1 || cfg->integrator == 1) && cfg->role_warps == 1)
-                             ? "glg_create: the fp32 throughput mode and the graded integrator run on kernel B only (role_warps 0, 4 or 8)"
+        (cfg->integrator != 0 && cfg->integrator != 1) || (cfg->precision == 1 && cfg->role_warps == 1)) {
+        g_create_error = (cfg->precision == 1 && cfg->role_warps == 1)
+                             ? "glg_create: the fp32 throughput mode runs on kernel B only (role_warps 0, 4 or 8)"
                              : "glg_create: invalid num_envs / n_sub / N / Np / dt / precision / role_warps / integrator";
         return GLG_ERR_ARG;
     }
@@ -578,19 +577,26 @@ static thread_local std::string g_evalf_error;
 
 template <bool GENERAL, bool PER_ENV_P>
 static cudaError_t launch_evalf(const GlgUniform &uni, const double *x, const double *u, const double *d, const double *p,
-                                double *xn, unsigned char *bad, int B, double dt, int n_sub, cudaStream_t s) {
+                                double *xn, unsigned char *bad, int B, double dt, int n_sub, int integrator, cudaStream_t s) {
     constexpr int NT = 64;
     const size_t smem = sizeof(double) * (size_t)(2 * GLG_NX + H_COUNT) * NT;
     cudaError_t e = cudaFuncSetAttribute(glg_evalf_kernel<GENERAL, PER_ENV_P, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    glg_evalf_kernel<GENERAL, PER_ENV_P, NT><<<(B + NT - 1) / NT, NT, smem, s>>>(uni, x, u, d, p, xn, bad, B, dt, n_sub);
+    glg_evalf_kernel<GENERAL, PER_ENV_P, NT><<<(B + NT - 1) / NT, NT, smem, s>>>(uni, x, u, d, p, xn, bad, B, dt, n_sub, integrator);
     return cudaGetLastError();
 }
 
 extern "C" int glg_evalf_batch(const double *x_dev, const double *u_dev, const double *d_dev, const double *p_dev,
                                int32_t p_stride, double *x_next_dev, uint8_t *bad_dev, int32_t B, double dt, int32_t n_sub,
                                int32_t device, void *stream) {
-    if (!x_dev || !u_dev || !d_dev || !p_dev || !x_next_dev || B < 1 || n_sub < 1 || (p_stride != 0 && p_stride != GLG_NP)) {
+    return glg_evalf_batch_ex(x_dev, u_dev, d_dev, p_dev, p_stride, x_next_dev, bad_dev, B, dt, n_sub, 0, device, stream);
+}
+
+extern "C" int glg_evalf_batch_ex(const double *x_dev, const double *u_dev, const double *d_dev, const double *p_dev,
+                                  int32_t p_stride, double *x_next_dev, uint8_t *bad_dev, int32_t B, double dt, int32_t n_sub,
+                                  int32_t integrator, int32_t device, void *stream) {
+    if (!x_dev || !u_dev || !d_dev || !p_dev || !x_next_dev || B < 1 || n_sub < 1 || (p_stride != 0 && p_stride != GLG_NP) ||
+        (integrator != 0 && integrator != 1)) {
         g_create_error = "glg_evalf_batch: invalid argument";
         return GLG_ERR_ARG;
     }
@@ -607,11 +613,11 @@ extern "C" int glg_evalf_batch(const double *x_dev, const double *u_dev, const d
                 glg_make_k(ph, uni.K);
                 glg_make_c(ph, uni.C);
                 e = glg_params_nominal_structure(ph)
-                        ? launch_evalf<false, false>(uni, x_dev, u_dev, d_dev, p_dev, x_next_dev, bad_dev, B, dt, n_sub, s)
-                        : launch_evalf<true, false>(uni, x_dev, u_dev, d_dev, p_dev, x_next_dev, bad_dev, B, dt, n_sub, s);
+                        ? launch_evalf<false, false>(uni, x_dev, u_dev, d_dev, p_dev, x_next_dev, bad_dev, B, dt, n_sub, integrator, s)
+                        : launch_evalf<true, false>(uni, x_dev, u_dev, d_dev, p_dev, x_next_dev, bad_dev, B, dt, n_sub, integrator, s);
             }
         } else {
-            e = launch_evalf<true, true>(uni, x_dev, u_dev, d_dev, p_dev, x_next_dev, bad_dev, B, dt, n_sub, s);
+            e = launch_evalf<true, true>(uni, x_dev, u_dev, d_dev, p_dev, x_next_dev, bad_dev, B, dt, n_sub, integrator, s);
         }
     }
     if (e != cudaSuccess) {

@@ -511,8 +511,8 @@ __global__ void __launch_bounds__(NT) glg_step_kernel(const __grid_constant__ Gl
         const unsigned int ctr = A.step_ctr[e];
         glg_env_prologue<NOISY>(U, A, e, wrow, ctr, Hc, Cc, x, u, d);
         const double fruit_prev = x[25];
-        if (NOISY) bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, Cc, Hc, GlgConstView{U.P}, u, d, x, A.dt, A.n_sub, st);
-        else bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, GlgConstView{U.C}, Hc, GlgConstView{U.P}, u, d, x, A.dt, A.n_sub, st);
+        if (NOISY) bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, Cc, Hc, GlgConstView{U.P}, u, d, x, A.dt, A.n_sub, st, A.integrator);
+        else bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, GlgConstView{U.C}, Hc, GlgConstView{U.P}, u, d, x, A.dt, A.n_sub, st, A.integrator);
         glg_env_epilogue(U, A, e, k, kw, tbl, wrow, x, fruit_prev, bad, ctr, o);
     }
     s_tbl[tid] = o.tbl_obs;
@@ -589,7 +589,7 @@ struct GlgLocalView {
 template <bool GENERAL, bool PER_ENV_P, int NT>
 __global__ void __launch_bounds__(NT) glg_evalf_kernel(const __grid_constant__ GlgUniform U, const double *xin, const double *uin,
                                                        const double *din, const double *pin, double *xout,
-                                                       unsigned char *bad_out, int B, double dt, int n_sub) {
+                                                       unsigned char *bad_out, int B, double dt, int n_sub, int integrator) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_cols = reinterpret_cast<double *>(smem_raw);  // [2*28 + H_COUNT][NT]
     const int tid = threadIdx.x;
@@ -611,10 +611,10 @@ __global__ void __launch_bounds__(NT) glg_evalf_kernel(const __grid_constant__ G
         glg_make_k(GlgLocalView{pe}, Kl);
         glg_make_c(GlgLocalView{pe}, Cl);
         glg_hoist(GlgLocalView{pe}, u, d, Hc);
-        bad = glg_rk4_step<GENERAL>(GlgLocalView{Kl}, GlgLocalView{Cl}, Hc, GlgLocalView{pe}, u, d, x, dt, n_sub, st);
+        bad = glg_rk4_step<GENERAL>(GlgLocalView{Kl}, GlgLocalView{Cl}, Hc, GlgLocalView{pe}, u, d, x, dt, n_sub, st, integrator);
     } else {
         glg_hoist(GlgConstView{U.P}, u, d, Hc);
-        bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, GlgConstView{U.C}, Hc, GlgConstView{U.P}, u, d, x, dt, n_sub, st);
+        bad = glg_rk4_step<GENERAL>(GlgConstView{U.K}, GlgConstView{U.C}, Hc, GlgConstView{U.P}, u, d, x, dt, n_sub, st, integrator);
     }
 #pragma unroll
     for (int i = 0; i < GLG_NX; ++i) xout[(size_t)e * GLG_NX + i] = x[i];

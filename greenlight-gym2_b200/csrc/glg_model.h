@@ -335,9 +335,11 @@ GLG_HD void glg_hoist(const P &p, const double *u, const double *d, HOUT &H) {
 // the 15 node sums and the current flux are live (the reference's ODE() sums ~10 aux values per state at the
 // end, which would keep ~60 fluxes = 120 registers alive across the whole evaluation).
 // ---------------------------------------------------------------------------------------------------------
+// Returns the transient-stiffness estimate of the graded integrator (same rule as glg_grp_airflow / glgo_stiffness); unused
+// by fixed-step callers.
 template <bool GENERAL, class KV, class CV, class HV, class P>
-GLG_HD void glg_rhs(const KV &K, const CV &C, const HV &H, const P &p, const double *u, const double *d,
-                    const double *x, double *S) {
+GLG_HD double glg_rhs(const KV &K, const CV &C, const HV &H, const P &p, const double *u, const double *d,
+                      const double *x, double *S) {
     const double tAir = x[2], tTop = x[3], tCan = x[4], tCovIn = x[5], tCovE = x[6];
     const double tThScr = x[7], tFlr = x[8], tPipe = x[9], tLamp = x[17], tBlScr = x[20];
 
@@ -626,6 +628,10 @@ GLG_HD void glg_rhs(const KV &K, const CV &C, const HV &H, const P &p, const dou
         const double mcAirCan = C[C_CO2RATIO] * (mcAirBuf - mcBufAir - (mcLeafAir + mcStemAir + mcFruitAir));  // a216
         S[0] = K[K_INVCAPCO2AIR] * (sCo2Air - mcAirCan);
     }
+    const double lamCov = 2.0 * K[K_HCOV] * K[K_INVCAPCOV];
+    const double lamTop = fabs(K[K_RHOCP]) * K[K_INVCAPTOP] * (1.5 * aScr + aVentRoof);
+    const double lamGas = (aScr + aVentRoof) * K[K_INVCAPCO2TOP];
+    return 1.07 * fmax(lamCov, fmax(lamTop, lamGas));
 }
 
 // Harvest-stiffness guard (same rule as the oracle's glgo_micro_steps): number of equal micro-steps a nominal RK4 substep

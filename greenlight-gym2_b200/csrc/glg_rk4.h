@@ -20,7 +20,7 @@ struct GlgLocalStore {  // host / local-memory policy
 // try/except -> terminated, tomato_env.py:119-123), else 0.
 template <bool GENERAL, class KV, class CV, class HV, class P, class STORE>
 GLG_HD int glg_rk4_step(const KV &K, const CV &C, const HV &H, const P &p, const double *u, const double *d,
-                        double *xc, double dt, int n_sub, STORE &st) {
+                        double *xc, double dt, int n_sub, STORE &st, int integrator = 0) {
     const double h_nom = dt / (double)n_sub;
     double xs[GLG_NX], k[GLG_NX];
 #pragma unroll
@@ -30,13 +30,23 @@ GLG_HD int glg_rk4_step(const KV &K, const CV &C, const HV &H, const P &p, const
     }
 #pragma unroll 1
     for (int s = 0; s < n_sub; ++s) {
-        // harvest-stiffness guard (glg_model.h): m equal micro-steps inside this nominal substep, m = 1 normally
-        const int m = glg_micro_steps(C, xs[23], xs[25], h_nom);
-        const double h = h_nom / (double)m;
+        // harvest-stiffness guard (glg_model.h): m equal micro-steps inside this nominal substep, m = 1 normally; the
+        // graded integrator (integrator = 1) adds its rules after the first evaluation (k1 does not depend on h)
+        int m = glg_micro_steps(C, xs[23], xs[25], h_nom);
+        double h = h_nom / (double)m;
 #pragma unroll 1
         for (int e = 0; e < 4 * m; ++e) {
             const int stage = e & 3;
-            glg_rhs<GENERAL>(K, C, H, p, u, d, xs, k);
+            const double lam = glg_rhs<GENERAL>(K, C, H, p, u, d, xs, k);
+            if (integrator == 1 && e == 0) {
+                int ms = 1 + (int)floor(h_nom * lam * GLG_STIFF_INV_CFL);
+                ms = ms > GLG_MAX_MICRO ? GLG_MAX_MICRO : (ms < 1 ? 1 : ms);
+                if (s < GLG_GRADED_SUBSTEPS && ms < GLG_GRADED_M) ms = GLG_GRADED_M;
+                if (ms > m) {
+                    m = ms;
+                    h = h_nom / (double)m;
+                }
+            }
             // stage weights: acc = k1 + 2k2 + 2k3 (+k4 at the end); next stage point x + c*k
             const double w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
             const double c = (stage == 2) ? h : 0.5 * h;

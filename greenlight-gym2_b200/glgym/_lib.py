@@ -64,6 +64,8 @@ SIGNATURES = {
     "glg_get_state": (C.c_int, [C.c_void_p, _DP, _DP, _IP]),
     "glg_evalf_batch": (C.c_int, [_DP, _DP, _DP, _DP, C.c_int32, _DP, _U8P, C.c_int32, C.c_double, C.c_int32,
                                   C.c_int32, _VP]),
+    "glg_evalf_batch_ex": (C.c_int, [_DP, _DP, _DP, _DP, C.c_int32, _DP, _U8P, C.c_int32, C.c_double, C.c_int32,
+                                     C.c_int32, C.c_int32, _VP]),
     "glg_launch_count": (C.c_int64, [C.c_void_p]),
     "glg_measure_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "glg_measure_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),

@@ -69,7 +69,7 @@ typedef struct glg_config {
                                 1 = graded RK4: the first 5 nominal substeps of every control interval are split in 4 (the
                                     controls just changed: fast transients) and any nominal substep is split further while the
                                     top-compartment / cover stiffness estimate asks for it (DESIGN.md "Graded integrator");
-                                    meant for n_sub = 300.  Kernel B only. */
+                                    meant for n_sub = 300. */
     int32_t reserved2;
 } glg_config;
 
@@ -152,6 +152,10 @@ int glg_get_state(glg_handle *h, double *x_host, double *u_host, int32_t *timest
  * x_next[B][28].  bad_dev: optional uint8[B], 1 where the result is not finite. */
 int glg_evalf_batch(const double *x_dev, const double *u_dev, const double *d_dev, const double *p_dev, int32_t p_stride,
                     double *x_next_dev, uint8_t *bad_dev, int32_t B, double dt, int32_t n_sub, int32_t device, void *stream);
+/* Same with the integrator choice of glg_config.integrator (0 fixed-step, 1 graded). */
+int glg_evalf_batch_ex(const double *x_dev, const double *u_dev, const double *d_dev, const double *p_dev, int32_t p_stride,
+                       double *x_next_dev, uint8_t *bad_dev, int32_t B, double dt, int32_t n_sub, int32_t integrator,
+                       int32_t device, void *stream);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t glg_launch_count(const glg_handle *h);

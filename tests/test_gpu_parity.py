@@ -645,8 +645,28 @@ def test_graded_integrator_matches_oracle(role_warps, weather0, params64):
         env.set_state(x=np.tile(orc.x, (B, 1)))
     assert extra > 0 and env.stats_t[15].item() == B * (3 * 315 + extra)
     env.close()
-    with pytest.raises(_lib.GlgError):
-        make_env(4, integrator="graded", role_warps=1)
+    # kernel A (one thread per env) and the evalF entry follow the same rules
+    if role_warps == 4:
+        ea = make_env(5, integrator="graded", role_warps=1)
+        ea.reset()
+        oa = ob.OracleEnv(weather0, params64, cfg)
+        for s in range(4):
+            ea.step_rule_based()
+            oa.step_rule(s29)
+            xa, ua, ka = ea.get_state()
+            assert rel_err(xa[4], oa.x) <= STEP_TOL
+            ea.set_state(x=np.tile(oa.x, (5, 1)))
+        ea.close()
+        from glgym.model import GreenLight
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rhs_golden.npz"))
+        n = 24
+        gl = GreenLight(integrator="graded")
+        idx = [i for i in range(g["x"].shape[0]) if np.array_equal(g["p"][i], g["p"][0])][:n]
+        y = gl.evalF_batch(g["x"][idx], g["u"][idx], g["d"][idx], g["p"][0]).cpu().numpy()
+        for j, i in enumerate(idx):
+            ref, bad, _ = ob.evalf_ex(g["x"][i], g["u"][i], g["d"][i], g["p"][0], 900.0, 300, 3)
+            if not bad:
+                assert rel_err(y[j], ref) <= 1e-9, i
     # free-running season prefix in fp32 + graded stays close to fp64 + graded
     e64, e32 = make_env(64, integrator="graded"), make_env(64, integrator="graded", precision="fp32")
     e64.reset_tensor(); e32.reset_tensor()
