@@ -24,6 +24,11 @@ def _build_test_libs():
     hdrs = [os.path.join(ROOT, "greenlight-gym2_b200", "csrc", h) for h in ("glg_model.h", "glg_math.h", "glg_rk4.h")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src], check=True)
+    # the product library: normally built by __graft_entry__.build(); on a fresh checkout build it here (nvcc cross-compiles
+    # sm_100a without a GPU, ~3 minutes) so the C-ABI export tests of the CPU tier can load it
+    lib = os.path.join(ROOT, "greenlight-gym2_b200", "glgym", "libglgym.so")
+    if not os.path.exists(lib):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "greenlight-gym2_b200", "csrc")], check=True, capture_output=True)
 
 
 @pytest.fixture(scope="session")
