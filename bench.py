@@ -151,7 +151,7 @@ def run_ours(args, rank, world, local):
     dev = torch.device("cuda", local)
     B, K, Wm = args.envs, args.steps, args.warmup
     env = GreenLightVecEnv(B, n_sub=args.n_sub, device=local, seed=0, env_id_offset=rank * B, role_warps=args.role_warps,
-                           reuse_output_buffers=True, precision=args.precision)
+                           precision=args.precision)
     obs_dim = env.obs_dim
     env.reset_tensor()
     g = torch.Generator(device=dev)
@@ -199,11 +199,11 @@ def run_ours(args, rank, world, local):
     e2e_value = world * B * K / e2e_s
     sampler.stop_flag = True  # clocks are sampled over both timed regions (device-resident and end-to-end)
     sampler.join(timeout=1.0)
-    # the same end-to-end loop with the constructor's defaults (every step returns a fresh copy of the observations)
+    # the same end-to-end loop with reuse_output_buffers=True (two alternating pinned buffers, no reference counting)
     e2e_default = None
     try:
         denv = GreenLightVecEnv(B, n_sub=args.n_sub, device=local, seed=0, env_id_offset=rank * B, role_warps=args.role_warps,
-                                precision=args.precision)
+                                precision=args.precision, reuse_output_buffers=True)
         denv.reset()
         for s in range(min(2, K)):
             denv.step(a_host[s])
@@ -284,8 +284,9 @@ def run_ours(args, rank, world, local):
                        parallelism=f"env-shard x{world}, no collective on the step path",
                        l2="flushed between timed steps (256 MiB memset outside the event pair)", state_finite=finite),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 6 * 4,
-                    "d2h_bytes_per_step": B * obs_dim * 4 + B * 8 + B, "api": "GreenLightVecEnv(reuse_output_buffers=True).step(numpy) -> glg_step_host; obs returned as views of "
-                           "two alternating pinned buffers", "value_with_default_copy_semantics": e2e_default},
+                    "d2h_bytes_per_step": B * obs_dim * 4 + B * 8 + B, "api": "GreenLightVecEnv(...).step(numpy) -> glg_step_host with the constructor's defaults: host actions in, "
+                           "observations / rewards / dones out as numpy arrays (page-locked buffers handed out by reference count, "
+                           "never overwritten while the caller holds them)", "value_with_reuse_output_buffers": e2e_default},
             "gpu_launches": int(launches), "graded_integrator": graded,
             "clocks": sampler.result(),
             "roofline": {"bound": args.precision, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",

@@ -15,6 +15,8 @@ the GreenLightEnv section, `constraints`, `reward_params`, `observation_modules`
 import ctypes as C
 from os.path import join
 
+import sys
+
 import numpy as np
 import torch
 
@@ -201,11 +203,14 @@ class GreenLightVecEnv:
         self._pin = [torch.empty((B, self.obs_dim), dtype=torch.float32).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory(),
                      torch.empty(B, dtype=torch.uint8).pin_memory(), torch.empty((B, self.nu), dtype=torch.float32).pin_memory()]
         self._obs_host, self._rew_host, self._done_host, self._act_host = (t.numpy() for t in self._pin)
-        # reuse_output_buffers: `step()` returns views of two alternating page-locked observation buffers instead of a fresh
-        # copy (saves a 263*4*B-byte host memcpy per step).  An array returned by step k is overwritten by step k+2 -- safe
+        # Default: `step()` returns page-locked observation buffers handed out by reference count (_free_pool_buffer) -- fresh
+        # arrays as far as the caller can tell, without a host copy.
+        # reuse_output_buffers: `step()` returns views of two alternating page-locked observation buffers instead
+        # (no reference counting at all).  An array returned by step k is overwritten by step k+2 -- safe
         # for SB3's collect loop (it copies `new_obs` into its rollout buffer before the next step); off by default because
         # the reference returns fresh arrays.
         self.reuse_output_buffers = bool(reuse_output_buffers)
+        self._obs_pool = None  # default path: lazily created pool of page-locked buffers handed out by reference count
         if self.reuse_output_buffers:
             self._pin.append(torch.empty((B, self.obs_dim), dtype=torch.float32).pin_memory())
             self._obs_ring = [self._obs_host, self._pin[-1].numpy()]
@@ -272,16 +277,39 @@ class GreenLightVecEnv:
         np.copyto(self._act_host, np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.nu))
         self._actions = self._act_host
 
+    def _free_pool_buffer(self):
+        """A page-locked observation buffer nobody outside this object references any more, or None.  The returned arrays
+        ARE these buffers (no host copy); one is reused only after the caller dropped every reference to it (and to views of
+        it), so the reference's fresh-array semantics hold."""
+        if self._obs_pool is None:
+            self._obs_pool = [torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._obs_pool_np = [t.numpy() for t in self._obs_pool]
+            self._pool_pos = 0
+        n = len(self._obs_pool_np)
+        for j in range(n):
+            i = (self._pool_pos + j) % n
+            if sys.getrefcount(self._obs_pool_np[i]) <= 2:  # the pool's own reference + getrefcount's argument
+                self._pool_pos = (i + 1) % n
+                return i
+        return None
+
     def step_wait(self):
+        pool_i = None
         if self.reuse_output_buffers:
             self._obs_turn ^= 1
             obs_buf = self._obs_ring[self._obs_turn]
         else:
-            obs_buf = self._obs_host
+            pool_i = self._free_pool_buffer()
+            obs_buf = self._obs_host if pool_i is None else self._obs_pool_np[pool_i]
         _lib.check(self._lib.glg_step_host(self._h, self._actions.ctypes.data, obs_buf.ctypes.data,
                                            self._rew_host.ctypes.data, self._done_host.ctypes.data), self._h, "glg_step_host")
         dones = self._done_host.astype(bool)
-        obs = obs_buf if self.reuse_output_buffers else obs_buf.copy()
+        if self.reuse_output_buffers:
+            obs = obs_buf
+        elif pool_i is not None:
+            obs = self._obs_pool_np[pool_i]  # zero-copy: the caller now holds a reference, the buffer is busy until it lets go
+        else:
+            obs = obs_buf.copy()             # every pool buffer is still referenced by the caller: plain copy
         return obs, self._rew_host.astype(np.float32), dones, self._make_infos(dones)
 
     def step(self, actions):

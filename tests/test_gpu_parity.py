@@ -532,6 +532,30 @@ def test_config1_rule_based_episode_replay(weather0, params64):
     env.close()
 
 
+def test_step_outputs_are_never_overwritten_while_referenced():
+    """`step()` hands out page-locked buffers by reference count instead of copying: an array the caller still holds (or a
+    view of it) must keep its content through later steps -- also when the caller keeps more arrays than the pool has."""
+    env = make_env(64, n_sub=20)
+    env.reset()
+    rng = np.random.default_rng(0)
+    held, copies = [], []
+    for s in range(7):  # more than the 4 pool buffers: the last ones are plain copies
+        o = env.step(rng.uniform(-1, 1, (64, 6)).astype(np.float32))[0]
+        held.append(o[3:5])          # a view keeps its base busy
+        copies.append(o[3:5].copy())
+        del o
+    assert all(np.array_equal(h, c) for h, c in zip(held, copies))
+    assert len({h.base.ctypes.data if h.base is not None else h.ctypes.data for h in held}) == 7
+    del held
+    a = env.step(np.zeros((64, 6), dtype=np.float32))[0]
+    pa = a.ctypes.data
+    del a
+    b = env.step(np.zeros((64, 6), dtype=np.float32))[0]
+    c = env.step(np.zeros((64, 6), dtype=np.float32))[0]
+    assert b.ctypes.data != c.ctypes.data and pa in {p.ctypes.data for p in env._obs_pool_np}  # released buffers are reused
+    env.close()
+
+
 def test_handle_errors_are_loud(L):
     from glgym import _lib
     cfg = _lib.GlgConfig()
