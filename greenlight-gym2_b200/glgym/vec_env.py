@@ -16,6 +16,7 @@ import ctypes as C
 from os.path import join
 
 import sys
+import types
 
 import numpy as np
 import torch
@@ -39,6 +40,8 @@ DEFAULT_REWARD_PARAMS = dict(
     fixed_greenhouse_cost=15.0, fixed_co2_cost=0.015, fixed_lamp_cost=0.07, fixed_screen_cost=2.0, elec_price=0.3,
     heating_price=0.09, co2_price=0.3, fruit_price=1.6, dmfm=0.065, pen_weights=[4.0e-4, 5.0e-3, 7.0e-4], pen_lamp=0.1,
 )
+_EMPTY_INFO = types.MappingProxyType({})
+
 INFO_KEYS = ("EPI", "revenue", "variable_costs", "fixed_costs", "co2_cost", "heat_cost", "elec_cost",
              "temp_violation", "co2_violation", "rh_violation", "lamp_violation")
 
@@ -330,13 +333,18 @@ class GreenLightVecEnv:
             infos = [dict(zip(INFO_KEYS, info[:, i].tolist()), controls=ctrl[:, i].copy(), **{"TimeLimit.truncated": False})
                      for i in range(self.num_envs)]
         else:
-            infos = [{} for _ in range(self.num_envs)]
+            # "minimal": envs that are not done share ONE read-only empty mapping (building 4096 dicts costs 0.1 ms per step,
+            # 65 536 of them 1.6 ms).  It supports everything SB3's wrappers do with an info (`.get`, `in`, `.copy()`);
+            # assigning into it raises TypeError instead of silently leaking into the other envs.
+            infos = [_EMPTY_INFO] * self.num_envs
         idx = np.nonzero(dones)[0]
         if idx.size:
             term = self.terminal_obs_t[torch.as_tensor(idx, device=self.device)].cpu().numpy()
             for j, i in enumerate(idx):
-                infos[i]["terminal_observation"] = term[j]
-                infos[i]["TimeLimit.truncated"] = False
+                info = dict(infos[i])
+                info["terminal_observation"] = term[j]
+                info["TimeLimit.truncated"] = False
+                infos[i] = info
         return infos
 
     def close(self):
