@@ -184,3 +184,16 @@ def test_capi_config_defaults_and_no_cpu_fallback():
     cfg.num_envs = 0
     h = C.c_void_p()
     assert lib.glg_create(C.byref(cfg), C.byref(h)) == _lib.GLG_ERR_ARG
+
+
+def test_results_frame_layout():
+    """glgym.evaluation.to_results_frame: one row per step, the reference's Results columns plus `episode` (common/results.py,
+    experiments/evaluate_baseline.py:63-67)."""
+    from glgym.evaluation import RESULT_COLUMNS_TAIL, to_results_frame
+    from glgym.vec_env import obs_names
+    cols = obs_names(48)[:23] + RESULT_COLUMNS_TAIL + ["episode"]
+    assert len(cols) == 33 and cols[23:29] == ["Rewards", "EPI", "Revenue", "Heat costs", "CO2 costs", "Elec costs"]
+    data = np.arange(2 * 3 * 32, dtype=np.float64).reshape(2, 3, 32)
+    df = to_results_frame(data, cols)
+    assert df.shape == (6, 33) and df["episode"].tolist() == [0, 0, 0, 1, 1, 1]
+    assert df["Rewards"].tolist() == data[:, :, 23].ravel().tolist() and df["co2_air"].iloc[4] == data[1, 1, 0]
