@@ -45,18 +45,11 @@ struct glg_handle {
     unsigned char *h_done = nullptr;
     cudaStream_t own_stream = nullptr;
     long long launches = 0;
-    unsigned long long uni_version = 0;  // bumped by glg_set_params; compared with the resident copy's version
     double ctrl[GLG_NCTRL];  // rule-based controller settings (defaults: configs/agents/rule_based.yml)
     std::string err;
 };
 static const double kDefaultCtrl[GLG_NCTRL] = {0, 18, -1, 366, 400, 10, 19.5, 16.5, 0, 5, 800, 4, 85, 2, 5, 1, -1, 5, 10, -1, 4, -2,
                                                2, 2, 100, 85, -1, -100, 1};
-
-// owner of the device's __constant__ glg_uni_c copy (kernel B's group functions read their constants from it)
-#include <mutex>
-static std::mutex g_uni_mutex;
-static const void *g_uni_owner[64] = {};  // per device ordinal: handle whose table is resident
-static unsigned long long g_uni_version[64] = {};
 
 #define GLG_CUDA(h, call)                                                                            \
     do {                                                                                             \
@@ -120,10 +113,6 @@ extern "C" void glg_destroy(glg_handle *h) {
     if (h->h_reward) cudaFreeHost(h->h_reward);
     if (h->h_done) cudaFreeHost(h->h_done);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
-    {
-        std::lock_guard<std::mutex> lk(g_uni_mutex);
-        if (h->cfg.device >= 0 && h->cfg.device < 64 && g_uni_owner[h->cfg.device] == h) g_uni_owner[h->cfg.device] = nullptr;
-    }
     delete h;
 }
 
@@ -135,10 +124,10 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     *out = nullptr;
     if (cfg->num_envs < 1 || cfg->n_sub < 1 || cfg->N < 0 || cfg->Np < 0 || !(cfg->dt > 0) ||
         (cfg->precision != 0 && cfg->precision != 1) ||
-        (cfg->role_warps != 0 && cfg->role_warps != 1 && cfg->role_warps != 4 && cfg->role_warps != 8) ||
+        (cfg->role_warps < 0 || cfg->role_warps > 3) ||
         (cfg->integrator != 0 && cfg->integrator != 1) || (cfg->precision == 1 && cfg->role_warps == 1)) {
         g_create_error = (cfg->precision == 1 && cfg->role_warps == 1)
-                             ? "glg_create: the fp32 throughput mode runs on kernel B only (role_warps 0, 4 or 8)"
+                             ? "glg_create: the fp32 throughput mode runs on kernel C only (role_warps 0, 2 or 3)"
                              : "glg_create: invalid num_envs / n_sub / N / Np / dt / precision / role_warps / integrator";
         return GLG_ERR_ARG;
     }
@@ -199,11 +188,6 @@ extern "C" int glg_set_params(glg_handle *h, const double *p_host) {
     for (int i = 0; i < K_COUNT; ++i) h->uni.Kf[i] = (float)h->uni.K[i];
     for (int i = 0; i < C_COUNT; ++i) h->uni.Cf[i] = (float)h->uni.C[i];
     h->general = !glg_params_nominal_structure(p_host);
-    static unsigned long long next_version = 1;
-    {
-        std::lock_guard<std::mutex> lk(g_uni_mutex);
-        h->uni_version = next_version++;
-    }
     h->have_params = true;
     return GLG_OK;
 }
@@ -311,65 +295,51 @@ static cudaError_t launch_step(glg_handle *h, const GlgStepArgs &a, cudaStream_t
     return cudaGetLastError();
 }
 
-// Makes this handle's constant table the resident __constant__ copy of its device.  Switching owners waits for the
-// device first: a kernel of the previous owner may still be reading the copy on another stream.
-[[maybe_unused]] static cudaError_t bind_uniform(glg_handle *h) {
-    const int d = h->cfg.device;
-    if (d < 0 || d >= 64) return cudaErrorInvalidDevice;
-    std::lock_guard<std::mutex> lk(g_uni_mutex);
-    if (g_uni_owner[d] == h && g_uni_version[d] == h->uni_version) return cudaSuccess;
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(glg_uni_c, &h->uni, sizeof(GlgUniform));
-    if (e == cudaSuccess) {
-        g_uni_owner[d] = h;
-        g_uni_version[d] = h->uni_version;
-    }
-    return e;
-}
-
-template <class T, bool GENERAL, bool NOISY, int NR, bool GRADED>
-static cudaError_t launch_step_roles_t(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
-#if GLG_NOINLINE_MASK
-    {
-        cudaError_t e = bind_uniform(h);
-        if (e != cudaSuccess) return e;
-    }
+// NG group warps for the fp64 / fp32 unit kernels; MINB = CTAs per SM the register budget is compiled for
+#ifndef GLG_NG
+#define GLG_NG 12
 #endif
-    const size_t smem = GlgRoleSmem<T, NOISY>::bytes(a.Np);
+#ifndef GLG_MINB_LAT
+#define GLG_MINB_LAT 1   // CTAs per SM of the latency variant (role_warps = 2)
+#endif
+#ifndef GLG_MINB_TPUT
+#define GLG_MINB_TPUT 4  // CTAs per SM of the throughput variant (role_warps = 3)
+#endif
+#ifndef GLG_TPUT_FUSED
+#define GLG_TPUT_FUSED true  // throughput variant: fused layout (4 warps = group role + owner), else dedicated owner warps
+#endif
+template <class T, bool GENERAL, bool NOISY, int MINB, bool FUSED>
+static cudaError_t launch_step_units_t(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
+    constexpr int NG = FUSED ? GLG_NO : GLG_NG;
+    const size_t smem = GlgRoleSmem<T, NG, GENERAL, NOISY>::bytes(a.Np);
     static size_t attr_smem_dev[64] = {};  // largest size opted into so far, per device (the attribute is per context)
     size_t &attr_smem = attr_smem_dev[h->cfg.device & 63];
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(glg_step_roles_kernel<T, GENERAL, NOISY, NR, GRADED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(glg_step_units_kernel<T, GENERAL, NOISY, NG, MINB, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_smem = smem;
     }
-#if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
-    if (const char *m = getenv("GLG_PROF_MASK")) {
-        const int mask = (int)strtol(m, nullptr, 0);
-        cudaMemcpyToSymbol(glg_prof_mask_dev, &mask, sizeof(int));
-    }
-#endif
-    glg_step_roles_kernel<T, GENERAL, NOISY, NR, GRADED><<<(a.B + a.role_lanes - 1) / a.role_lanes, 32 * NR, smem, s>>>(h->uni, a);
+    glg_step_units_kernel<T, GENERAL, NOISY, NG, MINB, FUSED><<<(a.B + a.role_lanes - 1) / a.role_lanes, 32 * (NG + (FUSED ? 0 : GLG_NO)), smem, s>>>(h->uni, a);
     return cudaGetLastError();
 }
-template <bool GENERAL, bool NOISY, int NR>
-static cudaError_t launch_step_roles(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
-    // precision 0: fp64 parity mode ; 1: flux groups in fp32, RK4 state / stage sums / epilogue in fp64
-    // the guarded loop is part of every NOISY variant; with nominal parameters the graded integrator has its own variant
-    if (!NOISY && h->cfg.integrator == 1)
-        return h->cfg.precision == 1 ? launch_step_roles_t<float, GENERAL, false, NR, true>(h, a, s)
-                                     : launch_step_roles_t<double, GENERAL, false, NR, true>(h, a, s);
-    return h->cfg.precision == 1 ? launch_step_roles_t<float, GENERAL, NOISY, NR, false>(h, a, s)
-                                 : launch_step_roles_t<double, GENERAL, NOISY, NR, false>(h, a, s);
+template <bool GENERAL, bool NOISY, int MINB, bool FUSED>
+static cudaError_t launch_step_units(glg_handle *h, const GlgStepArgs &a, cudaStream_t s) {
+    // precision 0: fp64 parity mode ; 1: flux units in fp32, RK4 state / stage sums / epilogue in fp64
+#ifdef GLG_DEV_FAST  // experimental builds (tools/ubench): only the fp64 nominal variants are compiled
+    if (GENERAL || NOISY || h->cfg.precision == 1) return cudaErrorNotSupported;
+    return launch_step_units_t<double, false, false, MINB, FUSED>(h, a, s);
+#else
+    return h->cfg.precision == 1 ? launch_step_units_t<float, GENERAL, NOISY, MINB, FUSED>(h, a, s)
+                                 : launch_step_units_t<double, GENERAL, NOISY, MINB, FUSED>(h, a, s);
+#endif
 }
 
-// Kernel variant: 1 = kernel A (one thread per env), 4 / 8 = kernel B with 4 / 8 warps per 32 envs.
-// Measured on B200 (profiles/): B is latency-bound per CTA, so the 8-warp layout wins while the batch leaves SM
-// sub-partitions idle; the 4-warp layout (16 resident warps/SM, fewer barriers per env) wins once they are full.
+// Kernel variant: 1 = kernel A (one thread per env), 2 = kernel C compiled for one CTA per SM (128 registers per thread:
+// the step time of a batch that leaves SMs under-filled is the latency of one CTA), 3 = kernel C compiled for two CTAs per SM
+// (64 registers: throughput once every SM holds two).
 static int pick_role_warps(const glg_handle *h) {
     if (h->cfg.role_warps != 0) return h->cfg.role_warps;
-    // 8-warp CTAs: 2 resident per SM (128 registers x 256 threads) => one wave holds 2 * SMs * 32 envs
-    return h->B <= 2 * h->sms * GLG_ROLE_LANES ? 8 : 4;
+    return h->B <= h->sms * GLG_ROLE_LANES ? 2 : 3;
 }
 
 static int step_common(glg_handle *h, const float *actions_dev, const double *controls_dev, const double *noise_dev,
@@ -389,12 +359,12 @@ static int step_common(glg_handle *h, const float *actions_dev, const double *co
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
     const int rw = pick_role_warps(h);
-    if (rw == 8) {
-        if (h->general) e = noisy ? launch_step_roles<true, true, 8>(h, a, s) : launch_step_roles<true, false, 8>(h, a, s);
-        else e = noisy ? launch_step_roles<false, true, 8>(h, a, s) : launch_step_roles<false, false, 8>(h, a, s);
-    } else if (rw == 4) {
-        if (h->general) e = noisy ? launch_step_roles<true, true, 4>(h, a, s) : launch_step_roles<true, false, 4>(h, a, s);
-        else e = noisy ? launch_step_roles<false, true, 4>(h, a, s) : launch_step_roles<false, false, 4>(h, a, s);
+    if (rw == 2) {
+        if (h->general) e = noisy ? launch_step_units<true, true, GLG_MINB_LAT, false>(h, a, s) : launch_step_units<true, false, GLG_MINB_LAT, false>(h, a, s);
+        else e = noisy ? launch_step_units<false, true, GLG_MINB_LAT, false>(h, a, s) : launch_step_units<false, false, GLG_MINB_LAT, false>(h, a, s);
+    } else if (rw == 3) {
+        if (h->general) e = noisy ? launch_step_units<true, true, GLG_MINB_TPUT, GLG_TPUT_FUSED>(h, a, s) : launch_step_units<true, false, GLG_MINB_TPUT, GLG_TPUT_FUSED>(h, a, s);
+        else e = noisy ? launch_step_units<false, true, GLG_MINB_TPUT, GLG_TPUT_FUSED>(h, a, s) : launch_step_units<false, false, GLG_MINB_TPUT, GLG_TPUT_FUSED>(h, a, s);
     } else {
         if (h->general) e = noisy ? launch_step<true, true>(h, a, s) : launch_step<true, false>(h, a, s);
         else e = noisy ? launch_step<false, true>(h, a, s) : launch_step<false, false>(h, a, s);

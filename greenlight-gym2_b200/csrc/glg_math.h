@@ -314,6 +314,34 @@ GLG_HD double glg_cbrt(double x) {
     return glg_fma(d, (r * r) * third, y);
 }
 
+// ---- x^(1/3) (cube = true) or x^(1/4) (cube = false) for x > 0, selected per lane WITHOUT divergence: fp32 seed of
+//      r = x^(-1/n) (MUFU.LG2/EX2), two Newton steps r <- r + r (1 - x r^n)/n (quadratic: 2^-22 -> 2^-44 -> rounding), then
+//      x^(1/n) = x r^(n-1).  Used where the model switches between the two roots on a state comparison (floor <-> air
+//      free convection, aux_states.hpp:876): a warp whose lanes disagree would otherwise execute both root routines in turn.
+GLG_HD double glg_root34(double x, bool cube) {
+    const double invn = cube ? 0x1.5555555555555p-2 : 0.25;
+#if defined(__CUDA_ARCH__)
+    const float xf = fmaxf(__double2float_rn(x), 1e-36f);
+    float lg, sd;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"((cube ? -0.33333334f : -0.25f) * lg));
+    double r = (double)sd;
+#else
+    double r = (double)(float)pow(fmax(x, 1e-36), cube ? -1.0 / 3.0 : -0.25) * (1.0 + 1e-7);  // deliberately imperfect seed
+#endif
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int it = 0; it < 2; ++it) {
+        const double r2 = r * r;
+        const double rn = r2 * (cube ? r : r2);
+        const double e = glg_fma(-x, rn, 1.0);
+        r = glg_fma(r * invn, e, r);
+    }
+    const double r2 = r * r;
+    return x * (cube ? r2 : r2 * r);
+}
+
 // dispatcher used by the accuracy tests (host build and the glg_debug_math kernel)
 GLG_HD double glg_math_eval(int op, double v) {
     switch (op) {
@@ -325,6 +353,8 @@ GLG_HD double glg_math_eval(int op, double v) {
         case 5: return glg_pow(v, 0.66);
         case 6: return glg_pow(v, 0.32);
         case 7: return glg_inv1pexp(v);
+        case 8: return glg_root34(v, true);
+        case 9: return glg_root34(v, false);
         default: return v;
     }
 }
@@ -392,6 +422,17 @@ GLG_HD float glg_cbrt(float x) {
     return x == 0.0f ? 0.0f : y - (y2 * y - x) * glg_rcp(3.0f * y2);
 #else
     return cbrtf(x);
+#endif
+}
+GLG_HD float glg_root34(float x, bool cube) {
+#if defined(__CUDA_ARCH__)
+    const float xc = fmaxf(x, 1e-36f);
+    float l, y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(xc));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"((cube ? 0.33333334f : 0.25f) * l));
+    return x == 0.0f ? 0.0f : y;
+#else
+    return cube ? cbrtf(x) : sqrtf(sqrtf(x));
 #endif
 }
 GLG_HD float glg_inv1pexp(float z) { return glg_rcp(1.0f + glg_exp(z)); }

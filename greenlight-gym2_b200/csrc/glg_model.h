@@ -86,6 +86,7 @@ enum GlgH {  // per-env-step constants (depend on u, d and p)
     H_VPOUT_T, H_MVAIROUT_C,
     H_MCEXT, H_CO2OUT, H_FVENTSIDE_ABS,
     H_HBOIL, H_LAMPNET,
+    H_HECIN, H_ZERO,  // copies of K_HECIN and 0.0 in the per-env column: the kernel's shared surface role reads all its coefficients from H
     H_COUNT
 };
 
@@ -325,6 +326,8 @@ GLG_HD void glg_hoist(const P &p, const double *u, const double *d, HOUT &H) {
     // actuators (:1216,1255) ; lamp node: a37 - (a77+a75+a72+a55+a69) - a233 with a77's definition folded in
     H[H_HBOIL] = u[0] * p[108] / p[46];
     H[H_LAMPNET] = qLamp - (p[174] + p[175]) * qLamp - p[186] * qLamp;
+    H[H_HECIN] = p[50] * p[47] / p[46];  // = K_HECIN
+    H[H_ZERO] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -668,442 +671,13 @@ GLG_HD bool glg_params_nominal_structure(const P &p) {
     return !(sky || gro || intl || kpar);
 }
 
-// =========================================================================================================
-// Group-split form of the same right-hand side (used by the warp-specialised kernel, glg_roles.cuh).
-//
-// The RHS is cut into GLG_NGROUPS = 8 flux groups that share no intermediate value, so several warps can evaluate
-// them concurrently for the same 32 envs (8 warps x 1 group for small batches, 4 warps x 2 groups otherwise).
-// Group g writes its contribution to state i's balance into PT[i] (one slot per (group, state) pair); the state's
-// owner adds the slots of the contributing groups (glg_group_mask) and multiplies by the capacity scale.  Cheap
-// values are recomputed instead of exchanged (LAI exponentials): an exchange inside one evaluation would cost an
-// extra CTA barrier.  Sizes are balanced to ~130-240 SASS instructions per group.
-//   G0 rad      : canopy PAR/NIR extinction and absorption (:299-470), slow linear states 21,26,27, canopy capacity scale,
-//                 grow-pipe convection (:930)
-//   G1 fir      : all FIR exchange (:493-632), cover conduction and outside convection, boiler and lamp net input,
-//                 soil chain (:888-910)
-//   G2 airflow  : roof ventilation, screen air flux, CO2 of the air compartments, sensible air/top/outside exchange,
-//                 air-borne vapour exchange (:733-814, :1015-1024, :1201-1209)
-//   G3 conv     : lamp / pipe / canopy / floor convection with the main air (:824-935)
-//   G4 screens  : thermal + blackout screen convection towards the main air and condensation (:835-861, :999-1005)
-//   G5 cover    : top-compartment -> cover convection and condensation (:866, :1011), blackout screen -> top convection,
-//                 transpiration (:959-981)
-//   G6 photo    : canopy photosynthesis and buffer inflow (:1041-1097)
-//   G7 flows    : carbohydrate flows buffer -> organs and growth respiration (:1103-1155), maintenance respiration and
-//                 harvest (:1161-1188)
-// XV: x[i] -> stage state value.  PT: pt[i] = v stores the group's contribution for state i.
-// =========================================================================================================
-#define GLG_NGROUPS 8
-
-// bit g set <=> group g contributes to state i
-GLG_HD constexpr unsigned glg_group_mask(int i) {
-    return i == 0 ? 0xC4u : i == 1 ? 0x04u : i == 2 ? 0x1Du : i == 3 ? 0x34u : i == 4 ? 0x2Bu : i == 5 ? 0x22u : i == 6 ? 0x02u
-         : i == 7 ? 0x12u : i == 8 ? 0x0Bu : i == 9 ? 0x0Au : (i >= 10 && i <= 14) ? 0x02u : i == 15 ? 0x34u : i == 16 ? 0x24u
-         : i == 17 ? 0x0Au : i == 18 ? 0x0Au : i == 19 ? 0x03u : i == 20 ? 0x32u : i == 21 ? 0x01u : i == 22 ? 0xC0u
-         : (i >= 23 && i <= 25) ? 0x80u : 0x01u;
-}
-
-// scalar type of a constant set (double in parity mode, float in throughput mode); all sets passed to one group
-// function use the same type
+// scalar type of a constant set (double in parity mode, float in throughput mode); all sets passed to one unit
+// function (glg_units.h) use the same type
 template <class V>
 using glg_scalar_t = typename std::remove_cv<typename std::remove_reference<decltype(std::declval<const V &>()[0])>::type>::type;
 
-// G0: canopy PAR/NIR.  Also returns the canopy capacity scale K_INVCAPLEAF/LAI (state 4's owner needs the stage LAI).
-template <bool GENERAL, class KV, class CV, class HV, class XV, class PT>
-GLG_HD glg_scalar_t<KV> glg_grp_rad(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
-    typedef glg_scalar_t<KV> T;
-    const T tCan = x[4];
-    pt[21] = (T(1.) / T(86400.)) * (tCan - x[21]);
-    pt[26] = (T(1.) / T(86400.)) * tCan;
-    pt[27] = T(1.) / T(86400.);
-    const T lai = C[C_SLA] * x[23];
-    const T ea[3] = {-K[K_K1PAR] * lai, -K[K_KNIR] * lai, -K[K_K2PAR] * lai};
-    T ey[3];
-    if (GENERAL) {
-        glg_exp_n<3>(ea, ey);
-    } else {  // k1Par == k2Par in the nominal structure
-        const T ea2[2] = {ea[0], ea[1]};
-        T ey2[2];
-        glg_exp_n<2>(ea2, ey2);
-        ey[0] = ey2[0]; ey[1] = ey2[1]; ey[2] = ey2[0];
-    }
-    const T e32 = ey[0], e34 = ey[1], e33 = ey[2];
-    const T gPar = (1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33);
-    const T parLampCanW = H[H_PARLAMP_W] * gPar;
-    const T parLampFlrW = H[H_PARLAMPFLR_W] * e32;
-    const T rhoCovNir = H[H_RHOCOVNIR];
-    const T rhoHat = K[K_RHOCANNIR] * (1 - e34);
-    const T den1 = glg_rcp(T(1.) - rhoCovNir * rhoHat);
-    const T tCC = H[H_TAUHATCOVNIR] * e34 * den1;
-    const T rUp = rhoCovNir + H[H_TAUHAT2] * rhoHat * den1;
-    const T rDn = rhoHat + e34 * e34 * rhoCovNir * den1;
-    const T den2 = glg_rcp(T(1.) - rDn * K[K_RHOFLRNIR]);
-    const T aFlrNir = tCC * K[K_TAUHATFLRNIR] * den2;
-    const T rCCF = rUp + tCC * tCC * K[K_RHOFLRNIR] * den2;
-    const T aCanNir = 1 - aFlrNir - rCCF;
-    const T nirLampCan = H[H_NIRLAMPCAN] * (1 - e34), nirLampFlr = H[H_NIRLAMPFLR] * e34;
-    pt[4] = H[H_PARCAN_W] * gPar + H[H_NIRSUN] * aCanNir + nirLampCan;
-    pt[8] = H[H_PARFLR_W] * e32 + H[H_NIRSUN] * aFlrNir + nirLampFlr;
-    const T tAir = x[2], tGroPipe = x[19];
-    const T hGroPipeAir = fabs(K[K_GROPIPEAIR]) * glg_pow(fabs(tGroPipe - tAir + T(1e-10)), T(0.32)) * (tGroPipe - tAir);
-    pt[19] = -hGroPipeAir;
-    pt[2] = (H[H_LAMPRAD] - parLampCanW - nirLampCan - parLampFlrW - nirLampFlr) +
-            (H[H_GLOBAIR_A] + H[H_GLOBAIR_B] * (aCanNir + aFlrNir)) + hGroPipeAir;
-    return K[K_INVCAPLEAF] * glg_rcp(lai);
-}
-
-// G1: FIR exchange, cover conduction, cover-outside convection
-template <bool GENERAL, class KV, class CV, class HV, class P, class XV, class PT>
-GLG_HD void glg_grp_fir(const KV &K, const CV &C, const HV &H, const P &p, const double *u, const XV &x, PT &pt) {
-    typedef glg_scalar_t<KV> T;
-    const T tCan = x[4], tCovIn = x[5], tCovE = x[6], tThScr = x[7], tFlr = x[8], tPipe = x[9];
-    const T tLamp = x[17], tBlScr = x[20];
-    const T lai = C[C_SLA] * x[23];
-    const T e35 = glg_exp(-K[K_KFIR] * lai);
-    const T aCan = 1 - e35;
-    T sCan, sFlr, sCovIn, sThScr, sBlScr, sPipe, sLamp, sCovE, sGroPipe = T(0.0), sIntLamp = T(0.0);
-    const T q4Can = glg_sq(glg_sq(tCan + T(GLG_C2K))), q4CovIn = glg_sq(glg_sq(tCovIn + T(GLG_C2K)));
-    const T q4ThScr = glg_sq(glg_sq(tThScr + T(GLG_C2K))), q4Flr = glg_sq(glg_sq(tFlr + T(GLG_C2K)));
-    const T q4Pipe = glg_sq(glg_sq(tPipe + T(GLG_C2K))), q4Lamp = glg_sq(glg_sq(tLamp + T(GLG_C2K)));
-    const T q4BlScr = glg_sq(glg_sq(tBlScr + T(GLG_C2K)));
-    T f;
-    f = aCan * H[H_C84] * (q4Can - q4CovIn);   sCan = -f; sCovIn = f;
-    f = aCan * H[H_C86] * (q4Can - q4ThScr);   sCan -= f; sThScr = f;
-    f = aCan * K[K_C87] * (q4Can - q4Flr);     sCan -= f; sFlr = f;
-    f = aCan * H[H_C108] * (q4Can - q4BlScr);  sCan -= f; sBlScr = f;
-    f = aCan * K[K_C92] * (q4Pipe - q4Can);    sCan += f; sPipe = H[H_HBOIL] - f;
-    f = aCan * K[K_C101] * (q4Lamp - q4Can);   sCan += f; sLamp = H[H_LAMPNET] - f;
-    f = e35 * H[H_C88] * (q4Pipe - q4CovIn);   sPipe -= f; sCovIn += f;
-    f = e35 * H[H_C90] * (q4Pipe - q4ThScr);   sPipe -= f; sThScr += f;
-    f = e35 * H[H_C93] * (q4Flr - q4CovIn);    sFlr -= f; sCovIn += f;
-    f = e35 * H[H_C95] * (q4Flr - q4ThScr);    sFlr -= f; sThScr += f;
-    f = e35 * K[K_C99] * (q4Lamp - q4Flr);     sLamp -= f; sFlr += f;
-    f = e35 * K[K_C100] * (q4Lamp - q4Pipe);   sLamp -= f; sPipe += f;
-    f = e35 * H[H_C106] * (q4Flr - q4BlScr);   sFlr -= f; sBlScr += f;
-    f = e35 * H[H_C107] * (q4Pipe - q4BlScr);  sPipe -= f; sBlScr += f;
-    f = K[K_C91] * (q4Pipe - q4Flr);           sPipe -= f; sFlr += f;
-    f = H[H_C96] * (q4ThScr - q4CovIn);        sThScr -= f; sCovIn += f;
-    f = H[H_C102] * (q4Lamp - q4ThScr);        sLamp -= f; sThScr += f;
-    f = H[H_C103] * (q4Lamp - q4CovIn);        sLamp -= f; sCovIn += f;
-    f = H[H_C109] * (q4BlScr - q4ThScr);       sBlScr -= f; sThScr += f;
-    f = H[H_C110] * (q4BlScr - q4CovIn);       sBlScr -= f; sCovIn += f;
-    f = H[H_C112] * (q4Lamp - q4BlScr);        sLamp -= f; sBlScr += f;
-    sCovE = H[H_GLOBCOV] - K[K_C98] * (glg_sq(glg_sq(tCovE + T(GLG_C2K))) - H[H_TSKY4]);
-    if (GENERAL) {
-        // Terms that are identically zero for the default table: sky FIR through the roof (tauRfFir p70),
-        // grow-pipe FIR (epsGroPipe p165), interlight FIR (p194,p195).  Written plainly.
-        const T sigma = p[2];
-        const T pi = T(3.14159265358979323846);
-        const T thScr = u[2], blScr = u[5];
-        const T tauCovFir = p[70];
-        const T tauThFir = 1 - thScr * (1 - p[81]), tauBlFir = 1 - blScr * (1 - p[91]);
-        const T fPipe = T(0.49) * pi * p[107] * p[105];
-        const T q4Sky = H[H_TSKY4];
-        const T q4Int = glg_sq(glg_sq(x[18] + T(GLG_C2K))), q4Gro = glg_sq(glg_sq(x[19] + T(GLG_C2K)));
-        const T f85 = aCan * p[3] * p[4] * (p[178] * tauCovFir * tauThFir * tauBlFir) * sigma * (q4Can - q4Sky);
-        const T f89 = p[124] * p[104] * p[4] * (p[199] * p[178] * tauCovFir * tauThFir * T(0.49) * e35) * sigma * (q4Pipe - q4Sky);
-        const T f94 = p[95] * p[4] * (p[199] * p[178] * tauCovFir * tauThFir * tauBlFir * (1 - fPipe) * e35) * sigma * (q4Flr - q4Sky);
-        const T f97 = p[74] * p[4] * (tauCovFir * thScr) * sigma * (q4ThScr - q4Sky);
-        const T f104 = p[181] * p[182] * p[4] * (tauCovFir * tauThFir * tauBlFir) * sigma * (q4Lamp - q4Sky);
-        const T f111 = blScr * p[85] * p[4] * (tauCovFir * tauThFir) * sigma * (q4BlScr - q4Sky);
-        const T f105 = p[169] * p[165] * p[3] * sigma * (q4Gro - q4Can);
-        const T upF = 1 - glg_exp(-p[203] * (1 - p[189]) * lai);
-        const T dnF = 1 - glg_exp(-p[203] * p[189] * lai);
-        const T ci = p[194] * p[195] * sigma;
-        const T f115 = ci * p[95] * ((1 - fPipe) * (1 - dnF)) * (q4Int - q4Flr);
-        const T f116 = ci * p[104] * (fPipe * (1 - dnF)) * (q4Int - q4Pipe);
-        const T f117 = ci * p[3] * (dnF + upF) * (q4Int - q4Can);
-        const T f118 = ci * p[183] * ((1 - upF) * p[181]) * (q4Int - q4Lamp);
-        const T f119 = ci * p[85] * (blScr * p[178] * (1 - upF)) * (q4Int - q4BlScr);
-        const T f120 = ci * p[74] * (thScr * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4ThScr);
-        const T f121 = ci * (1 - p[70] - p[67]) * (tauThFir * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4CovIn);
-        const T f122 = ci * p[4] * (tauCovFir * tauThFir * tauBlFir * p[178] * (1 - upF)) * (q4Int - q4Sky);
-        sCan += -f85 + f105 + f117;
-        sCovIn += f121;
-        sThScr += -f97 + f120;
-        sFlr += -f94 + f115;
-        sPipe += -f89 + f116;
-        sLamp += -f104 + f118;
-        sIntLamp = -f122 - f121 - f120 - f116 - f119 - f115 - f117 - f118;
-        sGroPipe = -f105;
-        sBlScr += -f111 + f119;
-    }
-    const T hCovInCovE = K[K_HCOV] * (tCovIn - tCovE);
-    // soil chain (:888-910)
-    const T hFlrSo1 = K[K_HFLRSO1] * (tFlr - x[10]);
-    {
-        const T hSo12 = K[K_HSO12] * (x[10] - x[11]);
-        const T hSo23 = K[K_HSO23] * (x[11] - x[12]);
-        const T hSo34 = K[K_HSO34] * (x[12] - x[13]);
-        const T hSo45 = K[K_HSO45] * (x[13] - x[14]);
-        const T hSo5Out = K[K_HSO5OUT] * (x[14] - H[H_TSOOUT]);
-        pt[10] = K[K_INVCAPSO1] * (hFlrSo1 - hSo12);
-        pt[11] = K[K_INVCAPSO2] * (hSo12 - hSo23);
-        pt[12] = K[K_INVCAPSO3] * (hSo23 - hSo34);
-        pt[13] = K[K_INVCAPSO4] * (hSo34 - hSo45);
-        pt[14] = K[K_INVCAPSO5] * (hSo45 - hSo5Out);
-    }
-    pt[4] = sCan;
-    pt[5] = sCovIn - hCovInCovE;
-    pt[6] = sCovE + hCovInCovE - H[H_HEC_COVEOUT] * (tCovE - H[H_TOUT]);
-    pt[7] = sThScr;
-    pt[8] = sFlr - hFlrSo1;
-    pt[9] = sPipe;
-    pt[17] = sLamp;
-    pt[18] = sIntLamp;
-    pt[19] = sGroPipe;
-    pt[20] = sBlScr;
-}
-
-// G2: ventilation, screen air flux, CO2 of the air compartments, sensible air/top/outside, air-borne vapour
-// Returns the transient-stiffness estimate lambda_est [1/s] of the graded integrator (same rule as the oracle's glgo_stiffness).
-template <class KV, class HV, class XV, class PT>
-GLG_HD glg_scalar_t<KV> glg_grp_airflow(const KV &K, const HV &H, const XV &x, PT &pt) {
-    typedef glg_scalar_t<KV> T;
-    const T co2Air = x[0], co2Top = x[1], tAir = x[2], tTop = x[3], vpAir = x[15], vpTop = x[16];
-    const T tOut = H[H_TOUT];
-    const T tkAir = tAir + T(GLG_C2K), tkTop = tTop + T(GLG_C2K);
-    const T ra[3] = {tkAir, tkTop, tAir + H[H_TOUT_2K]};
-    T ry[3];
-    glg_rcp_n<3>(ra, ry);
-    const T rAir = ry[0], rTop = ry[1];
-    T aScr, aVentRoof;
-    {
-        const T rhoTop = K[K_RHOC] * rTop, rhoAir = K[K_RHOC] * rAir;
-        const T rhoMean = T(0.5) * (rhoTop + rhoAir);
-        const T rMean = glg_rcp(rhoMean);
-        const T buoy = K[K_HALFG] * rhoMean * fabs(rhoAir - rhoTop);
-        const T pw66 = glg_pow(fabs(tAir - tTop + T(1e-10)), T(0.66));
-        const T oneMTh = H[H_1MTH], oneMBl = H[H_1MBL];
-        const T sa[3] = {fabs(K[K_GHVENT] * (tAir - tOut) * ry[2] + H[H_CW_WIND2]) + T(1e-300), buoy * oneMTh + T(1e-10),
-                              buoy * oneMBl + T(1e-10)};
-        T sy[3];
-        glg_sqrt_n<3>(sa, sy);
-        aVentRoof = fabs(H[H_VR_A] * sy[0] + H[H_VR_B]);
-        const T fThScr = H[H_THK] * pw66 + (oneMTh * rMean) * sy[1];
-        const T fBlScr = H[H_BLK] * pw66 + (oneMBl * rMean) * sy[2];
-        aScr = fabs(fmin(fThScr, fBlScr));
-    }
-    const T mcAirTop = aScr * (co2Air - co2Top);
-    pt[1] = mcAirTop - aVentRoof * (co2Top - H[H_CO2OUT]);
-    pt[0] = H[H_MCEXT] - mcAirTop - H[H_FVENTSIDE_ABS] * (co2Air - H[H_CO2OUT]);
-    const T hAirTop = fabs(K[K_RHOCP]) * aScr * (tAir - tTop);
-    pt[2] = -(H[H_HEC_AIROUT] * (tAir - tOut) + hAirTop);
-    pt[3] = hAirTop - fabs(K[K_RHOCP]) * aVentRoof * (tTop - tOut);
-    const T rAirF = rAir - T(GLG_C2K_F32_DELTA) * (rAir * rAir);  // 1/(tAir + 273.15f), aux_states.hpp:84
-    const T rTopF = rTop - T(GLG_C2K_F32_DELTA) * (rTop * rTop);
-    const T vAirT = vpAir * rAirF, vTopT = vpTop * rTopF;
-    const T mvAirTop = T(0.002165) * aScr * (vAirT - vTopT);
-    pt[16] = (K[K_INVVPTOP] * tkTop) * (mvAirTop - T(0.002165) * aVentRoof * (vTopT - H[H_VPOUT_T]));
-    pt[15] = -(K[K_INVVPAIR] * tkAir) * (mvAirTop + H[H_MVAIROUT_C] * (vAirT - H[H_VPOUT_T]));
-    const T lamCov = T(2.0) * K[K_HCOV] * K[K_INVCAPCOV];
-    const T lamTop = fabs(K[K_RHOCP]) * K[K_INVCAPTOP] * (T(1.5) * aScr + aVentRoof);
-    const T lamGas = (aScr + aVentRoof) * K[K_INVCAPCO2TOP];
-    return T(1.07) * fmax(lamCov, fmax(lamTop, lamGas));
-}
-
-// G3: lamp / pipe / canopy / floor convection with the main air
-template <bool GENERAL, class KV, class CV, class HV, class P, class XV, class PT>
-GLG_HD void glg_grp_conv(const KV &K, const CV &C, const HV &H, const P &p, const XV &x, PT &pt) {
-    typedef glg_scalar_t<KV> T;
-    const T tAir = x[2], tCan = x[4], tFlr = x[8], tPipe = x[9], tLamp = x[17];
-    const T hLampAir = K[K_HLAMPAIR] * (tLamp - tAir);
-    const T hPipeAir = fabs(K[K_PIPEAIR]) * glg_pow(fabs(tPipe - tAir + T(1e-10)), T(0.32)) * (tPipe - tAir);
-    const T hCanAir = fabs(K[K_2ALFA] * (C[C_SLA] * x[23])) * (tCan - tAir);
-    const T hecFlr = (tFlr > tAir) ? T(1.7) * glg_cbrt(fabs(tFlr - tAir + T(1e-10)))
-                                        : T(1.3) * glg_sqrt(glg_sqrt(fabs(tAir - tFlr + T(1e-10)) + T(1e-300)));
-    const T hAirFlr = hecFlr * (tAir - tFlr);
-    T sAir = hLampAir + hPipeAir + hCanAir - hAirFlr;
-    T sIntLamp = T(0.0);
-    if (GENERAL) {
-        const T hIntLampAir = fabs(p[198]) * (x[18] - tAir);  // a167
-        sAir += hIntLampAir;
-        sIntLamp = -hIntLampAir;
-    }
-    pt[2] = sAir;
-    pt[4] = -hCanAir;
-    pt[8] = hAirFlr;
-    pt[9] = -hPipeAir;
-    pt[17] = -hLampAir;
-    pt[18] = sIntLamp;
-}
-
-// G4: thermal and blackout screen: convection on both sides + condensation from the main air
-template <class KV, class HV, class XV, class PT>
-GLG_HD void glg_grp_screens(const KV &K, const HV &H, const XV &x, PT &pt) {
-    typedef glg_scalar_t<KV> T;
-    const T tAir = x[2], tTop = x[3], tThScr = x[7], vpAir = x[15], tBlScr = x[20];
-    const T L = K[K_L];
-    const T hec17Th = H[H_17TH], hec17Bl = H[H_17BL];
-    // three cube roots, two saturation pressures and two condensation sigmoids: independent chains, interleaved
-    const T ca[3] = {fabs(tAir - tThScr + T(1e-10)), fabs(tThScr - tTop + T(1e-10)), fabs(tAir - tBlScr + T(1e-10))};
-    T cy[3];
-    glg_cbrt_n<3>(ca, cy);
-    const T ra[2] = {tThScr + T(238.3), tBlScr + T(238.3)};
-    T ry[2];
-    glg_rcp_n<2>(ra, ry);
-    const T ea[2] = {T(17.2694) * (tThScr * ry[0]), T(17.2694) * (tBlScr * ry[1])};
-    T ey[2];
-    glg_exp_n<2>(ea, ey);
-    const T dvTh = vpAir - T(610.78) * ey[0], dvBl = vpAir - T(610.78) * ey[1];
-    const T eb[2] = {-T(0.1) * dvTh, -T(0.1) * dvBl};
-    T ez[2];
-    glg_exp_n<2>(eb, ez);
-    const T rb[2] = {T(1.0) + ez[0], T(1.0) + ez[1]};
-    T rz[2];
-    glg_rcp_n<2>(rb, rz);
-    const T hecAirTh = hec17Th * cy[0];
-    const T hAirThScr = fabs(hecAirTh) * (tAir - tThScr);
-    const T hThScrTop = fabs(hec17Th * cy[1]) * (tThScr - tTop);
-    const T mvAirThScr = T(6.4e-9) * hecAirTh * dvTh * rz[0];  // cond(), aux_states.hpp:60-63
-    pt[7] = hAirThScr - hThScrTop + L * mvAirThScr;
-    const T hecAirBl = hec17Bl * cy[2];
-    const T hAirBlScr = fabs(hecAirBl) * (tAir - tBlScr);
-    const T mvAirBlScr = T(6.4e-9) * hecAirBl * dvBl * rz[1];
-    pt[20] = hAirBlScr + L * mvAirBlScr;
-    pt[2] = -(hAirThScr + hAirBlScr);
-    pt[3] = hThScrTop;
-    pt[15] = -(K[K_INVVPAIR] * (tAir + T(GLG_C2K))) * (mvAirThScr + mvAirBlScr);
-}
-
-// G5: cover (convection from the top compartment + condensation) and canopy transpiration
-template <class KV, class CV, class HV, class XV, class PT>
-GLG_HD void glg_grp_cover(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
-    typedef glg_scalar_t<KV> T;
-    const T co2Air = x[0], tAir = x[2], tTop = x[3], tCan = x[4], tCovIn = x[5], vpAir = x[15], vpTop = x[16];
-    const T L = K[K_L];
-    const T tBlScr = x[20];
-    const T ca[2] = {fabs(tTop - tCovIn + T(1e-10)), fabs(tBlScr - tTop + T(1e-10))};
-    T cy[2];
-    glg_cbrt_n<2>(ca, cy);
-    const T ra[2] = {tCovIn + T(238.3), tCan + T(238.3)};
-    T ry[2];
-    glg_rcp_n<2>(ra, ry);
-    const T ea[2] = {T(17.2694) * (tCovIn * ry[0]), T(17.2694) * (tCan * ry[1])};
-    T ey[2];
-    glg_exp_n<2>(ea, ey);
-    const T hecTopCov = K[K_HECIN] * cy[0];
-    const T hTopCovIn = fabs(hecTopCov) * (tTop - tCovIn);
-    const T dvCov = vpTop - T(610.78) * ey[0];
-    const T vpd = T(610.78) * ey[1] - vpAir;
-    const T lai = C[C_SLA] * x[23];
-    const T rfCo2 = fmin(T(1.5), T(1.) + H[H_CEVAP3] * glg_sq(K[K_ETAMGPPM] * co2Air - 200));
-    const T rfVp = fmin(T(5.8), T(1.) + H[H_CEVAP4] * (vpd * vpd));
-    const T rS = H[H_RS] * rfCo2 * rfVp;
-    const T rb[2] = {T(1.0) + glg_exp(-T(0.1) * dvCov), K[K_RB] + rS};
-    T rz[2];
-    glg_rcp_n<2>(rb, rz);
-    const T mvTopCovIn = T(6.4e-9) * hecTopCov * dvCov * rz[0];  // cond(), aux_states.hpp:60-63
-    pt[5] = hTopCovIn + L * mvTopCovIn;
-    const T hBlScrTop = fabs(H[H_17BL] * cy[1]) * (tBlScr - tTop);
-    pt[20] = -hBlScrTop;
-    pt[3] = hBlScrTop - hTopCovIn;
-    pt[16] = -(K[K_INVVPTOP] * (tTop + T(GLG_C2K))) * mvTopCovIn;
-    const T mvCanAir = vpd * (K[K_VEC] * lai * rz[1]);
-    pt[4] = -(L * mvCanAir);
-    pt[15] = (K[K_INVVPAIR] * (tAir + T(GLG_C2K))) * mvCanAir;
-}
-
-// G6: canopy photosynthesis -> buffer inflow a200
-template <bool GENERAL, class KV, class CV, class HV, class XV, class PT>
-GLG_HD void glg_grp_photo(const KV &K, const CV &C, const HV &H, const XV &x, PT &pt) {
-    typedef glg_scalar_t<KV> T;
-    const T co2Air = x[0], tAir = x[2], tCan = x[4], cBuf = x[22];
-    const T lai = C[C_SLA] * x[23];
-    const T j25 = lai * C[C_J25];
-    const T co2Stom = C[C_ETASTOM] * (K[K_PPMC] * (tAir + T(GLG_C2K)) * co2Air);
-    const T ra[3] = {j25, tCan + T(GLG_C2K), co2Stom};
-    T ry[3];
-    glg_rcp_n<3>(ra, ry);
-    const T rj = C[C_J25] * ry[0], rCanK = ry[1], rStom = ry[2];
-    // PAR absorbed by the canopy in umol (a191): the extinction factor is recomputed (G0 has it too); the four
-    // exponentials of this group are independent and evaluated interleaved
-    const T ea[5] = {-K[K_K1PAR] * lai, C[C_ARR1] * (1 - C[C_T25K] * rCanK), C[C_ARR2A] - C[C_ARR2B] * rCanK,
-                          T(5e-4) * (cBuf - C[C_CBUFMAX]), -K[K_K2PAR] * lai};
-    T ey[5];
-    if (GENERAL) {
-        glg_exp_n<5>(ea, ey);
-    } else {
-        const T ea4[4] = {ea[0], ea[1], ea[2], ea[3]};
-        T ey4[4];
-        glg_exp_n<4>(ea4, ey4);
-        ey[0] = ey4[0]; ey[1] = ey4[1]; ey[2] = ey4[2]; ey[3] = ey4[3]; ey[4] = ey4[0];
-    }
-    const T e32 = ey[0], e33 = ey[4];
-    const T parCan = H[H_PARUMOL] * ((1 - e32) + e32 * K[K_RHOFLRPAR] * (1 - e33));
-    const T gamma = rj * C[C_CGAMMA] * tCan + C[C_20CGAMMA] * (1 - rj);
-    const T rb[3] = {T(1.0) + ey[2], T(1.0) + ey[3], 4 * (co2Stom + 2 * gamma)};
-    T rz[3];
-    glg_rcp_n<3>(rb, rz);
-    const T jPot = j25 * ey[1] * C[C_JPOTNUM] * rz[0];
-    const T jb = jPot + C[C_ALPHA] * parCan;
-    // smaller root of theta J^2 - jb J + jPot alpha par = 0 (:1076-1077) in its cancellation-free form
-    //   (jb - sqrt(D)) / (2 theta) = (jb^2 - D) / (2 theta (jb + sqrt(D))),  D = jb^2 - 4 theta alpha jPot par + 1e-10
-    // (the reference's form loses all fp32 digits when a perturbed t25k makes jPot >> alpha*par)
-    // Used in fp32 only; in fp64 the reference's own form is accurate to ~1e-12 and keeps a reciprocal off this group's
-    // critical path.
-    const T fourTc = C[C_4THETAALPHA] * jPot * parCan;
-    const T sqD = glg_sqrt(jb * jb - fourTc + T(1e-10));
-    const T jE = std::is_same<T, float>::value ? C[C_INV2THETA] * (fourTc - T(1e-10)) * glg_rcp(jb + sqD)
-                                               : C[C_INV2THETA] * (jb - sqD);
-    const T phot = jE * (co2Stom - gamma) * rz[2];
-    const T photNet = phot - phot * gamma * rStom;
-    const T mcAirBuf = C[C_MCH2O] * rz[1] * photNet;
-    pt[22] = mcAirBuf;
-    pt[0] = -(C[C_CO2RATIO] * mcAirBuf);
-}
-
-// G7: carbohydrate flows buffer -> leaves / stem / fruit with their growth respiration (:1103-1155), maintenance
-// respiration (:1161-1178) and harvest (:75-79,1184,1188).  Returns the harvest speed for the micro-step guard.
-template <class KV, class CV, class XV, class PT>
-GLG_HD glg_scalar_t<KV> glg_grp_flows(const KV &K, const CV &C, const XV &x, PT &pt) {
-    typedef glg_scalar_t<KV> T;
-    const T tCan = x[4], tCan24 = x[21], cBuf = x[22];
-    const T cLeaf = x[23], cStem = x[24], cFruit = x[25];
-    const T gT24 = T(0.047) * tCan24 + T(0.06);
-    const T kHar = T(2.0) * T(4.6052) / T(1e4);  // smoothHar(v, cutoff, 1e4, 5e4) = 5e4/(1+exp(-kHar (v-cutoff)))
-    // eight independent exponentials (two interleaved batches of four: eight at once spill), then five reciprocals
-    const T ea[4] = {-T(1.1587) * (tCan24 - C[C_T24MIN]), T(1.3904) * (tCan24 - C[C_T24MAX]), -T(0.869) * (tCan - C[C_TCANMIN]),
-                     T(0.5793) * (tCan - C[C_TCANMAX])};
-    const T eb[4] = {-T(5e-3) * (cBuf - C[C_CBUFMIN]), C[C_LNQ10X] * (tCan24 - 25), -kHar * (cLeaf - C[C_CLEAFMAX]),
-                     -kHar * (cFruit - C[C_CFRUITMAX])};
-    T ey[8];
-    {
-        T ya[4], yb[4];
-        glg_exp_n<4>(ea, ya);
-        glg_exp_n<4>(eb, yb);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            ey[i] = ya[i];
-            ey[4 + i] = yb[i];
-        }
-    }
-    const T ra[5] = {(T(1.) + ey[0]) * (T(1.) + ey[1]), (T(1.) + ey[2]) * (T(1.) + ey[3]), T(1.0) + ey[4], T(1.0) + ey[6],
-                     T(1.0) + ey[7]};
-    T ry[5];
-    glg_rcp_n<5>(ra, ry);
-    const T hT24 = ry[0], hTCan = ry[1];
-    const T sSum = x[26] * K[K_INVTENDSUM];
-    const T sSum1 = sSum - T(1.0);
-    const T hTSum = T(0.5) * (sSum + glg_sqrt(sSum * sSum + T(1e-4))) - T(0.5) * (sSum1 + glg_sqrt(sSum1 * sSum1 + T(1e-4)));
-    const T flow = ry[2] * hT24 * gT24;
-    const T mcBufLeaf = flow * C[C_RGLEAF];
-    const T mcBufStem = flow * C[C_RGSTEM];
-    const T mcBufFruit = flow * hTCan * hTSum * C[C_RGFRUIT];
-    const T mcBufAir = C[C_GLEAF] * mcBufLeaf + C[C_GSTEM] * mcBufStem + C[C_GFRUIT] * mcBufFruit;
-    const T maint = C[C_MAINT] * ey[5];
-    const T mcLeafAir = maint * cLeaf * C[C_MLEAF];
-    const T mcStemAir = maint * cStem * C[C_MSTEM];
-    const T mcFruitAir = maint * cFruit * C[C_MFRUIT];
-    pt[22] = -mcBufFruit - mcBufLeaf - mcBufStem - mcBufAir;
-    pt[23] = (mcBufLeaf - mcLeafAir) - T(5e4) * ry[3];
-    pt[24] = mcBufStem - mcStemAir;
-    pt[25] = (mcBufFruit - mcFruitAir) - T(5e4) * ry[4];
-    pt[0] = C[C_CO2RATIO] * (mcBufAir + (mcLeafAir + mcStemAir + mcFruitAir));
-    return glg_harvest_lambda(ry[3], ry[4]);
-}
-
-// index into K of the capacity scale the owner applies to state i's summed contributions; -1: 1.0 (the groups
-// already wrote a derivative), -2: the per-lane canopy scale returned by G0
+// index into K of the capacity scale the owner applies to state i's summed contributions; -1: 1.0 (the units
+// already wrote a derivative), -2: the per-lane canopy scale written by U_PIPES
 GLG_HD constexpr int glg_state_scale_index(int i) {
     return i == 0 ? (int)K_INVCAPCO2AIR : i == 1 ? (int)K_INVCAPCO2TOP : i == 2 ? (int)K_INVCAPAIR : i == 3 ? (int)K_INVCAPTOP
          : i == 4 ? -2 : (i == 5 || i == 6) ? (int)K_INVCAPCOV : i == 7 ? (int)K_INVCAPTHSCR : i == 8 ? (int)K_INVCAPFLR

@@ -1,116 +1,115 @@
-// glg_roles.cuh -- step kernel B: warp-specialised evaluation of the GreenLight RHS.
+// glg_roles.cuh -- step kernel C: warp-specialised evaluation of the GreenLight RHS with dedicated owner warps.
 //
-// One CTA = 32 envs x NR warps (NR = 4 or 8).  Lane l of every warp works on env (32*blockIdx.x + l); each warp
-// evaluates 8/NR of the eight flux groups of the RHS (glg_model.h: rad / fir / airflow / conv / screens / cover / photo /
-// flows) for those 32 envs, so the groups of one env run concurrently on the SM's sub-partitions.  Why: with one thread
-// per env a 4096-env batch (BASELINE config 2) is 128 warps on 592 SM sub-partitions and each lone warp is bound by the
-// 8-cycle FP64 dependency latency (ncu: "wait" stall dominant, FP64 pipe 17 % busy); splitting the RHS multiplies the
-// resident warps for the same batch, and because a warp needs only its groups' hoisted constants and owns 1/NR of the RK4
-// state, the kernel fits 128 registers / 37 KB shared memory per CTA => 16 resident warps per SM on large batches.
+// One CTA = 32 envs x (NO owner warps + NG group warps); lane l of every warp works on env (32*blockIdx.x + l).
+//   group warp g : evaluates its flux units (glg_units.h) for the 32 envs from the stage state in shared memory and stores
+//                  one partial balance sum per (warp, state) it touches -- nothing else lives in its registers, so ptxas has
+//                  the whole register budget for interleaving the transcendental chains of the units (the round-1 kernel
+//                  carried the RK4 state of a quarter of the states in every warp: ~75 registers across the group code made
+//                  ptxas serialise the chains: photosynthesis 1007 cycles in the kernel vs 570 compiled alone);
+//   owner warp o : owns 28/NO states: classical RK4 stage update from the partial sums, state and stage sum in fp64
+//                  registers, next stage value back to shared memory.  Also decides the micro-step count of every nominal
+//                  substep (harvest guard, graded integrator) and tells the group warps when to stop.
+// Synchronisation per RHS evaluation: two named barriers used producer/consumer style (PTX bar.arrive / bar.sync):
+//   BAR_PARTS : group warps arrive (do not wait), owner warps wait  -- "partial sums of this evaluation are in shared memory"
+//   BAR_XS    : owner warps arrive (do not wait), group warps wait  -- "stage state of the next evaluation is in shared memory"
+// so a warp blocks once per evaluation, on the data it needs.
+// Every role has its own loop (no per-evaluation dispatch).  The loop bodies together must stay below the SM's 32 KB
+// instruction cache (tools/ubench/icache2.cu), which is why the three "condensing surface" warps (thermal screen, blackout
+// screen, cover) share ONE copy of their code with all addresses in registers (glg_surface_loop).
 //
-// Data flow per RHS evaluation (4 * n_sub per env-step), all through shared memory, two CTA barriers:
-//   xs[28][32]        stage state, written by the owner of each state
-//   part[slot][32]    group g's contribution to state i (slot = glg_part_slot(g, i)); 55 (group,state) pairs
-//   group phase  : every warp reads the xs it needs, evaluates its flux groups, stores their contributions
-//   -- barrier --
-//   owner phase  : state i is owned by warp (i % NR): k_i = scale_i * sum_g part[g][i]; RK4 stage update; xs[i] <- new
-//   -- barrier --
-// The owner phase is ONE copy of code for all warps (tables in the constant bank): the SM's instruction cache holds
-// ~32 KB (tools/ubench/icache2.cu: four warps on 4 x 16 KB of distinct code run at 8 cycles/instruction instead of 1),
-// and the group streams already take ~29 KB of it.
+// Shared-memory layout of the exchange, chosen so that every owner-side address is base(owner) + immediate:
+//   plan entry n = j * NO + o  : row j of owner o; states sorted by their number of contributing warps (descending), dealt
+//                                round-robin, so row j loads as many slots as its hungriest state (its first entry)
+//   xs  [n][32]                : stage state of plan entry n (units read state i at row rank(i), a compile-time constant)
+//   part[(rowbase_j + c) * NO + o][32] : c-th partial sum of plan entry (j, o); unused (padding) slots stay 0.0
 // The env-level work (S1 control update, S2 noise, hoisting, S3-S8 epilogue) is done by warp 0 (lane = env) with the
 // same device functions as kernel A, so both kernels share one definition of the step semantics.
 #pragma once
 #include "glg_kernels.cuh"
+#include "glg_units.h"
 
 #define GLG_ROLE_LANES 32
+constexpr int GLG_NO = 4;  // owner warps: warps 0..3, one per SM sub-partition
+constexpr int GLG_BAR_PARTS = 1, GLG_BAR_XS = 2;
+constexpr int GLG_MAXCONTRIB = 8;
+constexpr int GLG_MAXROWS = 8;
 
-// number of (group, state) pairs before (g, i) in group-major order = slot index of group g's contribution to state i
-__host__ __device__ constexpr int glg_part_slot(int g, int i) {
-    int n = 0;
-    for (int gg = 0; gg < g; ++gg)
-        for (int j = 0; j < GLG_NX; ++j) n += (int)((glg_group_mask(j) >> gg) & 1u);
-    for (int j = 0; j < i; ++j) n += (int)((glg_group_mask(j) >> g) & 1u);
-    return n;
-}
-constexpr int GLG_NPART = glg_part_slot(GLG_NGROUPS, 0);
-constexpr int GLG_SLOT_ZERO = GLG_NPART;          // always 0.0
-constexpr int GLG_SLOT_CANSCALE = GLG_NPART + 1;  // canopy capacity scale of the current stage (written by G0's warp)
-constexpr int GLG_SLOT_LAMBDA = GLG_NPART + 2;    // harvest rate constant of the current stage state (written by G7's warp)
-constexpr int GLG_SLOT_STIFF = GLG_NPART + 3;     // transient-stiffness estimate of the current stage state (written by G2's warp)
-constexpr int GLG_NSLOTS = GLG_NPART + 4;
-constexpr int GLG_MAXCONTRIB = 4;
+__device__ __forceinline__ void glg_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// Scheduling fences: the value must be in a register at this point of the instruction stream (ptxas otherwise sinks work that
+// was meant to overlap a barrier wait behind the barrier, and re-reads kernel parameters from the constant bank inside loops).
+__device__ __forceinline__ void glg_pin(double &v) { asm volatile("" : "+d"(v)); }
+__device__ __forceinline__ void glg_pin(int &v) { asm volatile("" : "+r"(v)); }
+// Register re-balancing between warpgroups (sm_90+ setmaxnreg): in the throughput variants (64 registers per thread at launch)
+// the three group warpgroups give registers up and the owner warpgroup (RK4 state of 7 states per thread) takes them.
+template <int N>
+__device__ __forceinline__ void glg_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void glg_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void glg_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <class T>
-struct GlgXsCol {  // stage-state column of this lane
-    const T *b;
-    __device__ __forceinline__ T operator[](int i) const { return b[i * GLG_ROLE_LANES]; }
+// ---- owner plan and slot layout (see the header comment)
+struct GlgOwnerPlan {
+    int n_active;                         // states with at least one contribution
+    int nj;                               // rows per owner warp
+    int order[GLG_MAXROWS * GLG_NO];      // state of plan entry n, -1 pads
+    int rank[GLG_NX];                     // plan entry of state i (states without contribution come after the active ones)
+    int row_slots[GLG_MAXROWS];           // slots row j loads
+    int row_base[GLG_MAXROWS + 1];        // prefix sum of row_slots
+    int slot[16][GLG_NX];                 // part slot of (group warp, state), -1 if none
+    int scale_k[GLG_MAXROWS * GLG_NO];    // glg_state_scale_index of the entry's state (-1: 1.0, -2: canopy scale slot)
+    int n_slots;                          // NO * row_base[nj]
 };
-template <int G, class T>
-struct GlgPartCol {  // contribution slots of group G for this lane
-    T *b;
-    struct Ref {
-        T *p;
-        __device__ __forceinline__ void operator=(T v) { *p = v; }
-    };
-    __device__ __forceinline__ Ref operator[](int i) { return Ref{b + glg_part_slot(G, i) * GLG_ROLE_LANES}; }
-};
-
-// Owner plan.  States are sorted by their number of contributing groups (descending) and dealt round-robin to the NR
-// owner warps: row j of warp w is state order[j * NR + w].  All warps run ONE copy of straight-line owner code, so row j
-// loads as many slots as its hungriest state needs (the row's first entry): 4+2+1+1 = 8 shared-memory loads per warp
-// with 8 warps (4+3+2+2+1+1+1 = 14 with 4) instead of 4 per state -- the owner phase is bound by shared-memory
-// bandwidth (128 B/clk: one 32-lane fp64 load = 2 cycles), and padding loads of the zero slot were half of it.
-constexpr int GLG_PLAN_ROWS = 32;
-struct GlgOwnerTable {
-    short slot[GLG_NX][GLG_MAXCONTRIB];  // contribution slots to add (GLG_SLOT_ZERO pads)
-    short scale_k[GLG_NX];               // glg_state_scale_index
-    short order[GLG_PLAN_ROWS];          // states by contribution count, descending; -1 pads
-    short count[GLG_PLAN_ROWS];
-};
-__host__ __device__ constexpr int glg_popcount8(unsigned m) {
+constexpr GlgOwnerPlan glg_make_plan(const GlgWarpTable &wt, int ng) {
+    GlgOwnerPlan t{};
     int n = 0;
-    for (int g = 0; g < GLG_NGROUPS; ++g) n += (int)((m >> g) & 1u);
-    return n;
-}
-__host__ __device__ constexpr GlgOwnerTable glg_make_owner_table() {
-    GlgOwnerTable t{};
-    for (int i = 0; i < GLG_NX; ++i) {
-        int n = 0;
-        for (int g = 0; g < GLG_NGROUPS; ++g)
-            if ((glg_group_mask(i) >> g) & 1u) t.slot[i][n++] = (short)glg_part_slot(g, i);
-        for (; n < GLG_MAXCONTRIB; ++n) t.slot[i][n] = (short)GLG_SLOT_ZERO;
-        t.scale_k[i] = (short)glg_state_scale_index(i);
-    }
-    int n = 0;
-    for (int c = GLG_MAXCONTRIB; c >= 1; --c)
+    for (int c = GLG_MAXCONTRIB; c >= 0; --c)
         for (int i = 0; i < GLG_NX; ++i)
-            if (glg_popcount8(glg_group_mask(i)) == c) {
-                t.order[n] = (short)i;
-                t.count[n] = (short)c;
+            if (wt.contribs[i] == c) {
+                t.order[n] = i;
+                t.rank[i] = n;
+                t.scale_k[n] = glg_state_scale_index(i);
+                if (c > 0) t.n_active = n + 1;
                 ++n;
             }
-    for (; n < GLG_PLAN_ROWS; ++n) {
+    t.nj = (GLG_NX + GLG_NO - 1) / GLG_NO;
+    for (; n < GLG_MAXROWS * GLG_NO; ++n) {
         t.order[n] = -1;
-        t.count[n] = 1;
+        t.scale_k[n] = -1;
     }
+    t.row_base[0] = 0;
+    for (int j = 0; j < GLG_MAXROWS; ++j) {
+        const int st = j * GLG_NO < GLG_NX ? t.order[j * GLG_NO] : -1;
+        t.row_slots[j] = st >= 0 ? wt.contribs[st] : 0;
+        t.row_base[j + 1] = t.row_base[j] + t.row_slots[j];
+    }
+    t.n_slots = GLG_NO * t.row_base[t.nj];
+    for (int w = 0; w < 16; ++w)
+        for (int i = 0; i < GLG_NX; ++i) {
+            t.slot[w][i] = -1;
+            if (w < ng && (wt.states[w] >> i & 1u)) {
+                int c = 0;
+                for (int ww = 0; ww < w; ++ww) c += (int)(wt.states[ww] >> i & 1u);
+                const int r = t.rank[i];
+                t.slot[w][i] = (t.row_base[r / GLG_NO] + c) * GLG_NO + r % GLG_NO;
+            }
+        }
     return t;
 }
-__constant__ GlgOwnerTable glg_owner_table = glg_make_owner_table();
-template <int NR, int J>
-struct GlgRowSlots {  // slots row J loads (compile-time)
-    static constexpr int value = glg_make_owner_table().count[J * NR];
+template <int NG, bool GENERAL>
+struct GlgPlan {
+    static constexpr GlgOwnerPlan plan = glg_make_plan(GlgWT<NG, GENERAL>::t, NG);
+    static constexpr int NJ = plan.nj;
+    static constexpr int NPART = plan.n_slots;
+    static constexpr int CANSCALE = NPART;  // GlgSpecial fields
+    static constexpr int LAMBDA = NPART + 1;
+    static constexpr int AVENT = NPART + 2;
+    static constexpr int ASCR = NPART + 3;
+    static constexpr int DUMMY = NPART + 4;  // write-only slot (the cover's "far side" output in the shared surface role)
+    static constexpr int NSLOTS = NPART + 5;
+    static constexpr int XS_ROWS = NJ * GLG_NO;
+    static constexpr int canopy_entry = plan.rank[4];  // its capacity scale changes with the stage LAI
 };
-template <int NR>
-struct GlgCanopyPos {  // (warp, row) of the canopy state 4, whose capacity scale changes with the stage LAI
-    static constexpr int find() {
-        const GlgOwnerTable t = glg_make_owner_table();
-        for (int n = 0; n < GLG_PLAN_ROWS; ++n)
-            if (t.order[n] == 4) return n;
-        return -1;
-    }
-    static constexpr int warp = find() % NR, row = find() / NR;
-};
+
 template <int I>
 struct GlgInt {
     static constexpr int value = I;
@@ -123,106 +122,28 @@ __device__ __forceinline__ void glg_static_for(F &&f) {
     }
 }
 
-#ifndef GLG_NOINLINE_MASK
-#define GLG_NOINLINE_MASK 0x00  // see glg_dispatch_group
-#endif
-// per-warp copy of the owner tables in shared memory (used by the call build, where registers do not survive the calls)
-constexpr int GLG_OWNER_TAB_WORDS = 52;
-constexpr int GLG_OWNER_TAB_BYTES = GLG_NOINLINE_MASK ? 8 * GLG_OWNER_TAB_WORDS * 4 : 0;
-template <class T, bool NOISY>
+template <class T, int NG, bool GENERAL>
+struct GlgXsCol {  // stage-state column of this lane, rows in plan order
+    const T *b;
+    template <int I>
+    __device__ __forceinline__ T at() const {
+        constexpr int r = GlgPlan<NG, GENERAL>::plan.rank[I];
+        return b[r * GLG_ROLE_LANES];
+    }
+};
+
+template <class T, int NG, bool GENERAL, bool NOISY>
 struct GlgRoleSmem {
-    static constexpr int kColRows = (GLG_NX + 1) + GLG_NSLOTS + H_COUNT + (NOISY ? C_COUNT : 0);  // +1: dummy state row
+    using PL = GlgPlan<NG, GENERAL>;
+    static constexpr int kColRows = PL::XS_ROWS + PL::NSLOTS + H_COUNT + (NOISY ? C_COUNT : 0);
     // weather tile (f64) | final state (f64 [28][32]) | T columns | mbarrier | ints
     __host__ __device__ static size_t col_bytes() { return (sizeof(T) * (size_t)kColRows * GLG_ROLE_LANES + 15) / 16 * 16; }
     __host__ __device__ static size_t bytes(int Np) {
-        return sizeof(double) * ((size_t)(Np + 1) * GLG_ND + (size_t)GLG_NX * GLG_ROLE_LANES) + col_bytes() + 16 +
-               sizeof(int) * (5 * GLG_ROLE_LANES + 4) + GLG_OWNER_TAB_BYTES;
+        return sizeof(double) * ((size_t)(Np + 1) * GLG_ND + (size_t)(GLG_NX + 2) * GLG_ROLE_LANES) + col_bytes() + 16 +
+               sizeof(int) * (5 * GLG_ROLE_LANES + 4 + 16);
     }
 };
 
-// owner phase: the per-state table entries (shared-memory offsets of the contribution slots, capacity scale) are loop
-// invariants: they are fetched from the constant-bank table ONCE into registers (GlgOwnerRegs) -- dynamic constant-bank
-// indexing inside the loop cost ~600 cycles per evaluation.  The update itself is branch-free straight-line code (rows
-// without a state update a dummy slot), so the NJ load -> add -> scale -> RK4 chains of a warp overlap.
-constexpr int GLG_XS_ROWS = GLG_NX + 1;  // row GLG_NX is the dummy state slot
-template <int NR>
-struct GlgOwnerRegs {
-    static constexpr int NJ = (GLG_NX + NR - 1) / NR;
-    int off[NJ][GLG_MAXCONTRIB];  // element offsets of the contribution slots in this lane's column (first GlgRowSlots used)
-    double scale[NJ];             // capacity scale
-    int xs_off[NJ];               // element offset of the state in the xs column (dummy row for padding)
-};
-template <int NR>
-__device__ __forceinline__ void glg_owner_setup(const double *Kc, int warp, GlgOwnerRegs<NR> &o) {
-    glg_static_for<0, GlgOwnerRegs<NR>::NJ>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        const int i = glg_owner_table.order[j * NR + warp];
-        const bool valid = i >= 0;
-        const int ii = valid ? i : 0;
-#pragma unroll
-        for (int c = 0; c < GlgRowSlots<NR, j>::value; ++c)
-            o.off[j][c] = (valid ? glg_owner_table.slot[ii][c] : GLG_SLOT_ZERO) * GLG_ROLE_LANES;
-        const int sk = glg_owner_table.scale_k[ii];
-        o.scale[j] = (valid && sk >= 0) ? Kc[sk] : 1.0;
-        o.xs_off[j] = (valid ? i : GLG_NX) * GLG_ROLE_LANES;
-    });
-}
-// shared-memory image of GlgOwnerRegs: words [0,NJ*4) slot offsets, [NJ*4, NJ*5) xs offsets, then NJ doubles (8-byte aligned)
-template <int NR>
-__device__ __forceinline__ void glg_owner_store(const GlgOwnerRegs<NR> &o, int *tab) {
-    constexpr int NJ = GlgOwnerRegs<NR>::NJ;
-    glg_static_for<0, NJ>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-#pragma unroll
-        for (int c = 0; c < GlgRowSlots<NR, j>::value; ++c) tab[j * 4 + c] = o.off[j][c];
-        tab[NJ * 4 + j] = o.xs_off[j];
-        reinterpret_cast<double *>(tab + 36)[j] = o.scale[j];
-    });
-}
-template <int NR>
-__device__ __forceinline__ void glg_owner_fetch(GlgOwnerRegs<NR> &o, const int *tab) {
-    constexpr int NJ = GlgOwnerRegs<NR>::NJ;
-    glg_static_for<0, NJ>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-#pragma unroll
-        for (int c = 0; c < GlgRowSlots<NR, j>::value; ++c) o.off[j][c] = tab[j * 4 + c];
-        o.xs_off[j] = tab[NJ * 4 + j];
-        o.scale[j] = reinterpret_cast<const double *>(tab + 36)[j];
-    });
-}
-template <int NR, class T>
-__device__ __forceinline__ void glg_owner_update(const GlgOwnerRegs<NR> &o, int warp, T *xs_col, const T *part_col,
-                                                 double *xo, double *acc, int stage, double h, double h_sixth) {
-    // stage 0..2: acc = (stage ? acc : 0) + w k ; xs = x + c k        stage 3: x += h/6 (acc + k) ; xs = x
-    // h_sixth = h / 6.0 is passed in: the division is done once per (micro-)step size, not once per evaluation
-    const bool last = stage == 3;
-    const double w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
-    const double keep = stage == 0 ? 0.0 : 1.0;
-    const double m = last ? h_sixth : (stage == 2 ? h : 0.5 * h);
-    const double can_scale = (double)part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES];
-    double sum[GlgOwnerRegs<NR>::NJ];
-    glg_static_for<0, GlgOwnerRegs<NR>::NJ>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        constexpr int n = GlgRowSlots<NR, j>::value;
-        const double a = (double)part_col[o.off[j][0]];
-        if constexpr (n == 1) sum[j] = a;
-        else if constexpr (n == 2) sum[j] = a + (double)part_col[o.off[j][1]];
-        else if constexpr (n == 3) sum[j] = (a + (double)part_col[o.off[j][1]]) + (double)part_col[o.off[j][2]];
-        else sum[j] = (a + (double)part_col[o.off[j][1]]) + ((double)part_col[o.off[j][2]] + (double)part_col[o.off[j][3]]);
-    });
-#pragma unroll
-    for (int j = 0; j < GlgOwnerRegs<NR>::NJ; ++j) {
-        const double sc = (j == GlgCanopyPos<NR>::row && warp == GlgCanopyPos<NR>::warp) ? can_scale : o.scale[j];
-        const double k = sc * sum[j];
-        const double a_new = glg_fma(w, k, keep * acc[j]);
-        const double xn = glg_fma(m, last ? a_new : k, xo[j]);
-        acc[j] = a_new;
-        xo[j] = last ? xn : xo[j];
-        xs_col[o.xs_off[j]] = (T)xn;
-    }
-}
-
-// evaluates flux group G for this lane
 template <class T>
 struct GlgKView;
 template <>
@@ -238,121 +159,335 @@ struct GlgKView<float> {
     __device__ __forceinline__ static type c(const GlgUniform &U) { return type{U.Cf}; }
 };
 
-#if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
-__device__ int glg_prof_mask_dev = 0x1FF;  // bits 0..7: run group g ; bit 8: run the owner phase (timing experiments only)
-#endif
-template <int G, bool GENERAL, bool GUARD = true, class T, class CV, class HV>
-__device__ __forceinline__ void glg_run_group(const GlgUniform &U, const CV &Cv, const HV &Hc, const double *u, const GlgXsCol<T> &X,
-                                              T *part_col) {
-#if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
-    if (!((glg_prof_mask_dev >> G) & 1)) return;
-#endif
+// ---- one evaluation of the units of group warp W: stage state -> partial sums and specials in shared memory
+template <int NG, int W, bool GENERAL, bool NOISY, class T>
+__device__ __forceinline__ void glg_group_eval(const GlgUniform &U, const T *xs_col, T *part_col, T *h_col, T *c_col, const double *u) {
+    using PL = GlgPlan<NG, GENERAL>;
     const typename GlgKView<T>::type Kv = GlgKView<T>::k(U);
     const GlgConstView Pv{U.P};
-    GlgPartCol<G, T> pt{part_col};
-    if (G == 0) part_col[GLG_SLOT_CANSCALE * GLG_ROLE_LANES] = glg_grp_rad<GENERAL>(Kv, Cv, Hc, X, pt);
-    else if (G == 1) glg_grp_fir<GENERAL>(Kv, Cv, Hc, Pv, u, X, pt);
-    else if (G == 2) {  // the stiffness estimate is only consumed by the guarded loop
-        const T lam = glg_grp_airflow(Kv, Hc, X, pt);
-        if (GUARD) part_col[GLG_SLOT_STIFF * GLG_ROLE_LANES] = lam;
-    }
-    else if (G == 3) glg_grp_conv<GENERAL>(Kv, Cv, Hc, Pv, X, pt);
-    else if (G == 4) glg_grp_screens(Kv, Hc, X, pt);
-    else if (G == 5) glg_grp_cover(Kv, Cv, Hc, X, pt);
-    else if (G == 6) glg_grp_photo<GENERAL>(Kv, Cv, Hc, X, pt);
-    else part_col[GLG_SLOT_LAMBDA * GLG_ROLE_LANES] = glg_grp_flows(Kv, Cv, X, pt);
-}
-
-// Each flux group is a separate (__noinline__) device function.  Inlined into the kernel, ptxas serialises the hand-
-// interleaved chains of the math routines once the function holds all eight groups (FP64 producer distance <= 2 for 40 %
-// of the instructions vs 10 % when a group is compiled on its own -- tools/ubench/sched_probe.cu, tools/sass_dep_all.py),
-// which doubled the latency of the long groups.  A callee cannot see the kernel's __grid_constant__ parameter, so kernel
-// B's group functions read the constants from this __constant__ copy (direct c[3][imm] operands, like the kernel
-// parameter was).  There is ONE copy per device: the host uploads a handle's table before launching when another handle
-// used it last (glg_capi.cu: bind_uniform), after a device synchronise -- alternating handles on one device serialises.
-__constant__ GlgUniform glg_uni_c;
-
-template <int G, bool GENERAL, bool NOISY, bool GUARD, class T>
-__device__ __noinline__ void glg_group_call(const T *xs_col, T *part_col, T *h_col, T *c_col, double thScr, double blScr) {
-    const GlgUniform &U = glg_uni_c;
     const GlgColT<T, GLG_ROLE_LANES> Hc{h_col};
-    const GlgXsCol<T> X{xs_col};
-    const double u[GLG_NU] = {0.0, 0.0, thScr, 0.0, 0.0, blScr};  // only G1's GENERAL terms read the raw screen controls
-    if (NOISY) {
-        const GlgColT<T, GLG_ROLE_LANES> Cc{c_col};
-        glg_run_group<G, GENERAL, GUARD>(U, Cc, Hc, u, X, part_col);
-    } else {
-        glg_run_group<G, GENERAL, GUARD>(U, GlgKView<T>::c(U), Hc, u, X, part_col);
-    }
-}
-
-// GLG_NOINLINE_MASK: bit g set = group g runs as a __noinline__ call, else inlined into the kernel (default: all
-// inlined).  Measured on B200, B = 4096 (profiles/r1_noinline_groups.txt): in-kernel latency of a group running alone,
-// cycles -- inlined G0 693, G1 464, G2 723, G3 643, G4 722, G5 895, G6 1058, G7 1010; as calls G0 968, G4 564, G5 600,
-// G6 546, G7 680.  The calls keep the interleaved order and halve the long groups' latency, but the step gets SLOWER
-// (2.02 ms all inlined, 2.24 ms all calls, 2.39 ms calls for G4..G7 only): two warps share each SM sub-partition's FP64
-// pipe (1148 DFMA-class instructions per evaluation = 631 cycles per sub-partition at 2.2 cycles each), and once both
-// have ILP they queue on it.  Kept as an experiment switch for the round-2 work on group balance.
-
-template <int G, bool GENERAL, bool NOISY, bool GUARD, class T, class CV>
-__device__ __forceinline__ void glg_dispatch_group(const GlgUniform &U, const CV &Cv, const T *xs_col, T *part_col, T *h_col,
-                                                   T *c_col, const double *u) {
-    if ((GLG_NOINLINE_MASK >> G) & 1) {
-        glg_group_call<G, GENERAL, NOISY, GUARD, T>(xs_col, part_col, h_col, c_col, u[2], u[5]);
-    } else {
-        const GlgColT<T, GLG_ROLE_LANES> Hc{h_col};
-        const GlgXsCol<T> X{xs_col};
-        glg_run_group<G, GENERAL, GUARD>(U, Cv, Hc, u, X, part_col);
-    }
-}
-
-template <bool GENERAL, bool NOISY, bool GUARD, int NR, class T, class CV>
-__device__ __forceinline__ void glg_run_warp_groups(int warp, const GlgUniform &U, const CV &Cv, const T *xs_col, T *part_col,
-                                                    T *h_col, T *c_col, const double *u) {
-#define GLG_CALL(G) glg_dispatch_group<G, GENERAL, NOISY, GUARD, T>(U, Cv, xs_col, part_col, h_col, c_col, u)
-    if (NR == 8) {
-        switch (warp) {
-            case 0: GLG_CALL(0); break;
-            case 1: GLG_CALL(1); break;
-            case 2: GLG_CALL(2); break;
-            case 3: GLG_CALL(3); break;
-            case 4: GLG_CALL(4); break;
-            case 5: GLG_CALL(5); break;
-            case 6: GLG_CALL(6); break;
-            default: GLG_CALL(7); break;
+    const GlgColT<T, GLG_ROLE_LANES> Cc{c_col};
+    const GlgXsCol<T, NG, GENERAL> X{xs_col};
+    constexpr unsigned mask = GlgWT<NG, GENERAL>::t.states[W];
+    T v[GLG_NX];
+    GlgSpecial<T> sp;
+    if (NOISY) glg_run_warp_units<NG, W, 0, GENERAL>(Kv, Cc, Hc, Pv, u, X, v, sp);
+    else glg_run_warp_units<NG, W, 0, GENERAL>(Kv, GlgKView<T>::c(U), Hc, Pv, u, X, v, sp);
+    glg_static_for<0, GLG_NX>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if constexpr (mask >> i & 1u) {
+            constexpr int sl = PL::plan.slot[W][i];
+            part_col[sl * GLG_ROLE_LANES] = v[i];
         }
-    } else {  // NR == 4: pairs balanced by measured latency (rad+airflow, fir+conv, screens+cover, photo+flows)
-        switch (warp) {
-            case 0: GLG_CALL(0); GLG_CALL(2); break;
-            case 1: GLG_CALL(1); GLG_CALL(3); break;
-            case 2: GLG_CALL(4); GLG_CALL(5); break;
-            default: GLG_CALL(6); GLG_CALL(7); break;
-        }
+    });
+    if constexpr (GlgWT<NG, GENERAL>::has_unit(W, U_PIPES)) part_col[PL::CANSCALE * GLG_ROLE_LANES] = sp.canscale;
+    if constexpr (GlgWT<NG, GENERAL>::has_unit(W, U_MAINT)) part_col[PL::LAMBDA * GLG_ROLE_LANES] = sp.lambda;
+    if constexpr (GlgWT<NG, GENERAL>::has_unit(W, U_VENT)) part_col[PL::AVENT * GLG_ROLE_LANES] = sp.avent;
+    if constexpr (GlgWT<NG, GENERAL>::has_unit(W, U_SCR)) part_col[PL::ASCR * GLG_ROLE_LANES] = sp.ascr;
+}
+// per-evaluation dispatch on the warp index (fused layout: one loop for all warps)
+template <int NG, int W, bool GENERAL, bool NOISY, class T>
+__device__ __forceinline__ void glg_group_eval_dispatch(int gw, const GlgUniform &U, const T *xs_col, T *part_col, T *h_col, T *c_col,
+                                                        const double *u) {
+    if constexpr (W + 1 < NG) {
+        if (gw == W) glg_group_eval<NG, W, GENERAL, NOISY, T>(U, xs_col, part_col, h_col, c_col, u);
+        else glg_group_eval_dispatch<NG, W + 1, GENERAL, NOISY, T>(gw, U, xs_col, part_col, h_col, c_col, u);
+    } else {
+        glg_group_eval<NG, W, GENERAL, NOISY, T>(U, xs_col, part_col, h_col, c_col, u);
     }
-#undef GLG_CALL
 }
 
-// GRADED: compile the guarded (micro-stepping) loop although the parameters are nominal (NOISY variants always have it).
-template <class T, bool GENERAL, bool NOISY, int NR, bool GRADED = false>
-__global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const __grid_constant__ GlgUniform U,
-                                                                          const __grid_constant__ GlgStepArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// ---- group role: the evaluation loop of group warp W (generic: any unit list)
+template <int NG, int W, bool GENERAL, bool NOISY, class T>
+__device__ __forceinline__ void glg_group_loop(const GlgUniform &U, const T *xs_col, T *part_col, T *h_col, T *c_col, const double *u,
+                                               const volatile int *s_stop, int nthreads) {
+    int last_eval;
+#pragma unroll 1
+    do {
+        glg_bar_sync(GLG_BAR_XS, nthreads);
+        // one flag per group warp (the load's immediate offset identifies the role in the SASS, tools/sasssim); read with the
+        // stage state, consumed after the arrive: off the critical path
+        last_eval = s_stop[W];
+        glg_group_eval<NG, W, GENERAL, NOISY, T>(U, xs_col, part_col, h_col, c_col, u);
+        glg_bar_arrive(GLG_BAR_PARTS, nthreads);
+    } while (!last_eval);
+}
+
+// ---- surface role: U_THSCR / U_BLSCR / U_COVER when each is alone in its warp.  One copy of glg_surface_core for the three
+// warps; what differs (state rows, coefficient rows, output slots, vapour capacity scale) sits in registers.
+template <int NG, bool GENERAL>
+struct GlgSurfaceWarps {
+    using WT = GlgWT<NG, GENERAL>;
+    static constexpr int th = WT::unit_warp(U_THSCR), bl = WT::unit_warp(U_BLSCR), cv = WT::unit_warp(U_COVER);
+    static constexpr bool alone(int w, int u) { return w >= 0 && WT::t.units[w] == (1u << u); }
+    static constexpr bool shared = alone(th, U_THSCR) && alone(bl, U_BLSCR) && alone(cv, U_COVER);
+};
+template <int NG, bool GENERAL, int W>
+struct GlgIsSurface {
+    using SW = GlgSurfaceWarps<NG, GENERAL>;
+    static constexpr bool value = SW::shared && (W == SW::th || W == SW::bl || W == SW::cv);
+};
+template <int NG, bool GENERAL, class T>
+__device__ __forceinline__ void glg_surface_loop(int gw, const GlgUniform &U, const T *xs_col, T *part_col, const T *h_col,
+                                                 const volatile int *s_stop, int nthreads) {
+    using PL = GlgPlan<NG, GENERAL>;
+    using SW = GlgSurfaceWarps<NG, GENERAL>;
     constexpr int NL = GLG_ROLE_LANES;
-    constexpr int NJ = (GLG_NX + NR - 1) / NR;
+    const bool is_th = gw == SW::th, is_cv = gw == SW::cv;
+    constexpr int w_th = SW::th >= 0 ? SW::th : 0, w_bl = SW::bl >= 0 ? SW::bl : 0, w_cv = SW::cv >= 0 ? SW::cv : 0;
+    // A = air side (main air for the screens, top compartment for the cover), S = surface, B = far side, V = vapour pressure of A
+    constexpr int r2 = PL::plan.rank[2], r3 = PL::plan.rank[3], r5 = PL::plan.rank[5], r7 = PL::plan.rank[7], r15 = PL::plan.rank[15],
+                  r16 = PL::plan.rank[16], r20 = PL::plan.rank[20];
+    constexpr int s_th7 = PL::plan.slot[w_th][7], s_th2 = PL::plan.slot[w_th][2], s_th3 = PL::plan.slot[w_th][3], s_th15 = PL::plan.slot[w_th][15];
+    constexpr int s_bl20 = PL::plan.slot[w_bl][20], s_bl2 = PL::plan.slot[w_bl][2], s_bl3 = PL::plan.slot[w_bl][3], s_bl15 = PL::plan.slot[w_bl][15];
+    constexpr int s_cv5 = PL::plan.slot[w_cv][5], s_cv3 = PL::plan.slot[w_cv][3], s_cv16 = PL::plan.slot[w_cv][16];
+    const int xa = (is_cv ? r3 : r2) * NL;
+    const int xsf = (is_cv ? r5 : is_th ? r7 : r20) * NL;
+    const int xb = r3 * NL;  // the cover has no far side: its far coefficient is 0
+    const int xv = (is_cv ? r16 : r15) * NL;
+    const int ps = (is_cv ? s_cv5 : is_th ? s_th7 : s_bl20) * NL;
+    const int pa = (is_cv ? s_cv3 : is_th ? s_th2 : s_bl2) * NL;
+    const int pb = (is_cv ? PL::DUMMY : is_th ? s_th3 : s_bl3) * NL;
+    const int pv = (is_cv ? s_cv16 : is_th ? s_th15 : s_bl15) * NL;
+    const int ha = (is_cv ? (int)H_HECIN : is_th ? (int)H_17TH : (int)H_17BL) * NL;
+    const int hb = (is_cv ? (int)H_ZERO : is_th ? (int)H_17TH : (int)H_17BL) * NL;
+    const typename GlgKView<T>::type Kv = GlgKView<T>::k(U);
+    const T invvp = is_cv ? Kv[K_INVVPTOP] : Kv[K_INVVPAIR];
+    const T L = Kv[K_L];
+    const volatile int *stop = s_stop + gw;
+    int last_eval;
+#pragma unroll 1
+    do {
+        glg_bar_sync(GLG_BAR_XS, nthreads);
+        T surf, air, far, vp;
+        last_eval = *stop;
+        glg_surface_core<true, T>(xs_col[xa], xs_col[xsf], xs_col[xb], xs_col[xv], h_col[ha], h_col[hb], invvp, L, surf, air, far, vp);
+        part_col[ps] = surf;
+        part_col[pa] = air;
+        part_col[pb] = far;
+        part_col[pv] = vp;
+        glg_bar_arrive(GLG_BAR_PARTS, nthreads);
+    } while (!last_eval);
+}
+
+template <int NG, int W, bool GENERAL, bool NOISY, class T>
+__device__ __forceinline__ void glg_group_dispatch(int gw, const GlgUniform &U, const T *xs_col, T *part_col, T *h_col, T *c_col,
+                                                   const double *u, const volatile int *s_stop, int nthreads) {
+    if constexpr (W < NG) {
+        if constexpr (GlgIsSurface<NG, GENERAL, W>::value) {
+            glg_group_dispatch<NG, W + 1, GENERAL, NOISY, T>(gw, U, xs_col, part_col, h_col, c_col, u, s_stop, nthreads);
+        } else {
+            if (gw == W) glg_group_loop<NG, W, GENERAL, NOISY, T>(U, xs_col, part_col, h_col, c_col, u, s_stop, nthreads);
+            else glg_group_dispatch<NG, W + 1, GENERAL, NOISY, T>(gw, U, xs_col, part_col, h_col, c_col, u, s_stop, nthreads);
+        }
+    }
+}
+
+// ---- owner: RK4 state of the NJ plan rows of owner index o for this lane's env, and the micro-step bookkeeping.
+// One nominal RK4 substep = m micro-steps of h_nom/m, m per env = max of the harvest-stiffness guard (glg_model.h; 1 unless an
+// organ sits inside its harvest window) and, with integrator = 1, the graded start of the interval and the transient-stiffness
+// rule.  Lanes with a smaller m idle with h = 0 for the remaining micro-steps of the CTA, so an env's result never depends on
+// its CTA mates.
+// Stage update in unscaled units: s = sum of the partial sums, k = scale * s.
+//   stage 0..2: acc = (stage ? acc : 0) + w s ; xs = x + (c h scale) s        stage 3: x += (h/6 scale) (acc + s) ; xs = x
+// pre()  : everything that does not need the partial sums ((c h scale), the acc term of stage 3, the end-of-interval tests)
+// post() : load -> add tree -> one FMA -> store of the next stage state; decides the micro-step count on a first evaluation
+// book() : stage-sum / state / counter updates (off the critical path)
+template <class T, int NG, bool GENERAL>
+struct GlgOwner {
+    using PL = GlgPlan<NG, GENERAL>;
+    static constexpr int NJ = PL::NJ, NL = GLG_ROLE_LANES;
+    static constexpr int can_row = PL::canopy_entry / GLG_NO;
+    double xo[NJ], acc[NJ], scale[NJ];  // the RK4 state and stage sum stay fp64 in both precisions
+    double hc[NJ], base[NJ], sum[NJ], xn[NJ];
+    double h_nom, h_lane, cs, w;
+    int o, n_sub, graded, sub, q, stage, m_lane, m_cta, n_micro;
+    bool can_owner, first, last;
+    int final_eval, flag_next;
+
+    // state index of row j of this owner (compile-time tables, runtime owner index)
+    template <int J>
+    __device__ __forceinline__ int row_state() const {
+        constexpr int st0 = PL::plan.order[J * GLG_NO], st1 = PL::plan.order[J * GLG_NO + 1], st2 = PL::plan.order[J * GLG_NO + 2],
+                      st3 = PL::plan.order[J * GLG_NO + 3];
+        return o == 0 ? st0 : o == 1 ? st1 : o == 2 ? st2 : st3;
+    }
+    __device__ __forceinline__ void init(int owner, const GlgStepArgs &A, const double *s_xfin, const double *s_scale, int lane) {
+        o = owner;
+        glg_static_for<0, NJ>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            const int st = row_state<j>();
+            scale[j] = s_scale[j * GLG_NO + o];
+            xo[j] = st >= 0 ? s_xfin[st * NL + lane] : 0.0;
+            acc[j] = 0.0;
+        });
+        can_owner = o == PL::canopy_entry % GLG_NO;
+        h_nom = A.dt / (double)A.n_sub;
+        n_sub = A.n_sub;
+        graded = A.integrator == 1;
+        glg_pin(h_nom);  // kept in registers: ptxas otherwise re-reads the kernel parameters inside the loop
+        glg_pin(n_sub);
+        glg_pin(graded);
+        sub = q = stage = n_micro = 0;
+        m_lane = m_cta = 1;
+        h_lane = h_nom;
+    }
+    __device__ __forceinline__ void pre(int lane, bool pin) {
+        first = stage == 0 && q == 0;  // first evaluation of a nominal substep: the micro-step count is decided in post()
+        last = stage == 3;
+        cs = stage == 2 ? 1.0 : (last ? 1.0 / 6.0 : 0.5);
+        w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
+        // is this the last evaluation of the interval?  (m_cta of the last substep is known by its stage 3)
+        const bool last_micro = q + 1 >= m_cta && sub + 1 >= n_sub;
+        final_eval = last && last_micro;
+        flag_next = stage == 2 && last_micro && o == 0 && lane < 16;  // the group warps' next evaluation is the last one
+        // speculate m = 1 for a first evaluation (true except at the graded start of an interval and in stiff transients)
+        const double hcs = cs * (first ? h_nom : (q < m_lane ? h_lane : 0.0));
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            hc[j] = hcs * scale[j];
+            base[j] = xo[j];
+        }
+        if (last) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) base[j] = glg_fma(hc[j], acc[j], xo[j]);
+        }
+        if (pin) {  // keep the work above in front of the barrier wait that follows (costs 2 NJ live doubles across it)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                glg_pin(hc[j]);
+                glg_pin(base[j]);
+            }
+        }
+        glg_pin(final_eval);
+        glg_pin(flag_next);
+    }
+    __device__ __forceinline__ void post(const GlgUniform &U, const T *part_col, T *xs_col) {
+        const T *pbase = part_col + o * NL;  // row j, contribution c at pbase[(row_base[j] + c) * NO * NL]
+        T *xbase = xs_col + o * NL;          // row j at xbase[j * NO * NL]
+        glg_static_for<0, NJ>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            constexpr int n = PL::plan.row_slots[j];
+            if constexpr (n == 0) {
+                sum[j] = 0.0;
+            } else {
+                constexpr int rb = PL::plan.row_base[j];
+                double v[n];
+#pragma unroll
+                for (int c = 0; c < n; ++c) v[c] = (double)pbase[(rb + c) * GLG_NO * NL];
+#pragma unroll
+                for (int s = 1; s < n; s *= 2)  // pairwise summation tree
+#pragma unroll
+                    for (int c = 0; c + s < n; c += 2 * s) v[c] += v[c + s];
+                sum[j] = v[0];
+            }
+        });
+        // the canopy's capacity scale K_INVCAPLEAF / LAI changes with the stage: its sum is scaled here (its scale[] entry is 1)
+        sum[can_row] *= can_owner ? (double)part_col[PL::CANSCALE * NL] : 1.0;
+        if (first) {
+            // m = 1 for every env of the CTA unless a harvest window is active (2 h lambda >= 1), the graded integrator is at
+            // the start of the interval or its stiffness rule asks for a split: one compare + vote on the common path
+            const double lam_h = (double)part_col[PL::LAMBDA * NL];
+            double lam_s = 0.0;
+            if (graded) lam_s = glg_stiffness(GlgConstView{U.K}, (double)part_col[PL::ASCR * NL], (double)part_col[PL::AVENT * NL]);
+            const bool split = (2.0 * h_nom * lam_h >= 1.0) || (graded && (sub < GLG_GRADED_SUBSTEPS || h_nom * lam_s * GLG_STIFF_INV_CFL >= 1.0));
+            m_lane = 1;
+            m_cta = 1;
+            h_lane = h_nom;
+            if (__any_sync(0xffffffffu, split)) {
+                m_lane = glg_micro_steps_from_lambda(lam_h, h_nom);
+                if (graded) {
+                    int ms = 1 + (int)floor(h_nom * lam_s * GLG_STIFF_INV_CFL);
+                    ms = ms > GLG_MAX_MICRO ? GLG_MAX_MICRO : (ms < 1 ? 1 : ms);  // ms < 1 only for a NaN estimate
+                    if (sub < GLG_GRADED_SUBSTEPS && ms < GLG_GRADED_M) ms = GLG_GRADED_M;
+                    m_lane = max(m_lane, ms);
+                }
+                m_cta = __reduce_max_sync(0xffffffffu, m_lane);  // every owner warp sees the same 32 envs
+                // reciprocal + multiply instead of an IEEE division; the step size differs from h_nom/m by at most 1 ulp
+                h_lane = m_lane == 1 ? h_nom : h_nom * glg_rcp((double)m_lane);
+                const double hcs = cs * h_lane;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) hc[j] = hcs * scale[j];
+            }
+            n_micro += m_lane;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            xn[j] = glg_fma(hc[j], sum[j], base[j]);
+            xbase[j * GLG_NO * NL] = (T)xn[j];
+        }
+        if (final_eval) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) xo[j] = xn[j];
+        }
+    }
+    __device__ __forceinline__ void book() {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[j] = glg_fma(w, sum[j], acc[j]);
+        if (last) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                xo[j] = xn[j];
+                acc[j] = 0.0;
+            }
+        }
+        if (++stage == 4) {
+            stage = 0;
+            if (++q >= m_cta) {
+                q = 0;
+                ++sub;
+            }
+        }
+    }
+    // final state -> s_xfin; returns 1 if any of this owner's states is not finite
+    __device__ __forceinline__ int finish(double *s_xfin, int lane) const {
+        int bad = 0;
+        glg_static_for<0, NJ>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            const int st = row_state<j>();
+            bad |= !(fabs(xo[j]) <= 1.79769313486231570e308);
+            if (st >= 0) s_xfin[st * NL + lane] = xo[j];
+        });
+        return bad;
+    }
+};
+
+
+// Two layouts of the same machinery:
+//   FUSED = false (latency layout, small batches): NG group warps + GLG_NO dedicated owner warps per 32 envs, every role in its
+//           own loop, producer/consumer named barriers.  The step time of a batch that leaves SMs under-filled is the latency of
+//           one CTA, so the RHS is spread over as many warps as balance allows (NG = 12).
+//   FUSED = true (throughput layout, large batches): NG = GLG_NO = 4 warps per 32 envs; warp w evaluates the units of group
+//           warp w AND owns the plan rows of owner w (dedicated owner warps would idle most of the time and hold a quarter of the
+//           registers); one loop, two CTA barriers per evaluation, 4 CTAs per SM so that every SM sub-partition runs ONE role's
+//           code for four CTAs.  Compared with the round-1 kernel the owner side keeps only the RK4 state in registers (all
+//           addresses are immediates of the rank-ordered layout), so the unit code has ~95 registers for interleaving.
+// MINB = CTAs per SM the register budget is sized for.
+template <class T, bool GENERAL, bool NOISY, int NG, int MINB, bool FUSED>
+__global__ void __launch_bounds__(32 * (NG + (FUSED ? 0 : GLG_NO)), MINB) glg_step_units_kernel(const __grid_constant__ GlgUniform U,
+                                                                                                 const __grid_constant__ GlgStepArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(!FUSED || NG == GLG_NO, "fused layout: one group role per owner");
+    constexpr int NL = GLG_ROLE_LANES;
+    constexpr int NT = 32 * (NG + (FUSED ? 0 : GLG_NO));
+    using PL = GlgPlan<NG, GENERAL>;
+    using SW = GlgSurfaceWarps<NG, GENERAL>;
+    constexpr int NJ = PL::NJ;
     double *s_wtile = reinterpret_cast<double *>(smem_raw);  // [(Np+1)][10] f64
-    double *s_xfin = s_wtile + (size_t)(A.Np + 1) * GLG_ND;   // [28][32] f64: state in / final state out (owners <-> warp 0)
-    T *s_xs = reinterpret_cast<T *>(s_xfin + GLG_NX * NL);    // [28 + 1 dummy][32] stage state in the groups' precision
-    T *s_part = s_xs + (GLG_NX + 1) * NL;                     // [GLG_NSLOTS][32]: contributions, zero slot, canopy scale, lambda
-    T *s_H = s_part + GLG_NSLOTS * NL;                        // [H_COUNT][32]
+    double *s_xfin = s_wtile + (size_t)(A.Np + 1) * GLG_ND;   // [28 + 1][32] f64, state order: state in / final state out (owners <-> warp 0); row 28: fruit mass before the step
+    double *s_scale = s_xfin + (GLG_NX + 1) * NL;              // [XS_ROWS] capacity scale of plan entry n (throughput variant: read per evaluation)
+    T *s_xs = reinterpret_cast<T *>(s_xfin + (GLG_NX + 2) * NL);  // [XS_ROWS][32] stage state in the units' precision, plan order
+    T *s_part = s_xs + PL::XS_ROWS * NL;                      // [NSLOTS][32]: partial sums, specials
+    T *s_H = s_part + PL::NSLOTS * NL;                        // [H_COUNT][32]
     T *s_C = s_H + H_COUNT * NL;                              // [C_COUNT][32] (NOISY)
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_xs) + GlgRoleSmem<T, NOISY>::col_bytes());
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_xs) + GlgRoleSmem<T, NG, GENERAL, NOISY>::col_bytes());
     int *s_tbl = reinterpret_cast<int *>(s_bar + 2);
     int *s_k = s_tbl + NL;
     int *s_tbl_t = s_k + NL;
     int *s_k_t = s_tbl_t + NL;
     int *s_bad = s_k_t + NL;
-    int *s_misc = s_bad + NL;
-    int *s_owntab = s_misc + 4;  // [NR][GLG_OWNER_TAB_WORDS]
+    int *s_misc = s_bad + NL;            // [0..1] weather staging
+    volatile int *s_stop = s_misc + 4;   // [16] stop flag, one copy per group warp
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -369,7 +504,7 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
     const int uniform = glg_stage_weather(A, s_wtile, s_bar, s_misc, active, kw, tbl, bk, bt);
     const double *wrow = uniform ? s_wtile : (A.weather + ((size_t)tbl * A.rows + (size_t)kw) * GLG_ND);
 
-    // ---- prologue: warp 0, lane = env
+    // ---- prologue: warp 0, lane = env; the other warps clear the exchange slots (padding slots must read 0.0)
     double u[GLG_NU], d[GLG_ND];
 #pragma unroll
     for (int i = 0; i < GLG_NU; ++i) u[i] = 0.0;
@@ -395,141 +530,107 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
             }
             glg_hoist(GlgConstView{U.P}, u, d0, Hc);
         }
-#pragma unroll
-        for (int i = 0; i < GLG_NX; ++i) {
-            s_xs[i * NL + lane] = (T)x[i];
+        glg_static_for<0, GLG_NX>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int r = PL::plan.rank[i];
+            s_xs[r * NL + lane] = (T)x[i];
             s_xfin[i * NL + lane] = x[i];
-        }
+        });
+        // what the epilogue needs goes through shared memory, so that nothing of it stays in registers across the loops
+        s_xfin[GLG_NX * NL + lane] = fruit_prev;
+        s_k[lane] = k;
+        s_tbl[lane] = tbl;
         s_bad[lane] = 0;
-        s_part[GLG_SLOT_ZERO * NL + lane] = (T)0;
-    }
-    __syncthreads();
-    if (GENERAL && warp == 1 && active) {
-        // G1's general terms read the raw screen controls (its warp is 1 in both layouts); warp 0's prologue stored
-        // the updated controls before the barrier above
-#pragma unroll
-        for (int i = 0; i < GLG_NU; ++i) u[i] = A.u[(size_t)i * A.B + e];
-    }
-
-    // ---- integration: group phase / owner phase
-    T *xs_col = s_xs + lane;
-    T *part_col = s_part + lane;
-    const GlgXsCol<T> X{xs_col};
-    double xo[NJ], acc[NJ];  // the RK4 state and stage sum stay fp64 in both precisions
-    GlgOwnerRegs<NR> own;
-    glg_owner_setup<NR>(U.K, warp, own);
-#if GLG_NOINLINE_MASK
-    if (lane == 0) glg_owner_store<NR>(own, s_owntab + warp * GLG_OWNER_TAB_WORDS);
-    __syncwarp();
-#endif
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const int i = glg_owner_table.order[j * NR + warp];
-        xo[j] = i >= 0 ? s_xfin[i * NL + lane] : 0.0;
-        acc[j] = 0.0;
-    }
-    const double h_nom = A.dt / (double)A.n_sub;
-    const double h_nom_sixth = h_nom / 6.0;
-    int n_micro = 0;  // RK4 micro-steps this env executed (guarded loop only)
-#ifdef GLG_PROFILE_GROUPS
-    long long t_grp = 0, t_b1 = 0, t_own = 0, t_b2 = 0;
-#endif
-    constexpr bool GUARDED = NOISY || GRADED;
-    if (!GUARDED) {
-        // nominal parameters, fixed-step integrator: plain loop (the harvest guard cannot trigger: the crop approaches cLeafMax from
-        // below and lambda stays ~1e-5 1/s; the guarded loop's extra state costs ~8 % at B = 4096)
-        const int n_eval = 4 * A.n_sub;
-#pragma unroll 1
-        for (int ev = 0; ev < n_eval; ++ev) {
-#ifdef GLG_PROFILE_GROUPS
-            const long long c0 = clock64();
-#endif
-            glg_run_warp_groups<GENERAL, NOISY, false, NR, T>(warp, U, GlgKView<T>::c(U), xs_col, part_col, s_H + lane, s_C + lane, u);
-#if GLG_NOINLINE_MASK
-            glg_owner_fetch<NR>(own, s_owntab + warp * GLG_OWNER_TAB_WORDS);
-#endif
-#ifdef GLG_PROFILE_GROUPS
-            const long long c1 = clock64();
-#endif
-            __syncthreads();
-#ifdef GLG_PROFILE_GROUPS
-            const long long c2 = clock64();
-#endif
-#if defined(GLG_PROFILE_GROUPS) || defined(GLG_PROFILE_MASK)
-            if ((glg_prof_mask_dev >> 8) & 1)
-#endif
-            glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, ev & 3, h_nom, h_nom_sixth);
-#ifdef GLG_PROFILE_GROUPS
-            const long long c3 = clock64();
-#endif
-            __syncthreads();
-#ifdef GLG_PROFILE_GROUPS
-            const long long c4 = clock64();
-            t_grp += c1 - c0; t_b1 += c2 - c1; t_own += c3 - c2; t_b2 += c4 - c3;
-#endif
+        if (lane < 16) s_stop[lane] = 0;
+        if (lane < PL::XS_ROWS) {
+            int sk = -1;
+            glg_static_for<0, PL::XS_ROWS>([&](auto nc) {
+                constexpr int n = decltype(nc)::value;
+                constexpr int v = PL::plan.scale_k[n];
+                sk = lane == n ? v : sk;
+            });
+            s_scale[lane] = sk >= 0 ? U.K[sk] : 1.0;  // -1: the units wrote a derivative; -2 (canopy): scaled per stage in the loop
+        }
+        if (lane == 0) {
+            s_misc[2] = uniform;
+            s_misc[3] = 0;
         }
     } else {
-        // Guarded loop (parametric uncertainty and / or the graded integrator): one nominal RK4 substep = m micro-steps of
-        // h_nom/m, m per env = max of the harvest-stiffness guard (glg_model.h; 1 unless an organ sits inside its harvest
-        // window) and, with integrator = 1, the graded start of the interval and the transient-stiffness rule.  Lanes with a
-        // smaller m idle with h = 0 for the remaining micro-steps of the CTA, so an env's result never depends on its CTA mates.
-        int sub = 0, q = 0, stage = 0, m_lane = 1, m_cta = 1;
-        double h_lane = h_nom, h_sixth = h_nom_sixth;
-#pragma unroll 1
-        while (sub < A.n_sub) {
-            if (NOISY) glg_run_warp_groups<GENERAL, true, true, NR, T>(warp, U, Cc, xs_col, part_col, s_H + lane, s_C + lane, u);
-            else glg_run_warp_groups<GENERAL, false, true, NR, T>(warp, U, GlgKView<T>::c(U), xs_col, part_col, s_H + lane, s_C + lane, u);
-#if GLG_NOINLINE_MASK
-            glg_owner_fetch<NR>(own, s_owntab + warp * GLG_OWNER_TAB_WORDS);
-#endif
-            __syncthreads();
-            if (stage == 0) {
-                if (q == 0) {
-                    m_lane = glg_micro_steps_from_lambda((double)part_col[GLG_SLOT_LAMBDA * NL], h_nom);
-                    if (A.integrator == 1) {
-                        int ms = 1 + (int)floor(h_nom * (double)part_col[GLG_SLOT_STIFF * NL] * GLG_STIFF_INV_CFL);
-                        ms = ms > GLG_MAX_MICRO ? GLG_MAX_MICRO : (ms < 1 ? 1 : ms);  // ms < 1 only for a NaN estimate
-                        if (sub < GLG_GRADED_SUBSTEPS && ms < GLG_GRADED_M) ms = GLG_GRADED_M;
-                        m_lane = max(m_lane, ms);
-                    }
-                    n_micro += m_lane;
-                    m_cta = __reduce_max_sync(0xffffffffu, m_lane);  // every warp sees the same 32 envs
-                    // reciprocal + multiply instead of IEEE divisions: three of them (with their slow paths) pushed the loop
-                    // body past the 32 KB instruction cache; the step size differs from h_nom/m by at most 1 ulp
-                    h_lane = h_nom * glg_rcp((double)m_lane);
-                    h_sixth = h_lane * (1.0 / 6.0);
-                }
-            }
-            glg_owner_update<NR>(own, warp, xs_col, part_col, xo, acc, stage, q < m_lane ? h_lane : 0.0, q < m_lane ? h_sixth : 0.0);
-            __syncthreads();
-            if (++stage == 4) {
-                stage = 0;
-                if (++q >= m_cta) {
-                    q = 0;
-                    ++sub;
-                }
-            }
-        }
+        for (int i = tid - 32; i < PL::NSLOTS * NL; i += NT - 32) s_part[i] = (T)0;
     }
-#ifdef GLG_PROFILE_GROUPS
-    if (blockIdx.x == 0 && lane == 0)
-        printf("warp %d: group %lld  barrier1 %lld  owner %lld  barrier2 %lld  cycles/eval\n", warp, t_grp / (4 * A.n_sub),
-               t_b1 / (4 * A.n_sub), t_own / (4 * A.n_sub), t_b2 / (4 * A.n_sub));
-#endif
-    {
-        int bad = 0;
+    __syncthreads();
+
+    T *xs_col = s_xs + lane;
+    T *part_col = s_part + lane;
+    int n_micro = 0;  // RK4 micro-steps this env executed (owner warp 0 counts)
+    // register budget per thread at launch, and after re-balancing (throughput variants only)
+    constexpr int kLaunchRegs = (65536 / (MINB * NT)) / 8 * 8 > 255 ? 248 : (65536 / (MINB * NT)) / 8 * 8;
+    constexpr int kGroupRegs = kLaunchRegs >= 80 ? 64 : kLaunchRegs >= 64 ? 56 : 48;
+    constexpr int kOwnerRegs = (kLaunchRegs + (kLaunchRegs - kGroupRegs) * NG / GLG_NO) / 8 * 8;
+    constexpr bool kRebalance = !FUSED && MINB > 1 && kLaunchRegs > kGroupRegs && kLaunchRegs <= 80 && NG % 4 == 0;
+    if (FUSED) {
+        // ---- fused layout: every warp is group warp `warp` and owner `warp`
+        if (GENERAL && active && warp == GlgWT<NG, GENERAL>::unit_warp(U_FIR)) {
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            bad |= !(fabs(xo[j]) <= 1.79769313486231570e308);
-            const int i = glg_owner_table.order[j * NR + warp];
-            if (i >= 0) s_xfin[i * NL + lane] = xo[j];
+            for (int i = 0; i < GLG_NU; ++i) u[i] = A.u[(size_t)i * A.B + e];
         }
+        GlgOwner<T, NG, GENERAL> own;
+        own.init(warp, A, s_xfin, s_scale, lane);
+#pragma unroll 1
+        for (;;) {
+            glg_group_eval_dispatch<NG, 0, GENERAL, NOISY, T>(warp, U, xs_col, part_col, s_H + lane, s_C + lane, u);
+            own.pre(lane, false);
+            __syncthreads();
+            own.post(U, part_col, xs_col);
+            if (own.final_eval) break;
+            own.book();
+            __syncthreads();
+        }
+        n_micro = own.n_micro;
+        if (own.finish(s_xfin, lane)) s_bad[lane] = 1;  // benign race: every writer stores 1
+    } else if (warp >= GLG_NO) {
+        // ---- group warps
+        if (kRebalance) glg_reg_dec<kGroupRegs>();
+        const int gw = warp - GLG_NO;
+        if (GENERAL && active && gw == GlgWT<NG, GENERAL>::unit_warp(U_FIR)) {
+            // U_FIR's general terms read the raw screen controls; warp 0's prologue stored the updated controls before the barrier
+#pragma unroll
+            for (int i = 0; i < GLG_NU; ++i) u[i] = A.u[(size_t)i * A.B + e];
+        }
+        if (SW::shared && (gw == SW::th || gw == SW::bl || gw == SW::cv)) glg_surface_loop<NG, GENERAL, T>(gw, U, xs_col, part_col, s_H + lane, s_stop, NT);
+        else glg_group_dispatch<NG, 0, GENERAL, NOISY, T>(gw, U, xs_col, part_col, s_H + lane, s_C + lane, u, s_stop, NT);
+        if (kRebalance) glg_reg_inc<kLaunchRegs>();
+    } else {
+        // ---- owner warps (GlgOwner)
+        if (kRebalance) glg_reg_inc<kOwnerRegs>();
+        GlgOwner<T, NG, GENERAL> own;
+        own.init(warp, A, s_xfin, s_scale, lane);
+        glg_bar_arrive(GLG_BAR_XS, NT);  // the prologue's stage state is in shared memory: release the group warps' first evaluation
+#pragma unroll 1
+        for (;;) {
+            own.pre(lane, MINB == 1);
+            glg_bar_sync(GLG_BAR_PARTS, NT);
+            own.post(U, part_col, xs_col);
+            if (own.final_eval) break;
+            if (own.flag_next) s_stop[lane] = 1;
+            glg_bar_arrive(GLG_BAR_XS, NT);
+            own.book();  // after the arrive: off the critical path
+        }
+        n_micro = own.n_micro;
+        const int bad = own.finish(s_xfin, lane);
         if (bad) s_bad[lane] = 1;  // benign race: every writer stores 1
+        if (kRebalance) glg_reg_dec<kLaunchRegs>();
     }
     __syncthreads();
 
     // ---- epilogue: warp 0, lane = env
+    const int uniform2 = s_misc[2], bk2 = s_misc[0], bt2 = s_misc[1];
     if (warp == 0) {
+        const int e = blockIdx.x * A.role_lanes + lane;
+        const bool active = lane < A.role_lanes && e < A.B;
+        const int k = s_k[lane], tbl = s_tbl[lane];
+        const int kw = min(k, A.rows - A.Np - 1);
+        const double *wrow = uniform2 ? s_wtile : (A.weather + ((size_t)tbl * A.rows + (size_t)kw) * GLG_ND);
         GlgEnvOut o;
         o.done = 0; o.k_obs = -1; o.tbl_obs = 0; o.k_term = -1; o.tbl_term = 0; o.fin_ret = 0.0; o.fin_len = 0.0;
 #pragma unroll
@@ -539,18 +640,16 @@ __global__ void __launch_bounds__(32 * NR, 16 / NR) glg_step_roles_kernel(const 
             double x[GLG_NX];
 #pragma unroll
             for (int i = 0; i < GLG_NX; ++i) x[i] = s_xfin[i * NL + lane];
-            glg_env_epilogue(U, A, e, k, kw, tbl, wrow, x, fruit_prev, bad, ctr, o);
+            glg_env_epilogue(U, A, e, k, kw, tbl, wrow, x, s_xfin[GLG_NX * NL + lane], bad, A.step_ctr[e], o);
         }
         s_tbl[lane] = o.tbl_obs;
         s_k[lane] = o.k_obs;
         s_tbl_t[lane] = o.tbl_term;
         s_k_t[lane] = o.k_term;
         glg_stats_reduce(A, active, bad, o);
-        if (GUARDED) {
-            const int tot = __reduce_add_sync(0xffffffffu, active ? n_micro : 0);
-            if (lane == 0 && tot > 0) atomicAdd(&A.stats[15], (double)tot);
-        }
+        const int tot = __reduce_add_sync(0xffffffffu, active ? n_micro : 0);
+        if (lane == 0 && tot > 0) atomicAdd(&A.stats[15], (double)tot);
     }
     __syncthreads();
-    glg_write_forecast(A, A.role_lanes, s_tbl, s_k, s_tbl_t, s_k_t, s_wtile, uniform, bk, bt);
+    glg_write_forecast(A, A.role_lanes, s_tbl, s_k, s_tbl_t, s_k_t, s_wtile, uniform2, bk2, bt2);
 }

@@ -177,8 +177,8 @@ class GreenLightVecEnv:
         cfg.seed = int(seed) & (2**64 - 1)
         cfg.env_id_offset = int(env_id_offset)
         cfg.integrator = 0 if integrator == "fixed" else 1
-        cfg.reserved = int(role_lanes)    # kernel B envs-per-CTA override (0 = auto)
-        cfg.role_warps = int(role_warps)  # 0 auto, 1 = one thread per env, 4 = warp-specialised RHS
+        cfg.reserved = int(role_lanes)    # kernel C envs-per-CTA override (0 = auto)
+        cfg.role_warps = int(role_warps)  # 0 auto, 1 = one thread per env, 2 / 3 = warp-specialised kernel (1 / 2 CTAs per SM)
         self.reward_params = rp
         self._seed = int(seed)
         self._h = C.c_void_p()

@@ -63,8 +63,9 @@ typedef struct glg_config {
     double uncertainty_scale;/* tomato_env.py:34,118 ; 0 = nominal parameters */
     uint64_t seed;           /* Philox key */
     int64_t env_id_offset;   /* global index of local env 0 (multi-GPU sharding; RNG streams follow the global id) */
-    int32_t role_warps;      /* kernel variant: 0 = auto, 1 = one thread per env (kernel A), 4 / 8 = kernel B with 4 / 8 warps per 32 envs */
-    int32_t reserved;        /* 0, or 1..32: override of kernel B's envs-per-CTA (tuning / tests) */
+    int32_t role_warps;      /* kernel variant: 0 = auto, 1 = one thread per env (kernel A), 2 / 3 = warp-specialised kernel C (4 owner +
+                              * 12 flux-unit warps per 32 envs) compiled for one CTA per SM (latency: small batches) / two (throughput) */
+    int32_t reserved;        /* 0, or 1..32: override of kernel C's envs-per-CTA (tuning / tests) */
     int32_t integrator;      /* 0 = fixed-step RK4, n_sub equal substeps (the parity contract);
                                 1 = graded RK4: the first 5 nominal substeps of every control interval are split in 4 (the
                                     controls just changed: fast transients) and any nominal substep is split further while the

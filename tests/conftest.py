@@ -21,7 +21,7 @@ def _build_test_libs():
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
     so = os.path.join(ROOT, "tests", "hostmath", "libhostmath.so")
     src = os.path.join(ROOT, "tests", "hostmath", "hostmath.cpp")
-    hdrs = [os.path.join(ROOT, "greenlight-gym2_b200", "csrc", h) for h in ("glg_model.h", "glg_math.h", "glg_rk4.h")]
+    hdrs = [os.path.join(ROOT, "greenlight-gym2_b200", "csrc", h) for h in ("glg_model.h", "glg_math.h", "glg_rk4.h", "glg_units.h")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src], check=True)
     # the product library: normally built by __graft_entry__.build(); on a fresh checkout build it here (nvcc cross-compiles

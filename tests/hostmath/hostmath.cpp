@@ -2,6 +2,7 @@
 // Lets `pytest -m "not gpu"` check the restructured RHS / RK4 against the oracle without a GPU.
 #include "../../greenlight-gym2_b200/csrc/glg_model.h"
 #include "../../greenlight-gym2_b200/csrc/glg_rk4.h"
+#include "../../greenlight-gym2_b200/csrc/glg_units.h"
 
 extern "C" {
 void hm_math(int op, const double *in, double *out, int n) {
@@ -18,69 +19,73 @@ void hm_rhs(const double *x, const double *u, const double *d, const double *p, 
     else glg_rhs<false>(K, C, H, p, u, d, x, S);
 }
 
-// RHS assembled from the eight group functions + owner-side summation/scaling (the warp-specialised kernel's data flow)
-void hm_rhs_roles(const double *x, const double *u, const double *d, const double *p, int general, double *S) {
-    double K[K_COUNT], C[C_COUNT], H[H_COUNT], part[GLG_NGROUPS][GLG_NX] = {};
-    glg_make_k(p, K);
-    glg_make_c(p, C);
-    glg_hoist(p, u, d, H);
-    double *q[GLG_NGROUPS];
-    for (int g = 0; g < GLG_NGROUPS; ++g) q[g] = part[g];
-    double can_scale;
-    if (general) {
-        can_scale = glg_grp_rad<true>(K, C, H, x, q[0]);
-        glg_grp_fir<true>(K, C, H, p, u, x, q[1]);
-        glg_grp_conv<true>(K, C, H, p, x, q[3]);
-        glg_grp_photo<true>(K, C, H, x, q[6]);
-    } else {
-        can_scale = glg_grp_rad<false>(K, C, H, x, q[0]);
-        glg_grp_fir<false>(K, C, H, p, u, x, q[1]);
-        glg_grp_conv<false>(K, C, H, p, x, q[3]);
-        glg_grp_photo<false>(K, C, H, x, q[6]);
-    }
-    glg_grp_airflow(K, H, x, q[2]);
-    glg_grp_screens(K, H, x, q[4]);
-    glg_grp_cover(K, C, H, x, q[5]);
-    glg_grp_flows(K, C, x, q[7]);
-    for (int i = 0; i < GLG_NX; ++i) {
-        double sum = 0.0;
-        for (int g = 0; g < GLG_NGROUPS; ++g)
-            if (glg_group_mask(i) >> g & 1u) sum += part[g][i];
-        const int sk = glg_state_scale_index(i);
-        S[i] = (sk >= 0 ? K[sk] : (sk == -1 ? 1.0 : can_scale)) * sum;
+// RHS assembled from the flux units + owner-side summation/scaling (the warp-specialised kernel's data flow): every group warp
+// of the NG-warp assignment accumulates its units into its own partial sums, the owner adds the warps' sums in warp order.
+}  // extern "C"
+template <class T>
+struct HmView { const T *b; T operator[](int i) const { return b[i]; } };
+template <class T>
+struct HmX { const T *p; template <int I> T at() const { return p[I]; } };
+template <int NG, int W, bool GENERAL, class T>
+static void hm_warps(const HmView<T> &K, const HmView<T> &C, const HmView<T> &H, const double *p, const double *u, const HmX<T> &X,
+                     double *sum, GlgSpecial<T> &sp) {
+    if constexpr (W < NG) {
+        T v[GLG_NX] = {};
+        glg_run_warp_units<NG, W, 0, GENERAL>(K, C, H, HmView<double>{p}, u, X, v, sp);
+        constexpr unsigned mask = GlgWT<NG, GENERAL>::t.states[W];
+        for (int i = 0; i < GLG_NX; ++i)
+            if (mask >> i & 1u) sum[i] += (double)v[i];
+        hm_warps<NG, W + 1, GENERAL, T>(K, C, H, p, u, X, sum, sp);
     }
 }
-
-// the same group functions instantiated in float (throughput mode): contributions in fp32, owner-side sum/scale in fp64
-struct HmF32View { const float *b; float operator[](int i) const { return b[i]; } };
-void hm_rhs_roles_f32(const double *x, const double *u, const double *d, const double *p, double *S) {
+template <int NG, bool GENERAL, class T>
+static void hm_units_rhs(const double *x, const double *u, const double *d, const double *p, double *S) {
     double Kd[K_COUNT], Cd[C_COUNT], Hd[H_COUNT];
     glg_make_k(p, Kd);
     glg_make_c(p, Cd);
     glg_hoist(p, u, d, Hd);
-    float Kf[K_COUNT], Cf[C_COUNT], Hf[H_COUNT], xf[GLG_NX], part[GLG_NGROUPS][GLG_NX] = {};
-    for (int i = 0; i < K_COUNT; ++i) Kf[i] = (float)Kd[i];
-    for (int i = 0; i < C_COUNT; ++i) Cf[i] = (float)Cd[i];
-    for (int i = 0; i < H_COUNT; ++i) Hf[i] = (float)Hd[i];
-    for (int i = 0; i < GLG_NX; ++i) xf[i] = (float)x[i];
-    HmF32View K{Kf}, C{Cf}, H{Hf}, X{xf};
-    float *q[GLG_NGROUPS];
-    for (int g = 0; g < GLG_NGROUPS; ++g) q[g] = part[g];
-    const float can_scale = glg_grp_rad<false>(K, C, H, X, q[0]);
-    glg_grp_fir<false>(K, C, H, p, u, X, q[1]);
-    glg_grp_airflow(K, H, X, q[2]);
-    glg_grp_conv<false>(K, C, H, p, X, q[3]);
-    glg_grp_screens(K, H, X, q[4]);
-    glg_grp_cover(K, C, H, X, q[5]);
-    glg_grp_photo<false>(K, C, H, X, q[6]);
-    glg_grp_flows(K, C, X, q[7]);
+    T Kt[K_COUNT], Ct[C_COUNT], Ht[H_COUNT], xt[GLG_NX];
+    for (int i = 0; i < K_COUNT; ++i) Kt[i] = (T)Kd[i];
+    for (int i = 0; i < C_COUNT; ++i) Ct[i] = (T)Cd[i];
+    for (int i = 0; i < H_COUNT; ++i) Ht[i] = (T)Hd[i];
+    for (int i = 0; i < GLG_NX; ++i) xt[i] = (T)x[i];
+    double sum[GLG_NX] = {};
+    GlgSpecial<T> sp{};
+    hm_warps<NG, 0, GENERAL, T>(HmView<T>{Kt}, HmView<T>{Ct}, HmView<T>{Ht}, p, u, HmX<T>{xt}, sum, sp);
     for (int i = 0; i < GLG_NX; ++i) {
-        double sum = 0.0;
-        for (int g = 0; g < GLG_NGROUPS; ++g)
-            if (glg_group_mask(i) >> g & 1u) sum += (double)part[g][i];
         const int sk = glg_state_scale_index(i);
-        S[i] = (sk >= 0 ? Kd[sk] : (sk == -1 ? 1.0 : (double)can_scale)) * sum;
+        S[i] = (sk >= 0 ? Kd[sk] : (sk == -1 ? 1.0 : (double)sp.canscale)) * sum[i];
     }
+    S[28] = (double)sp.lambda;
+    S[29] = glg_stiffness(HmView<double>{Kd}, (double)sp.ascr, (double)sp.avent);
+}
+extern "C" {
+// S has 30 entries: 28 derivatives, the harvest speed and the transient-stiffness estimate
+void hm_rhs_units(const double *x, const double *u, const double *d, const double *p, int general, int ng, int f32, double *S) {
+    if (f32) {
+        if (ng == 8) hm_units_rhs<8, false, float>(x, u, d, p, S);
+        else hm_units_rhs<12, false, float>(x, u, d, p, S);
+    } else if (ng == 4) {
+        if (general) hm_units_rhs<4, true, double>(x, u, d, p, S);
+        else hm_units_rhs<4, false, double>(x, u, d, p, S);
+    } else if (ng == 8) {
+        if (general) hm_units_rhs<8, true, double>(x, u, d, p, S);
+        else hm_units_rhs<8, false, double>(x, u, d, p, S);
+    } else if (ng == 12) {
+        if (general) hm_units_rhs<12, true, double>(x, u, d, p, S);
+        else hm_units_rhs<12, false, double>(x, u, d, p, S);
+    } else {
+        if (general) hm_units_rhs<13, true, double>(x, u, d, p, S);
+        else hm_units_rhs<13, false, double>(x, u, d, p, S);
+    }
+}
+// stiffness estimate and harvest speed as glg_rhs (kernel A) computes them, for comparison with the unit form
+double hm_rhs_stiffness(const double *x, const double *u, const double *d, const double *p) {
+    double K[K_COUNT], C[C_COUNT], H[H_COUNT], S[GLG_NX];
+    glg_make_k(p, K);
+    glg_make_c(p, C);
+    glg_hoist(p, u, d, H);
+    return glg_rhs<true>(K, C, H, p, u, d, x, S);
 }
 
 int hm_evalf(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub, int general,

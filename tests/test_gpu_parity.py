@@ -60,6 +60,7 @@ def test_device_math_accuracy(L):
     x = np.exp(rng.uniform(-25, 6, 1 << 18))
     assert np.max(np.abs(dev(4, x) / np.cbrt(x) - 1)) <= 4e-16
     assert np.max(np.abs(dev(5, x) / x ** 0.66 - 1)) <= 4e-15 and np.max(np.abs(dev(6, x) / x ** 0.32 - 1)) <= 2e-15
+    assert np.max(np.abs(dev(8, x) / np.cbrt(x) - 1)) <= 1e-15 and np.max(np.abs(dev(9, x) / x ** 0.25 - 1)) <= 1e-15
     z = rng.uniform(-800, 800, 1 << 16)
     assert np.max(np.abs(dev(7, z) - 1 / (1 + np.exp(np.clip(z, -708, 709))))) <= 4e-16
     sat = dev(0, np.array([-1e4, 1e4, np.nan]))
@@ -108,7 +109,7 @@ def test_evalf_nonfinite_raises_like_reference(weather0, params64):
 
 
 # ------------------------------------------------------------------------------------------------ fused step
-@pytest.mark.parametrize("role_warps", [1, 4, 8])
+@pytest.mark.parametrize("role_warps", [1, 2, 3])
 def test_step_matches_reference_env_trace(role_warps, shell_trace, weather0):
     """GPU step() against the trace of the reference's own TomatoEnv (golden, n_sub=300): obs, reward, info, state."""
     t = shell_trace
@@ -129,7 +130,7 @@ def test_step_matches_reference_env_trace(role_warps, shell_trace, weather0):
     env.close()
 
 
-@pytest.mark.parametrize("role_warps", [1, 4, 8])
+@pytest.mark.parametrize("role_warps", [1, 2, 3])
 def test_step_teacher_forced_vs_oracle(role_warps, weather0, params64):
     """Per-step gate: identical (x,u,d,p) into GPU and oracle each step, 96 envs with different actions
     (one full + one partial CTA for kernel A, three CTAs for kernel B), n_sub=600."""
@@ -155,7 +156,7 @@ def test_step_teacher_forced_vs_oracle(role_warps, weather0, params64):
     env.close()
 
 
-@pytest.mark.parametrize("role_warps", [1, 4, 8])
+@pytest.mark.parametrize("role_warps", [1, 2, 3])
 def test_step_general_parameter_structure(role_warps, weather0, params64):
     """A parameter table that switches on the terms the default table zeroes (sky FIR through the roof p70, interlights
     p194/p195/p198, grow-pipe FIR p165, k1Par != k2Par): `glg_set_params` must select the GENERAL kernel variants and the step
@@ -310,7 +311,7 @@ def test_parametric_noise_external_and_philox(shell_trace, weather0, params64):
     # (c) harvest-stiffness guard: external noise that drops cLeafMax below the leaf mass in env 1 only
     n = np.zeros((3, 34))
     n[1, 141 - 128], n[1, 142 - 128] = -0.15, 0.15
-    for rw in (4, 8, 1):
+    for rw in (3, 2, 1):
         env = make_env(3, n_sub=600, uncertainty_scale=0.3, role_warps=rw)
         env.reset()
         env.step_tensor(torch.zeros(3, 6, device="cuda"), noise=torch.as_tensor(n, device="cuda"))
@@ -323,7 +324,7 @@ def test_parametric_noise_external_and_philox(shell_trace, weather0, params64):
         env.close()
 
 
-@pytest.mark.parametrize("role_warps", [1, 4, 8])
+@pytest.mark.parametrize("role_warps", [1, 2, 3])
 def test_termination_autoreset_and_stats(role_warps, weather0, params64):
     """S6/S8 + SB3 VecEnv semantics: the step with timestep == N is terminal (episode length 5761,
     tests/env_test.py:77-92); done envs keep their terminal observation and restart from init_state in the same call."""
@@ -400,7 +401,7 @@ def test_full_batch_properties_4096():
     B = 4096
     g = torch.Generator(device="cuda")
     outs = {}
-    for tag, kw in (("A", dict(role_warps=1)), ("B", dict(role_warps=4)), ("B2", dict(role_warps=4))):
+    for tag, kw in (("A", dict(role_warps=1)), ("B", dict(role_warps=3)), ("B2", dict(role_warps=3))):
         env = make_env(B, n_sub=600, **kw)
         env.reset_tensor()
         g.manual_seed(0)
@@ -414,7 +415,7 @@ def test_full_batch_properties_4096():
     assert rel_err(outs["A"][0], outs["B"][0]) <= 1e-12                                                 # same math, two kernels
     assert np.isfinite(outs["A"][0]).all() and np.isfinite(outs["A"][2]).all()
     # shard independence: replay envs 1000..1063 alone
-    env = make_env(64, n_sub=600, role_warps=4, env_id_offset=1000)
+    env = make_env(64, n_sub=600, role_warps=3, env_id_offset=1000)
     env.reset_tensor()
     g.manual_seed(0)
     for s in range(3):
@@ -430,7 +431,7 @@ def test_free_running_episode_vs_oracle(weather0, params64):
     the oracle; relative error at episode end <= 1e-6 per state; same episode return; auto-reset fires on step 5761."""
     B, N = 4, 5760
     rng = np.random.default_rng(123)
-    env = make_env(B, n_sub=600, role_warps=4)
+    env = make_env(B, n_sub=600, role_warps=3)
     env.reset()
     orc = [ob.OracleEnv(weather0, params64) for _ in range(B)]
     ret_gpu = np.zeros(B)
@@ -470,7 +471,7 @@ def test_free_running_season_graded_integrator(weather0, params64):
     RK4 steps counted by the kernel equal the oracle's."""
     B, N = 2, 5760
     rng = np.random.default_rng(321)
-    env = make_env(B, integrator="graded", role_warps=8)
+    env = make_env(B, integrator="graded", role_warps=2)
     env.reset()
     cfg = ob.default_cfg(n_sub=300)
     cfg.stiff_guard = 3
@@ -615,12 +616,14 @@ def test_fp32_mode_matches_fp64_mode_config3_features():
 def test_config3_full_size_properties():
     """BASELINE config 3 at its full size (262 144 envs, fp32, uncertainty 0.3, randomised start day) through
     size-independent properties: finite states, run-to-run determinism, shard independence (a 64-env shard created with
-    env_id_offset reproduces its slice bit for bit), distinct noise per env, and agreement of a sample of envs with the
-    fp64 parity mode."""
+    env_id_offset reproduces its slice bit for bit when it runs the same kernel layout -- the latency and throughput layouts
+    add the partial sums in different orders, so across layouts envs agree to rounding, not bit for bit), distinct noise per
+    env, and agreement of a sample of envs with the fp64 parity mode."""
     from glgym.weather import load_weather_data
     days = (0, 6, 13, 18)
     tabs = np.stack([load_weather_data(None, "Bleiswijk", "GL", 2009, sd, 60, 49, 900, 10) for sd in days])
-    kw = dict(n_sub=600, uncertainty_scale=0.3, seed=7, weather_tables=tabs, table_start_days=np.array(days, dtype=np.float64))
+    kw = dict(n_sub=600, uncertainty_scale=0.3, seed=7, weather_tables=tabs, table_start_days=np.array(days, dtype=np.float64),
+              role_warps=3)
     B, off, nsh, steps = 262144, 100000, 64, 3
     g = torch.Generator(device="cuda")
     g.manual_seed(3)
@@ -651,7 +654,7 @@ def test_config3_full_size_properties():
     assert rel_err(xs.cpu().numpy(), x64.cpu().numpy()) <= 1e-4
 
 
-@pytest.mark.parametrize("role_warps", [4, 8])
+@pytest.mark.parametrize("role_warps", [2, 3])
 def test_graded_integrator_matches_oracle(role_warps, weather0, params64):
     """integrator="graded" (n_sub 300, graded start + transient-stiffness rule): teacher-forced parity with the oracle's
     glgo_evalf_ex(stiff_guard=3) under the rule-based controller through the B.6 transient steps, the executed-micro-step
@@ -701,7 +704,7 @@ def test_graded_integrator_matches_oracle(role_warps, weather0, params64):
     assert extra > 0 and env.stats_t[15].item() == B * (3 * 315 + extra)
     env.close()
     # kernel A (one thread per env) and the evalF entry follow the same rules
-    if role_warps == 4:
+    if role_warps == 3:
         ea = make_env(5, integrator="graded", role_warps=1)
         ea.reset()
         oa = ob.OracleEnv(weather0, params64, cfg)

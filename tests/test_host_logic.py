@@ -21,6 +21,9 @@ def P(a):
 def hm():
     lib = C.CDLL(os.path.join(ROOT, "tests", "hostmath", "libhostmath.so"))
     lib.hm_evalf.argtypes = [DP, DP, DP, DP, C.c_double, C.c_int, C.c_int, DP]
+    lib.hm_rhs_units.argtypes = [DP, DP, DP, DP, C.c_int, C.c_int, C.c_int, DP]
+    lib.hm_rhs_stiffness.argtypes = [DP, DP, DP, DP]
+    lib.hm_rhs_stiffness.restype = C.c_double
     return lib
 
 
@@ -101,19 +104,24 @@ def test_oracle_rule_based_step_matches_reference_trace(shell_trace, weather0, p
 
 
 def test_kernel_math_restructuring_matches_oracle(hm, rhs_golden):
-    """The hoisted / streaming RHS of csrc/glg_model.h (host build) and its role-split form against the oracle."""
+    """The hoisted / streaming RHS of csrc/glg_model.h (host build) and its unit-split form (csrc/glg_units.h, every unit ->
+    warp assignment the kernel can be built with) against the oracle."""
     g = rhs_golden
     worst = np.zeros(28)
     for i in range(g["x"].shape[0]):
         x, u, d, p = (g[k][i].copy() for k in ("x", "u", "d", "p"))
         general = 0 if hm.hm_nominal_structure(P(p)) else 1
         assert general == (1 if i % 4 == 3 else 0)
-        f, s1, s2 = g["f"][i], np.zeros(28), np.zeros(28)
+        f, s1 = g["f"][i], np.zeros(28)
         hm.hm_rhs(P(x), P(u), P(d), P(p), general, P(s1))
-        hm.hm_rhs_roles(P(x), P(u), P(d), P(p), general, P(s2))
         scale = np.maximum(np.abs(f), 1e-12 * np.maximum(1.0, np.abs(x)))
         worst = np.maximum(worst, np.abs(s1 - f) / scale)
-        assert np.all(np.abs(s1 - s2) <= 1e-12 * np.maximum(np.abs(s1), 1e-9 * np.maximum(1, np.abs(x)))), i
+        lam = hm.hm_rhs_stiffness(P(x), P(u), P(d), P(p))
+        for ng in (4, 8, 12, 13):
+            s2 = np.zeros(30)
+            hm.hm_rhs_units(P(x), P(u), P(d), P(p), general, ng, 0, P(s2))
+            assert np.all(np.abs(s1 - s2[:28]) <= 1e-12 * np.maximum(np.abs(s1), 1e-9 * np.maximum(1, np.abs(x)))), (i, ng)
+            assert abs(s2[29] - lam) <= 1e-12 * abs(lam), (i, ng)  # transient-stiffness estimate of the graded integrator
     # derivative-level agreement; the two carbohydrate balances cancel to ~1e-8 of their terms (see DESIGN.md)
     assert np.all(np.delete(worst, [22, 23, 25]) <= 1e-9) and np.all(worst <= 1e-6), worst
 
@@ -150,6 +158,8 @@ def test_branch_free_math_accuracy(hm):
     x = np.exp(rng.uniform(-25, 6, 200000))
     assert np.max(np.abs(run(4, x) / np.cbrt(x) - 1)) <= 4e-16
     assert np.max(np.abs(run(5, x) / x ** 0.66 - 1)) <= 4e-15 and np.max(np.abs(run(6, x) / x ** 0.32 - 1)) <= 2e-15
+    # branch-free per-lane root (floor convection): x^(1/3) / x^(1/4), no final correction step => a few ulp
+    assert np.max(np.abs(run(8, x) / np.cbrt(x) - 1)) <= 1e-15 and np.max(np.abs(run(9, x) / x ** 0.25 - 1)) <= 1e-15
     assert run(4, np.array([0.0]))[0] == 0.0
 
 

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "greenlight-gym2_b200"))
 import torch
 from glgym.vec_env import GreenLightVecEnv
-for kw in (dict(), dict(role_warps=4), dict(integrator="graded", n_sub=6), dict(uncertainty_scale=0.3), dict(precision="fp32"),
+for kw in (dict(), dict(role_warps=3), dict(integrator="graded", n_sub=6), dict(uncertainty_scale=0.3), dict(precision="fp32"),
            dict(role_warps=1)):
     kw.setdefault("n_sub", 8)
     env = GreenLightVecEnv(70, **kw); env.reset_tensor()
