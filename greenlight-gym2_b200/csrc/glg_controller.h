@@ -4,7 +4,7 @@
 // gl_gym/configs/agents/rule_based.yml) for one env: u[6] from the state before the step, the weather row of the
 // current timestep (all 10 columns) and the env clock -- what experiments/evaluate_baseline.py:21-23 does on the host
 // between two step_raw_control calls.  Fused into the step kernels' prologue (control mode 2) so a rule-based rollout
-// needs no host round trip.  Evaluated once per env-step: plain IEEE division and the accurate branch-free glg_exp.
+// needs no host round trip.  Evaluated once per env-step: plain IEEE division and the accurate branch-free glg_exp_acc.
 #pragma once
 #include "glg_math.h"
 
@@ -19,7 +19,7 @@ enum GlgCtrl {  // order of configs/agents/rule_based.yml
 // sigmoid proportional band, baseline.py:226-227
 GLG_HD double glg_prop_ctrl(double pv, double sp, double pb, double minv, double maxv) {
     const double ln100 = 4.605170185988092;  // np.log(100)
-    const double e = glg_exp(-2.0 / pb * ln100 * (pv - sp - pb / 2.0));
+    const double e = glg_exp_acc(-2.0 / pb * ln100 * (pv - sp - pb / 2.0));
     return minv + (maxv - minv) * (1.0 / (1.0 + e));
 }
 // 1 inside the open interval (lo, hi); an interval with lo > hi wraps around (baseline.py:76-77, :85-86)
@@ -41,7 +41,7 @@ GLG_HD void glg_rule_control(const S &s, const double *x, const double *d, doubl
     const double heat_sp = is_day * s[CT_TSP_DAY] + (1 - is_day) * s[CT_TSP_NIGHT] + s[CT_HEAT_CORR] * lamp_no_cons;
     const double heat_max = heat_sp + s[CT_HEAT_DEAD];
     const double co2_ppm = 1e6 * 8.3144598 * (tAir + 273.15) * (1e-6 * x[0]) / (101325 * 44.01e-3);  // utils.py:352-361
-    const double rh_in = 100 * x[15] / (610.78 * glg_exp(17.2694 * tAir / (tAir + 238.3)));         // utils.py:363-364 (unclipped)
+    const double rh_in = 100 * x[15] / (610.78 * glg_exp_acc(17.2694 * tAir / (tAir + 238.3)));         // utils.py:363-364 (unclipped)
     const double vent_heat = glg_prop_ctrl(tAir, heat_max, s[CT_VENT_HEAT_PB], 0, 1);
     const double vent_rh = glg_prop_ctrl(rh_in, s[CT_RH_MAX] + 0 * s[CT_MECH_PB], s[CT_VENT_RH_PB], 0, 1);
     const double vent_cold = glg_prop_ctrl(tAir, heat_sp - s[CT_T_VENT_OFF], s[CT_VENT_COLD_PB], 1, 0);

@@ -34,34 +34,51 @@
 #else
 #define GLG_COEF static const
 #endif
-// Table-driven exp: x = (64 m + j) ln2/64 + r, |r| <= ln2/128; exp(x) = 2^m T[j] (1 + expm1(r)) with a degree-5 Taylor
-// polynomial (remainder r^6/720 < 4e-17).  10 FP64 instructions per exp instead of 17 -- exp is 43 % of the FP64
-// instruction stream of the RHS.  T[j] = 2^(j/64) is per-lane indexed: it lives in global memory and is read through the
-// L1 (4 cache lines; the load is issued right after the reduction and consumed by the last FMA).
-GLG_COEF double glg_kExpT[7] = {0x1.71547652b82fep+6 /*64/ln2*/, -0x1.62e42fef00000p-7 /*-(ln2/64)_hi, 34 bits*/,
-                                -0x1.473de6af278edp-40 /*-(ln2/64)_lo*/, 0x1.1111111111111p-7 /*1/120*/,
+// Table-driven exp: x = (128 m + j) ln2/128 + r, |r| <= ln2/256; exp(x) = 2^m T[j] (1 + expm1(r)) with a degree-4 Taylor
+// polynomial (remainder r^5/120 < 1.3e-15) and a one-constant argument reduction (error 1.2e-16 |x| relative): 8 FP64
+// instructions per exp -- exp is the largest single item of the FP64 instruction stream of the RHS (25 per evaluation).
+// Accuracy: <= 2e-15 + 1.2e-16 |x| relative (the model's arguments that matter stay below |x| ~ 40; the parity gate is 1e-9
+// per env-step).  T[j] = 2^(j/128) is per-lane indexed: it lives in global memory and is read through the L1 (8 cache
+// lines; the load is issued right after the reduction and consumed by the last FMA).
+GLG_COEF double glg_kExpT[5] = {0x1.71547652b82fep+7 /*128/ln2*/, -0x1.62e42fefa39efp-8 /*-(ln2/128)*/,
                                 0x1.5555555555555p-5 /*1/24*/, 0x1.5555555555555p-3 /*1/6*/, 0x1.0000000000000p-1};
 #define GLG_EXP_TABLE_VALUES \
-    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0, \
-    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0, \
-    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0, \
-    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0, \
-    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0, \
-    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0, \
-    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0, \
-    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0, \
-    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0, \
-    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0, \
-    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0, \
-    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0, \
-    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0, \
-    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0, \
-    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0, \
-    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0
+    0x1.0000000000000p+0, 0x1.0163da9fb3335p+0, 0x1.02c9a3e778061p+0, 0x1.04315e86e7f85p+0, \
+    0x1.059b0d3158574p+0, 0x1.0706b29ddf6dep+0, 0x1.0874518759bc8p+0, 0x1.09e3ecac6f383p+0, \
+    0x1.0b5586cf9890fp+0, 0x1.0cc922b7247f7p+0, 0x1.0e3ec32d3d1a2p+0, 0x1.0fb66affed31bp+0, \
+    0x1.11301d0125b51p+0, 0x1.12abdc06c31ccp+0, 0x1.1429aaea92de0p+0, 0x1.15a98c8a58e51p+0, \
+    0x1.172b83c7d517bp+0, 0x1.18af9388c8deap+0, 0x1.1a35beb6fcb75p+0, 0x1.1bbe084045cd4p+0, \
+    0x1.1d4873168b9aap+0, 0x1.1ed5022fcd91dp+0, 0x1.2063b88628cd6p+0, 0x1.21f49917ddc96p+0, \
+    0x1.2387a6e756238p+0, 0x1.251ce4fb2a63fp+0, 0x1.26b4565e27cddp+0, 0x1.284dfe1f56381p+0, \
+    0x1.29e9df51fdee1p+0, 0x1.2b87fd0dad990p+0, 0x1.2d285a6e4030bp+0, 0x1.2ecafa93e2f56p+0, \
+    0x1.306fe0a31b715p+0, 0x1.32170fc4cd831p+0, 0x1.33c08b26416ffp+0, 0x1.356c55f929ff1p+0, \
+    0x1.371a7373aa9cbp+0, 0x1.38cae6d05d866p+0, 0x1.3a7db34e59ff7p+0, 0x1.3c32dc313a8e5p+0, \
+    0x1.3dea64c123422p+0, 0x1.3fa4504ac801cp+0, 0x1.4160a21f72e2ap+0, 0x1.431f5d950a897p+0, \
+    0x1.44e086061892dp+0, 0x1.46a41ed1d0057p+0, 0x1.486a2b5c13cd0p+0, 0x1.4a32af0d7d3dep+0, \
+    0x1.4bfdad5362a27p+0, 0x1.4dcb299fddd0dp+0, 0x1.4f9b2769d2ca7p+0, 0x1.516daa2cf6642p+0, \
+    0x1.5342b569d4f82p+0, 0x1.551a4ca5d920fp+0, 0x1.56f4736b527dap+0, 0x1.58d12d497c7fdp+0, \
+    0x1.5ab07dd485429p+0, 0x1.5c9268a5946b7p+0, 0x1.5e76f15ad2148p+0, 0x1.605e1b976dc09p+0, \
+    0x1.6247eb03a5585p+0, 0x1.6434634ccc320p+0, 0x1.6623882552225p+0, 0x1.68155d44ca973p+0, \
+    0x1.6a09e667f3bcdp+0, 0x1.6c012750bdabfp+0, 0x1.6dfb23c651a2fp+0, 0x1.6ff7df9519484p+0, \
+    0x1.71f75e8ec5f74p+0, 0x1.73f9a48a58174p+0, 0x1.75feb564267c9p+0, 0x1.780694fde5d3fp+0, \
+    0x1.7a11473eb0187p+0, 0x1.7c1ed0130c132p+0, 0x1.7e2f336cf4e62p+0, 0x1.80427543e1a12p+0, \
+    0x1.82589994cce13p+0, 0x1.8471a4623c7adp+0, 0x1.868d99b4492edp+0, 0x1.88ac7d98a6699p+0, \
+    0x1.8ace5422aa0dbp+0, 0x1.8cf3216b5448cp+0, 0x1.8f1ae99157736p+0, 0x1.9145b0b91ffc6p+0, \
+    0x1.93737b0cdc5e5p+0, 0x1.95a44cbc8520fp+0, 0x1.97d829fde4e50p+0, 0x1.9a0f170ca07bap+0, \
+    0x1.9c49182a3f090p+0, 0x1.9e86319e32323p+0, 0x1.a0c667b5de565p+0, 0x1.a309bec4a2d33p+0, \
+    0x1.a5503b23e255dp+0, 0x1.a799e1330b358p+0, 0x1.a9e6b5579fdbfp+0, 0x1.ac36bbfd3f37ap+0, \
+    0x1.ae89f995ad3adp+0, 0x1.b0e07298db666p+0, 0x1.b33a2b84f15fbp+0, 0x1.b59728de5593ap+0, \
+    0x1.b7f76f2fb5e47p+0, 0x1.ba5b030a1064ap+0, 0x1.bcc1e904bc1d2p+0, 0x1.bf2c25bd71e09p+0, \
+    0x1.c199bdd85529cp+0, 0x1.c40ab5fffd07ap+0, 0x1.c67f12e57d14bp+0, 0x1.c8f6d9406e7b5p+0, \
+    0x1.cb720dcef9069p+0, 0x1.cdf0b555dc3fap+0, 0x1.d072d4a07897cp+0, 0x1.d2f87080d89f2p+0, \
+    0x1.d5818dcfba487p+0, 0x1.d80e316c98398p+0, 0x1.da9e603db3285p+0, 0x1.dd321f301b460p+0, \
+    0x1.dfc97337b9b5fp+0, 0x1.e264614f5a129p+0, 0x1.e502ee78b3ff6p+0, 0x1.e7a51fbc74c83p+0, \
+    0x1.ea4afa2a490dap+0, 0x1.ecf482d8e67f1p+0, 0x1.efa1bee615a27p+0, 0x1.f252b376bba97p+0, \
+    0x1.f50765b6e4540p+0, 0x1.f7bfdad9cbe14p+0, 0x1.fa7c1819e90d8p+0, 0x1.fd3c22b8f71f1p+0
 #if defined(__CUDACC__)
-__device__ const double glg_exp_tbl_dev[64] = {GLG_EXP_TABLE_VALUES};
+__device__ const double glg_exp_tbl_dev[128] = {GLG_EXP_TABLE_VALUES};
 #endif
-static const double glg_exp_tbl_host[64] = {GLG_EXP_TABLE_VALUES};
+static const double glg_exp_tbl_host[128] = {GLG_EXP_TABLE_VALUES};
 GLG_COEF double glg_kLog[9] = {
     0x1.2b584aae78a57p-3, 0x1.39fe606542ddep-3, 0x1.7462b4ab2ef6bp-3, 0x1.c71c62e5800a1p-3, 0x1.2492492df148dp-2,
     0x1.99999999952e2p-2, 0x1.5555555555558p-1, 0x1.62e42fee00000p-1 /*ln2_hi*/, 0x1.a39ef35793c76p-33 /*ln2_lo*/};
@@ -106,16 +123,13 @@ GLG_HD double glg_rcp(double x) {
 }
 GLG_HD double glg_div(double a, double b) { return a * glg_rcp(b); }
 
-// ---- sqrt for x > 0: rsqrt seed (MUFU.RSQ64H) + two coupled Goldschmidt steps + a final residual correction
+// ---- sqrt for x > 0: rsqrt seed (MUFU.RSQ64H, ~2^-20) + one coupled Goldschmidt step (2^-40) + a residual correction
 GLG_HD double glg_sqrt(double x) {
 #if defined(__CUDA_ARCH__)
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     double g = x * r, h = 0.5 * r;
-    double e = __fma_rn(-h, g, 0.5);
-    g = __fma_rn(g, e, g);
-    h = __fma_rn(h, e, h);
-    e = __fma_rn(-h, g, 0.5);
+    const double e = __fma_rn(-h, g, 0.5);
     g = __fma_rn(g, e, g);
     h = __fma_rn(h, e, h);
     const double d = __fma_rn(-g, g, x);
@@ -138,17 +152,34 @@ GLG_HD double glg_exp(double x) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to nearest integer in the low word
     const double t = glg_fma(x, glg_kExpT[0], MAGIC);
     const double kf = t - MAGIC;
-    const int k = (int)(uint32_t)(uint64_t)glg_d2bits(t);  // two's complement in the low word, valid for |x| < 2^24
-    const double T = glg_exp_tbl(k & 63);
-    double r = glg_fma(kf, glg_kExpT[1], x);
-    r = glg_fma(kf, glg_kExpT[2], r);
+    const int k = (int)(uint32_t)(uint64_t)glg_d2bits(t);  // two's complement in the low word, valid for |x| < 2^23
+    const double T = glg_exp_tbl(k & 127);
+    const double r = glg_fma(kf, glg_kExpT[1], x);
     const double r2 = r * r;
-    double q = glg_fma(r, glg_kExpT[3], glg_kExpT[4]);
-    q = glg_fma(r, q, glg_kExpT[5]);
-    q = glg_fma(r, q, glg_kExpT[6]);
+    double q = glg_fma(r, glg_kExpT[2], glg_kExpT[3]);
+    q = glg_fma(r, q, glg_kExpT[4]);
     const double p = glg_fma(r2, q, r);  // expm1(r)
     const double y = glg_fma(T, p, T);   // in [1, 2)
-    int m = k >> 6;
+    int m = k >> 7;
+    m = m < -1021 ? -1021 : (m > 1023 ? 1023 : m);
+    return glg_bits2d(glg_d2bits(y) + ((long long)m << 52));
+}
+
+// ---- accurate exp (<= 4e-16 relative): two-constant argument reduction, degree-5 polynomial.  For once-per-env-step code
+//      whose closed loop amplifies rounding differences (rule-based controller, glg_controller.h); not used by the RHS.
+GLG_HD double glg_exp_acc(double x) {
+    const double MAGIC = 6755399441055744.0;
+    const double t = glg_fma(x, glg_kExpT[0], MAGIC);
+    const double kf = t - MAGIC;
+    const int k = (int)(uint32_t)(uint64_t)glg_d2bits(t);
+    const double T = glg_exp_tbl(k & 127);
+    double r = glg_fma(kf, -0x1.62e42fef80000p-8 /*-(ln2/128)_hi, 34 bits*/, x);
+    r = glg_fma(kf, -0x1.1cf79abc9e3b4p-43 /*-(ln2/128)_lo*/, r);
+    double q = glg_fma(r, 0x1.1111111111111p-7 /*1/120*/, glg_kExpT[2]);
+    q = glg_fma(r, q, glg_kExpT[3]);
+    q = glg_fma(r, q, glg_kExpT[4]);
+    const double y = glg_fma(T, glg_fma(r * r, q, r), T);
+    int m = k >> 7;
     m = m < -1021 ? -1021 : (m > 1023 ? 1023 : m);
     return glg_bits2d(glg_d2bits(y) + ((long long)m << 52));
 }
@@ -166,24 +197,20 @@ GLG_HD void glg_exp_n(const double (&x)[N], double (&y)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         k[i] = (int)(uint32_t)(uint64_t)glg_d2bits(t[i]);
-        T[i] = glg_exp_tbl(k[i] & 63);
+        T[i] = glg_exp_tbl(k[i] & 127);
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) r[i] = glg_fma(t[i] - MAGIC, glg_kExpT[1], x[i]);
 #pragma unroll
-    for (int i = 0; i < N; ++i) r[i] = glg_fma(t[i] - MAGIC, glg_kExpT[2], r[i]);
+    for (int i = 0; i < N; ++i) { r2[i] = r[i] * r[i]; q[i] = glg_fma(r[i], glg_kExpT[2], glg_kExpT[3]); }
 #pragma unroll
-    for (int i = 0; i < N; ++i) { r2[i] = r[i] * r[i]; q[i] = glg_fma(r[i], glg_kExpT[3], glg_kExpT[4]); }
-#pragma unroll
-    for (int i = 0; i < N; ++i) q[i] = glg_fma(r[i], q[i], glg_kExpT[5]);
-#pragma unroll
-    for (int i = 0; i < N; ++i) q[i] = glg_fma(r[i], q[i], glg_kExpT[6]);
+    for (int i = 0; i < N; ++i) q[i] = glg_fma(r[i], q[i], glg_kExpT[4]);
 #pragma unroll
     for (int i = 0; i < N; ++i) q[i] = glg_fma(r2[i], q[i], r[i]);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const double v = glg_fma(T[i], q[i], T[i]);
-        int m = k[i] >> 6;
+        int m = k[i] >> 7;
         m = m < -1021 ? -1021 : (m > 1023 ? 1023 : m);
         y[i] = glg_bits2d(glg_d2bits(v) + ((long long)m << 52));
     }
@@ -216,12 +243,9 @@ GLG_HD void glg_sqrt_n(const double (&x)[N], double (&y)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) { g[i] = x[i] * h[i]; h[i] = 0.5 * h[i]; }
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int i = 0; i < N; ++i) e[i] = __fma_rn(-h[i], g[i], 0.5);
 #pragma unroll
-        for (int i = 0; i < N; ++i) e[i] = __fma_rn(-h[i], g[i], 0.5);
-#pragma unroll
-        for (int i = 0; i < N; ++i) { g[i] = __fma_rn(g[i], e[i], g[i]); h[i] = __fma_rn(h[i], e[i], h[i]); }
-    }
+    for (int i = 0; i < N; ++i) { g[i] = __fma_rn(g[i], e[i], g[i]); h[i] = __fma_rn(h[i], e[i], h[i]); }
 #pragma unroll
     for (int i = 0; i < N; ++i) e[i] = __fma_rn(-g[i], g[i], x[i]);
 #pragma unroll
@@ -231,9 +255,9 @@ GLG_HD void glg_sqrt_n(const double (&x)[N], double (&y)[N]) {
 #endif
 }
 template <int N>
-GLG_HD void glg_cbrt_n(const double (&x)[N], double (&y)[N]) {
+GLG_HD void glg_cbrt_n(const double (&x)[N], double (&y)[N]) {  // see glg_cbrt
     const double third = 0x1.5555555555555p-2;
-    double r[N], e[N];
+    double r[N], s[N], d[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #if defined(__CUDA_ARCH__)
@@ -247,18 +271,18 @@ GLG_HD void glg_cbrt_n(const double (&x)[N], double (&y)[N]) {
 #endif
     }
 #pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = r[i] * r[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { y[i] = x[i] * r[i]; s[i] = r[i] * third; }
+#pragma unroll
     for (int it = 0; it < 2; ++it) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) e[i] = glg_fma(-x[i] * r[i], r[i] * r[i], 1.0);
+        for (int i = 0; i < N; ++i) d[i] = y[i] * y[i];
 #pragma unroll
-        for (int i = 0; i < N; ++i) r[i] = glg_fma(r[i] * third, e[i], r[i]);
+        for (int i = 0; i < N; ++i) d[i] = glg_fma(-d[i], y[i], x[i]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = glg_fma(d[i], s[i], y[i]);
     }
-#pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = x[i] * (r[i] * r[i]);
-#pragma unroll
-    for (int i = 0; i < N; ++i) e[i] = glg_fma(-y[i] * y[i], y[i], x[i]);
-#pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = glg_fma(e[i], (r[i] * r[i]) * third, y[i]);
 }
 
 // ---- 1/(1+exp(z)) -- the model's ubiquitous sigmoid building block
@@ -288,8 +312,9 @@ GLG_HD double glg_log(double x) {
 }
 GLG_HD double glg_pow(double b, double e) { return glg_exp(e * glg_log(b)); }  // b > 0
 
-// ---- cube root for x > 0: fp32 seed of x^(-1/3) (MUFU.LG2/EX2), two Newton steps on r -> r + r(1 - x r^3)/3,
-//      then cbrt = x r^2 with a final Newton correction on y^3 = x.
+// ---- cube root for x > 0: fp32 seed r ~ x^(-1/3) (MUFU.LG2/EX2, relative error d ~ 2^-21), y0 = x r^2, then two steps of
+//      y <- y + (x - y^3) s with the FIXED slope s = r^2/3 ~ 1/(3 y^2): the error goes d -> d^2 -> d^3 (2^-63), at 3 FP64
+//      instructions per step and no division: 9 FP64 instructions in all.
 GLG_HD double glg_cbrt(double x) {
 #if defined(__CUDA_ARCH__)
     // seed in fp32 on the MUFU pipe; clamped so x = 0 gives a finite r (and then cbrt = 0 * r^2 = 0)
@@ -297,21 +322,16 @@ GLG_HD double glg_cbrt(double x) {
     float lg, sd;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(-0.33333334f * lg));
-    double r = (double)sd;
+    const double r = (double)sd;
 #else
-    double r = (double)(float)(1.0 / cbrt(fmax(x, 1e-36))) * (1.0 + 1e-7);  // deliberately imperfect seed, like the device's
+    const double r = (double)(float)(1.0 / cbrt(fmax(x, 1e-36))) * (1.0 + 1e-7);  // deliberately imperfect seed, like the device's
 #endif
-    const double third = 0x1.5555555555555p-2;
-    double r2 = r * r;
-    double e = glg_fma(-x * r, r2, 1.0);
-    r = glg_fma(r * third, e, r);
-    r2 = r * r;
-    e = glg_fma(-x * r, r2, 1.0);
-    r = glg_fma(r * third, e, r);
-    double y = x * (r * r);
-    // y <- y - (y^3 - x)/(3 y^2) = y + (x - y^3) * (r^2/3) * ...; use r ~ x^(-1/3): 1/(3y^2) ~ r^2/3
-    const double d = glg_fma(-y * y, y, x);
-    return glg_fma(d, (r * r) * third, y);
+    const double r2 = r * r;
+    const double s = r2 * 0x1.5555555555555p-2;
+    double y = x * r2;
+    y = glg_fma(glg_fma(-(y * y), y, x), s, y);
+    y = glg_fma(glg_fma(-(y * y), y, x), s, y);
+    return y;
 }
 
 // ---- x^(1/3) (cube = true) or x^(1/4) (cube = false) for x > 0, selected per lane WITHOUT divergence: fp32 seed of
@@ -355,6 +375,7 @@ GLG_HD double glg_math_eval(int op, double v) {
         case 7: return glg_inv1pexp(v);
         case 8: return glg_root34(v, true);
         case 9: return glg_root34(v, false);
+        case 10: return glg_exp_acc(v);
         default: return v;
     }
 }

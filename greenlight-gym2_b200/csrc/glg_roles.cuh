@@ -136,10 +136,13 @@ template <class T, int NG, bool GENERAL, bool NOISY>
 struct GlgRoleSmem {
     using PL = GlgPlan<NG, GENERAL>;
     static constexpr int kColRows = PL::XS_ROWS + PL::NSLOTS + H_COUNT + (NOISY ? C_COUNT : 0);
-    // weather tile (f64) | final state (f64 [28][32]) | T columns | mbarrier | ints
+    // fp32 units: the step's start / end state crosses between warp 0 and the owners in fp64 through its own [28][32] block;
+    // fp64 units: the stage-state block itself holds it (the last evaluation leaves the final state there)
+    static constexpr int kXfinRows = sizeof(T) == sizeof(double) ? 0 : GLG_NX;
+    // weather tile (f64) | fruit row, scale row, [state block] (f64) | T columns | mbarrier | ints
     __host__ __device__ static size_t col_bytes() { return (sizeof(T) * (size_t)kColRows * GLG_ROLE_LANES + 15) / 16 * 16; }
     __host__ __device__ static size_t bytes(int Np) {
-        return sizeof(double) * ((size_t)(Np + 1) * GLG_ND + (size_t)(GLG_NX + 2) * GLG_ROLE_LANES) + col_bytes() + 16 +
+        return sizeof(double) * ((size_t)(Np + 1) * GLG_ND + (size_t)(kXfinRows + 2) * GLG_ROLE_LANES) + col_bytes() + 16 +
                sizeof(int) * (5 * GLG_ROLE_LANES + 4 + 16);
     }
 };
@@ -312,13 +315,16 @@ struct GlgOwner {
                       st3 = PL::plan.order[J * GLG_NO + 3];
         return o == 0 ? st0 : o == 1 ? st1 : o == 2 ? st2 : st3;
     }
-    __device__ __forceinline__ void init(int owner, const GlgStepArgs &A, const double *s_xfin, const double *s_scale, int lane) {
+    static constexpr bool kStateInXs = sizeof(T) == sizeof(double);  // see GlgRoleSmem::kXfinRows
+    __device__ __forceinline__ void init(int owner, const GlgStepArgs &A, const double *s_xfin, const double *s_scale, const T *xs_col,
+                                         int lane) {
         o = owner;
         glg_static_for<0, NJ>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             const int st = row_state<j>();
             scale[j] = s_scale[j * GLG_NO + o];
-            xo[j] = st >= 0 ? s_xfin[st * NL + lane] : 0.0;
+            if (kStateInXs) xo[j] = (double)xs_col[(j * GLG_NO + o) * NL];
+            else xo[j] = st >= 0 ? s_xfin[st * NL + lane] : 0.0;
             acc[j] = 0.0;
         });
         can_owner = o == PL::canopy_entry % GLG_NO;
@@ -446,7 +452,7 @@ struct GlgOwner {
             constexpr int j = decltype(jc)::value;
             const int st = row_state<j>();
             bad |= !(fabs(xo[j]) <= 1.79769313486231570e308);
-            if (st >= 0) s_xfin[st * NL + lane] = xo[j];
+            if (!kStateInXs && st >= 0) s_xfin[st * NL + lane] = xo[j];  // fp64 units: post() left it in the stage-state block
         });
         return bad;
     }
@@ -474,9 +480,12 @@ __global__ void __launch_bounds__(32 * (NG + (FUSED ? 0 : GLG_NO)), MINB) glg_st
     using SW = GlgSurfaceWarps<NG, GENERAL>;
     constexpr int NJ = PL::NJ;
     double *s_wtile = reinterpret_cast<double *>(smem_raw);  // [(Np+1)][10] f64
-    double *s_xfin = s_wtile + (size_t)(A.Np + 1) * GLG_ND;   // [28 + 1][32] f64, state order: state in / final state out (owners <-> warp 0); row 28: fruit mass before the step
-    double *s_scale = s_xfin + (GLG_NX + 1) * NL;              // [XS_ROWS] capacity scale of plan entry n (throughput variant: read per evaluation)
-    T *s_xs = reinterpret_cast<T *>(s_xfin + (GLG_NX + 2) * NL);  // [XS_ROWS][32] stage state in the units' precision, plan order
+    constexpr int kXfinRows = GlgRoleSmem<T, NG, GENERAL, NOISY>::kXfinRows;
+    constexpr bool kStateInXs = kXfinRows == 0;
+    double *s_fruit = s_wtile + (size_t)(A.Np + 1) * GLG_ND;  // [32] fruit mass before the step (reward)
+    double *s_scale = s_fruit + NL;                            // [XS_ROWS] capacity scale of plan entry n
+    double *s_xfin = s_scale + NL;                             // fp32 units only: [28][32] f64, state order: state in / final state out
+    T *s_xs = reinterpret_cast<T *>(s_xfin + kXfinRows * NL);  // [XS_ROWS][32] stage state in the units' precision, plan order
     T *s_part = s_xs + PL::XS_ROWS * NL;                      // [NSLOTS][32]: partial sums, specials
     T *s_H = s_part + PL::NSLOTS * NL;                        // [H_COUNT][32]
     T *s_C = s_H + H_COUNT * NL;                              // [C_COUNT][32] (NOISY)
@@ -534,10 +543,10 @@ __global__ void __launch_bounds__(32 * (NG + (FUSED ? 0 : GLG_NO)), MINB) glg_st
             constexpr int i = decltype(ic)::value;
             constexpr int r = PL::plan.rank[i];
             s_xs[r * NL + lane] = (T)x[i];
-            s_xfin[i * NL + lane] = x[i];
+            if (!kStateInXs) s_xfin[i * NL + lane] = x[i];
         });
         // what the epilogue needs goes through shared memory, so that nothing of it stays in registers across the loops
-        s_xfin[GLG_NX * NL + lane] = fruit_prev;
+        s_fruit[lane] = fruit_prev;
         s_k[lane] = k;
         s_tbl[lane] = tbl;
         s_bad[lane] = 0;
@@ -575,7 +584,7 @@ __global__ void __launch_bounds__(32 * (NG + (FUSED ? 0 : GLG_NO)), MINB) glg_st
             for (int i = 0; i < GLG_NU; ++i) u[i] = A.u[(size_t)i * A.B + e];
         }
         GlgOwner<T, NG, GENERAL> own;
-        own.init(warp, A, s_xfin, s_scale, lane);
+        own.init(warp, A, s_xfin, s_scale, xs_col, lane);
 #pragma unroll 1
         for (;;) {
             glg_group_eval_dispatch<NG, 0, GENERAL, NOISY, T>(warp, U, xs_col, part_col, s_H + lane, s_C + lane, u);
@@ -604,7 +613,7 @@ __global__ void __launch_bounds__(32 * (NG + (FUSED ? 0 : GLG_NO)), MINB) glg_st
         // ---- owner warps (GlgOwner)
         if (kRebalance) glg_reg_inc<kOwnerRegs>();
         GlgOwner<T, NG, GENERAL> own;
-        own.init(warp, A, s_xfin, s_scale, lane);
+        own.init(warp, A, s_xfin, s_scale, xs_col, lane);
         glg_bar_arrive(GLG_BAR_XS, NT);  // the prologue's stage state is in shared memory: release the group warps' first evaluation
 #pragma unroll 1
         for (;;) {
@@ -638,9 +647,12 @@ __global__ void __launch_bounds__(32 * (NG + (FUSED ? 0 : GLG_NO)), MINB) glg_st
         const int bad = s_bad[lane];
         if (active) {
             double x[GLG_NX];
-#pragma unroll
-            for (int i = 0; i < GLG_NX; ++i) x[i] = s_xfin[i * NL + lane];
-            glg_env_epilogue(U, A, e, k, kw, tbl, wrow, x, s_xfin[GLG_NX * NL + lane], bad, A.step_ctr[e], o);
+            glg_static_for<0, GLG_NX>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int r = PL::plan.rank[i];
+                x[i] = kStateInXs ? (double)s_xs[r * NL + lane] : s_xfin[i * NL + lane];
+            });
+            glg_env_epilogue(U, A, e, k, kw, tbl, wrow, x, s_fruit[lane], bad, A.step_ctr[e], o);
         }
         s_tbl[lane] = o.tbl_obs;
         s_k[lane] = o.k_obs;
