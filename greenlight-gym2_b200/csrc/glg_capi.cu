@@ -639,6 +639,12 @@ static int measure_peak(int device, double *out) {
 extern "C" int glg_measure_fp64_peak(int32_t device, double *flops) { return measure_peak<double>(device, flops); }
 extern "C" int glg_measure_fp32_peak(int32_t device, double *flops) { return measure_peak<float>(device, flops); }
 
+#ifdef GLG_TRACE
+extern "C" int glg_debug_trace(long long *out_host) {  // [32 evaluations][16 warps][wake, arrive] clock64 stamps of CTA 0
+    return cudaMemcpyFromSymbol(out_host, glg_trace, sizeof(long long) * 32 * 16 * 2) == cudaSuccess ? GLG_OK : GLG_ERR_CUDA;
+}
+#endif
+
 extern "C" int glg_debug_math(int32_t op, const double *in_dev, double *out_dev, int32_t n, void *stream) {
     if (!in_dev || !out_dev || n < 1) return GLG_ERR_ARG;
     glg_math_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(op, in_dev, out_dev, n);

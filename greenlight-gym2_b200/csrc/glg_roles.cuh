@@ -9,10 +9,12 @@
 //   owner warp o : owns 28/NO states: classical RK4 stage update from the partial sums, state and stage sum in fp64
 //                  registers, next stage value back to shared memory.  Also decides the micro-step count of every nominal
 //                  substep (harvest guard, graded integrator) and tells the group warps when to stop.
-// Synchronisation per RHS evaluation: two named barriers used producer/consumer style (PTX bar.arrive / bar.sync):
-//   BAR_PARTS : group warps arrive (do not wait), owner warps wait  -- "partial sums of this evaluation are in shared memory"
-//   BAR_XS    : owner warps arrive (do not wait), group warps wait  -- "stage state of the next evaluation is in shared memory"
-// so a warp blocks once per evaluation, on the data it needs.
+// Synchronisation per RHS evaluation: three named barriers used producer/consumer style (PTX bar.arrive / bar.sync):
+//   BAR_PARTS : early group warps arrive (do not wait), owner warps wait -- "partial sums of the early warps are in shared memory"
+//   BAR_LATE  : late group warps arrive, owner warps wait                -- "... of the late warps (glg_late_mask) too"
+//   BAR_XS    : owner warps arrive (do not wait), group warps wait       -- "stage state of the next evaluation is in shared memory"
+// so a group warp blocks once per evaluation, on the data it needs, and the owners have everything but the late warps' few
+// contributions added up by the time the slowest group warp arrives.
 // Every role has its own loop (no per-evaluation dispatch).  The loop bodies together must stay below the SM's 32 KB
 // instruction cache (tools/ubench/icache2.cu), which is why the three "condensing surface" warps (thermal screen, blackout
 // screen, cover) share ONE copy of their code with all addresses in registers (glg_surface_loop).
@@ -30,10 +32,32 @@
 
 #define GLG_ROLE_LANES 32
 constexpr int GLG_NO = 4;  // owner warps: warps 0..3, one per SM sub-partition
-constexpr int GLG_BAR_PARTS = 1, GLG_BAR_XS = 2;
+constexpr int GLG_BAR_PARTS = 1, GLG_BAR_XS = 2, GLG_BAR_LATE = 3;
+// Experiment switches (DESIGN.md "round 2 kernel experiments": every one of them measured slower at B = 4096 -- the role loops
+// together sit at the SM's ~32 KB instruction cache, and whatever grows them costs more than it saves):
+//   GLG_HREG        per-env-step constants of a group role in registers instead of re-read from shared memory per evaluation
+//   GLG_ORDER_TOKEN make the owners' barrier wait data-dependent on the work meant to precede it (ptxas sinks it otherwise)
+//   GLG_LATE_MASK   (glg_units.h) early / late split of the owners' reduction
+#ifndef GLG_HREG
+#define GLG_HREG 0
+#endif
+#ifndef GLG_ORDER_TOKEN
+#define GLG_ORDER_TOKEN 0
+#endif
 constexpr int GLG_MAXCONTRIB = 8;
 constexpr int GLG_MAXROWS = 8;
 
+// -DGLG_TRACE: per-warp clock64() stamps of CTA 0 (wake-up after the barrier wait, arrival at the next barrier) for evaluations
+// 64..95 of a step, read back with glg_debug_trace (tools/trace_timeline.py).  Development builds only.
+#ifdef GLG_TRACE
+__device__ long long glg_trace[32][16][2];
+#define GLG_TRACE_MARK(warp_, slot_, ev_)                                                          \
+    do {                                                                                             \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (ev_) >= 64 && (ev_) < 96) glg_trace[(ev_) - 64][warp_][slot_] = clock64(); \
+    } while (0)
+#else
+#define GLG_TRACE_MARK(warp_, slot_, ev_) do {} while (0)
+#endif
 __device__ __forceinline__ void glg_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // Scheduling fences: the value must be in a register at this point of the instruction stream (ptxas otherwise sinks work that
 // was meant to overlap a barrier wait behind the barrier, and re-reads kernel parameters from the constant bank inside loops).
@@ -45,6 +69,12 @@ template <int N>
 __device__ __forceinline__ void glg_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
 __device__ __forceinline__ void glg_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+// bar.sync that ptxas cannot hoist above the computation of `token` (always 0 at run time, opaque at compile time): the barrier
+// is predicated on it.  Keeps the barrier id an immediate (a register id costs: the whole kernel then reserves 16 barriers).
+template <int ID>
+__device__ __forceinline__ void glg_bar_sync_after(int nthreads, int token) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p bar.sync %2, %0;\n\t}" ::"r"(nthreads), "r"(token), "n"(ID) : "memory");
+}
 __device__ __forceinline__ void glg_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---- owner plan and slot layout (see the header comment)
@@ -53,22 +83,37 @@ struct GlgOwnerPlan {
     int nj;                               // rows per owner warp
     int order[GLG_MAXROWS * GLG_NO];      // state of plan entry n, -1 pads
     int rank[GLG_NX];                     // plan entry of state i (states without contribution come after the active ones)
-    int row_slots[GLG_MAXROWS];           // slots row j loads
-    int row_base[GLG_MAXROWS + 1];        // prefix sum of row_slots
+    int row_early[GLG_MAXROWS];           // slots of early group warps row j loads (behind the first barrier)
+    int row_late[GLG_MAXROWS];            // slots of late group warps row j loads (behind the second barrier)
+    int row_base[GLG_MAXROWS + 1];        // prefix sum of row_early + row_late
     int slot[16][GLG_NX];                 // part slot of (group warp, state), -1 if none
     int scale_k[GLG_MAXROWS * GLG_NO];    // glg_state_scale_index of the entry's state (-1: 1.0, -2: canopy scale slot)
     int n_slots;                          // NO * row_base[nj]
+    int n_early_warps, n_late_warps;
 };
-constexpr GlgOwnerPlan glg_make_plan(const GlgWarpTable &wt, int ng) {
+constexpr GlgOwnerPlan glg_make_plan(const GlgWarpTable &wt, int ng, unsigned late_mask) {
     GlgOwnerPlan t{};
+    int ne[GLG_NX] = {}, nl[GLG_NX] = {};
+    for (int i = 0; i < GLG_NX; ++i)
+        for (int w = 0; w < ng; ++w)
+            if (wt.states[w] >> i & 1u) {
+                if (late_mask >> w & 1u) ++nl[i];
+                else ++ne[i];
+            }
+    for (int w = 0; w < ng; ++w) {
+        if (late_mask >> w & 1u) ++t.n_late_warps;
+        else ++t.n_early_warps;
+    }
+    // states sorted by (late, early) contribution counts, descending, and dealt round-robin to the owners: a row loads as many
+    // slots as its hungriest state
     int n = 0;
-    for (int c = GLG_MAXCONTRIB; c >= 0; --c)
+    for (int key = GLG_MAXCONTRIB * 16 + GLG_MAXCONTRIB; key >= 0; --key)
         for (int i = 0; i < GLG_NX; ++i)
-            if (wt.contribs[i] == c) {
+            if (nl[i] * 16 + ne[i] == key) {
                 t.order[n] = i;
                 t.rank[i] = n;
                 t.scale_k[n] = glg_state_scale_index(i);
-                if (c > 0) t.n_active = n + 1;
+                if (key > 0) t.n_active = n + 1;
                 ++n;
             }
     t.nj = (GLG_NX + GLG_NO - 1) / GLG_NO;
@@ -78,26 +123,36 @@ constexpr GlgOwnerPlan glg_make_plan(const GlgWarpTable &wt, int ng) {
     }
     t.row_base[0] = 0;
     for (int j = 0; j < GLG_MAXROWS; ++j) {
-        const int st = j * GLG_NO < GLG_NX ? t.order[j * GLG_NO] : -1;
-        t.row_slots[j] = st >= 0 ? wt.contribs[st] : 0;
-        t.row_base[j + 1] = t.row_base[j] + t.row_slots[j];
+        int e = 0, l = 0;
+        for (int o = 0; o < GLG_NO; ++o) {
+            const int st = j * GLG_NO + o < GLG_NX ? t.order[j * GLG_NO + o] : -1;
+            if (st >= 0) {
+                e = ne[st] > e ? ne[st] : e;
+                l = nl[st] > l ? nl[st] : l;
+            }
+        }
+        t.row_early[j] = e;
+        t.row_late[j] = l;
+        t.row_base[j + 1] = t.row_base[j] + e + l;
     }
     t.n_slots = GLG_NO * t.row_base[t.nj];
     for (int w = 0; w < 16; ++w)
         for (int i = 0; i < GLG_NX; ++i) {
             t.slot[w][i] = -1;
             if (w < ng && (wt.states[w] >> i & 1u)) {
-                int c = 0;
-                for (int ww = 0; ww < w; ++ww) c += (int)(wt.states[ww] >> i & 1u);
-                const int r = t.rank[i];
-                t.slot[w][i] = (t.row_base[r / GLG_NO] + c) * GLG_NO + r % GLG_NO;
+                const bool late = late_mask >> w & 1u;
+                int c = 0;  // contributing warps of the same class in front of w
+                for (int ww = 0; ww < w; ++ww) c += (int)((wt.states[ww] >> i & 1u) && ((late_mask >> ww & 1u) != 0) == late);
+                const int r = t.rank[i], j = r / GLG_NO;
+                t.slot[w][i] = (t.row_base[j] + (late ? t.row_early[j] : 0) + c) * GLG_NO + r % GLG_NO;
             }
         }
     return t;
 }
 template <int NG, bool GENERAL>
 struct GlgPlan {
-    static constexpr GlgOwnerPlan plan = glg_make_plan(GlgWT<NG, GENERAL>::t, NG);
+    static constexpr GlgOwnerPlan plan = glg_make_plan(GlgWT<NG, GENERAL>::t, NG, glg_late_mask(NG));
+    static constexpr unsigned late_mask = glg_late_mask(NG);
     static constexpr int NJ = plan.nj;
     static constexpr int NPART = plan.n_slots;
     static constexpr int CANSCALE = NPART;  // GlgSpecial fields
@@ -132,6 +187,18 @@ struct GlgXsCol {  // stage-state column of this lane, rows in plan order
     }
 };
 
+// per-env-step constants of this lane copied to registers in front of a role's loop (indices are compile-time constants after
+// inlining, so the array is scalarised and the entries the role never reads cost nothing)
+template <class T, int N>
+struct GlgRegCol {
+    T v[N];
+    __device__ __forceinline__ void load(const T *col) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = col[i * GLG_ROLE_LANES];
+    }
+    __device__ __forceinline__ T operator[](int i) const { return v[i]; }
+};
+
 template <class T, int NG, bool GENERAL, bool NOISY>
 struct GlgRoleSmem {
     using PL = GlgPlan<NG, GENERAL>;
@@ -163,18 +230,17 @@ struct GlgKView<float> {
 };
 
 // ---- one evaluation of the units of group warp W: stage state -> partial sums and specials in shared memory
-template <int NG, int W, bool GENERAL, bool NOISY, class T>
-__device__ __forceinline__ void glg_group_eval(const GlgUniform &U, const T *xs_col, T *part_col, T *h_col, T *c_col, const double *u) {
+// HV / CV: views of the per-env-step constants H and (NOISY) the per-env crop constants C: shared-memory columns or registers
+template <int NG, int W, bool GENERAL, bool NOISY, class T, class HV, class CV>
+__device__ __forceinline__ void glg_group_eval_v(const GlgUniform &U, const T *xs_col, T *part_col, const HV &Hc, const CV &Cc, const double *u) {
     using PL = GlgPlan<NG, GENERAL>;
     const typename GlgKView<T>::type Kv = GlgKView<T>::k(U);
     const GlgConstView Pv{U.P};
-    const GlgColT<T, GLG_ROLE_LANES> Hc{h_col};
-    const GlgColT<T, GLG_ROLE_LANES> Cc{c_col};
     const GlgXsCol<T, NG, GENERAL> X{xs_col};
     constexpr unsigned mask = GlgWT<NG, GENERAL>::t.states[W];
     T v[GLG_NX];
     GlgSpecial<T> sp;
-    if (NOISY) glg_run_warp_units<NG, W, 0, GENERAL>(Kv, Cc, Hc, Pv, u, X, v, sp);
+    if constexpr (NOISY) glg_run_warp_units<NG, W, 0, GENERAL>(Kv, Cc, Hc, Pv, u, X, v, sp);
     else glg_run_warp_units<NG, W, 0, GENERAL>(Kv, GlgKView<T>::c(U), Hc, Pv, u, X, v, sp);
     glg_static_for<0, GLG_NX>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
@@ -188,6 +254,10 @@ __device__ __forceinline__ void glg_group_eval(const GlgUniform &U, const T *xs_
     if constexpr (GlgWT<NG, GENERAL>::has_unit(W, U_VENT)) part_col[PL::AVENT * GLG_ROLE_LANES] = sp.avent;
     if constexpr (GlgWT<NG, GENERAL>::has_unit(W, U_SCR)) part_col[PL::ASCR * GLG_ROLE_LANES] = sp.ascr;
 }
+template <int NG, int W, bool GENERAL, bool NOISY, class T>
+__device__ __forceinline__ void glg_group_eval(const GlgUniform &U, const T *xs_col, T *part_col, T *h_col, T *c_col, const double *u) {
+    glg_group_eval_v<NG, W, GENERAL, NOISY, T>(U, xs_col, part_col, GlgColT<T, GLG_ROLE_LANES>{h_col}, GlgColT<T, GLG_ROLE_LANES>{c_col}, u);
+}
 // per-evaluation dispatch on the warp index (fused layout: one loop for all warps)
 template <int NG, int W, bool GENERAL, bool NOISY, class T>
 __device__ __forceinline__ void glg_group_eval_dispatch(int gw, const GlgUniform &U, const T *xs_col, T *part_col, T *h_col, T *c_col,
@@ -200,19 +270,40 @@ __device__ __forceinline__ void glg_group_eval_dispatch(int gw, const GlgUniform
     }
 }
 
-// ---- group role: the evaluation loop of group warp W (generic: any unit list)
+// ---- group role: the evaluation loop of group warp W (generic: any unit list).  The per-env-step constants are loop
+// invariants: they are read from shared memory once, in front of the loop (the barriers' memory clobber would otherwise force a
+// reload per evaluation: ~60 of the group warps' 139 shared-memory loads per evaluation, tools/sasssim).
+template <int NG, int W, bool GENERAL>
+struct GlgArrive {  // barrier a group warp reports to, and that barrier's thread count
+    using PL = GlgPlan<NG, GENERAL>;
+    static constexpr bool late = (PL::late_mask >> W & 1u) != 0;
+    static constexpr int id = late ? GLG_BAR_LATE : GLG_BAR_PARTS;
+    static constexpr int count = 32 * (GLG_NO + (late ? PL::plan.n_late_warps : PL::plan.n_early_warps));
+};
 template <int NG, int W, bool GENERAL, bool NOISY, class T>
 __device__ __forceinline__ void glg_group_loop(const GlgUniform &U, const T *xs_col, T *part_col, T *h_col, T *c_col, const double *u,
                                                const volatile int *s_stop, int nthreads) {
+#if GLG_HREG
+    GlgRegCol<T, H_COUNT> Hr;
+    Hr.load(h_col);
+    GlgRegCol<T, NOISY ? C_COUNT : 1> Cr;
+    if (NOISY) Cr.load(c_col);
+#else
+    const GlgColT<T, GLG_ROLE_LANES> Hr{h_col}, Cr{c_col};
+#endif
     int last_eval;
+    [[maybe_unused]] int ev = 0;
 #pragma unroll 1
     do {
         glg_bar_sync(GLG_BAR_XS, nthreads);
+        GLG_TRACE_MARK(GLG_NO + W, 0, ev);
         // one flag per group warp (the load's immediate offset identifies the role in the SASS, tools/sasssim); read with the
         // stage state, consumed after the arrive: off the critical path
         last_eval = s_stop[W];
-        glg_group_eval<NG, W, GENERAL, NOISY, T>(U, xs_col, part_col, h_col, c_col, u);
-        glg_bar_arrive(GLG_BAR_PARTS, nthreads);
+        glg_group_eval_v<NG, W, GENERAL, NOISY, T>(U, xs_col, part_col, Hr, Cr, u);
+        GLG_TRACE_MARK(GLG_NO + W, 1, ev);
+        ++ev;
+        glg_bar_arrive(GlgArrive<NG, W, GENERAL>::id, GlgArrive<NG, W, GENERAL>::count);
     } while (!last_eval);
 }
 
@@ -258,18 +349,25 @@ __device__ __forceinline__ void glg_surface_loop(int gw, const GlgUniform &U, co
     const T invvp = is_cv ? Kv[K_INVVPTOP] : Kv[K_INVVPAIR];
     const T L = Kv[K_L];
     const volatile int *stop = s_stop + gw;
+    static_assert(!SW::shared || ((PL::late_mask >> w_th | PL::late_mask >> w_bl | PL::late_mask >> w_cv) & 1u) == 0, "surface warps are early warps");
+    constexpr int n_arrive = 32 * (GLG_NO + PL::plan.n_early_warps);
+    const T coef_a = h_col[ha], coef_b = h_col[hb];  // loop invariants
     int last_eval;
+    [[maybe_unused]] int ev = 0;
 #pragma unroll 1
     do {
         glg_bar_sync(GLG_BAR_XS, nthreads);
+        GLG_TRACE_MARK(GLG_NO + gw, 0, ev);
         T surf, air, far, vp;
         last_eval = *stop;
-        glg_surface_core<true, T>(xs_col[xa], xs_col[xsf], xs_col[xb], xs_col[xv], h_col[ha], h_col[hb], invvp, L, surf, air, far, vp);
+        glg_surface_core<true, T>(xs_col[xa], xs_col[xsf], xs_col[xb], xs_col[xv], coef_a, coef_b, invvp, L, surf, air, far, vp);
         part_col[ps] = surf;
         part_col[pa] = air;
         part_col[pb] = far;
         part_col[pv] = vp;
-        glg_bar_arrive(GLG_BAR_PARTS, nthreads);
+        GLG_TRACE_MARK(GLG_NO + gw, 1, ev);
+        ++ev;
+        glg_bar_arrive(GLG_BAR_PARTS, n_arrive);
     } while (!last_eval);
 }
 
@@ -293,19 +391,24 @@ __device__ __forceinline__ void glg_group_dispatch(int gw, const GlgUniform &U, 
 // its CTA mates.
 // Stage update in unscaled units: s = sum of the partial sums, k = scale * s.
 //   stage 0..2: acc = (stage ? acc : 0) + w s ; xs = x + (c h scale) s        stage 3: x += (h/6 scale) (acc + s) ; xs = x
-// pre()  : everything that does not need the partial sums ((c h scale), the acc term of stage 3, the end-of-interval tests)
-// post() : load -> add tree -> one FMA -> store of the next stage state; decides the micro-step count on a first evaluation
-// book() : stage-sum / state / counter updates (off the critical path)
+// One evaluation, in program order (the order matters: everything in front of the last barrier wait is off the critical path,
+// what follows it is the CTA's serial section behind its slowest group warp):
+//   book()       : stage-sum / state / counter updates of the PREVIOUS evaluation
+//   pre()        : (c h scale), the acc term of stage 3, the end-of-interval tests
+//   post_early() : partial sums of the early group warps -> pairwise tree -> pre-accumulated into the stage state
+//   order_token(): data dependence of the late barrier on all of the above (ptxas otherwise sinks it behind the barrier)
+//   post_late()  : partial sums of the late group warps -> one add + one FMA per affected row -> next stage state to shared memory
 template <class T, int NG, bool GENERAL>
 struct GlgOwner {
     using PL = GlgPlan<NG, GENERAL>;
     static constexpr int NJ = PL::NJ, NL = GLG_ROLE_LANES;
     static constexpr int can_row = PL::canopy_entry / GLG_NO;
+    static constexpr bool kHasLate = PL::late_mask != 0u;
     double xo[NJ], acc[NJ], scale[NJ];  // the RK4 state and stage sum stay fp64 in both precisions
     double hc[NJ], base[NJ], sum[NJ], xn[NJ];
-    double h_nom, h_lane, cs, w;
+    double h_nom, h_lane, cs, w, can_cs;
     int o, n_sub, graded, sub, q, stage, m_lane, m_cta, n_micro;
-    bool can_owner, first, last;
+    bool can_owner, first, last, split_h;
     int final_eval, flag_next;
 
     // state index of row j of this owner (compile-time tables, runtime owner index)
@@ -316,8 +419,9 @@ struct GlgOwner {
         return o == 0 ? st0 : o == 1 ? st1 : o == 2 ? st2 : st3;
     }
     static constexpr bool kStateInXs = sizeof(T) == sizeof(double);  // see GlgRoleSmem::kXfinRows
+    // book_first: the caller's loop runs book() at its top (of the previous evaluation), so the first call has nothing to book
     __device__ __forceinline__ void init(int owner, const GlgStepArgs &A, const double *s_xfin, const double *s_scale, const T *xs_col,
-                                         int lane) {
+                                         int lane, bool book_first) {
         o = owner;
         glg_static_for<0, NJ>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
@@ -326,6 +430,8 @@ struct GlgOwner {
             if (kStateInXs) xo[j] = (double)xs_col[(j * GLG_NO + o) * NL];
             else xo[j] = st >= 0 ? s_xfin[st * NL + lane] : 0.0;
             acc[j] = 0.0;
+            sum[j] = 0.0;
+            xn[j] = xo[j];
         });
         can_owner = o == PL::canopy_entry % GLG_NO;
         h_nom = A.dt / (double)A.n_sub;
@@ -334,98 +440,12 @@ struct GlgOwner {
         glg_pin(h_nom);  // kept in registers: ptxas otherwise re-reads the kernel parameters inside the loop
         glg_pin(n_sub);
         glg_pin(graded);
-        sub = q = stage = n_micro = 0;
+        sub = q = n_micro = 0;
+        stage = book_first ? -1 : 0;  // a leading book() has nothing to book: w = 0, sum = 0
+        w = 0.0;
+        last = false;
         m_lane = m_cta = 1;
         h_lane = h_nom;
-    }
-    __device__ __forceinline__ void pre(int lane, bool pin) {
-        first = stage == 0 && q == 0;  // first evaluation of a nominal substep: the micro-step count is decided in post()
-        last = stage == 3;
-        cs = stage == 2 ? 1.0 : (last ? 1.0 / 6.0 : 0.5);
-        w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
-        // is this the last evaluation of the interval?  (m_cta of the last substep is known by its stage 3)
-        const bool last_micro = q + 1 >= m_cta && sub + 1 >= n_sub;
-        final_eval = last && last_micro;
-        flag_next = stage == 2 && last_micro && o == 0 && lane < 16;  // the group warps' next evaluation is the last one
-        // speculate m = 1 for a first evaluation (true except at the graded start of an interval and in stiff transients)
-        const double hcs = cs * (first ? h_nom : (q < m_lane ? h_lane : 0.0));
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            hc[j] = hcs * scale[j];
-            base[j] = xo[j];
-        }
-        if (last) {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) base[j] = glg_fma(hc[j], acc[j], xo[j]);
-        }
-        if (pin) {  // keep the work above in front of the barrier wait that follows (costs 2 NJ live doubles across it)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                glg_pin(hc[j]);
-                glg_pin(base[j]);
-            }
-        }
-        glg_pin(final_eval);
-        glg_pin(flag_next);
-    }
-    __device__ __forceinline__ void post(const GlgUniform &U, const T *part_col, T *xs_col) {
-        const T *pbase = part_col + o * NL;  // row j, contribution c at pbase[(row_base[j] + c) * NO * NL]
-        T *xbase = xs_col + o * NL;          // row j at xbase[j * NO * NL]
-        glg_static_for<0, NJ>([&](auto jc) {
-            constexpr int j = decltype(jc)::value;
-            constexpr int n = PL::plan.row_slots[j];
-            if constexpr (n == 0) {
-                sum[j] = 0.0;
-            } else {
-                constexpr int rb = PL::plan.row_base[j];
-                double v[n];
-#pragma unroll
-                for (int c = 0; c < n; ++c) v[c] = (double)pbase[(rb + c) * GLG_NO * NL];
-#pragma unroll
-                for (int s = 1; s < n; s *= 2)  // pairwise summation tree
-#pragma unroll
-                    for (int c = 0; c + s < n; c += 2 * s) v[c] += v[c + s];
-                sum[j] = v[0];
-            }
-        });
-        // the canopy's capacity scale K_INVCAPLEAF / LAI changes with the stage: its sum is scaled here (its scale[] entry is 1)
-        sum[can_row] *= can_owner ? (double)part_col[PL::CANSCALE * NL] : 1.0;
-        if (first) {
-            // m = 1 for every env of the CTA unless a harvest window is active (2 h lambda >= 1), the graded integrator is at
-            // the start of the interval or its stiffness rule asks for a split: one compare + vote on the common path
-            const double lam_h = (double)part_col[PL::LAMBDA * NL];
-            double lam_s = 0.0;
-            if (graded) lam_s = glg_stiffness(GlgConstView{U.K}, (double)part_col[PL::ASCR * NL], (double)part_col[PL::AVENT * NL]);
-            const bool split = (2.0 * h_nom * lam_h >= 1.0) || (graded && (sub < GLG_GRADED_SUBSTEPS || h_nom * lam_s * GLG_STIFF_INV_CFL >= 1.0));
-            m_lane = 1;
-            m_cta = 1;
-            h_lane = h_nom;
-            if (__any_sync(0xffffffffu, split)) {
-                m_lane = glg_micro_steps_from_lambda(lam_h, h_nom);
-                if (graded) {
-                    int ms = 1 + (int)floor(h_nom * lam_s * GLG_STIFF_INV_CFL);
-                    ms = ms > GLG_MAX_MICRO ? GLG_MAX_MICRO : (ms < 1 ? 1 : ms);  // ms < 1 only for a NaN estimate
-                    if (sub < GLG_GRADED_SUBSTEPS && ms < GLG_GRADED_M) ms = GLG_GRADED_M;
-                    m_lane = max(m_lane, ms);
-                }
-                m_cta = __reduce_max_sync(0xffffffffu, m_lane);  // every owner warp sees the same 32 envs
-                // reciprocal + multiply instead of an IEEE division; the step size differs from h_nom/m by at most 1 ulp
-                h_lane = m_lane == 1 ? h_nom : h_nom * glg_rcp((double)m_lane);
-                const double hcs = cs * h_lane;
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) hc[j] = hcs * scale[j];
-            }
-            n_micro += m_lane;
-        }
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            xn[j] = glg_fma(hc[j], sum[j], base[j]);
-            xbase[j * GLG_NO * NL] = (T)xn[j];
-        }
-        if (final_eval) {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) xo[j] = xn[j];
-        }
     }
     __device__ __forceinline__ void book() {
 #pragma unroll
@@ -445,6 +465,132 @@ struct GlgOwner {
             }
         }
     }
+    __device__ __forceinline__ void pre(int lane) {
+        first = stage == 0 && q == 0;  // first evaluation of a nominal substep: the micro-step count is decided in post_late()
+        last = stage == 3;
+        cs = stage == 2 ? 1.0 : (last ? 1.0 / 6.0 : 0.5);
+        w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
+        // is this the last evaluation of the interval?  (m_cta of the last substep is known by its stage 3)
+        const bool last_micro = q + 1 >= m_cta && sub + 1 >= n_sub;
+        final_eval = last && last_micro;
+        flag_next = stage == 2 && last_micro && o == 0 && lane < 16;  // the group warps' next evaluation is the last one
+        // speculate m = 1 for a first evaluation (true except at the graded start of an interval and in stiff transients)
+        const double hcs = cs * (first ? h_nom : (q < m_lane ? h_lane : 0.0));
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            hc[j] = hcs * scale[j];
+            base[j] = xo[j];
+        }
+        if (last) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) base[j] = glg_fma(hc[j], acc[j], xo[j]);
+        }
+    }
+    // pairwise tree over n slots of row J starting at slot index s0 (in units of NO * NL elements)
+    template <int N>
+    __device__ __forceinline__ static double tree(const T *p0) {
+        double v[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) v[c] = (double)p0[c * GLG_NO * NL];
+#pragma unroll
+        for (int s = 1; s < N; s *= 2)
+#pragma unroll
+            for (int c = 0; c + s < N; c += 2 * s) v[c] += v[c + s];
+        return v[0];
+    }
+    __device__ __forceinline__ void post_early(const T *part_col) {
+        const T *pbase = part_col + o * NL;  // row j, contribution c at pbase[(row_base[j] + c) * NO * NL]
+        glg_static_for<0, NJ>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            constexpr int n = PL::plan.row_early[j];
+            constexpr int rb = PL::plan.row_base[j];
+            if constexpr (n == 0) sum[j] = 0.0;
+            else sum[j] = tree<n>(pbase + rb * GLG_NO * NL);
+        });
+        // the canopy's capacity scale K_INVCAPLEAF / LAI changes with the stage (its scale[] entry is 1); U_PIPES is an early unit
+        can_cs = can_owner ? (double)part_col[PL::CANSCALE * NL] : 1.0;
+        sum[can_row] *= can_cs;
+        // harvest guard: m = 1 unless an organ is inside its harvest window (2 h lambda >= 1); U_MAINT is an early unit
+        split_h = first && (2.0 * h_nom * (double)part_col[PL::LAMBDA * NL] >= 1.0);
+        if (kHasLate) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) base[j] = glg_fma(hc[j], sum[j], base[j]);
+        }
+    }
+    // 0 for the caller as far as ptxas can tell (zero is an opaque 0): added to the id of the barrier that follows, it makes the
+    // barrier wait data-dependent on everything computed so far
+    __device__ __forceinline__ int order_token(int zero) const {
+        int t = 0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) t ^= __double2loint(hc[j]) ^ __double2loint(base[j]) ^ __double2loint(acc[j]) ^ __double2loint(sum[j]);
+        t ^= (int)split_h ^ final_eval ^ flag_next;
+#if GLG_ORDER_TOKEN
+        return t & zero;
+#else
+        return 0;
+#endif
+    }
+    __device__ __forceinline__ void post_late(const GlgUniform &U, const T *part_col, T *xs_col) {
+        const T *pbase = part_col + o * NL;
+        T *xbase = xs_col + o * NL;  // row j at xbase[j * NO * NL]
+        if (kHasLate) {
+            glg_static_for<0, NJ>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                constexpr int n = PL::plan.row_late[j];
+                if constexpr (n == 0) {
+                    xn[j] = base[j];
+                } else {
+                    constexpr int rb = PL::plan.row_base[j] + PL::plan.row_early[j];
+                    double l = tree<n>(pbase + rb * GLG_NO * NL);
+                    if constexpr (j == can_row) l *= can_cs;
+                    xn[j] = glg_fma(hc[j], l, base[j]);
+                    sum[j] += l;
+                }
+            });
+        }
+        if (first) {
+            // m = 1 for every env of the CTA unless a harvest window is active, the graded integrator is at the start of the
+            // interval or its stiffness rule asks for a split: one vote on the common path
+            double lam_s = 0.0;
+            if (graded) lam_s = glg_stiffness(GlgConstView{U.K}, (double)part_col[PL::ASCR * NL], (double)part_col[PL::AVENT * NL]);
+            const bool split = split_h || (graded && (sub < GLG_GRADED_SUBSTEPS || h_nom * lam_s * GLG_STIFF_INV_CFL >= 1.0));
+            m_lane = 1;
+            m_cta = 1;
+            h_lane = h_nom;
+            if (__any_sync(0xffffffffu, split)) {
+                m_lane = glg_micro_steps_from_lambda((double)part_col[PL::LAMBDA * NL], h_nom);
+                if (graded) {
+                    int ms = 1 + (int)floor(h_nom * lam_s * GLG_STIFF_INV_CFL);
+                    ms = ms > GLG_MAX_MICRO ? GLG_MAX_MICRO : (ms < 1 ? 1 : ms);  // ms < 1 only for a NaN estimate
+                    if (sub < GLG_GRADED_SUBSTEPS && ms < GLG_GRADED_M) ms = GLG_GRADED_M;
+                    m_lane = max(m_lane, ms);
+                }
+                m_cta = __reduce_max_sync(0xffffffffu, m_lane);  // every owner warp sees the same 32 envs
+                // reciprocal + multiply instead of an IEEE division; the step size differs from h_nom/m by at most 1 ulp
+                h_lane = m_lane == 1 ? h_nom : h_nom * glg_rcp((double)m_lane);
+                const double hcs = cs * h_lane;
+                // redo the stage update with the right step (first evaluation: stage 0, base = x)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    hc[j] = hcs * scale[j];
+                    xn[j] = glg_fma(hc[j], sum[j], xo[j]);
+                }
+            } else if (!kHasLate) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) xn[j] = glg_fma(hc[j], sum[j], base[j]);
+            }
+            n_micro += m_lane;
+        } else if (!kHasLate) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) xn[j] = glg_fma(hc[j], sum[j], base[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) xbase[j * GLG_NO * NL] = (T)xn[j];
+        if (final_eval) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) xo[j] = xn[j];
+        }
+    }
     // final state -> s_xfin; returns 1 if any of this owner's states is not finite
     __device__ __forceinline__ int finish(double *s_xfin, int lane) const {
         int bad = 0;
@@ -452,7 +598,7 @@ struct GlgOwner {
             constexpr int j = decltype(jc)::value;
             const int st = row_state<j>();
             bad |= !(fabs(xo[j]) <= 1.79769313486231570e308);
-            if (!kStateInXs && st >= 0) s_xfin[st * NL + lane] = xo[j];  // fp64 units: post() left it in the stage-state block
+            if (!kStateInXs && st >= 0) s_xfin[st * NL + lane] = xo[j];  // fp64 units: post_late() left it in the stage-state block
         });
         return bad;
     }
@@ -584,15 +730,16 @@ __global__ void __launch_bounds__(32 * (NG + (FUSED ? 0 : GLG_NO)), MINB) glg_st
             for (int i = 0; i < GLG_NU; ++i) u[i] = A.u[(size_t)i * A.B + e];
         }
         GlgOwner<T, NG, GENERAL> own;
-        own.init(warp, A, s_xfin, s_scale, xs_col, lane);
+        own.init(warp, A, s_xfin, s_scale, xs_col, lane, false);
 #pragma unroll 1
         for (;;) {
             glg_group_eval_dispatch<NG, 0, GENERAL, NOISY, T>(warp, U, xs_col, part_col, s_H + lane, s_C + lane, u);
-            own.pre(lane, false);
+            own.pre(lane);
             __syncthreads();
-            own.post(U, part_col, xs_col);
+            own.post_early(part_col);
+            own.post_late(U, part_col, xs_col);
             if (own.final_eval) break;
-            own.book();
+            own.book();  // in front of the barrier: measured 13 % faster at B = 262 144 than at the top of the loop (more spills there)
             __syncthreads();
         }
         n_micro = own.n_micro;
@@ -613,17 +760,30 @@ __global__ void __launch_bounds__(32 * (NG + (FUSED ? 0 : GLG_NO)), MINB) glg_st
         // ---- owner warps (GlgOwner)
         if (kRebalance) glg_reg_inc<kOwnerRegs>();
         GlgOwner<T, NG, GENERAL> own;
-        own.init(warp, A, s_xfin, s_scale, xs_col, lane);
+        own.init(warp, A, s_xfin, s_scale, xs_col, lane, true);
+        const int zero = *reinterpret_cast<const volatile int *>(s_misc + 3);  // 0, but not as far as ptxas knows (order_token)
+        constexpr int n_early = 32 * (GLG_NO + PL::plan.n_early_warps), n_late = 32 * (GLG_NO + PL::plan.n_late_warps);
         glg_bar_arrive(GLG_BAR_XS, NT);  // the prologue's stage state is in shared memory: release the group warps' first evaluation
+        [[maybe_unused]] int ev = 0;
 #pragma unroll 1
         for (;;) {
-            own.pre(lane, MINB == 1);
-            glg_bar_sync(GLG_BAR_PARTS, NT);
-            own.post(U, part_col, xs_col);
+            own.book();
+            own.pre(lane);
+            if (PL::late_mask != 0u) {
+                glg_bar_sync(GLG_BAR_PARTS, n_early);
+                own.post_early(part_col);
+                glg_bar_sync_after<GLG_BAR_LATE>(n_late, own.order_token(zero));
+            } else {
+                glg_bar_sync_after<GLG_BAR_PARTS>(n_early, own.order_token(zero));
+                own.post_early(part_col);
+            }
+            GLG_TRACE_MARK(warp, 0, ev);
+            own.post_late(U, part_col, xs_col);
             if (own.final_eval) break;
             if (own.flag_next) s_stop[lane] = 1;
+            GLG_TRACE_MARK(warp, 1, ev);
+            ++ev;
             glg_bar_arrive(GLG_BAR_XS, NT);
-            own.book();  // after the arrive: off the critical path
         }
         n_micro = own.n_micro;
         const int bad = own.finish(s_xfin, lane);

@@ -693,8 +693,16 @@ int glgo_env_step(const glgo_env_cfg *c, glgo_env *e, const double *p_nom, const
         glgo_param_noise(p_nom, noise34, p_step);
         pp = p_step;
     }
-    bad = glgo_evalf_ex(e->x, e->u, e->weather + (size_t)e->timestep * GLGO_ND, pp, c->dt, c->n_sub, c->stiff_guard, x_next,
-                        &e->n_micro);
+    if (c->stiff_guard & 16) {
+        long st[4] = {0, 0, 0, 0};
+        /* bit 5: carry the Jacobian from the previous control interval of this env (e->jac allocated by the caller) */
+        bad = glgo_evalf_bdf(e->x, e->u, e->weather + (size_t)e->timestep * GLGO_ND, pp, c->dt, 1e-6, 1e-6, x_next,
+                             ((c->stiff_guard & 32) && e->jac) ? e->jac : NULL, ((c->stiff_guard & 32) && e->jac) ? &e->jac_valid : NULL, st);
+        e->n_micro = st[0];
+    } else {
+        bad = glgo_evalf_ex(e->x, e->u, e->weather + (size_t)e->timestep * GLGO_ND, pp, c->dt, c->n_sub, c->stiff_guard, x_next,
+                            &e->n_micro);
+    }
     memcpy(e->x, x_next, sizeof x_next);
     if (bad) e->terminated = 1; /* mirrors the bare except -> terminated (tomato_env.py:121-123) */
 
@@ -809,6 +817,7 @@ static void rollout_item(void *vc, int b, int tid) {
     double rew, info[GLGO_NINFO];
     glgo_env e;
     int s;
+    memset(&e, 0, sizeof e); /* no carried Jacobian */
     glgo_env_reset(&e, r->weather, r->rows, 0.0);
     for (s = 0; s < r->n_steps; ++s) {
         int done = glgo_env_step(r->c, &e, r->p_nom, r->actions + ((size_t)s * r->B + b) * 6, 0, NULL, obs, &rew, info);
@@ -837,6 +846,8 @@ struct glgo_batch {
     double *p_nom, *weather;
     int rows, B;
     glgo_env *envs;
+    double *jac; /* [B][28*28] Jacobians carried between control intervals (stiff_guard bit 5) */
+    long *work;  /* [B] cumulative n_micro (RK4 micro-steps, or right-hand-side evaluations of the implicit solver) */
     const float *actions;
     float *obs_f32;
     double *reward;
@@ -853,7 +864,13 @@ glgo_batch *glgo_batch_create(const glgo_env_cfg *c, const double *p_nom, const 
     b->weather = (double *)malloc(sizeof(double) * (size_t)rows * GLGO_ND);
     memcpy(b->weather, weather, sizeof(double) * (size_t)rows * GLGO_ND);
     b->envs = (glgo_env *)calloc((size_t)B, sizeof(glgo_env));
-    for (i = 0; i < B; ++i) glgo_env_reset(&b->envs[i], b->weather, rows, 0.0);
+    b->work = (long *)calloc((size_t)B, sizeof(long));
+    if (c->stiff_guard & 32) b->jac = (double *)calloc((size_t)B * GLGO_NX * GLGO_NX, sizeof(double));
+    for (i = 0; i < B; ++i) {
+        glgo_env_reset(&b->envs[i], b->weather, rows, 0.0);
+        b->envs[i].jac = b->jac ? b->jac + (size_t)i * GLGO_NX * GLGO_NX : NULL;
+        b->envs[i].jac_valid = 0;
+    }
     return b;
 }
 static void batch_item(void *vc, int i, int tid) {
@@ -863,8 +880,12 @@ static void batch_item(void *vc, int i, int tid) {
     int j, done;
     (void)tid;
     done = glgo_env_step(&b->cfg, &b->envs[i], b->p_nom, b->actions + (size_t)i * 6, 0, NULL, obs, &r, info);
+    b->work[i] += b->envs[i].n_micro;
     if (done) {
+        double *jac = b->envs[i].jac;
         glgo_env_reset(&b->envs[i], b->weather, b->rows, 0.0);
+        b->envs[i].jac = jac;
+        b->envs[i].jac_valid = 0;
         glgo_env_obs(&b->cfg, &b->envs[i], obs);
     }
     if (b->obs_f32)
@@ -879,8 +900,16 @@ void glgo_batch_step(glgo_batch *b, const float *actions, float *obs_f32, double
     b->done = done;
     glgo_parallel_for(batch_item, b, b->B, n_threads);
 }
+long glgo_batch_work(const glgo_batch *b) {
+    long t = 0;
+    int i;
+    for (i = 0; i < b->B; ++i) t += b->work[i];
+    return t;
+}
 void glgo_batch_destroy(glgo_batch *b) {
     if (!b) return;
+    free(b->jac);
+    free(b->work);
     free(b->p_nom);
     free(b->weather);
     free(b->envs);

@@ -43,6 +43,11 @@ int glgo_evalf_ex(const double *x, const double *u, const double *d, const doubl
 /* R3/R4: x_next = RK4^n_sub(x; u,d,p const).  returns 0, or 1 if the result is not finite */
 int glgo_evalf(const double *x, const double *u, const double *d, const double *p, double dt, int n_sub,
                double *x_next);
+/* CVODES-class CPU baseline (glg_oracle_bdf.c): adaptive variable-order BDF/NDF 1..5, simplified Newton, dense LU, forward-
+ * difference Jacobian.  J_io [28*28] + jac_valid_io carry the Jacobian between calls (both may be NULL); stats[4] (may be
+ * NULL) += {rhs evaluations, Jacobian evaluations, LU factorisations, accepted steps}.  Not a parity checker. */
+int glgo_evalf_bdf(const double *x, const double *u, const double *d, const double *p, double dt, double rtol, double atol,
+                   double *x_next, double *J_io, int *jac_valid_io, long *stats);
 /* batched, AoS rows: x[B][28] u[B][6] d[B][10] p[B][208] (p_stride = 0 => shared p) ; OpenMP over envs */
 int glgo_evalf_batch(const double *x, const double *u, const double *d, const double *p, int p_stride, double dt,
                      int n_sub, double *x_next, int B, int n_threads);
@@ -59,7 +64,9 @@ typedef struct glgo_env_cfg {
     double elec_price, heating_price, co2_price, fruit_price, dmfm;
     double uncertainty_scale;
     double fixed_costs;     /* rewards.py:69-70,154: yearly/365/(86400//dt); reported in info only */
-    int stiff_guard;        /* opt-in transient-stiffness micro-step rule (glgo_evalf_ex); 0 = the fixed-step contract */
+    int stiff_guard;        /* integrator of glgo_env_step: 0 = the fixed-step RK4 contract; bits 0/1 = graded RK4 rules
+                               (glgo_evalf_ex); 16 = adaptive implicit BDF at rtol = atol = 1e-6 (glgo_evalf_bdf, the
+                               CVODES-class CPU baseline; n_micro then counts right-hand-side evaluations) */
 } glgo_env_cfg;
 
 typedef struct glgo_env {
@@ -69,7 +76,9 @@ typedef struct glgo_env {
     int terminated;
     const double *weather; /* [rows][10] */
     int weather_rows;
-    long n_micro;          /* RK4 micro-steps executed by the last step */
+    long n_micro;          /* RK4 micro-steps executed by the last step (implicit solver: right-hand-side evaluations) */
+    double *jac;           /* optional [28*28] Jacobian carried between steps by the implicit solver (stiff_guard bit 5) */
+    int jac_valid;
 } glgo_env;
 
 void glgo_init_state(const double *d0, double *x);                                   /* utils.py:13-46 */
@@ -108,6 +117,9 @@ typedef struct glgo_batch glgo_batch;
 glgo_batch *glgo_batch_create(const glgo_env_cfg *c, const double *p_nom, const double *weather, int rows, int B);
 /* actions float32 [B][6]; reward [B] doubles; done [B] bytes; obs_f32 may be NULL or float [B][23+5Np] */
 void glgo_batch_step(glgo_batch *b, const float *actions, float *obs_f32, double *reward, unsigned char *done, int n_threads);
+/* cumulative work of the batch: RK4 micro-steps (x4 = right-hand-side evaluations), or right-hand-side evaluations of the
+ * implicit solver including those spent on finite-difference Jacobians */
+long glgo_batch_work(const glgo_batch *b);
 void glgo_batch_destroy(glgo_batch *b);
 
 #ifdef __cplusplus

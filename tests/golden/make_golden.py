@@ -122,7 +122,7 @@ def main():
     x0 = init_state(W[0])
 
     # ---- RHS goldens from the reference source text
-    rt.check_helpers()
+    # the 12 helper functions are translated from the header text like the model body (ref_translate.translate_helpers)
     aux, ode, na, no = rt.load_reference_rhs()
     assert (na, no) == (239, 28)
     N = 400

@@ -24,7 +24,8 @@ class EnvCfg(C.Structure):
 class Env(C.Structure):
     _fields_ = [("x", C.c_double * 28), ("x_prev", C.c_double * 28), ("u", C.c_double * 6),
                 ("day_of_year", C.c_double), ("hour_of_day", C.c_double), ("timestep", C.c_int),
-                ("terminated", C.c_int), ("weather", _DP), ("weather_rows", C.c_int), ("n_micro", C.c_long)]
+                ("terminated", C.c_int), ("weather", _DP), ("weather_rows", C.c_int), ("n_micro", C.c_long),
+                ("jac", _DP), ("jac_valid", C.c_int)]
 
 
 def build():
@@ -47,6 +48,9 @@ def load():
         lib.glgo_evalf.restype = C.c_int
         lib.glgo_evalf_ex.argtypes = [_DP, _DP, _DP, _DP, C.c_double, C.c_int, C.c_int, _DP, C.POINTER(C.c_long)]
         lib.glgo_evalf_ex.restype = C.c_int
+        lib.glgo_evalf_bdf.argtypes = [_DP, _DP, _DP, _DP, C.c_double, C.c_double, C.c_double, _DP, _DP, C.POINTER(C.c_int),
+                                       C.POINTER(C.c_long)]
+        lib.glgo_evalf_bdf.restype = C.c_int
         lib.glgo_evalf_batch.argtypes = [_DP, _DP, _DP, _DP, C.c_int, C.c_double, C.c_int, _DP, C.c_int, C.c_int]
         lib.glgo_evalf_batch.restype = C.c_int
         lib.glgo_init_state.argtypes = [_DP, _DP]
@@ -65,6 +69,8 @@ def load():
         lib.glgo_batch_create.restype = C.c_void_p
         lib.glgo_batch_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.glgo_batch_destroy.argtypes = [C.c_void_p]
+        lib.glgo_batch_work.argtypes = [C.c_void_p]
+        lib.glgo_batch_work.restype = C.c_long
         _lib = lib
     return _lib
 
@@ -73,8 +79,12 @@ def P(a):
     return a.ctypes.data_as(_DP)
 
 
-def default_cfg(n_sub=600, N=5760, Np=48, dt=900.0):
+INTEGRATOR_RK4, INTEGRATOR_GRADED, INTEGRATOR_BDF, INTEGRATOR_BDF_KEEP_JAC = 0, 3, 16, 48  # glgo_env_cfg.stiff_guard
+
+
+def default_cfg(n_sub=600, N=5760, Np=48, dt=900.0, stiff_guard=0):
     c = EnvCfg()
+    c.stiff_guard = int(stiff_guard)
     c.dt, c.n_sub, c.N, c.Np = dt, n_sub, N, Np
     c.delta_u_max_f32 = float(np.float32(0.1))
     for i in range(6):
@@ -115,6 +125,15 @@ def evalf_ex(x, u, d, p, dt=900.0, n_sub=600, stiff_guard=0):
                                P(np.ascontiguousarray(d, dtype=np.float64)), P(np.ascontiguousarray(p, dtype=np.float64)),
                                float(dt), int(n_sub), int(stiff_guard), P(y), C.byref(n))
     return y, bool(bad), n.value
+
+
+def evalf_bdf(x, u, d, p, dt=900.0, rtol=1e-6, atol=1e-6):
+    """CVODES-class adaptive implicit solve (oracle/glg_oracle_bdf.c) -> (x_next, bad, {rhs, jac, lu, steps})"""
+    y, st = np.zeros(28), (C.c_long * 4)(0, 0, 0, 0)
+    bad = load().glgo_evalf_bdf(P(np.ascontiguousarray(x, dtype=np.float64)), P(np.ascontiguousarray(u, dtype=np.float64)),
+                                P(np.ascontiguousarray(d, dtype=np.float64)), P(np.ascontiguousarray(p, dtype=np.float64)),
+                                float(dt), float(rtol), float(atol), P(y), None, None, st)
+    return y, bool(bad), dict(rhs=st[0], jac=st[1], lu=st[2], steps=st[3])
 
 
 def evalf_batch(x, u, d, p, dt=900.0, n_sub=600, n_threads=0):
@@ -201,6 +220,10 @@ class OracleBatch:
         load().glgo_batch_step(self.h, a.ctypes.data, self.obs.ctypes.data, self.reward.ctypes.data, self.done.ctypes.data,
                                self.n_threads)
         return self.obs, self.reward, self.done
+
+    def work(self):
+        """cumulative RK4 micro-steps (RK4 integrators) or right-hand-side evaluations (implicit solver) of all envs"""
+        return int(load().glgo_batch_work(self.h))
 
     def close(self):
         if self.h:
