@@ -3,6 +3,7 @@
 #include "../../include/glgym.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -46,6 +47,8 @@ struct glg_handle {
     cudaStream_t own_stream = nullptr;
     long long launches = 0;
     double ctrl[GLG_NCTRL];  // rule-based controller settings (defaults: configs/agents/rule_based.yml)
+    int obs_nmod = 0, obs_mod[GLG_MAXOBSMOD] = {}, obs_off[GLG_MAXOBSMOD] = {}, fc_off = -1;
+    void *nccl_comm = nullptr;  // ncclComm_t (glg_nccl_init)
     std::string err;
 };
 static const double kDefaultCtrl[GLG_NCTRL] = {0, 18, -1, 366, 400, 10, 19.5, 16.5, 0, 5, 800, 4, 85, 2, 5, 1, -1, 5, 10, -1, 4, -2,
@@ -90,6 +93,8 @@ extern "C" void glg_default_config(glg_config *c) {
     c->seed = 0;
     c->env_id_offset = 0;
     c->role_warps = 0;
+    c->role_lanes = 0;
+    for (int i = 0; i < 8; ++i) c->obs_modules[i] = 0;  // empty = the default stack of TomatoEnv.yml
 }
 
 extern "C" const char *glg_last_error(const glg_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -99,6 +104,46 @@ static cudaError_t dev_alloc(T **p, size_t n) {
     cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
     if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
     return e;
+}
+
+// ---- episode-statistics all-reduce over NCCL, bound at run time ---------------------------------------------
+struct NcclId {  // ncclUniqueId: 128 opaque bytes, passed by value
+    char internal[128];
+};
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi *nccl_api(std::string *err) {
+    static NcclApi api;
+    if (api.lib) return &api;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) {
+        *err = std::string("NCCL not found (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : "");
+        return nullptr;
+    }
+    api.GetUniqueId = (int (*)(void *))dlsym(lib, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    api.CommDestroy = (int (*)(void *))dlsym(lib, "ncclCommDestroy");
+    api.GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
+        *err = "libnccl.so.2 lacks a required symbol";
+        return nullptr;
+    }
+    api.lib = lib;
+    return &api;
 }
 
 extern "C" void glg_destroy(glg_handle *h) {
@@ -113,6 +158,11 @@ extern "C" void glg_destroy(glg_handle *h) {
     if (h->h_reward) cudaFreeHost(h->h_reward);
     if (h->h_done) cudaFreeHost(h->h_done);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->nccl_comm) {
+        std::string e;
+        NcclApi *n = nccl_api(&e);
+        if (n) n->CommDestroy(h->nccl_comm);
+    }
     delete h;
 }
 
@@ -143,11 +193,39 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     h->cfg = *cfg;
     for (int i = 0; i < GLG_NCTRL; ++i) h->ctrl[i] = kDefaultCtrl[i];
     h->B = cfg->num_envs;
-    h->obs_dim = GLG_NOBS_FIXED + 5 * cfg->Np;
+    {
+        // observation row layout from the module list (tomato_env.py:77-96)
+        static const int kDefault[6] = {GLG_OBS_CLIMATE, GLG_OBS_CROP, GLG_OBS_CONTROL, GLG_OBS_WEATHER, GLG_OBS_TIME, GLG_OBS_FORECAST};
+        const int sizes[8] = {0, GLG_NOBS_STATE, 4, 3, 6, 5, 5, 5 * cfg->Np};
+        unsigned seen = 0;
+        int off = 0;
+        bool ok = true;
+        const bool use_default = cfg->obs_modules[0] == 0;
+        for (int m = 0; m < GLG_MAXOBSMOD; ++m) {
+            const int id = use_default ? (m < 6 ? kDefault[m] : 0) : cfg->obs_modules[m];
+            if (id == 0) break;
+            if (id < 1 || id > 7 || (seen >> id & 1u)) {
+                ok = false;
+                break;
+            }
+            seen |= 1u << id;
+            h->obs_mod[h->obs_nmod] = id;
+            h->obs_off[h->obs_nmod] = off;
+            if (id == GLG_OBS_FORECAST) h->fc_off = off;
+            off += sizes[id];
+            ++h->obs_nmod;
+        }
+        if (!ok || off < 3) {
+            g_create_error = "glg_create: obs_modules must list distinct module ids 1..7 with at least 3 observation entries in total";
+            delete h;
+            return GLG_ERR_ARG;
+        }
+        h->obs_dim = off;
+    }
     h->nt = 64;
     // kernel B: envs per CTA.  32 (full warps) is fastest at every batch size measured: a CTA's step time grows with the
     // number of co-resident CTAs faster than under-filled warps could win back (profiles/r1_lane_sweep.txt).
-    h->role_lanes = (cfg->reserved >= 1 && cfg->reserved <= 32) ? cfg->reserved : 32;
+    h->role_lanes = (cfg->role_lanes >= 1 && cfg->role_lanes <= 32) ? cfg->role_lanes : 32;
     {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->sms = prop.multiProcessorCount;
@@ -177,6 +255,12 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
         return GLG_ERR_CUDA;
     }
     *out = h;
+    return GLG_OK;
+}
+
+extern "C" int glg_set_seed(glg_handle *h, uint64_t seed) {
+    if (!h) return GLG_ERR_ARG;
+    h->cfg.seed = seed;
     return GLG_OK;
 }
 
@@ -252,6 +336,12 @@ static void fill_args(const glg_handle *h, GlgStepArgs *a) {
     a->seed = c.seed; a->env_id_offset = c.env_id_offset;
     a->role_lanes = h->role_lanes;
     a->integrator = c.integrator;
+    a->obs_nmod = h->obs_nmod;
+    for (int i = 0; i < GLG_MAXOBSMOD; ++i) {
+        a->obs_mod[i] = h->obs_mod[i];
+        a->obs_off[i] = h->obs_off[i];
+    }
+    a->fc_off = h->fc_off;
     a->weather = h->weather; a->start_day = h->start_day; a->reset_tables = h->reset_tables;
     a->x = h->x; a->u = h->u; a->time = h->time; a->ep_return = h->ep_return; a->ep_info = h->ep_info;
     a->timestep = h->timestep; a->table = h->table; a->ep_len = h->ep_len; a->step_ctr = h->step_ctr;
@@ -518,7 +608,29 @@ extern "C" int glg_set_state(glg_handle *h, const double *x_host, const double *
         to_soa(u_host, tmp.data(), B, GLG_NU);
         GLG_CUDA(h, cudaMemcpy(h->u, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
-    if (timestep_host) GLG_CUDA(h, cudaMemcpy(h->timestep, timestep_host, (size_t)B * sizeof(int), cudaMemcpyHostToDevice));
+    if (timestep_host) {
+        // the env clock follows the timestep (tomato_env.py:126-128, :246-247): doy = start_day(table) + k dt/86400 (summed the way
+        // the step does, one increment per step), hod = (k dt/3600) mod 24
+        if (!h->have_weather) return fail(h, GLG_ERR_STATE, "glg_set_state: set the weather bank first");
+        for (int b = 0; b < B; ++b)
+            if (timestep_host[b] < 0 || timestep_host[b] > h->cfg.N) return fail(h, GLG_ERR_ARG, "glg_set_state: timestep outside [0, N]");
+        std::vector<int> tb(B);
+        std::vector<double> sd(h->n_tables), tm((size_t)2 * B);
+        GLG_CUDA(h, cudaMemcpy(tb.data(), h->table, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost));
+        GLG_CUDA(h, cudaMemcpy(sd.data(), h->start_day, (size_t)h->n_tables * sizeof(double), cudaMemcpyDeviceToHost));
+        const double ddoy = fmod(h->cfg.dt / 86400.0, 365.0), dhod = h->cfg.dt / 3600.0;
+        for (int b = 0; b < B; ++b) {
+            double doy = sd[tb[b]], hod = 0.0;
+            for (int k = 0; k < timestep_host[b]; ++k) {
+                doy += ddoy;
+                hod = fmod(hod + dhod, 24.0);
+            }
+            tm[b] = doy;
+            tm[(size_t)B + b] = hod;
+        }
+        GLG_CUDA(h, cudaMemcpy(h->time, tm.data(), tm.size() * sizeof(double), cudaMemcpyHostToDevice));
+        GLG_CUDA(h, cudaMemcpy(h->timestep, timestep_host, (size_t)B * sizeof(int), cudaMemcpyHostToDevice));
+    }
     return GLG_OK;
 }
 
@@ -539,6 +651,100 @@ extern "C" int glg_get_state(glg_handle *h, double *x_host, double *u_host, int3
         to_aos(tmp.data(), u_host, B, GLG_NU);
     }
     if (timestep_host) GLG_CUDA(h, cudaMemcpy(timestep_host, h->timestep, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost));
+    return GLG_OK;
+}
+
+// full per-env state: checkpoint / restore
+template <class T>
+static cudaError_t copy_field(bool to_dev, T *dev, T *host, size_t n_per_env, int B, bool soa) {
+    if (!host) return cudaSuccess;
+    const size_t n = n_per_env * (size_t)B;
+    if (!soa || n_per_env == 1) return to_dev ? cudaMemcpy(dev, host, n * sizeof(T), cudaMemcpyHostToDevice) : cudaMemcpy(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost);
+    std::vector<T> tmp(n);
+    if (to_dev) {
+        for (int b = 0; b < B; ++b)
+            for (size_t i = 0; i < n_per_env; ++i) tmp[i * B + b] = host[(size_t)b * n_per_env + i];
+        return cudaMemcpy(dev, tmp.data(), n * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    cudaError_t e = cudaMemcpy(tmp.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost);
+    for (int b = 0; b < B; ++b)
+        for (size_t i = 0; i < n_per_env; ++i) host[(size_t)b * n_per_env + i] = tmp[i * B + b];
+    return e;
+}
+static int state_ex(glg_handle *h, const glg_env_state *s, bool to_dev) {
+    if (!h || !s) return GLG_ERR_ARG;
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    GLG_CUDA(h, cudaDeviceSynchronize());
+    const int B = h->B;
+    if (to_dev) {
+        if (s->table) {
+            if (!h->have_weather) return fail(h, GLG_ERR_STATE, "glg_set_state_ex: set the weather bank first");
+            for (int b = 0; b < B; ++b)
+                if (s->table[b] < 0 || s->table[b] >= h->n_tables) return fail(h, GLG_ERR_ARG, "glg_set_state_ex: table id out of range");
+        }
+        if (s->timestep)
+            for (int b = 0; b < B; ++b)
+                if (s->timestep[b] < 0 || s->timestep[b] > h->cfg.N + 1) return fail(h, GLG_ERR_ARG, "glg_set_state_ex: timestep outside [0, N + 1]");
+    }
+    GLG_CUDA(h, copy_field(to_dev, h->x, s->x, GLG_NX, B, true));
+    GLG_CUDA(h, copy_field(to_dev, h->u, s->u, GLG_NU, B, true));
+    GLG_CUDA(h, copy_field(to_dev, h->timestep, s->timestep, 1, B, false));
+    GLG_CUDA(h, copy_field(to_dev, h->table, s->table, 1, B, false));
+    GLG_CUDA(h, copy_field(to_dev, h->time, s->time, 2, B, true));
+    GLG_CUDA(h, copy_field(to_dev, h->step_ctr, s->step_ctr, 1, B, false));
+    GLG_CUDA(h, copy_field(to_dev, h->ep_return, s->ep_return, 1, B, false));
+    GLG_CUDA(h, copy_field(to_dev, h->ep_len, s->ep_len, 1, B, false));
+    GLG_CUDA(h, copy_field(to_dev, h->ep_info, s->ep_info, GLG_NINFO, B, true));
+    if (to_dev) h->is_reset = true;
+    return GLG_OK;
+}
+extern "C" int glg_get_state_ex(glg_handle *h, const glg_env_state *out_host) { return state_ex(h, out_host, false); }
+extern "C" int glg_set_state_ex(glg_handle *h, const glg_env_state *in_host) { return state_ex(h, in_host, true); }
+
+// ---- episode-statistics all-reduce over NCCL (run-time binding: nccl_api above)
+extern "C" int glg_nccl_unique_id(uint8_t id_out[128]) {
+    if (!id_out) return GLG_ERR_ARG;
+    std::string err;
+    NcclApi *n = nccl_api(&err);
+    if (!n) {
+        g_create_error = err;
+        return GLG_ERR_STATE;
+    }
+    NcclId id;
+    const int rc = n->GetUniqueId(&id);
+    if (rc != 0) {
+        g_create_error = std::string("ncclGetUniqueId: ") + (n->GetErrorString ? n->GetErrorString(rc) : "error");
+        return GLG_ERR_CUDA;
+    }
+    memcpy(id_out, id.internal, 128);
+    return GLG_OK;
+}
+extern "C" int glg_nccl_init(glg_handle *h, const uint8_t id[128], int32_t rank, int32_t world_size) {
+    if (!h || !id || world_size < 1 || rank < 0 || rank >= world_size) return GLG_ERR_ARG;
+    NcclApi *n = nccl_api(&h->err);
+    if (!n) return GLG_ERR_STATE;
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->nccl_comm) {
+        n->CommDestroy(h->nccl_comm);
+        h->nccl_comm = nullptr;
+    }
+    NcclId nid;
+    memcpy(nid.internal, id, 128);
+    const int rc = n->CommInitRank(&h->nccl_comm, world_size, nid, rank);
+    if (rc != 0) {
+        h->nccl_comm = nullptr;
+        return fail(h, GLG_ERR_CUDA, (std::string("ncclCommInitRank: ") + (n->GetErrorString ? n->GetErrorString(rc) : "error")).c_str());
+    }
+    return GLG_OK;
+}
+extern "C" int glg_allreduce_stats(glg_handle *h, void *stream) {
+    if (!h) return GLG_ERR_ARG;
+    if (!h->nccl_comm) return fail(h, GLG_ERR_STATE, "glg_allreduce_stats: no communicator (glg_nccl_init)");
+    NcclApi *n = nccl_api(&h->err);
+    if (!n) return GLG_ERR_STATE;
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int rc = n->AllReduce(h->stats, h->stats, GLG_NSTATS, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->nccl_comm, (cudaStream_t)stream);
+    if (rc != 0) return fail(h, GLG_ERR_CUDA, (std::string("ncclAllReduce: ") + (n->GetErrorString ? n->GetErrorString(rc) : "error")).c_str());
     return GLG_OK;
 }
 

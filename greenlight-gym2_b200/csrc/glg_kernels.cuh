@@ -24,6 +24,16 @@
 #include "glg_rk4.h"
 
 #define GLG_NOBS_FIXED 23
+// observation modules (observations.py:35-182); ids as in glg_config.obs_modules
+#define GLG_MAXOBSMOD 8
+#define GLG_OBS_STATE 1     // StateObservations: 27 uniform random numbers (observations.py:57)
+#define GLG_OBS_CLIMATE 2   // IndoorClimateObservations (4)
+#define GLG_OBS_CROP 3      // BasicCropObservations (3)
+#define GLG_OBS_CONTROL 4   // ControlObservations (6)
+#define GLG_OBS_WEATHER 5   // WeatherObservations (5)
+#define GLG_OBS_TIME 6      // TimeObservations (5)
+#define GLG_OBS_FORECAST 7  // WeatherForecastObservations (5 Np)
+#define GLG_NOBS_STATE 27
 #define GLG_NINFO 11
 #define GLG_NSTATS 16
 
@@ -38,6 +48,9 @@ struct GlgUniform {  // passed as a __grid_constant__ kernel parameter: lives in
 struct GlgStepArgs {
     int B, n_sub, N, Np, rows, n_tables, obs_dim, auto_reset, raw_control, n_reset_tables;
     int integrator;  // 0 fixed-step, 1 graded (kernel B's guarded loop)
+    // observation row layout (tomato_env.py:77-96,193-198): ordered module list, offset of each module in the row
+    int obs_nmod, obs_mod[GLG_MAXOBSMOD], obs_off[GLG_MAXOBSMOD];
+    int fc_off;      // offset of the forecast block in the row, -1 if the stack has no WeatherForecastObservations
     int role_lanes;  // kernel B: envs per CTA (<= 32); fewer envs per CTA = more CTAs = more resident warps for small batches
     // raw_control: 0 = actions through S1, 1 = caller's controls as-is, 2 = rule-based controller evaluated in the prologue
     double ctrl[GLG_NCTRL];  // rule-based controller settings (glg_controller.h)
@@ -158,36 +171,71 @@ __device__ __forceinline__ void glg_init_state(const double *w0, double *x) {
     x[27] = 0.;
 }
 
-// The 23 non-forecast observation entries (observations.py:59-161) for state x, controls u, weather row w,
-// timestep k (pre-increment), day_of_year, hour_of_day.  o3[3] receives obs[0:3] in fp64 for the reward.
+// The 23 entries of the five per-env modules (observations.py:59-161) for state x, controls u, weather row w, timestep k
+// (pre-increment), day_of_year, hour_of_day, in the canonical order climate(4) crop(3) control(6) weather(5) time(5), fp64.
 __device__ __forceinline__ void glg_obs_head(const double *x, const double *u, const double *w, int k, double doy,
-                                             double hod, float *row, double *o3) {
+                                             double hod, double *hd) {
     const double two_pi = 2 * 3.14159265358979323846;
-    o3[0] = glg_dens2ppm(x[2], x[0] * 1e-6);
-    o3[1] = x[2];
-    o3[2] = glg_rh(x[2], x[15]);
-    row[0] = (float)o3[0];
-    row[1] = (float)o3[1];
-    row[2] = (float)o3[2];
-    row[3] = (float)x[9];
-    row[4] = (float)x[21];
-    row[5] = (float)x[25];
-    row[6] = (float)x[26];
+    hd[0] = glg_dens2ppm(x[2], x[0] * 1e-6);
+    hd[1] = x[2];
+    hd[2] = glg_rh(x[2], x[15]);
+    hd[3] = x[9];
+    hd[4] = x[21];
+    hd[5] = x[25];
+    hd[6] = x[26];
 #pragma unroll
-    for (int i = 0; i < GLG_NU; ++i) row[7 + i] = (float)u[i];
-    row[13] = (float)w[0];
-    row[14] = (float)w[1];
-    row[15] = (float)glg_rh(w[1], w[2]);
-    row[16] = (float)glg_dens2ppm(w[1], w[3] * 1e-6);
-    row[17] = (float)w[4];
-    row[18] = (float)k;
+    for (int i = 0; i < GLG_NU; ++i) hd[7 + i] = u[i];
+    hd[13] = w[0];
+    hd[14] = w[1];
+    hd[15] = glg_rh(w[1], w[2]);
+    hd[16] = glg_dens2ppm(w[1], w[3] * 1e-6);
+    hd[17] = w[4];
+    hd[18] = (double)k;
     double s, c;
     sincos(two_pi * doy / 365.0, &s, &c);
-    row[19] = (float)s;
-    row[20] = (float)c;
+    hd[19] = s;
+    hd[20] = c;
     sincos(two_pi * hod / 24.0, &s, &c);
-    row[21] = (float)s;
-    row[22] = (float)c;
+    hd[21] = s;
+    hd[22] = c;
+}
+// Writes the per-env part of one observation row in the configured module order (everything but the forecast block, which
+// the whole CTA writes cooperatively) and returns the row's first three entries in fp64: the reward's constraint terms
+// read obs[[0, 1, 2]] whatever the stack puts there (rewards.py:191-198).  wnext = weather row k+1 (first forecast row).
+// StateObservations is `np.random.rand(27)` in the reference (global numpy RNG, observations.py:57): here 27 Philox uniforms
+// keyed by (seed, global env id, step counter), draw blocks 96.. (disjoint from the noise and reset-table blocks).
+__device__ __forceinline__ void glg_write_obs_row(const GlgStepArgs &A, const double *hd, const double *wnext, unsigned long long env_id,
+                                                  unsigned int ctr, float *orow, double *o3) {
+    const int seg0[5] = {0, 4, 7, 13, 18}, segn[5] = {4, 3, 6, 5, 5};
+#pragma unroll 1
+    for (int m = 0; m < A.obs_nmod; ++m) {
+        const int id = A.obs_mod[m], off = A.obs_off[m];
+        if (id >= GLG_OBS_CLIMATE && id <= GLG_OBS_TIME) {
+            const int s0 = seg0[id - GLG_OBS_CLIMATE], n = segn[id - GLG_OBS_CLIMATE];
+#pragma unroll 1
+            for (int i = 0; i < n; ++i) {
+                const double v = hd[s0 + i];
+                orow[off + i] = (float)v;
+                if (off + i < 3) o3[off + i] = v;
+            }
+        } else if (id == GLG_OBS_STATE) {
+#pragma unroll 1
+            for (int b = 0; b < (GLG_NOBS_STATE + 1) / 2; ++b) {
+                const GlgPhilox4 r = glg_philox4x32_10(96u + (uint32_t)b, ctr, (uint32_t)env_id, (uint32_t)(env_id >> 32),
+                                                       (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+                const double v0 = glg_u01(r.v[0], r.v[1]), v1 = glg_u01(r.v[2], r.v[3]);
+                orow[off + 2 * b] = (float)v0;
+                if (off + 2 * b < 3) o3[off + 2 * b] = v0;
+                if (2 * b + 1 < GLG_NOBS_STATE) {
+                    orow[off + 2 * b + 1] = (float)v1;
+                    if (off + 2 * b + 1 < 3) o3[off + 2 * b + 1] = v1;
+                }
+            }
+        } else if (id == GLG_OBS_FORECAST) {
+#pragma unroll 1
+            for (int i = 0; off + i < 3 && i < 5 * A.Np; ++i) o3[off + i] = wnext[(i / 5) * GLG_ND + (i % 5)];
+        }
+    }
 }
 
 __device__ __forceinline__ double glg_warp_sum(double v) {
@@ -313,11 +361,17 @@ __device__ __forceinline__ void glg_env_epilogue(const GlgUniform &U, const GlgS
     for (int i = 0; i < GLG_NU; ++i) u[i] = A.u[(size_t)i * B + e];
 #pragma unroll
     for (int i = 0; i < 5; ++i) d[i] = wrow[i];
-    float row[GLG_NOBS_FIXED];
-    double o3[3];
-    glg_obs_head(x, u, d, k, doy, hod, row, o3);
+    double hd[GLG_NOBS_FIXED];
+    double o3[3] = {0.0, 0.0, 0.0};
+    glg_obs_head(x, u, d, k, doy, hod, hd);
+    float *orow = A.obs + (size_t)e * A.obs_dim;
+    const unsigned long long env_gid = (unsigned long long)(A.env_id_offset + e);
+    // the row of this step: written to obs, or (when the env terminates and resets in place) to the terminal observation
+    float *step_row = orow;
     // S6: termination (tomato_env.py:68-75,131-132)
     if (k >= A.N) done = 1;
+    if (done && A.auto_reset) step_row = A.term_obs + (size_t)e * A.obs_dim;
+    glg_write_obs_row(A, hd, wrow + GLG_ND, env_gid, ctr, step_row, o3);
     // S5/S7: reward and info with the nominal parameters (rewards.py:156-231), same operation order
     double reward, info[GLG_NINFO];
     {
@@ -361,12 +415,8 @@ __device__ __forceinline__ void glg_env_epilogue(const GlgUniform &U, const GlgS
     o.tbl_obs = tbl;
     o.k_term = -1;
     o.tbl_term = 0;
-    float *orow = A.obs + (size_t)e * A.obs_dim;
     if (done && A.auto_reset) {
-        // SB3 VecEnv semantics: keep the terminal observation, then reset in place (tomato_env.py:231-270)
-        float *trow = A.term_obs + (size_t)e * A.obs_dim;
-#pragma unroll
-        for (int i = 0; i < GLG_NOBS_FIXED; ++i) trow[i] = row[i];
+        // SB3 VecEnv semantics: keep the terminal observation (written above), then reset in place (tomato_env.py:231-270)
         o.k_term = kw;
         o.tbl_term = tbl;
         tbl = A.n_reset_tables > 1
@@ -384,12 +434,12 @@ __device__ __forceinline__ void glg_env_epilogue(const GlgUniform &U, const GlgS
         k = 0;
         doy = A.start_day[tbl];
         hod = 0.0;
-        glg_obs_head(x, u, d, 0, doy, hod, row, o3);
+        glg_obs_head(x, u, d, 0, doy, hod, hd);
+        double o3r[3];
+        glg_write_obs_row(A, hd, w0 + GLG_ND, env_gid, ctr + 0x80000000u, orow, o3r);
         o.k_obs = 0;
         o.tbl_obs = tbl;
     }
-#pragma unroll
-    for (int i = 0; i < GLG_NOBS_FIXED; ++i) orow[i] = row[i];
     // state out
 #pragma unroll
     for (int i = 0; i < GLG_NX; ++i) A.x[(size_t)i * B + e] = x[i];
@@ -435,6 +485,7 @@ __device__ __forceinline__ void glg_stats_reduce(const GlgStepArgs &A, bool acti
 __device__ __forceinline__ void glg_write_forecast(const GlgStepArgs &A, int NR, const int *s_tbl, const int *s_k,
                                                    const int *s_tbl_t, const int *s_k_t, const double *s_wtile,
                                                    int uniform, int bk, int bt) {
+    if (A.fc_off < 0) return;  // the observation stack has no forecast block
     const size_t table_stride = (size_t)A.rows * GLG_ND;
     const int nf = 5 * A.Np;
     const int row0 = blockIdx.x * NR;
@@ -444,7 +495,7 @@ __device__ __forceinline__ void glg_write_forecast(const GlgStepArgs &A, int NR,
         if (kk < 0) continue;
         const int tb = s_tbl[r];
         const double *src = (uniform && tb == bt && kk == bk) ? s_wtile : (A.weather + (size_t)tb * table_stride + (size_t)kk * GLG_ND);
-        float *orow = A.obs + (size_t)(row0 + r) * A.obs_dim + GLG_NOBS_FIXED;
+        float *orow = A.obs + (size_t)(row0 + r) * A.obs_dim + A.fc_off;
         for (int j = threadIdx.x; j < nf; j += blockDim.x) {
             const int i = j / 5, c = j - 5 * i;
             orow[j] = (float)src[(size_t)(1 + i) * GLG_ND + c];
@@ -452,7 +503,7 @@ __device__ __forceinline__ void glg_write_forecast(const GlgStepArgs &A, int NR,
         const int kt = s_k_t[r];
         if (kt >= 0) {
             const double *srct = A.weather + (size_t)s_tbl_t[r] * table_stride + (size_t)kt * GLG_ND;
-            float *trow = A.term_obs + (size_t)(row0 + r) * A.obs_dim + GLG_NOBS_FIXED;
+            float *trow = A.term_obs + (size_t)(row0 + r) * A.obs_dim + A.fc_off;
             for (int j = threadIdx.x; j < nf; j += blockDim.x) {
                 const int i = j / 5, c = j - 5 * i;
                 trow[j] = (float)srct[(size_t)(1 + i) * GLG_ND + c];
@@ -565,15 +616,16 @@ __global__ void __launch_bounds__(NT) glg_reset_kernel(const __grid_constant__ G
     for (int j = 0; j < GLG_NINFO; ++j) A.ep_info[(size_t)j * B + e] = 0.0;
     A.done[e] = 0;
     A.reward[e] = 0.0;
-    float row[GLG_NOBS_FIXED];
-    glg_obs_head(x, u, d, 0, doy, 0.0, row, o3);
+    double hd[GLG_NOBS_FIXED];
+    glg_obs_head(x, u, d, 0, doy, 0.0, hd);
     float *orow = A.obs + (size_t)e * A.obs_dim;
-#pragma unroll
-    for (int i = 0; i < GLG_NOBS_FIXED; ++i) orow[i] = row[i];
-    const int nf = 5 * A.Np;
-    for (int j = 0; j < nf; ++j) {
-        const int i = j / 5, c = j - 5 * i;
-        orow[GLG_NOBS_FIXED + j] = (float)w0[(size_t)(1 + i) * GLG_ND + c];
+    glg_write_obs_row(A, hd, w0 + GLG_ND, (unsigned long long)(A.env_id_offset + e), ctr + 0x80000000u, orow, o3);
+    if (A.fc_off >= 0) {
+        const int nf = 5 * A.Np;
+        for (int j = 0; j < nf; ++j) {
+            const int i = j / 5, c = j - 5 * i;
+            orow[A.fc_off + j] = (float)w0[(size_t)(1 + i) * GLG_ND + c];
+        }
     }
 }
 

@@ -41,7 +41,7 @@ GLG_HD int glg_rk4_step(const KV &K, const CV &C, const HV &H, const P &p, const
             if (integrator == 1 && e == 0) {
                 int ms = 1 + (int)floor(h_nom * lam * GLG_STIFF_INV_CFL);
                 ms = ms > GLG_MAX_MICRO ? GLG_MAX_MICRO : (ms < 1 ? 1 : ms);
-                if (s < GLG_GRADED_SUBSTEPS && ms < GLG_GRADED_M) ms = GLG_GRADED_M;
+                if (ms < glg_graded_m(s)) ms = glg_graded_m(s);
                 if (ms > m) {
                     m = ms;
                     h = h_nom / (double)m;

@@ -562,7 +562,7 @@ struct GlgOwner {
                 if (graded) {
                     int ms = 1 + (int)floor(h_nom * lam_s * GLG_STIFF_INV_CFL);
                     ms = ms > GLG_MAX_MICRO ? GLG_MAX_MICRO : (ms < 1 ? 1 : ms);  // ms < 1 only for a NaN estimate
-                    if (sub < GLG_GRADED_SUBSTEPS && ms < GLG_GRADED_M) ms = GLG_GRADED_M;
+                    if (ms < glg_graded_m(sub)) ms = glg_graded_m(sub);
                     m_lane = max(m_lane, ms);
                 }
                 m_cta = __reduce_max_sync(0xffffffffu, m_lane);  // every owner warp sees the same 32 envs

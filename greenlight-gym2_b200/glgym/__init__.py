@@ -7,6 +7,9 @@ def __getattr__(name):  # lazy: importing the package must not require torch/CUD
     if name == "GreenLightVecEnv":
         from .vec_env import GreenLightVecEnv
         return GreenLightVecEnv
+    if name == "TomatoEnv":
+        from .tomato_env import TomatoEnv
+        return TomatoEnv
     if name == "GreenLight":
         from .model import GreenLight
         return GreenLight

@@ -26,8 +26,15 @@ class GlgConfig(C.Structure):
         ("elec_price", C.c_double), ("heating_price", C.c_double), ("co2_price", C.c_double),
         ("fruit_price", C.c_double), ("dmfm", C.c_double), ("fixed_costs", C.c_double),
         ("uncertainty_scale", C.c_double), ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
-        ("role_warps", C.c_int32), ("reserved", C.c_int32), ("integrator", C.c_int32), ("reserved2", C.c_int32),
+        ("role_warps", C.c_int32), ("role_lanes", C.c_int32), ("integrator", C.c_int32), ("reserved2", C.c_int32),
+        ("obs_modules", C.c_int32 * 8),
     ]
+
+
+class GlgEnvState(C.Structure):
+    """struct glg_env_state (include/glgym.h): host pointers, NULL = skip."""
+    _fields_ = [("x", C.c_void_p), ("u", C.c_void_p), ("timestep", C.c_void_p), ("table", C.c_void_p), ("time", C.c_void_p),
+                ("step_ctr", C.c_void_p), ("ep_return", C.c_void_p), ("ep_len", C.c_void_p), ("ep_info", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/glgym.h declares
@@ -62,6 +69,12 @@ SIGNATURES = {
     "glg_clear_stats": (C.c_int, [C.c_void_p, _VP]),
     "glg_set_state": (C.c_int, [C.c_void_p, _DP, _DP, _IP]),
     "glg_get_state": (C.c_int, [C.c_void_p, _DP, _DP, _IP]),
+    "glg_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "glg_get_state_ex": (C.c_int, [C.c_void_p, C.POINTER(GlgEnvState)]),
+    "glg_set_state_ex": (C.c_int, [C.c_void_p, C.POINTER(GlgEnvState)]),
+    "glg_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "glg_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "glg_allreduce_stats": (C.c_int, [C.c_void_p, _VP]),
     "glg_evalf_batch": (C.c_int, [_DP, _DP, _DP, _DP, C.c_int32, _DP, _U8P, C.c_int32, C.c_double, C.c_int32,
                                   C.c_int32, _VP]),
     "glg_evalf_batch_ex": (C.c_int, [_DP, _DP, _DP, _DP, C.c_int32, _DP, _U8P, C.c_int32, C.c_double, C.c_int32,

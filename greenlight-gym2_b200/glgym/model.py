@@ -2,8 +2,9 @@
 `GreenLight(nx, nu, nd, np, dt).evalF(x, u, d, p) -> list[float]`, executed by the CUDA evalF kernel.
 
 `evalF_batch` is the batched form the B200 path is built for (B independent evalF calls in one launch).
-The integrator is fixed-step RK4 with `n_sub` substeps (BASELINE.json north_star); the reference's CVODES
-(abstol=reltol=1e-6) is a third-party solver that is not available here -- see DESIGN.md.
+The integrator is classical RK4 with zero-order hold on `n_sub` nominal substeps (BASELINE.json north_star): "graded" (default,
+grid refined at the start of the interval, DESIGN.md "Integrator contract") or "fixed" (equal substeps); the reference's CVODES
+(abstol=reltol=1e-6) is a third-party solver that is not available here.
 """
 import numpy as np
 import torch
@@ -12,10 +13,13 @@ from . import _lib
 
 
 class GreenLight:
-    def __init__(self, nx=28, nu=6, nd=10, np_=208, dt=900.0, n_sub=None, device=0, integrator="fixed"):
+    def __init__(self, nx=28, nu=6, nd=10, np_=208, dt=900.0, n_sub=None, device=0, integrator=None):
         if (nx, nu, nd, np_) != (_lib.NX, _lib.NU, _lib.ND, _lib.NP):
             raise ValueError("GreenLight model dimensions are fixed: nx=28, nu=6, nd=10, np=208")
         self.dt = float(dt)
+        if integrator is None:
+            from .vec_env import DEFAULT_INTEGRATOR
+            integrator = DEFAULT_INTEGRATOR
         if integrator not in ("fixed", "graded"):
             raise ValueError("integrator must be 'fixed' or 'graded'")
         self.integrator = integrator  # "graded": DESIGN.md "Graded integrator" (default n_sub 300)

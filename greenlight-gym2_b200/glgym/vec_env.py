@@ -15,7 +15,6 @@ the GreenLightEnv section, `constraints`, `reward_params`, `observation_modules`
 import ctypes as C
 from os.path import join
 
-import sys
 import types
 
 import numpy as np
@@ -25,6 +24,13 @@ from . import _lib
 from .params import init_default_params
 from .spaces import Box
 from .weather import DEFAULT_WEATHER_DIR, load_weather_data
+
+# Integrator contract of a freshly constructed env: "graded" = classical RK4 with zero-order hold on a grid refined at the start
+# of every control interval and wherever the transient-stiffness estimate asks for it (n_sub = 300 nominal substeps, ~315 RK4
+# steps per interval).  Chosen on accuracy grounds (DESIGN.md "Integrator contract"): against tight-tolerance solutions of 250
+# rule-based control intervals its worst-step error sits inside the reference solver's 1e-6 band, the fixed 600-substep grid's
+# does not.  integrator="fixed" keeps the equal-substep contract (n_sub = 600).
+DEFAULT_INTEGRATOR = "graded"
 
 DEFAULT_OBSERVATION_MODULES = [
     "IndoorClimateObservations", "BasicCropObservations", "ControlObservations", "WeatherObservations",
@@ -54,13 +60,29 @@ class _DevArray:
                                          "version": 2}
 
 
-def obs_names(Np):
-    """Same names as TomatoEnv.get_obs_names() (tomato_env.py:200-206) for the default module stack."""
-    names = ["co2_air", "temp_air", "rh_air", "pipe_temp", "24CanTemp", "cFruit", "tSum",
-             "uBoil", "uCo2", "uThScr", "uVent", "uLamp", "uBlScr",
-             "glob_rad", "temp_out", "rh_out", "co2_out", "wind_speed",
-             "timestep", "day of year sin", "day of year cos", "hour of day sin", "hour of day cos"]
-    return names + ["glob_rad", "temp_out", "rh_out", "co2_out", "wind_speed"] * Np
+# observation modules (observations.py:35-182): name -> (id in glg_config.obs_modules, names, (low, high) of its Box)
+_WEATHER_NAMES = ["glob_rad", "temp_out", "rh_out", "co2_out", "wind_speed"]
+OBSERVATION_MODULES = {
+    "StateObservations": (1, ["co2_air", "co2_top", "temp_air", "temp_top", "can_temp", "covin_temp", "covex_temp", "thScr_temp",
+                              "flr_temp", "pipe_temp", "soil1_temp", "soil2_temp", "soil3_temp", "soil4_temp", "soil5_temp",
+                              "vp_air", "vp_top", "lamp_temp", "intlamp_temp", "grow_pipe_temp", "blscr_temp", "24_can_temp",
+                              "cBuf", "cleaves", "cstem", "cFruit", "tsum"], (-np.inf, np.inf)),
+    "IndoorClimateObservations": (2, ["co2_air", "temp_air", "rh_air", "pipe_temp"], (-1e-4, 1e4)),
+    "BasicCropObservations": (3, ["24CanTemp", "cFruit", "tSum"], (-1e-4, 1e4)),
+    "ControlObservations": (4, ["uBoil", "uCo2", "uThScr", "uVent", "uLamp", "uBlScr"], (0.0, 1.0)),
+    "WeatherObservations": (5, list(_WEATHER_NAMES), (-1e-4, 1e4)),
+    "TimeObservations": (6, ["timestep", "day of year sin", "day of year cos", "hour of day sin", "hour of day cos"], (-1e-4, 1e4)),
+    "WeatherForecastObservations": (7, None, (-1e-4, 1e4)),  # 5 Np entries
+}
+
+
+def obs_names(Np, modules=None):
+    """Same names as TomatoEnv.get_obs_names() (tomato_env.py:200-206) for an ordered module list (default stack if None)."""
+    names = []
+    for m in (modules or DEFAULT_OBSERVATION_MODULES):
+        n = OBSERVATION_MODULES[m][1]
+        names += list(n) if n is not None else _WEATHER_NAMES * Np
+    return names
 
 
 class GreenLightVecEnv:
@@ -72,13 +94,13 @@ class GreenLightVecEnv:
                  eval_options=None, reward_params=None, base_env_params=None, uncertainty_scale=0.0,
                  n_sub=None, device=0, seed=0, auto_reset=True, env_id_offset=0, weather_tables=None,
                  table_start_days=None, params=None, info_mode=None, role_warps=0, role_lanes=0, precision="fp64",
-                 reuse_output_buffers=False, integrator="fixed"):
+                 reuse_output_buffers=False, integrator=None, obs_ring=4):
         if reward_function != "GreenhouseReward":
             raise ValueError("only GreenhouseReward exists in the reference (tomato_env.py:14)")
         mods = list(observation_modules or DEFAULT_OBSERVATION_MODULES)
-        if mods != DEFAULT_OBSERVATION_MODULES:
-            raise ValueError("the fused kernel implements the default observation stack of configs/envs/TomatoEnv.yml: "
-                             f"{DEFAULT_OBSERVATION_MODULES}")
+        unknown = [m for m in mods if m not in OBSERVATION_MODULES]
+        if unknown or len(set(mods)) != len(mods):
+            raise ValueError(f"observation_modules must be distinct names out of {list(OBSERVATION_MODULES)}; got {mods}")
         bp = dict(DEFAULT_BASE_ENV_PARAMS)
         bp.update(base_env_params or {})
         self.base_env_params = bp
@@ -108,18 +130,21 @@ class GreenLightVecEnv:
         self.train_days = list(range(bp["start_train_day"], bp["end_train_day"] + 1))
         # integrator: "fixed" = n_sub equal RK4 substeps (default 600, the parity contract); "graded" = RK4 with a refined
         # start of every control interval and a transient-stiffness rule (default n_sub 300; DESIGN.md "Graded integrator")
+        integrator = integrator or DEFAULT_INTEGRATOR
         if integrator not in ("fixed", "graded"):
             raise ValueError("integrator must be 'fixed' or 'graded'")
         self.integrator = integrator
         self.n_sub = int(n_sub) if n_sub is not None else (600 if integrator == "fixed" else 300)
         self.observation_modules = mods
-        self.obs_dim = 23 + 5 * self.Np
-        # spaces: tomato_env.py:83-98 / observations.py observation_space() of each module
-        low = np.concatenate([np.full(4, -1e-4), np.full(3, -1e-4), np.zeros(6), np.full(5, -1e-4), np.full(5, -1e-4),
-                              np.full(5 * self.Np, -1e-4)]).astype(np.float32)
-        high = np.concatenate([np.full(4, 1e4), np.full(3, 1e4), np.ones(6), np.full(5, 1e4), np.full(5, 1e4),
-                               np.full(5 * self.Np, 1e4)]).astype(np.float32)
+        # spaces: tomato_env.py:83-98 / observations.py observation_space() of each module, concatenated in stack order
+        sizes = [len(OBSERVATION_MODULES[m][1]) if OBSERVATION_MODULES[m][1] is not None else 5 * self.Np for m in mods]
+        self.obs_dim = int(sum(sizes))
+        if self.obs_dim < 3:
+            raise ValueError("the reward reads obs[0:3] (rewards.py:191-198): the observation stack needs at least 3 entries")
+        low = np.concatenate([np.full(n, OBSERVATION_MODULES[m][2][0]) for m, n in zip(mods, sizes)]).astype(np.float32)
+        high = np.concatenate([np.full(n, OBSERVATION_MODULES[m][2][1]) for m, n in zip(mods, sizes)]).astype(np.float32)
         self.observation_space = Box(low=low, high=high, dtype=np.float32)
+        self.forecast_offset = int(sum(sizes[:mods.index("WeatherForecastObservations")])) if "WeatherForecastObservations" in mods else -1
         self.action_space = Box(low=-1, high=1, shape=(self.nu,), dtype=np.float32)
         self.constraints_low = np.array([con["co2_min"], con["temp_min"], con["rh_min"]])
         self.constraints_high = np.array([con["co2_max"], con["temp_max"], con["rh_max"]])
@@ -177,7 +202,9 @@ class GreenLightVecEnv:
         cfg.seed = int(seed) & (2**64 - 1)
         cfg.env_id_offset = int(env_id_offset)
         cfg.integrator = 0 if integrator == "fixed" else 1
-        cfg.reserved = int(role_lanes)    # kernel C envs-per-CTA override (0 = auto)
+        cfg.role_lanes = int(role_lanes)  # kernel C envs-per-CTA override (0 = auto)
+        for i, m in enumerate(mods):
+            cfg.obs_modules[i] = OBSERVATION_MODULES[m][0]
         cfg.role_warps = int(role_warps)  # 0 auto, 1 = one thread per env, 2 / 3 = warp-specialised kernel (1 / 2 CTAs per SM)
         self.reward_params = rp
         self._seed = int(seed)
@@ -187,6 +214,7 @@ class GreenLightVecEnv:
         _lib.check(self._lib.glg_set_params(self._h, p64.ctypes.data), self._h, "glg_set_params")
         _lib.check(self._lib.glg_set_weather(self._h, weather_tables.ctypes.data, n_tables, rows,
                                              self.table_start_days.ctypes.data), self._h, "glg_set_weather")
+        assert int(self._lib.glg_obs_dim(self._h)) == self.obs_dim
         B, dev = self.num_envs, self.device
         view = lambda ptr, shape, ts: torch.as_tensor(_DevArray(ptr, shape, ts), device=dev)
         L = self._lib
@@ -206,18 +234,21 @@ class GreenLightVecEnv:
         self._pin = [torch.empty((B, self.obs_dim), dtype=torch.float32).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory(),
                      torch.empty(B, dtype=torch.uint8).pin_memory(), torch.empty((B, self.nu), dtype=torch.float32).pin_memory()]
         self._obs_host, self._rew_host, self._done_host, self._act_host = (t.numpy() for t in self._pin)
-        # Default: `step()` returns page-locked observation buffers handed out by reference count (_free_pool_buffer) -- fresh
-        # arrays as far as the caller can tell, without a host copy.
-        # reuse_output_buffers: `step()` returns views of two alternating page-locked observation buffers instead
-        # (no reference counting at all).  An array returned by step k is overwritten by step k+2 -- safe
-        # for SB3's collect loop (it copies `new_obs` into its rollout buffer before the next step); off by default because
-        # the reference returns fresh arrays.
+        # Observation arrays returned by `step()` (numpy path) -- explicit ownership, no reference counting:
+        #   obs_ring = n >= 2 (default 4): the arrays ARE page-locked buffers of a ring of n, handed out round-robin; the array
+        #       returned by step k stays untouched until step k + n (no host copy: 0.29 ms per step at B = 4096).  Safe for SB3's
+        #       collect loop (it copies `new_obs` into its rollout buffer before the next step) and for any consumer that is done
+        #       with an observation within n - 1 further steps -- including asynchronous ones (non_blocking H2D from this pinned
+        #       memory), which reference counting cannot see.
+        #   obs_ring = 0: a fresh pageable copy every step (the reference's semantics, for callers that keep observations).
+        #   reuse_output_buffers=True is the old name of obs_ring = 2.
         self.reuse_output_buffers = bool(reuse_output_buffers)
-        self._obs_pool = None  # default path: lazily created pool of page-locked buffers handed out by reference count
-        if self.reuse_output_buffers:
-            self._pin.append(torch.empty((B, self.obs_dim), dtype=torch.float32).pin_memory())
-            self._obs_ring = [self._obs_host, self._pin[-1].numpy()]
-            self._obs_turn = 0
+        self.obs_ring = 2 if self.reuse_output_buffers else int(obs_ring)
+        if self.obs_ring == 1 or self.obs_ring < 0:
+            raise ValueError("obs_ring must be 0 (copy every step) or >= 2")
+        self._ring = [self._obs_host] + [torch.empty((B, self.obs_dim), dtype=torch.float32).pin_memory() for _ in range(max(self.obs_ring - 1, 0))]
+        self._ring_np = [self._obs_host] + [t.numpy() for t in self._ring[1:]]
+        self._ring_pos = 0
 
     # ------------------------------------------------------------------ tensor fast path
     def _stream(self):
@@ -280,39 +311,18 @@ class GreenLightVecEnv:
         np.copyto(self._act_host, np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.nu))
         self._actions = self._act_host
 
-    def _free_pool_buffer(self):
-        """A page-locked observation buffer nobody outside this object references any more, or None.  The returned arrays
-        ARE these buffers (no host copy); one is reused only after the caller dropped every reference to it (and to views of
-        it), so the reference's fresh-array semantics hold."""
-        if self._obs_pool is None:
-            self._obs_pool = [torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32).pin_memory() for _ in range(4)]
-            self._obs_pool_np = [t.numpy() for t in self._obs_pool]
-            self._pool_pos = 0
-        n = len(self._obs_pool_np)
-        for j in range(n):
-            i = (self._pool_pos + j) % n
-            if sys.getrefcount(self._obs_pool_np[i]) <= 2:  # the pool's own reference + getrefcount's argument
-                self._pool_pos = (i + 1) % n
-                return i
-        return None
-
     def step_wait(self):
-        pool_i = None
-        if self.reuse_output_buffers:
-            self._obs_turn ^= 1
-            obs_buf = self._obs_ring[self._obs_turn]
-        else:
-            pool_i = self._free_pool_buffer()
-            obs_buf = self._obs_host if pool_i is None else self._obs_pool_np[pool_i]
+        n = len(self._ring_np)
+        obs_buf = self._ring_np[self._ring_pos]
+        self._ring_pos = (self._ring_pos + 1) % n
+        # glg_step_host works on the handle's own stream: order it behind whatever the caller enqueued on torch's current
+        # stream (reset_tensor / step_tensor / episode_stats(clear=True) followed by step())
+        torch.cuda.current_stream(self.device).synchronize()
         _lib.check(self._lib.glg_step_host(self._h, self._actions.ctypes.data, obs_buf.ctypes.data,
                                            self._rew_host.ctypes.data, self._done_host.ctypes.data), self._h, "glg_step_host")
         dones = self._done_host.astype(bool)
-        if self.reuse_output_buffers:
-            obs = obs_buf
-        elif pool_i is not None:
-            obs = self._obs_pool_np[pool_i]  # zero-copy: the caller now holds a reference, the buffer is busy until it lets go
-        else:
-            obs = obs_buf.copy()             # every pool buffer is still referenced by the caller: plain copy
+        obs = obs_buf.copy() if self.obs_ring == 0 else obs_buf
+        # rewards: float64 on the device (the reference returns a Python float); the VecEnv protocol carries float32
         return obs, self._rew_host.astype(np.float32), dones, self._make_infos(dones)
 
     def step(self, actions):
@@ -385,29 +395,54 @@ class GreenLightVecEnv:
         return [getattr(self, attr_name) for _ in idx]
 
     def set_attr(self, attr_name, value, indices=None):
+        """Per-env attributes that live on the device ("u", "x", "timestep") are written for `indices`; anything else is an
+        attribute of the batch as a whole and only accepts indices=None / all envs."""
+        idx = list(self._indices(indices))
+        if attr_name in ("u", "x", "timestep"):
+            x, u, k = self.get_state()
+            arr = {"u": u, "x": x, "timestep": k}[attr_name]
+            arr[idx] = value
+            self.set_state(**{attr_name: arr})
+            return
+        if len(idx) != self.num_envs:
+            raise ValueError(f"attribute {attr_name!r} is shared by all envs of the batch; set it with indices=None")
         setattr(self, attr_name, value)
 
     def env_method(self, method_name, *args, indices=None, **kwargs):
         idx = list(self._indices(indices))
         if method_name == "get_obs_names":
-            return [obs_names(self.Np) for _ in idx]
+            return [obs_names(self.Np, self.observation_modules) for _ in idx]
         if method_name == "set_seed":
-            return [None for _ in idx]  # RNG streams are keyed by (seed, global env id); see seed()
+            # RNG streams are keyed by (seed, global env id): one key for the batch.  SB3 scripts call set_seed(seed + rank) per
+            # env; the first env's argument re-keys the handle, the per-env offset is what the global env id already provides.
+            if args:
+                self.reseed(int(args[0]))
+            return [None for _ in idx]
+        if method_name in ("_reset_eval_idx", "increase_eval_idx"):
+            self.eval_idx = 0 if method_name == "_reset_eval_idx" else getattr(self, "eval_idx", 0) + 1
+            return [None for _ in idx]
         raise AttributeError(f"env_method {method_name!r} is not provided by the batched env")
 
     def env_is_wrapped(self, wrapper_class, indices=None):
         return [False for _ in self._indices(indices)]
 
+    def reseed(self, seed):
+        """New key for the handle's Philox streams (parametric noise, reset-table choice, StateObservations); takes effect with
+        the next launch.  base_env.py:166-170 `set_seed`."""
+        self._seed = int(seed)
+        _lib.check(self._lib.glg_set_seed(self._h, C.c_uint64(self._seed & (2**64 - 1))), self._h, "glg_set_seed")
+
     def seed(self, seed=None):
         return [None if seed is None else seed + i for i in range(self.num_envs)]
 
     def get_obs_names(self):
-        return obs_names(self.Np)
+        return obs_names(self.Np, self.observation_modules)
 
     # ------------------------------------------------------------------ helpers
     def set_state(self, x=None, u=None, timestep=None):
-        """Teacher forcing / checkpoint restore: x [B,28], u [B,6] float64, timestep [B] int32 (host arrays)."""
-        ptr = lambda a, dt: 0 if a is None else np.ascontiguousarray(a, dtype=dt).ctypes.data
+        """Teacher forcing: x [B,28], u [B,6] float64, timestep [B] int32 (host arrays).  Setting the timestep also moves the
+        env clock to it (day of year / hour of day as after `timestep` steps from the env's table start day); for a complete
+        checkpoint / restore use state_dict() / load_state_dict()."""
         keep = [None if a is None else np.ascontiguousarray(a, dtype=dt) for a, dt in
                 ((x, np.float64), (u, np.float64), (timestep, np.int32))]
         _lib.check(self._lib.glg_set_state(self._h, *[0 if a is None else a.ctypes.data for a in keep]), self._h, "glg_set_state")
@@ -419,8 +454,54 @@ class GreenLightVecEnv:
         _lib.check(self._lib.glg_get_state(self._h, x.ctypes.data, u.ctypes.data, k.ctypes.data), self._h, "glg_get_state")
         return x, u, k
 
+    _STATE_FIELDS = (("x", np.float64, _lib.NX), ("u", np.float64, _lib.NU), ("timestep", np.int32, 0), ("table", np.int32, 0),
+                     ("time", np.float64, 2), ("step_ctr", np.uint32, 0), ("ep_return", np.float64, 0), ("ep_len", np.int32, 0),
+                     ("ep_info", np.float64, _lib.NINFO))
+
+    def state_dict(self):
+        """Everything a step reads besides the parameter table and the weather bank: state, controls, timestep, weather table,
+        clock, Philox stream position and the episode accumulators (host arrays)."""
+        B = self.num_envs
+        out = {n: np.empty((B, w) if w else B, dtype=dt) for n, dt, w in self._STATE_FIELDS}
+        st = _lib.GlgEnvState(**{n: out[n].ctypes.data for n, _, _ in self._STATE_FIELDS})
+        _lib.check(self._lib.glg_get_state_ex(self._h, C.byref(st)), self._h, "glg_get_state_ex")
+        return out
+
+    def load_state_dict(self, state):
+        """Restores (a subset of) state_dict(); table ids and timesteps are range-checked by the library."""
+        B = self.num_envs
+        keep = {}
+        for n, dt, w in self._STATE_FIELDS:
+            if n in state and state[n] is not None:
+                keep[n] = np.ascontiguousarray(state[n], dtype=dt).reshape((B, w) if w else B)
+        st = _lib.GlgEnvState(**{n: a.ctypes.data for n, a in keep.items()})
+        _lib.check(self._lib.glg_set_state_ex(self._h, C.byref(st)), self._h, "glg_set_state_ex")
+
     def launch_count(self):
         return int(self._lib.glg_launch_count(self._h))
+
+    def init_stats_allreduce(self):
+        """Creates the handle's NCCL communicator over torch.distributed's ranks (the 128-byte NCCL id travels in a
+        broadcast); afterwards allreduce_stats() sums the episode statistics of all ranks' handles on the device."""
+        import torch.distributed as dist
+        ident = torch.zeros(128, dtype=torch.uint8)
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+        if rank == 0:
+            buf = np.zeros(128, dtype=np.uint8)
+            _lib.check(self._lib.glg_nccl_unique_id(buf.ctypes.data), None, "glg_nccl_unique_id")
+            ident = torch.from_numpy(buf)
+        if world > 1:
+            t = ident.to(self.device) if dist.get_backend() == "nccl" else ident
+            dist.broadcast(t, src=0)
+            ident = t.cpu()
+        buf = np.ascontiguousarray(ident.numpy())
+        _lib.check(self._lib.glg_nccl_init(self._h, buf.ctypes.data, rank, world), self._h, "glg_nccl_init")
+
+    def allreduce_stats(self):
+        """In-place sum over ranks of the 16-entry statistics vector (ncclAllReduce on torch's current stream); stats_t then
+        holds the global sums on every rank."""
+        _lib.check(self._lib.glg_allreduce_stats(self._h, self._stream()), self._h, "glg_allreduce_stats")
+        return self.stats_t
 
     def episode_stats(self, clear=False):
         s = self.stats_t.cpu().numpy().copy()

@@ -65,13 +65,20 @@ typedef struct glg_config {
     int64_t env_id_offset;   /* global index of local env 0 (multi-GPU sharding; RNG streams follow the global id) */
     int32_t role_warps;      /* kernel variant: 0 = auto, 1 = one thread per env (kernel A), 2 / 3 = warp-specialised kernel C (4 owner +
                               * 12 flux-unit warps per 32 envs) compiled for one CTA per SM (latency: small batches) / two (throughput) */
-    int32_t reserved;        /* 0, or 1..32: override of kernel C's envs-per-CTA (tuning / tests) */
+    int32_t role_lanes;      /* 0 = auto (32), or 1..32: kernel C's envs-per-CTA (tuning / tests) */
     int32_t integrator;      /* 0 = fixed-step RK4, n_sub equal substeps (the parity contract);
                                 1 = graded RK4: the first 5 nominal substeps of every control interval are split in 4 (the
                                     controls just changed: fast transients) and any nominal substep is split further while the
                                     top-compartment / cover stiffness estimate asks for it (DESIGN.md "Graded integrator");
                                     meant for n_sub = 300. */
     int32_t reserved2;
+    /* Observation stack (tomato_env.py:77-96, configs/envs/TomatoEnv.yml:26-33): ordered list of module ids, terminated by 0;
+     * an empty list (obs_modules[0] == 0) is the default stack {2,3,4,5,6,7}.  ids (observations.py:35-182):
+     *   1 StateObservations (27; `np.random.rand` in the reference -> Philox uniforms here), 2 IndoorClimateObservations (4),
+     *   3 BasicCropObservations (3), 4 ControlObservations (6), 5 WeatherObservations (5), 6 TimeObservations (5),
+     *   7 WeatherForecastObservations (5 Np).  A module may appear at most once; the row must have at least 3 entries (the
+     *   reward reads obs[0:3], rewards.py:191-198). */
+    int32_t obs_modules[8];
 } glg_config;
 
 /* Fills *cfg with the defaults of configs/envs/TomatoEnv.yml (dt 900, N 5760, Np 48, n_sub 600, ...). */
@@ -82,6 +89,8 @@ void glg_destroy(glg_handle *h);
 /* Last error text of the handle (or of the failed glg_create when h is NULL). Never NULL. */
 const char *glg_last_error(const glg_handle *h);
 
+/* New key for the handle's Philox streams (base_env.py:166-170 set_seed); takes effect with the next launch. */
+int glg_set_seed(glg_handle *h, uint64_t seed);
 /* Nominal parameter table, 208 doubles (float32-rounded values as produced by init_default_params,
  * parameters.py:4-261).  Derives the parameter-only constants on the host and selects the kernel variant. */
 int glg_set_params(glg_handle *h, const double *p_host);
@@ -144,9 +153,36 @@ double *glg_time_dev(glg_handle *h);               /* double [2][B]: day_of_year
 double *glg_stats_dev(glg_handle *h);
 int glg_clear_stats(glg_handle *h, void *stream);
 
-/* Test / checkpoint helpers (host arrays, synchronous).  x_host double [B][28], u_host double [B][6]. */
+/* Test / teacher-forcing helpers (host arrays, synchronous).  x_host double [B][28], u_host double [B][6].
+ * glg_set_state with a timestep also moves each env's clock to that timestep (day_of_year = start_day(table) + k dt/86400,
+ * hour_of_day = (k dt/3600) mod 24, tomato_env.py:126-128,246-247); timesteps outside [0, N] are rejected. */
 int glg_set_state(glg_handle *h, const double *x_host, const double *u_host, const int32_t *timestep_host);
 int glg_get_state(glg_handle *h, double *x_host, double *u_host, int32_t *timestep_host);
+/* Full per-env state for checkpoint / restore: everything a step reads besides the parameter table and the weather bank.
+ * Any pointer may be NULL (skipped).  Host arrays: x [B][28], u [B][6], timestep [B], table [B] (0 <= id < n_tables),
+ * time [B][2] (day_of_year, hour_of_day), step_ctr [B] (Philox stream position), ep_return [B], ep_len [B],
+ * ep_info [B][11] (episode accumulators of the VecMonitor-style statistics). */
+typedef struct glg_env_state {
+    double *x, *u;
+    int32_t *timestep, *table;
+    double *time;
+    uint32_t *step_ctr;
+    double *ep_return;
+    int32_t *ep_len;
+    double *ep_info;
+} glg_env_state;
+int glg_get_state_ex(glg_handle *h, const glg_env_state *out_host);
+int glg_set_state_ex(glg_handle *h, const glg_env_state *in_host);
+
+/* Multi-GPU episode statistics: the step path has no collective; the one exchange is a sum of the 16-entry
+ * statistics vector over the ranks' handles, once per logging interval -- ncclAllReduce on the handle's device buffer.
+ * NCCL is bound at run time (dlopen of libnccl.so.2, the copy torch already loaded when there is one), so libglgym.so has no
+ * link-time dependency on it.  Protocol: rank 0 calls glg_nccl_unique_id and broadcasts the 128 bytes by any means
+ * (torch.distributed, MPI, a file); every rank calls glg_nccl_init with its rank; then glg_allreduce_stats enqueues the
+ * all-reduce (in place, sum, float64 x 16) on `stream`.  The communicator is destroyed with the handle. */
+int glg_nccl_unique_id(uint8_t id_out[128]);
+int glg_nccl_init(glg_handle *h, const uint8_t id[128], int32_t rank, int32_t world_size);
+int glg_allreduce_stats(glg_handle *h, void *stream);
 
 /* evalF for a batch (pure function; replaces B calls of GreenLight::evalF, greenlight_model.cpp:96-120).
  * Row-major device arrays x[B][28], u[B][6], d[B][10], p[B][208] (p_stride = 208) or one shared p (p_stride = 0),

@@ -67,6 +67,9 @@ typedef struct glgo_env_cfg {
     int stiff_guard;        /* integrator of glgo_env_step: 0 = the fixed-step RK4 contract; bits 0/1 = graded RK4 rules
                                (glgo_evalf_ex); 16 = adaptive implicit BDF at rtol = atol = 1e-6 (glgo_evalf_bdf, the
                                CVODES-class CPU baseline; n_micro then counts right-hand-side evaluations) */
+    int obs_modules[8];     /* ordered observation module ids (tomato_env.py:77-96), 0-terminated; empty = default stack
+                               {2,3,4,5,6,7}: 1 State(27) 2 IndoorClimate(4) 3 BasicCrop(3) 4 Control(6) 5 Weather(5) 6 Time(5)
+                               7 WeatherForecast(5 Np) */
 } glgo_env_cfg;
 
 typedef struct glgo_env {
@@ -79,13 +82,16 @@ typedef struct glgo_env {
     long n_micro;          /* RK4 micro-steps executed by the last step (implicit solver: right-hand-side evaluations) */
     double *jac;           /* optional [28*28] Jacobian carried between steps by the implicit solver (stiff_guard bit 5) */
     int jac_valid;
+    const double *state_obs; /* optional [27]: the StateObservations entries of the next observation (random in the reference) */
 } glgo_env;
 
 void glgo_init_state(const double *d0, double *x);                                   /* utils.py:13-46 */
 void glgo_env_reset(glgo_env *e, const double *weather, int rows, double start_day); /* tomato_env.py:231-270 */
 /* S2: noise.py:3-23 given the 34 uniform draws n_i in (-s/2, s/2) (already scaled). p_out float32-rounded. */
 void glgo_param_noise(const double *p_nom, const double *noise34, double *p_out);
-/* obs for the current (x,u,timestep,time) -- observations.py:59-182 ; obs has 23+5*Np entries */
+/* length of the observation row for c->obs_modules (23 + 5 Np for the default stack) */
+int glgo_obs_dim(const glgo_env_cfg *c);
+/* obs for the current (x,u,timestep,time) -- observations.py:59-182 ; obs has glgo_obs_dim(c) entries */
 void glgo_env_obs(const glgo_env_cfg *c, const glgo_env *e, double *obs);
 /* tomato_env.py:115-146.  action: 6 float32 values (raw_control=0) or 6 doubles u (raw_control=1,
  * step_raw_control :148-173).  noise34 may be NULL (scale 0).  Outputs obs[23+5Np], reward, info[11].

@@ -14,6 +14,7 @@
                       Pins the step semantics S1..S8 (obs, reward, info, termination, time, noise application).
                       numpy-1.26 promotion (the reference's pinned version) is emulated: env.p stays float32 (legacy
                       table), the reward reads it widened to float64 (see make_env).
+  shell_trace_obs.npz: the same reference env with four non-default observation stacks (module subsets / orders), 12 steps each.
   truth_step.npz    : x(900 s) for 6 (x,u,d) points from scipy Radau rtol=atol=1e-12 on the reference-translated RHS:
                       bounds the method error of RK4(n_sub) (the reference's CVODES itself is not available).
 usage: python tests/golden/make_golden.py
@@ -78,7 +79,7 @@ def install_stubs(n_sub):
     sys.modules["gl_gym.environments.models.greenlight_model"] = native
 
 
-def make_env(uncertainty_scale=0.0):
+def make_env(uncertainty_scale=0.0, mods=None):
     from gl_gym.environments.tomato_env import TomatoEnv
     base = dict(weather_data_dir=REF_WEATHER, location="Bleiswijk", data_source="GL", num_params=208, nx=28, nu=6, nd=10,
                 dt=900, u_min=[0] * 6, u_max=[1] * 6, delta_u_max=0.1, pred_horizon=0.5, season_length=60,
@@ -86,8 +87,8 @@ def make_env(uncertainty_scale=0.0):
     con = dict(co2_min=300., co2_max=1600., temp_min=15., temp_max=34., rh_min=50., rh_max=85.)
     rp = dict(fixed_greenhouse_cost=15., fixed_co2_cost=0.015, fixed_lamp_cost=0.07, fixed_screen_cost=2., elec_price=0.3,
               heating_price=0.09, co2_price=0.3, fruit_price=1.6, dmfm=0.065, pen_weights=[4.e-4, 5.e-3, 7.e-4], pen_lamp=0.1)
-    mods = ["IndoorClimateObservations", "BasicCropObservations", "ControlObservations", "WeatherObservations",
-            "TimeObservations", "WeatherForecastObservations"]
+    mods = mods or ["IndoorClimateObservations", "BasicCropObservations", "ControlObservations", "WeatherObservations",
+                    "TimeObservations", "WeatherForecastObservations"]
     env = TomatoEnv("GreenhouseReward", mods, con, dict(eval_days=[0], eval_years=[2009], location="Bleiswijk", data_source="GL"),
                     rp, base, uncertainty_scale)
     # numpy-1.26 emulation (the reference's pinned numpy): env.p stays a float32 array like in the reference, holding
@@ -109,6 +110,37 @@ def make_env(uncertainty_scale=0.0):
     env.reward.max_profit = env.reward.max_profit_reward()
     env.reward.min_profit = env.reward.min_profit_reward()
     return env
+
+
+OBS_STACKS = [  # non-default observation stacks (tomato_env.py:77-96): ablations an RL user would try
+    ["IndoorClimateObservations", "BasicCropObservations", "ControlObservations", "WeatherObservations", "TimeObservations"],
+    ["TimeObservations", "ControlObservations", "IndoorClimateObservations"],
+    ["WeatherForecastObservations", "BasicCropObservations", "IndoorClimateObservations"],
+    ["WeatherObservations", "IndoorClimateObservations", "WeatherForecastObservations", "TimeObservations"],
+]
+
+
+def obs_stack_traces():
+    """shell_trace_obs.npz: the reference's own env with non-default observation stacks, 12 steps of seeded random actions
+    each (reset observation, observations, rewards -- the reward reads obs[0:3] whatever the stack puts there)."""
+    NSUB = 300
+    install_stubs(NSUB)
+    out = dict(n_sub=NSUB, n_stacks=len(OBS_STACKS))
+    arng = np.random.default_rng(11)
+    for si, mods in enumerate(OBS_STACKS):
+        env = make_env(0.0, mods)
+        o0, _ = env.reset(seed=666)
+        acts, obs_l, rew_l = [], [], []
+        for s in range(12):
+            a = arng.uniform(-1, 1, 6).astype(np.float32)
+            o, r, term, trunc, info = env.step(a)
+            acts.append(a); obs_l.append(np.asarray(o, dtype=np.float64)); rew_l.append(float(r))
+        assert env.get_obs_names() and len(env.get_obs_names()) == len(o0)
+        out.update({f"mods{si}": np.array(mods), f"reset_obs{si}": np.asarray(o0, dtype=np.float64), f"actions{si}": np.array(acts),
+                    f"obs{si}": np.array(obs_l), f"reward{si}": np.array(rew_l), f"names{si}": np.array(env.get_obs_names()),
+                    f"low{si}": env.observation_space.low, f"high{si}": env.observation_space.high})
+    np.savez_compressed(os.path.join(HERE, "shell_trace_obs.npz"), **out)
+    print("shell_trace_obs.npz written:", [len(out[f"reset_obs{i}"]) for i in range(len(OBS_STACKS))])
 
 
 def main():
@@ -276,4 +308,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "obs":
+        obs_stack_traces()  # only the observation-stack traces (the other fixtures stay as committed)
+    else:
+        main()
+        obs_stack_traces()

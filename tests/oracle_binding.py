@@ -18,14 +18,14 @@ class EnvCfg(C.Structure):
                 ("con_low", C.c_double * 3), ("con_high", C.c_double * 3),
                 ("elec_price", C.c_double), ("heating_price", C.c_double), ("co2_price", C.c_double),
                 ("fruit_price", C.c_double), ("dmfm", C.c_double), ("uncertainty_scale", C.c_double),
-                ("fixed_costs", C.c_double), ("stiff_guard", C.c_int)]
+                ("fixed_costs", C.c_double), ("stiff_guard", C.c_int), ("obs_modules", C.c_int * 8)]
 
 
 class Env(C.Structure):
     _fields_ = [("x", C.c_double * 28), ("x_prev", C.c_double * 28), ("u", C.c_double * 6),
                 ("day_of_year", C.c_double), ("hour_of_day", C.c_double), ("timestep", C.c_int),
                 ("terminated", C.c_int), ("weather", _DP), ("weather_rows", C.c_int), ("n_micro", C.c_long),
-                ("jac", _DP), ("jac_valid", C.c_int)]
+                ("jac", _DP), ("jac_valid", C.c_int), ("state_obs", _DP)]
 
 
 def build():
@@ -56,6 +56,8 @@ def load():
         lib.glgo_init_state.argtypes = [_DP, _DP]
         lib.glgo_env_reset.argtypes = [C.POINTER(Env), _DP, C.c_int, C.c_double]
         lib.glgo_param_noise.argtypes = [_DP, _DP, _DP]
+        lib.glgo_obs_dim.argtypes = [C.POINTER(EnvCfg)]
+        lib.glgo_obs_dim.restype = C.c_int
         lib.glgo_env_obs.argtypes = [C.POINTER(EnvCfg), C.POINTER(Env), _DP]
         lib.glgo_env_step.argtypes = [C.POINTER(EnvCfg), C.POINTER(Env), _DP, C.c_void_p, C.c_int, _DP, _DP, _DP, _DP]
         lib.glgo_env_step.restype = C.c_int
@@ -82,9 +84,15 @@ def P(a):
 INTEGRATOR_RK4, INTEGRATOR_GRADED, INTEGRATOR_BDF, INTEGRATOR_BDF_KEEP_JAC = 0, 3, 16, 48  # glgo_env_cfg.stiff_guard
 
 
-def default_cfg(n_sub=600, N=5760, Np=48, dt=900.0, stiff_guard=0):
+OBS_MODULE_IDS = {"StateObservations": 1, "IndoorClimateObservations": 2, "BasicCropObservations": 3, "ControlObservations": 4,
+                  "WeatherObservations": 5, "TimeObservations": 6, "WeatherForecastObservations": 7}
+
+
+def default_cfg(n_sub=600, N=5760, Np=48, dt=900.0, stiff_guard=0, obs_modules=None):
     c = EnvCfg()
     c.stiff_guard = int(stiff_guard)
+    for i, m in enumerate(obs_modules or []):
+        c.obs_modules[i] = OBS_MODULE_IDS[m] if isinstance(m, str) else int(m)
     c.dt, c.n_sub, c.N, c.Np = dt, n_sub, N, Np
     c.delta_u_max_f32 = float(np.float32(0.1))
     for i in range(6):
@@ -162,7 +170,8 @@ class OracleEnv:
         self.p = np.ascontiguousarray(p_nom, dtype=np.float64)
         self.e = Env()
         self.start_day = start_day
-        self.nobs = 23 + 5 * self.cfg.Np
+        self.nobs = load().glgo_obs_dim(C.byref(self.cfg))
+        self._state_obs = None
         self.reset()
 
     def reset(self):
@@ -170,6 +179,11 @@ class OracleEnv:
         obs = np.zeros(self.nobs)
         load().glgo_env_obs(C.byref(self.cfg), C.byref(self.e), P(obs))
         return obs
+
+    def set_state_obs(self, values27):
+        """The 27 StateObservations entries of the observations computed from now on (random numbers in the reference)."""
+        self._state_obs = None if values27 is None else np.ascontiguousarray(values27, dtype=np.float64)
+        self.e.state_obs = None if self._state_obs is None else P(self._state_obs)
 
     def step(self, action=None, control=None, noise34=None):
         obs, r, info = np.zeros(self.nobs), C.c_double(0.0), np.zeros(11)
@@ -213,7 +227,7 @@ class OracleBatch:
         self.h = load().glgo_batch_create(C.byref(self.cfg), P(self.p), P(self.W), self.W.shape[0], self.B)
         self.reward = np.zeros(self.B)
         self.done = np.zeros(self.B, dtype=np.uint8)
-        self.obs = np.zeros((self.B, 23 + 5 * self.cfg.Np), dtype=np.float32)
+        self.obs = np.zeros((self.B, load().glgo_obs_dim(C.byref(self.cfg))), dtype=np.float32)
 
     def step(self, actions):
         a = np.ascontiguousarray(actions, dtype=np.float32)

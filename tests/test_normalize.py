@@ -109,7 +109,7 @@ def test_device_vec_normalize_on_cuda_env():
     """The wrapper around the real CUDA env equals the numpy restatement applied to the raw outputs of an identical env."""
     from glgym.vec_env import GreenLightVecEnv
     B = 128
-    env, raw = GreenLightVecEnv(B, n_sub=600, seed=5), GreenLightVecEnv(B, n_sub=600, seed=5)
+    env, raw = GreenLightVecEnv(B, n_sub=600, integrator="fixed", seed=5), GreenLightVecEnv(B, n_sub=600, integrator="fixed", seed=5)
     dv, ref = DeviceVecNormalize(env, gamma=0.9631), NpVecNormalize(B, env.obs_dim, 0.9631)
     g = torch.Generator(device="cuda"); g.manual_seed(0)
     o = dv.reset_tensor()

@@ -6,7 +6,7 @@ import numpy as np, torch
 from glgym.vec_env import GreenLightVecEnv
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 B = 64
-e64 = GreenLightVecEnv(B, n_sub=600, precision="fp64"); e32 = GreenLightVecEnv(B, n_sub=600, precision="fp32")
+e64 = GreenLightVecEnv(B, n_sub=600, precision="fp64"); e32 = GreenLightVecEnv(B, n_sub=600, integrator="fixed", precision="fp32")
 e64.reset_tensor(); e32.reset_tensor()
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 worst = np.zeros(28); r_err = 0.0
@@ -19,7 +19,7 @@ for s in range(steps):
     if s in (0, 9, 99, steps - 1): print(f"step {s+1}: max rel state err {err.max():.2e} (state {err.argmax()}), max |reward diff| so far {r_err:.2e}")
 print("per-state max rel err over the run:"); print(np.array2string(worst, precision=1))
 for Bt, rw in ((4096, 0), (65536, 0), (262144, 0)):
-    env = GreenLightVecEnv(Bt, n_sub=600, precision="fp32", role_warps=rw); env.reset_tensor()
+    env = GreenLightVecEnv(Bt, n_sub=600, integrator="fixed", precision="fp32", role_warps=rw); env.reset_tensor()
     A = torch.rand(Bt, 6, device="cuda") * 2 - 1
     for _ in range(2): env.step_tensor(A)
     torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -7,7 +7,7 @@ from glgym.vec_env import GreenLightVecEnv
 for prec in ("fp64", "fp32"):
     for B in (4096, 65536):
         for unc in (0.0, 0.1, 0.3):
-            env = GreenLightVecEnv(B, n_sub=600, uncertainty_scale=unc, precision=prec); env.reset_tensor()
+            env = GreenLightVecEnv(B, n_sub=600, integrator="fixed", uncertainty_scale=unc, precision=prec); env.reset_tensor()
             A = torch.rand(B, 6, device="cuda") * 2 - 1
             for _ in range(3): env.step_tensor(A)
             torch.cuda.synchronize()

@@ -27,7 +27,7 @@ W = load_weather_data(None, "Bleiswijk", "GL", 2009, 0, 60, 49, 900, 10)
 kw = {}
 if len(sys.argv) > 1: kw["role_warps"] = int(sys.argv[1])
 B = 96
-env = GreenLightVecEnv(B, n_sub=600, **kw); env.reset()
+env = GreenLightVecEnv(B, n_sub=600, integrator="fixed", **kw); env.reset()
 orc = [ob.OracleEnv(W, p) for _ in range(0, B, 5)]
 for o in orc: o.reset()
 for s in range(3):
@@ -41,7 +41,7 @@ for s in range(3):
     print(f"step {s}: state rel {ws:.2e} obs rel {wo:.2e} reward abs {wr:.2e}")
 env.close()
 for B in (4096, 16384, 65536, 262144):
-    env = GreenLightVecEnv(B, n_sub=600, **kw); env.reset_tensor()
+    env = GreenLightVecEnv(B, n_sub=600, integrator="fixed", **kw); env.reset_tensor()
     A = torch.rand(B, 6, device="cuda") * 2 - 1
     for _ in range(2): env.step_tensor(A)
     torch.cuda.synchronize()

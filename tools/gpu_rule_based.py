@@ -7,7 +7,7 @@ from glgym.vec_env import GreenLightVecEnv
 from glgym.controller import RuleBasedController
 ctrl = RuleBasedController()
 for B, steps in ((1, 400), (30, 400), (4096, 60)):
-    env = GreenLightVecEnv(B, n_sub=600, info_mode=None); env.reset()
+    env = GreenLightVecEnv(B, n_sub=600, integrator="fixed", info_mode=None); env.reset()
     W = env.weather_tables[0] if hasattr(env, "weather_tables") else None
     t0 = time.perf_counter()
     for s in range(steps):
@@ -18,7 +18,7 @@ for B, steps in ((1, 400), (30, 400), (4096, 60)):
         env.step_raw_control(uu)
     host = B * steps / (time.perf_counter() - t0)
     env.close()
-    env = GreenLightVecEnv(B, n_sub=600, info_mode=None); env.reset_tensor()
+    env = GreenLightVecEnv(B, n_sub=600, integrator="fixed", info_mode=None); env.reset_tensor()
     for _ in range(3): env.step_rule_based_tensor()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for s in range(steps): env.step_rule_based_tensor()

@@ -6,7 +6,7 @@ import torch
 from glgym.vec_env import GreenLightVecEnv
 rw = int(sys.argv[1]); rl = int(os.environ.get("ROLE_LANES", "0")); Bs = [int(b) for b in sys.argv[2:]] or [4096, 65536, 262144]
 for B in Bs:
-    env = GreenLightVecEnv(B, n_sub=600, role_warps=rw, role_lanes=rl); env.reset_tensor()
+    env = GreenLightVecEnv(B, n_sub=600, integrator="fixed", role_warps=rw, role_lanes=rl); env.reset_tensor()
     A = torch.rand(B, 6, device="cuda") * 2 - 1
     for _ in range(2): env.step_tensor(A)
     torch.cuda.synchronize()

@@ -7,7 +7,7 @@ _lib.LIB_PATH = os.path.join(ROOT, "tools", "ubench", "libglgym_prof.so")
 import torch
 from glgym.vec_env import GreenLightVecEnv
 B = int(sys.argv[1]); rw = int(sys.argv[2]); prec = sys.argv[3] if len(sys.argv) > 3 else "fp64"
-env = GreenLightVecEnv(B, n_sub=600, role_warps=rw, precision=prec); env.reset_tensor()
+env = GreenLightVecEnv(B, n_sub=600, integrator="fixed", role_warps=rw, precision=prec); env.reset_tensor()
 A = torch.rand(B, 6, device="cuda") * 2 - 1
 for _ in range(2): env.step_tensor(A)
 torch.cuda.synchronize()

@@ -8,7 +8,7 @@ import torch
 from glgym.vec_env import GreenLightVecEnv
 rw, B, n_sub = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 steps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
-env = GreenLightVecEnv(B, n_sub=n_sub, role_warps=rw); env.reset_tensor()
+env = GreenLightVecEnv(B, n_sub=n_sub, integrator="fixed", role_warps=rw); env.reset_tensor()
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 for _ in range(steps):
     env.step_tensor(torch.rand(B, 6, device="cuda", generator=g) * 2 - 1)

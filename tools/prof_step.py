@@ -8,7 +8,7 @@ B, n_sub = int(sys.argv[1]), int(sys.argv[2])
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 kw = {}
 if len(sys.argv) > 4: kw["role_warps"] = int(sys.argv[4])
-env = GreenLightVecEnv(B, n_sub=n_sub, **kw)
+env = GreenLightVecEnv(B, n_sub=n_sub, integrator="fixed", **kw)
 env.reset_tensor()
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 for _ in range(steps):

@@ -10,7 +10,7 @@ B, n_sub = int(sys.argv[1]), int(sys.argv[2])
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 kw = {}
 if len(sys.argv) > 4: kw["role_warps"] = int(sys.argv[4])
-env = GreenLightVecEnv(B, n_sub=n_sub, **kw); env.reset_tensor()
+env = GreenLightVecEnv(B, n_sub=n_sub, integrator="fixed", **kw); env.reset_tensor()
 A = torch.rand(B, 6, device="cuda") * 2 - 1
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 env.step_tensor(A); torch.cuda.synchronize(); e0.record()

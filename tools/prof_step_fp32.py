@@ -6,7 +6,7 @@ import torch
 from glgym.vec_env import GreenLightVecEnv
 B, n_sub = int(sys.argv[1]), int(sys.argv[2])
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-env = GreenLightVecEnv(B, n_sub=n_sub, precision="fp32"); env.reset_tensor()
+env = GreenLightVecEnv(B, n_sub=n_sub, integrator="fixed", precision="fp32"); env.reset_tensor()
 A = torch.rand(B, 6, device="cuda") * 2 - 1
 for _ in range(steps): env.step_tensor(A)
 torch.cuda.synchronize()

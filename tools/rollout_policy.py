@@ -37,7 +37,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    env = GreenLightVecEnv(a.envs, n_sub=600, device=local, seed=0, env_id_offset=rank * a.envs, precision=a.precision,
+    env = GreenLightVecEnv(a.envs, n_sub=600, integrator="fixed", device=local, seed=0, env_id_offset=rank * a.envs, precision=a.precision,
                            uncertainty_scale=a.uncertainty)
     venv = DeviceVecNormalize(env, gamma=0.9631)
     mon = EpisodeMonitor(a.envs, dev)

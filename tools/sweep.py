@@ -15,7 +15,7 @@ print(f"{'envs':>9} {'prec':>5} {'kernel':>8} {'ms/step':>9} {'env-steps/s':>12}
 for lb in range(10, top + 1, 2):
     B = 1 << lb
     for prec, pk in (("fp64", pk64.value), ("fp32", pk32.value)):
-        env = GreenLightVecEnv(B, n_sub=600, precision=prec); env.reset_tensor()
+        env = GreenLightVecEnv(B, n_sub=600, integrator="fixed", precision=prec); env.reset_tensor()
         A = torch.rand(B, 6, device="cuda") * 2 - 1
         n = 6 if B <= 65536 else 2
         for _ in range(2): env.step_tensor(A)

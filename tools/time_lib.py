@@ -10,7 +10,7 @@ from glgym.vec_env import GreenLightVecEnv
 rw = int(sys.argv[2]); Bs = [int(b) for b in sys.argv[3:]] or [4096]
 tag = os.path.basename(sys.argv[1])
 # cross-check against kernel A (one thread per env, same library): 3 steps, 96 envs, random actions
-ea, eb = GreenLightVecEnv(96, n_sub=600, role_warps=1), GreenLightVecEnv(96, n_sub=600, role_warps=rw)
+ea, eb = GreenLightVecEnv(96, n_sub=600, role_warps=1), GreenLightVecEnv(96, n_sub=600, integrator="fixed", role_warps=rw)
 ea.reset_tensor(); eb.reset_tensor()
 g = torch.Generator(device="cuda"); g.manual_seed(3)
 worst = 0.0
@@ -22,7 +22,7 @@ for _ in range(3):
 print(f"{tag} role_warps={rw}: max rel diff vs kernel A after 3 steps {worst:.2e}", flush=True)
 ea.close(); eb.close()
 for B in Bs:
-    env = GreenLightVecEnv(B, n_sub=600, role_warps=rw); env.reset_tensor()
+    env = GreenLightVecEnv(B, n_sub=600, integrator="fixed", role_warps=rw); env.reset_tensor()
     A = torch.rand(B, 6, device="cuda") * 2 - 1
     for _ in range(2): env.step_tensor(A)
     torch.cuda.synchronize()

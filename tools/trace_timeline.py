@@ -9,7 +9,7 @@ _lib.LIB_PATH = os.path.abspath(sys.argv[1])
 import numpy as np, torch
 from glgym.vec_env import GreenLightVecEnv
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-env = GreenLightVecEnv(B, n_sub=600, role_warps=2); env.reset_tensor()
+env = GreenLightVecEnv(B, n_sub=600, integrator="fixed", role_warps=2); env.reset_tensor()
 A = torch.rand(B, 6, device="cuda") * 2 - 1
 for _ in range(3): env.step_tensor(A)
 torch.cuda.synchronize()
