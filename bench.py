@@ -1,25 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- GreenLight env-steps/sec on B200 (BASELINE.json metric), fp64 parity mode.
 
-Workload (config.workload): BASELINE.json configs[1] -- "TomatoEnv 4096 batched envs fp64 parity mode, nominal
-parameters, fixed weather year": 4096 envs PER GPU (weak scaling: every rank owns its own 4096-env shard, no
-collective on the step path), Bleiswijk GL2009 weather table (start day 0), RK4 n_sub=600 substeps per 900 s control
-interval, U(-1,1) float32 actions through the rate-limited action->control map, observations (263 f32), reward,
-info, termination and auto-reset all inside the one fused kernel launch per step.
+Headline workload (config.workload): BASELINE.json configs[1] -- "TomatoEnv 4096 batched envs fp64 parity mode, nominal
+parameters, fixed weather year": 4096 envs PER GPU (weak scaling: every rank owns its own 4096-env shard, no collective on
+the step path), Bleiswijk GL2009 weather table (start day 0), the package's default integrator contract (graded RK4 with
+zero-order hold, n_sub = 300 nominal substeps, 349 RK4 steps per 900 s control interval; DESIGN.md "Integrator contract"),
+U(-1,1) float32 actions through the rate-limited action->control map, observations (263 f32), reward, info, termination and
+auto-reset all inside the one fused kernel launch per step.
 
-One "step" = one vector env step (B env-steps per GPU).  `value` = whole-job env-steps/s with inputs resident in HBM
-(actions pre-generated on the device, CUDA-event timing per step, max over ranks).  `e2e` = the same metric through the
-numpy SB3-VecEnv call (`env.step(actions)`: host actions -> pinned -> device, kernel, obs/reward/done -> host), timed
-with the wall clock around K calls.  `roofline` is against the FP64 pipe (this path is FP64-bound by > 100x over
-HBM): achieved = env-steps/s x F_step(n_sub) algorithmic flop, peak = DFMA throughput measured live
-on the same GPU (glg_measure_fp64_peak; MEASURED_PEAKS.json carries no FP64 figure); the HBM view is reported
-beside it.  `cpu_baseline` = the CPU oracle (a port of the reference algorithm; the reference's CasADi/CVODES
-extension is not installable here) on all host cores over a bounded sample.
+One "step" = one vector env step (B env-steps per GPU).
+  value      whole-job env-steps/s with inputs resident in HBM (actions pre-generated on the device, CUDA-event timing per
+             step on the launching stream, L2 flushed between steps, max over ranks).
+  e2e        the same metric through the numpy SB3-VecEnv call (`env.step(actions)`: host actions -> pinned -> device, kernel,
+             obs / reward / done -> host), wall clock around K calls.
+  roofline   FP64 pipe (this path is FP64-bound by > 100x over HBM): achieved = env-steps/s x algorithmic
+             flop per env-step, F = 3968 x (RK4 steps the kernel reports having executed) + 529; peak = DFMA throughput
+             measured live on the same GPU (MEASURED_PEAKS.json carries no FP64 figure).  `traffic` / `ncu` come from the
+             committed ncu capture and are attached only if that capture was taken with the kernel sources now in the tree.
+  configs    further workloads timed inside the same run, each with its own ms_per_step / value / roofline: the equal-
+             substep RK4(600) contract at B = 4096 (round 1's headline), the saturated regime B = 262 144 in fp64, BASELINE
+             configs[2] (B = 262 144, fp32 throughput mode, uncertainty_scale 0.3, start day randomised over 19 tables), and
+             under --gpus 8 also 65 536 envs per GPU.
+  cpu_baseline  both CPU arms on the box's host cores over bounded samples: "port" = the oracle with the same RK4 contract,
+             "port-implicit" = the oracle's right-hand side under an adaptive variable-order BDF at rtol = atol = 1e-6 (the
+             class of solver the reference uses, CasADi CVODES, which is not installable here) -- the faster one is `value`.
+  --impl reference  times that faster CPU arm alone (rank 0), sample sized for >= 10 s whatever --steps is.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs B] [--n-sub S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs B] [--integrator graded|fixed]
     torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU)
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -35,15 +46,27 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "GreenLight env-steps/sec (fp64 parity)"
 UNIT = "env-steps/s"
 F_RHS, F_SUBSTEP_OVERHEAD, F_STEP_CONST = 880, 448, 529  # algorithmic flop model
+F_RK4_STEP = 4 * F_RHS + F_SUBSTEP_OVERHEAD               # 3968 per RK4 step
 
 
-def flop_per_env_step(n_sub):
-    return (4 * F_RHS + F_SUBSTEP_OVERHEAD) * n_sub + F_STEP_CONST
+def flop_per_env_step(rk4_steps):
+    return F_RK4_STEP * rk4_steps + F_STEP_CONST
 
 
 def algorithmic_bytes_per_env_step(obs_dim):
     # read x,u,action,scalars ; write x,u,obs,reward,done,info (+ per-CTA weather tile, amortised)
     return (224 + 48 + 24 + 16) + (224 + 48 + obs_dim * 4 + 8 + 1 + 88) + 16
+
+
+def csrc_hash():
+    """sha256 (first 16 hex digits) of the kernel sources: an ncu capture is only quoted for the sources it was taken with."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "greenlight-gym2_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler(threading.Thread):
@@ -91,52 +114,135 @@ def load_inputs():
     return init_default_params().astype(np.float64), load_weather_data(None, "Bleiswijk", "GL", 2009, 0, 60, 49, 900, 10)
 
 
-def cpu_rate(B, n_steps, n_sub, threads, warmup=0):
-    """env-steps/s of the CPU oracle batch (reference semantics, RK4 n_sub) on `threads` host threads."""
+# ---------------------------------------------------------------------------------------------------- CPU arms
+def oracle_cfg(kind, integrator, n_sub):
+    """glgo_env_cfg of a CPU arm: "port" = the same RK4 contract as the GPU arm, "port-implicit" = adaptive BDF at 1e-6."""
+    import oracle_binding as ob
+    if kind == "port-implicit":
+        return ob.default_cfg(n_sub=n_sub, stiff_guard=ob.INTEGRATOR_BDF)
+    return ob.default_cfg(n_sub=n_sub, stiff_guard=ob.INTEGRATOR_GRADED if integrator == "graded" else ob.INTEGRATOR_RK4)
+
+
+def cpu_rate(kind, integrator, n_sub, B, n_steps, threads, warmup=0):
+    """(env-steps/s, seconds, right-hand-side evaluations per env-step) of a CPU arm: B envs stepped by `threads` host threads"""
     import oracle_binding as ob
     p, W = load_inputs()
-    batch = ob.OracleBatch(W, p, B, ob.default_cfg(n_sub=n_sub), n_threads=threads)
+    batch = ob.OracleBatch(W, p, B, oracle_cfg(kind, integrator, n_sub), n_threads=threads)
     rng = np.random.default_rng(0)
     acts = rng.uniform(-1, 1, (warmup + n_steps, B, 6)).astype(np.float32)
     for s in range(warmup):
         batch.step(acts[s])
+    w0 = batch.work()
     t0 = time.perf_counter()
     for s in range(n_steps):
         batch.step(acts[warmup + s])
     dt = time.perf_counter() - t0
+    work = (batch.work() - w0) / (B * n_steps)
     batch.close()
-    return B * n_steps / dt, dt
+    return B * n_steps / dt, dt, work * (1 if kind == "port-implicit" else 4)
+
+
+def cpu_arm(kind, integrator, n_sub, seconds, cores):
+    """One CPU arm over a bounded sample sized for about `seconds` of work: 4 envs per thread, as many steps as fit."""
+    B = 4 * cores
+    probe, _, _ = cpu_rate(kind, integrator, n_sub, B, 2, cores)
+    steps = max(3, int(seconds * probe / B))
+    rate, dt, rhs = cpu_rate(kind, integrator, n_sub, B, steps, cores)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "rhs_evals_per_env_step": rhs,
+            "sample": f"{B} envs x {steps} steps on {cores} threads ({dt:.1f} s), same weather / action distribution"}
 
 
 def workload_config(args):
-    """The `config` both arms report: the workload is the same, only how a step is sampled differs."""
-    mode = "fp64 parity mode" if getattr(args, "precision", "fp64") == "fp64" else "fp32 throughput mode"
-    return {"workload": f"TomatoEnv {args.envs} batched envs per GPU, {mode}, nominal parameters, fixed weather year "
+    """The `config` both arms report."""
+    nominal = 300 if args.integrator == "graded" else 600
+    n_sub = args.n_sub or nominal
+    integ = (f"graded RK4, zero-order hold: {n_sub} nominal substeps, the first 15 split 16/8/8/4x4/2x8, transient-stiffness rule "
+             f"(349 RK4 steps per interval at n_sub 300)" if args.integrator == "graded" else f"RK4, {n_sub} equal substeps, zero-order hold")
+    return {"workload": f"TomatoEnv {args.envs} batched envs per GPU, fp64 parity mode, nominal parameters, fixed weather year "
                         "(BASELINE configs[1])",
-            "envs_per_gpu": args.envs, "n_sub": args.n_sub, "dt": 900, "integrator": "RK4 fixed step", "obs_dim": 263}
+            "envs_per_gpu": args.envs, "n_sub": n_sub, "dt": 900, "integrator": integ, "obs_dim": 263,
+            "parallelism": f"env-shard x{args.gpus}, no collective on the step path",
+            "l2": "GPU arm: flushed between timed steps (256 MiB memset outside the event pair); CPU arm: not applicable",
+            "kernel": {0: "GPU arm: glg_step_units_kernel (auto: latency layout, 4 owner + 12 flux-unit warps per 32 envs, up to SMs*32 envs; "
+                          "else throughput layout, 4 fused warps per 32 envs x 4 CTAs per SM)",
+                       1: "GPU arm: glg_step_kernel (thread per env)", 2: "GPU arm: glg_step_units_kernel latency layout",
+                       3: "GPU arm: glg_step_units_kernel throughput layout"}[args.role_warps]}
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the reference's CPU implementation of the path.  CasADi/SUNDIALS cannot be installed in this
-    image (no wheel, no network), so this is the CPU oracle port with all host threads; rank 0 only."""
+    """`--impl reference`: the reference's CPU implementation of the path.  CasADi / SUNDIALS cannot be installed in this image
+    (no wheel, no network), so this is the CPU oracle -- its right-hand side under the adaptive implicit BDF solver at the
+    reference's tolerances ("port-implicit", the faster of the two CPU arms) -- on all host threads; rank 0 only.  Each of the
+    --steps steps advances a bounded sample of the workload's envs, sized so that the run takes >= 10 s."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 4 * cores  # envs per vector step: a bounded sample of the 4096-env workload
-    rate, dt = cpu_rate(sample, args.steps, args.n_sub, cores, warmup=args.warmup)
+    n_sub = args.n_sub or (300 if args.integrator == "graded" else 600)
+    kind = "port-implicit"
+    probe, _, _ = cpu_rate(kind, args.integrator, n_sub, 4 * cores, 2, cores)
+    sample = max(4 * cores, int(np.ceil(12.0 * probe / max(args.steps, 1) / cores)) * cores)  # envs per step: >= 10 s in total
+    rate, dt, rhs = cpu_rate(kind, args.integrator, n_sub, sample, args.steps, cores, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic actions; Bleiswijk GL2009 weather table shipped with the reference",
-        "config": dict(workload_config(args), reference_sample=f"each step advances a bounded sample of {sample} of the "
-                       f"{args.envs} envs on {cores} host threads",
-                       note="CPU oracle port; the reference's CasADi CVODES extension is not installable here"),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} envs x {args.steps} steps, {cores} threads"},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "rhs_evals_per_env_step": rhs,
+                         "sample": f"each step advances a bounded sample of {sample} of the {args.envs} envs on {cores} host threads; "
+                                   f"{args.steps} steps in {dt:.1f} s",
+                         "note": "CPU oracle right-hand side under an adaptive variable-order BDF (rtol = atol = 1e-6, finite-difference "
+                                 "Jacobian, cold start per control interval like CasADi's integrator); the reference's CasADi CVODES "
+                                 "extension is not installable here"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def time_steps(env, actions, K, Wm, flush, barrier, dev, world):
+    """W warm-up steps, then K steps timed one by one with CUDA events on the launching stream (L2 flushed between steps).
+    Returns (sum of step times [ms] max over ranks, mean step time of this rank [ms], RK4 steps per env-step, launches)."""
+    import torch
+    from glgym.distributed import max_over_ranks
+    for s in range(Wm):
+        env.step_tensor(actions[s % actions.shape[0]])
+    env.episode_stats(clear=True)
+    launches0 = env.launch_count()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for s in range(K):
+        flush.zero_()
+        ev[s][0].record()
+        env.step_tensor(actions[(Wm + s) % actions.shape[0]])
+        ev[s][1].record()
+    barrier()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    micro = env.stats_t[15].item() / (env.num_envs * K)
+    return max_over_ranks(sum(ms), dev), float(np.mean(ms)), micro, env.launch_count() - launches0
+
+
+def extra_config(name, desc, ctor_kwargs, B, K, Wm, flush, barrier, dev, world, rank, local, peak):
+    """One entry of the line's `configs` object."""
+    import torch
+    from glgym.vec_env import GreenLightVecEnv
+    try:
+        env = GreenLightVecEnv(B, device=local, seed=0, env_id_offset=rank * B, **ctor_kwargs)
+        env.reset_tensor()
+        g = torch.Generator(device=dev)
+        g.manual_seed(99 + rank)
+        actions = torch.rand(4, B, 6, device=dev, generator=g) * 2 - 1
+        total_ms, mean_ms, micro, _ = time_steps(env, actions, K, Wm, flush, barrier, dev, world)
+        finite = bool(torch.isfinite(env.state_t).all().item())
+        env.close()
+        F = flop_per_env_step(micro)
+        per_gpu = B / (mean_ms * 1e-3)
+        return {"workload": desc, "envs_per_gpu": B, "value": world * B * K / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / K,
+                "steps": K, "warmup": Wm, "rk4_steps_per_env_step": micro, "flop_per_env_step": F, "state_finite": finite,
+                "roofline": {"bound": peak[0], "achieved": per_gpu * F / 1e12, "peak": peak[1], "unit": "TFLOP/s",
+                             "frac": per_gpu * F / 1e12 / peak[1] if peak[1] else None}}
+    except Exception as exc:  # never lose the headline because of an extra measurement
+        return {"workload": desc, "error": str(exc)[:300]}
 
 
 def run_ours(args, rank, world, local):
@@ -150,8 +256,9 @@ def run_ours(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B, K, Wm = args.envs, args.steps, args.warmup
-    env = GreenLightVecEnv(B, n_sub=args.n_sub, device=local, seed=0, env_id_offset=rank * B, role_warps=args.role_warps,
-                           precision=args.precision)
+    ctor = dict(device=local, seed=0, env_id_offset=rank * B, role_warps=args.role_warps, precision=args.precision,
+                integrator=args.integrator, n_sub=args.n_sub)
+    env = GreenLightVecEnv(B, **ctor)
     obs_dim = env.obs_dim
     env.reset_tensor()
     g = torch.Generator(device=dev)
@@ -164,25 +271,17 @@ def run_ours(args, rank, world, local):
         if world > 1:
             dist.barrier()
 
-    # ---- device-resident throughput: per-step CUDA events on the launching stream, L2 flushed between steps
-    for s in range(Wm):
-        env.step_tensor(actions[s])
+    L = _lib.load()
+    pk64, pk32 = C.c_double(), C.c_double()
+    L.glg_measure_fp64_peak(local, C.byref(pk64))
+    L.glg_measure_fp32_peak(local, C.byref(pk32))
+    peak64, peak32 = ("fp64", pk64.value / 1e12), ("fp32", pk32.value / 1e12)
+
+    # ---- device-resident throughput
     sampler = ClockSampler(local)
-    launches0 = env.launch_count()
-    barrier()
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for s in range(K):
-        flush.zero_()
-        ev[s][0].record()
-        env.step_tensor(actions[Wm + s])
-        ev[s][1].record()
-    barrier()
-    launches = env.launch_count() - launches0
-    dev_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = max_over_ranks(sum(dev_ms), dev)
+    total_ms, kernel_ms, micro, launches = time_steps(env, actions, K, Wm, flush, barrier, dev, world)
     value = world * B * K / (total_ms * 1e-3)
-    kernel_ms = float(np.mean(dev_ms))
     finite = bool(torch.isfinite(env.state_t).all().item())
 
     # ---- end to end through the numpy VecEnv API (host buffers, copies inside the timed region)
@@ -199,58 +298,92 @@ def run_ours(args, rank, world, local):
     e2e_value = world * B * K / e2e_s
     sampler.stop_flag = True  # clocks are sampled over both timed regions (device-resident and end-to-end)
     sampler.join(timeout=1.0)
-    # the same end-to-end loop with reuse_output_buffers=True (two alternating pinned buffers, no reference counting)
-    e2e_default = None
+    # the opt-in split observation layout (per-env columns over PCIe, forecast block from the host's weather bank)
+    e2e_split = None
     try:
-        denv = GreenLightVecEnv(B, n_sub=args.n_sub, device=local, seed=0, env_id_offset=rank * B, role_warps=args.role_warps,
-                                precision=args.precision, reuse_output_buffers=True)
-        denv.reset()
         for s in range(min(2, K)):
-            denv.step(a_host[s])
+            env.step_split(a_host[s])
         barrier()
         t0 = time.perf_counter()
         for s in range(K):
-            denv.step(a_host[s])
-        d_s = max_over_ranks(time.perf_counter() - t0, dev)
-        e2e_default = world * B * K / d_s
-        denv.close()
+            env.step_split(a_host[s])
+        e2e_split = world * B * K / max_over_ranks(time.perf_counter() - t0, dev)
+    except Exception:
+        pass
+    # the same loop returning a fresh pageable copy per step (obs_ring = 0: the reference's array semantics)
+    e2e_copy = None
+    try:
+        cenv = GreenLightVecEnv(B, obs_ring=0, **ctor)
+        cenv.reset()
+        for s in range(min(2, K)):
+            cenv.step(a_host[s])
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(K):
+            cenv.step(a_host[s])
+        e2e_copy = world * B * K / max_over_ranks(time.perf_counter() - t0, dev)
+        cenv.close()
     except Exception:
         pass
 
-    # ---- the opt-in graded integrator on the same workload (extra information; the headline stays the fixed 600-substep contract)
-    graded = None
+    # ---- the one collective of the path, on hardware: episode statistics summed over the ranks' handles
+    stats_allreduce = None
     try:
-        env.close()
-        genv = GreenLightVecEnv(B, device=local, seed=0, env_id_offset=rank * B, role_warps=args.role_warps,
-                                precision=args.precision, integrator="graded")
-        genv.reset_tensor()
-        for s in range(Wm):
-            genv.step_tensor(actions[s])
-        genv.episode_stats(clear=True)
+        x, u, k = env.get_state()
+        env.set_state(timestep=np.full(B, env.N, dtype=np.int32))  # forced episode end: the next step terminates every env
+        env.episode_stats(clear=True)
+        env.step_tensor(actions[0])
+        env.init_stats_allreduce()
         barrier()
-        gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        for s in range(K):
-            flush.zero_()
-            gev[s][0].record()
-            genv.step_tensor(actions[Wm + s])
-            gev[s][1].record()
+        local_eps = float(env.stats_t[0].item())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        env.allreduce_stats()  # first call: communicator warm-up
+        torch.cuda.synchronize(dev)
+        glob_eps = float(env.stats_t[0].item())
+        reps = 20
+        zero = torch.zeros_like(env.stats_t)
+        env.stats_t.copy_(zero)
         barrier()
-        g_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in gev), dev)
-        micro = genv.stats_t[15].item() / (B * K)
-        graded = {"value": world * B * K / (g_ms * 1e-3), "unit": UNIT, "ms_per_step": g_ms / K, "n_sub": genv.n_sub,
-                  "rk4_micro_steps_per_env_step": micro, "flop_per_env_step": 3968 * micro + 529,
-                  "note": "integrator='graded' (DESIGN.md): more accurate than the fixed 600-substep contract at ~315 RK4 steps"}
-        genv.close()
-    except Exception as exc:  # never lose the headline because of the extra measurement
-        graded = {"error": str(exc)[:200]}
+        e0.record()
+        for _ in range(reps):
+            env.allreduce_stats()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = max_over_ranks(e0.elapsed_time(e1) / reps * 1e3, dev)
+        stats_allreduce = {"us": us, "episodes_local": local_eps, "episodes_global": glob_eps, "ranks": world,
+                           "ok": bool(local_eps == B and glob_eps == world * B),
+                           "api": "glg_allreduce_stats: ncclAllReduce(sum, 16 x f64) on the handle's statistics buffer"}
+    except Exception as exc:
+        stats_allreduce = {"error": str(exc)[:300]}
+    env.close()
+
+    # ---- further workloads inside the same run
+    Kx, Wx = max(3, min(K, 6)), 3
+    configs = {}
+    other = "fixed" if args.integrator == "graded" else "graded"
+    configs[f"config2_{other}"] = extra_config(
+        f"config2_{other}", f"BASELINE configs[1] with integrator='{other}' (" + ("RK4, 600 equal substeps: round 1's headline contract)" if other == "fixed"
+                                                                                   else "graded RK4, n_sub 300)"),
+        dict(integrator=other, precision="fp64"), B, K, Wm, flush, barrier, dev, world, rank, local, peak64)
+    configs["saturated_fp64"] = extra_config(
+        "saturated_fp64", "262 144 envs per GPU, fp64 parity mode, nominal parameters, one weather table (the regime the one-CTA-per-32-envs "
+        "design is built for; BASELINE configs[4] sweep point)", dict(integrator=args.integrator, precision="fp64"), 262144, Kx, Wx, flush,
+        barrier, dev, world, rank, local, peak64)
+    configs["config3_fp32_uncertainty"] = extra_config(
+        "config3_fp32_uncertainty", "BASELINE configs[2]: 262 144 envs per GPU, fp32 throughput mode (flux units fp32, RK4 state fp64), "
+        "uncertainty_scale 0.3 (device Philox, 34 draws per env-step), start day randomised over the 19 Bleiswijk GL2009 tables",
+        dict(integrator=args.integrator, precision="fp32", uncertainty_scale=0.3, base_env_params=dict(start_train_day=0, end_train_day=18)),
+        262144, Kx, Wx, flush, barrier, dev, world, rank, local, peak32)
+    if world >= 8:
+        configs["config4_65536_per_gpu"] = extra_config(
+            "config4_65536_per_gpu", "BASELINE configs[3] shape: 65 536 envs per GPU x 8 GPUs, fp64, U(-1,1) actions resident on the device",
+            dict(integrator=args.integrator, precision="fp64"), 65536, Kx, Wx, flush, barrier, dev, world, rank, local, peak64)
 
     if rank == 0:
-        L = _lib.load()
-        pk = C.c_double()
-        (L.glg_measure_fp64_peak if args.precision == "fp64" else L.glg_measure_fp32_peak)(local, C.byref(pk))
-        peak_tf = pk.value / 1e12
+        peak = peak64 if args.precision == "fp64" else peak32
         per_gpu_rate = B / (kernel_ms * 1e-3)
-        achieved_tf = per_gpu_rate * flop_per_env_step(args.n_sub) / 1e12
+        F = flop_per_env_step(micro)
+        achieved_tf = per_gpu_rate * F / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -260,49 +393,52 @@ def run_ours(args, rank, world, local):
         hbm_gbs = per_gpu_rate * algorithmic_bytes_per_env_step(obs_dim) / 1e9
         traffic, ncu_info = None, None
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if args.precision == "fp64" and B == prof.get("B") and args.n_sub == prof.get("n_sub"):
-                traffic = prof.get("dram_bytes_per_launch")
-                ncu_info = {"fp64_pipe_active_pct": prof.get("fp64_pipe_active_pct"), "issue_active_pct": prof.get("issue_active_pct"),
-                            "source": prof.get("source")}
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            ent = prof.get(f"{args.integrator}_{args.precision}_B{B}")
+            if ent and prof.get("csrc_sha16") == csrc_hash():
+                traffic = ent.get("dram_bytes_per_launch")
+                ncu_info = {k: ent.get(k) for k in ("fp64_pipe_active_pct", "issue_active_pct", "kernel", "source")}
+            elif ent:
+                ncu_info = {"stale": "profiles/r2_traffic.json was captured with other kernel sources (csrc hash differs); not quoted"}
         except Exception:
             pass
         cores = os.cpu_count() or 1
-        cpu_B = 4 * cores
-        probe_rate, _ = cpu_rate(cpu_B, 2, args.n_sub, cores)           # size the sample for ~15 s of CPU work
-        cpu_steps = max(3, int(15.0 * probe_rate / cpu_B))
-        cpu_val, cpu_dt = cpu_rate(cpu_B, cpu_steps, args.n_sub, cores)
+        n_sub = env.n_sub
+        arm_rk4 = cpu_arm("port", args.integrator, n_sub, 8.0, cores)
+        arm_bdf = cpu_arm("port-implicit", args.integrator, n_sub, 10.0, cores)
+        best = arm_bdf if arm_bdf["value"] >= arm_rk4["value"] else arm_rk4
         line = {
             "metric": METRIC if args.precision == "fp64" else "GreenLight env-steps/sec (fp32 throughput mode)",
             "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == "fp64" else "f32 (RK4 state f64)",
             "data": "synthetic actions; Bleiswijk GL2009 weather table shipped with the reference",
-            "config": dict(workload_config(args),
-                       kernel= {0: "glg_step_roles_kernel (auto: 8 warps per 32 envs up to 2*SMs*32 envs, else 4)", 1: "glg_step_kernel (thread per env)",
-                                  4: "glg_step_roles_kernel<4 warps>", 8: "glg_step_roles_kernel<8 warps>"}[args.role_warps],
-                       parallelism=f"env-shard x{world}, no collective on the step path",
-                       l2="flushed between timed steps (256 MiB memset outside the event pair)", state_finite=finite),
+            "config": workload_config(args),  # identical in both arms
+            "run": {"state_finite": finite, "rk4_steps_per_env_step": micro},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 6 * 4,
-                    "d2h_bytes_per_step": B * obs_dim * 4 + B * 8 + B, "api": "GreenLightVecEnv(...).step(numpy) -> glg_step_host with the constructor's defaults: host actions in, "
-                           "observations / rewards / dones out as numpy arrays (page-locked buffers handed out by reference count, "
-                           "never overwritten while the caller holds them)", "value_with_reuse_output_buffers": e2e_default},
-            "gpu_launches": int(launches), "graded_integrator": graded,
+                    "d2h_bytes_per_step": B * obs_dim * 4 + B * 8 + B,
+                    "api": "GreenLightVecEnv(...).step(numpy) -> glg_step_host with the constructor's defaults: host actions in, observations / "
+                           "rewards / dones out as numpy arrays (observations are page-locked buffers of a ring of 4: valid for the next 3 steps)",
+                    "value_with_copy_per_step": e2e_copy,
+                    "value_split_layout": e2e_split, "split_layout_d2h_bytes_per_step": B * (obs_dim - 240) * 4 + B * 8 + B * 8 + B,
+                    "split_layout_note": "opt-in env.step_split(): every column but the 240-float forecast block crosses PCIe; the forecast is "
+                                         "read from the host's copy of the weather bank"},
+            "gpu_launches": int(launches), "configs": configs, "stats_allreduce": stats_allreduce,
             "clocks": sampler.result(),
-            "roofline": {"bound": args.precision, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+            "roofline": {"bound": args.precision, "achieved": achieved_tf, "peak": peak[1], "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak[1] if peak[1] else None, "traffic": traffic,
                          "peak_source": ("glg_measure_fp64_peak: DFMA" if args.precision == "fp64" else "glg_measure_fp32_peak: FFMA")
                                         + " micro-benchmark measured live on this GPU (MEASURED_PEAKS.json has no FP64/FP32 pipe entry)",
-                         "flop_per_env_step": flop_per_env_step(args.n_sub), "kernel_ms": kernel_ms, "ncu": ncu_info,
+                         "flop_per_env_step": F, "flop_model": "3968 x RK4 steps executed (kernel counter) + 529", "kernel_ms": kernel_ms,
+                         "ncu": ncu_info, "csrc_sha16": csrc_hash(),
                          "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                                  "bytes_per_env_step": algorithmic_bytes_per_env_step(obs_dim),
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"}},
-            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{cpu_B} envs x {cpu_steps} steps on {cores} threads ({cpu_dt:.1f} s), same n_sub / weather / "
-                                       "action distribution"},
+            "cpu_baseline": dict(best, arms={"port": arm_rk4, "port-implicit": arm_bdf},
+                                 note="value = the faster CPU arm; 'port' runs the GPU arm's RK4 contract, 'port-implicit' an adaptive BDF at the "
+                                      "reference solver's tolerances (rtol = atol = 1e-6) on the same right-hand side"),
         }
         print(json.dumps(line))
-    env.close()
 
 
 def main():
@@ -312,11 +448,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
-    ap.add_argument("--n-sub", type=int, default=600)
+    ap.add_argument("--integrator", default=None, choices=["graded", "fixed"], help="default: the package's default contract")
+    ap.add_argument("--n-sub", type=int, default=None, help="nominal RK4 substeps (default 300 graded / 600 fixed)")
     ap.add_argument("--role-warps", type=int, default=0)
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
                     help="fp64 = parity mode (the BASELINE metric); fp32 = throughput mode (flux groups in fp32, RK4 state in fp64)")
     args = ap.parse_args()
+    if args.integrator is None:
+        args.integrator = "graded"  # == glgym.vec_env.DEFAULT_INTEGRATOR (not imported here: --impl reference must not need torch)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":

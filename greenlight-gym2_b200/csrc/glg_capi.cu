@@ -21,6 +21,7 @@
 #undef GLG_NSTATS
 #include "glg_kernels.cuh"
 #include "glg_roles.cuh"
+#include "glg_rollout.cuh"
 
 
 static thread_local std::string g_create_error = "";
@@ -34,7 +35,7 @@ struct glg_handle {
     double *x = nullptr, *u = nullptr, *time = nullptr, *ep_return = nullptr, *ep_info = nullptr;
     int *timestep = nullptr, *table = nullptr, *ep_len = nullptr;
     unsigned int *step_ctr = nullptr;
-    float *obs = nullptr, *term_obs = nullptr, *actions = nullptr;
+    float *obs = nullptr, *term_obs = nullptr, *actions = nullptr, *obs_head = nullptr;
     double *reward = nullptr, *info = nullptr, *stats = nullptr;
     unsigned char *done = nullptr;
     double *weather = nullptr, *start_day = nullptr;
@@ -49,6 +50,12 @@ struct glg_handle {
     double ctrl[GLG_NCTRL];  // rule-based controller settings (defaults: configs/agents/rule_based.yml)
     int obs_nmod = 0, obs_mod[GLG_MAXOBSMOD] = {}, obs_off[GLG_MAXOBSMOD] = {}, fc_off = -1;
     void *nccl_comm = nullptr;  // ncclComm_t (glg_nccl_init)
+    // device rollout (glg_rollout_create)
+    glg_rollout_config roll = {};
+    bool have_roll = false;
+    int roll_blocks = 0;
+    float *roll_obs = nullptr, *roll_rew = nullptr, *roll_starts = nullptr, *roll_adv = nullptr, *roll_ret = nullptr;
+    double *roll_stat = nullptr, *roll_partial = nullptr, *roll_norm = nullptr, *roll_acc = nullptr;
     std::string err;
 };
 static const double kDefaultCtrl[GLG_NCTRL] = {0, 18, -1, 366, 400, 10, 19.5, 16.5, 0, 5, 800, 4, 85, 2, 5, 1, -1, 5, 10, -1, 4, -2,
@@ -151,12 +158,15 @@ extern "C" void glg_destroy(glg_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->x); cudaFree(h->u); cudaFree(h->time); cudaFree(h->ep_return); cudaFree(h->ep_info);
     cudaFree(h->timestep); cudaFree(h->table); cudaFree(h->ep_len); cudaFree(h->step_ctr);
+    cudaFree(h->obs_head);
     cudaFree(h->obs); cudaFree(h->term_obs); cudaFree(h->actions); cudaFree(h->reward); cudaFree(h->info);
     cudaFree(h->stats); cudaFree(h->done); cudaFree(h->weather); cudaFree(h->start_day); cudaFree(h->reset_tables);
     if (h->h_actions) cudaFreeHost(h->h_actions);
     if (h->h_obs) cudaFreeHost(h->h_obs);
     if (h->h_reward) cudaFreeHost(h->h_reward);
     if (h->h_done) cudaFreeHost(h->h_done);
+    cudaFree(h->roll_obs); cudaFree(h->roll_rew); cudaFree(h->roll_starts); cudaFree(h->roll_adv); cudaFree(h->roll_ret);
+    cudaFree(h->roll_stat); cudaFree(h->roll_partial); cudaFree(h->roll_norm); cudaFree(h->roll_acc);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->nccl_comm) {
         std::string e;
@@ -243,6 +253,7 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     if (e == cudaSuccess) e = dev_alloc(&h->step_ctr, B);
     if (e == cudaSuccess) e = dev_alloc(&h->obs, (size_t)h->obs_dim * B);
     if (e == cudaSuccess) e = dev_alloc(&h->term_obs, (size_t)h->obs_dim * B);
+    if (e == cudaSuccess) e = dev_alloc(&h->obs_head, (size_t)(h->obs_dim - (h->fc_off >= 0 ? 5 * cfg->Np : 0)) * B);
     if (e == cudaSuccess) e = dev_alloc(&h->actions, GLG_NU * B);
     if (e == cudaSuccess) e = dev_alloc(&h->reward, B);
     if (e == cudaSuccess) e = dev_alloc(&h->info, GLG_NINFO * B);
@@ -345,6 +356,7 @@ static void fill_args(const glg_handle *h, GlgStepArgs *a) {
     a->weather = h->weather; a->start_day = h->start_day; a->reset_tables = h->reset_tables;
     a->x = h->x; a->u = h->u; a->time = h->time; a->ep_return = h->ep_return; a->ep_info = h->ep_info;
     a->timestep = h->timestep; a->table = h->table; a->ep_len = h->ep_len; a->step_ctr = h->step_ctr;
+    a->obs_head = h->obs_head;
     a->obs = h->obs; a->term_obs = h->term_obs; a->reward = h->reward; a->info = h->info; a->stats = h->stats;
     a->done = h->done;
 }
@@ -561,6 +573,28 @@ extern "C" int glg_step_host(glg_handle *h, const float *actions_host, float *ob
     return GLG_OK;
 }
 
+extern "C" int glg_step_host_split(glg_handle *h, const float *actions_host, float *head_host, int32_t *timestep_host,
+                                   int32_t *table_host, double *reward_host, uint8_t *done_host) {
+    if (!h || !actions_host) return GLG_ERR_ARG;
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t B = (size_t)h->B;
+    cudaStream_t s = h->own_stream;
+    // pageable buffers work too (the runtime stages them); page-locked ones (the Python wrapper's) make the copies asynchronous
+    GLG_CUDA(h, cudaMemcpyAsync(h->actions, actions_host, GLG_NU * B * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = step_common(h, h->actions, nullptr, nullptr, s);
+    if (rc) return rc;
+    if (head_host) {  // the kernels write the row without its forecast block a second time, packed: one contiguous copy
+        const size_t n_head = (size_t)(h->obs_dim - (h->fc_off >= 0 ? 5 * h->cfg.Np : 0));
+        GLG_CUDA(h, cudaMemcpyAsync(head_host, h->obs_head, n_head * B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    if (timestep_host) GLG_CUDA(h, cudaMemcpyAsync(timestep_host, h->timestep, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (table_host) GLG_CUDA(h, cudaMemcpyAsync(table_host, h->table, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (reward_host) GLG_CUDA(h, cudaMemcpyAsync(reward_host, h->reward, B * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (done_host) GLG_CUDA(h, cudaMemcpyAsync(done_host, h->done, B, cudaMemcpyDeviceToHost, s));
+    GLG_CUDA(h, cudaStreamSynchronize(s));
+    return GLG_OK;
+}
+
 extern "C" int32_t glg_obs_dim(const glg_handle *h) { return h ? h->obs_dim : 0; }
 extern "C" float *glg_obs_dev(glg_handle *h) { return h ? h->obs : nullptr; }
 extern "C" float *glg_terminal_obs_dev(glg_handle *h) { return h ? h->term_obs : nullptr; }
@@ -700,6 +734,92 @@ static int state_ex(glg_handle *h, const glg_env_state *s, bool to_dev) {
 }
 extern "C" int glg_get_state_ex(glg_handle *h, const glg_env_state *out_host) { return state_ex(h, out_host, false); }
 extern "C" int glg_set_state_ex(glg_handle *h, const glg_env_state *in_host) { return state_ex(h, in_host, true); }
+
+// ---- device rollout: VecNormalize + rollout buffer + GAE (glg_rollout.cuh) -------------------------------------
+extern "C" int glg_rollout_create(glg_handle *h, const glg_rollout_config *cfg) {
+    if (!h || !cfg) return GLG_ERR_ARG;
+    if (cfg->n_steps < 1 || !(cfg->gamma >= 0.0 && cfg->gamma <= 1.0) || !(cfg->gae_lambda >= 0.0 && cfg->gae_lambda <= 1.0) ||
+        !(cfg->clip_obs > 0) || !(cfg->clip_reward > 0) || !(cfg->epsilon > 0))
+        return fail(h, GLG_ERR_ARG, "glg_rollout_create: invalid n_steps / gamma / gae_lambda / clip / epsilon");
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaFree(h->roll_obs); cudaFree(h->roll_rew); cudaFree(h->roll_starts); cudaFree(h->roll_adv); cudaFree(h->roll_ret);
+    cudaFree(h->roll_stat); cudaFree(h->roll_partial); cudaFree(h->roll_norm); cudaFree(h->roll_acc);
+    h->roll_obs = h->roll_rew = h->roll_starts = h->roll_adv = h->roll_ret = nullptr;
+    h->roll_stat = h->roll_partial = h->roll_norm = h->roll_acc = nullptr;
+    h->have_roll = false;
+    const size_t B = (size_t)h->B, T = (size_t)cfg->n_steps, D = (size_t)h->obs_dim;
+    h->roll_blocks = (int)((B + GLG_ROLL_ROWS - 1) / GLG_ROLL_ROWS);
+    GLG_CUDA(h, dev_alloc(&h->roll_obs, (T + 1) * B * D));
+    GLG_CUDA(h, dev_alloc(&h->roll_rew, T * B));
+    GLG_CUDA(h, dev_alloc(&h->roll_starts, (T + 1) * B));
+    GLG_CUDA(h, dev_alloc(&h->roll_adv, T * B));
+    GLG_CUDA(h, dev_alloc(&h->roll_ret, T * B));
+    GLG_CUDA(h, dev_alloc(&h->roll_stat, (D + 1) * 3));
+    GLG_CUDA(h, dev_alloc(&h->roll_partial, (size_t)h->roll_blocks * (D + 1) * 2));
+    GLG_CUDA(h, dev_alloc(&h->roll_norm, (D + 1) * 2));
+    GLG_CUDA(h, dev_alloc(&h->roll_acc, B));
+    std::vector<double> st((D + 1) * 3);
+    for (size_t c = 0; c <= D; ++c) {  // RunningMeanStd: mean 0, var 1, count 1e-4
+        st[3 * c] = 0.0;
+        st[3 * c + 1] = 1.0;
+        st[3 * c + 2] = 1e-4;
+    }
+    GLG_CUDA(h, cudaMemcpy(h->roll_stat, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->roll = *cfg;
+    h->have_roll = true;
+    return GLG_OK;
+}
+extern "C" int glg_rollout_store(glg_handle *h, int32_t t, void *stream) {
+    if (!h) return GLG_ERR_ARG;
+    if (!h->have_roll) return fail(h, GLG_ERR_STATE, "glg_rollout_store: no rollout buffer (glg_rollout_create)");
+    if (t < -1 || t >= h->roll.n_steps) return fail(h, GLG_ERR_ARG, "glg_rollout_store: t outside [-1, n_steps)");
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t B = (size_t)h->B, D = (size_t)h->obs_dim;
+    GlgRollArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = h->B; a.obs_dim = h->obs_dim; a.n_blocks = h->roll_blocks;
+    a.training = h->roll.training; a.norm_obs = h->roll.norm_obs; a.norm_reward = h->roll.norm_reward;
+    a.gamma = h->roll.gamma; a.clip_obs = h->roll.clip_obs; a.clip_reward = h->roll.clip_reward; a.epsilon = h->roll.epsilon;
+    a.obs = h->obs;
+    a.reward = t >= 0 ? h->reward : nullptr;
+    a.done = t >= 0 ? h->done : nullptr;
+    a.ret = h->roll_acc; a.stat = h->roll_stat; a.partial = h->roll_partial; a.norm64 = h->roll_norm;
+    a.obs_out = h->roll_obs + (size_t)(t + 1) * B * D;
+    a.reward_out = t >= 0 ? h->roll_rew + (size_t)t * B : nullptr;
+    a.starts_out = h->roll_starts + (size_t)(t + 1) * B;
+    cudaStream_t s = (cudaStream_t)stream;
+    glg_roll_moments_kernel<<<h->roll_blocks, GLG_ROLL_NT, 0, s>>>(a);
+    glg_roll_finish_kernel<<<(h->obs_dim + 1 + GLG_ROLL_NT - 1) / GLG_ROLL_NT, GLG_ROLL_NT, 0, s>>>(a);
+    glg_roll_apply_kernel<<<h->roll_blocks, GLG_ROLL_NT, 0, s>>>(a);
+    h->launches += 3;
+    GLG_CUDA(h, cudaGetLastError());
+    return GLG_OK;
+}
+extern "C" int glg_rollout_carry(glg_handle *h, void *stream) {
+    if (!h) return GLG_ERR_ARG;
+    if (!h->have_roll) return fail(h, GLG_ERR_STATE, "glg_rollout_carry: no rollout buffer (glg_rollout_create)");
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t B = (size_t)h->B, D = (size_t)h->obs_dim, T = (size_t)h->roll.n_steps;
+    GLG_CUDA(h, cudaMemcpyAsync(h->roll_obs, h->roll_obs + T * B * D, B * D * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    GLG_CUDA(h, cudaMemcpyAsync(h->roll_starts, h->roll_starts + T * B, B * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GLG_OK;
+}
+extern "C" int glg_rollout_gae(glg_handle *h, const float *values_dev, void *stream) {
+    if (!h || !values_dev) return GLG_ERR_ARG;
+    if (!h->have_roll) return fail(h, GLG_ERR_STATE, "glg_rollout_gae: no rollout buffer (glg_rollout_create)");
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    glg_roll_gae_kernel<<<(h->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->roll.n_steps, h->B, h->roll.gamma, h->roll.gae_lambda, h->roll_rew,
+                                                                              values_dev, h->roll_starts, h->roll_adv, h->roll_ret);
+    h->launches += 1;
+    GLG_CUDA(h, cudaGetLastError());
+    return GLG_OK;
+}
+extern "C" float *glg_rollout_obs_dev(glg_handle *h) { return h ? h->roll_obs : nullptr; }
+extern "C" float *glg_rollout_rewards_dev(glg_handle *h) { return h ? h->roll_rew : nullptr; }
+extern "C" float *glg_rollout_starts_dev(glg_handle *h) { return h ? h->roll_starts : nullptr; }
+extern "C" float *glg_rollout_advantages_dev(glg_handle *h) { return h ? h->roll_adv : nullptr; }
+extern "C" float *glg_rollout_returns_dev(glg_handle *h) { return h ? h->roll_ret : nullptr; }
+extern "C" double *glg_rollout_stats_dev(glg_handle *h) { return h ? h->roll_stat : nullptr; }
 
 // ---- episode-statistics all-reduce over NCCL (run-time binding: nccl_api above)
 extern "C" int glg_nccl_unique_id(uint8_t id_out[128]) {

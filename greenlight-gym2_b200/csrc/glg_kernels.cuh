@@ -72,6 +72,7 @@ struct GlgStepArgs {
     int *timestep, *table, *ep_len;
     unsigned int *step_ctr;
     float *obs, *term_obs;
+    float *obs_head;  // [B][obs_dim - 5 Np]: the row without its forecast block, packed (host path glg_step_host_split)
     double *reward, *info, *stats;
     unsigned char *done;
 };
@@ -204,18 +205,21 @@ __device__ __forceinline__ void glg_obs_head(const double *x, const double *u, c
 // read obs[[0, 1, 2]] whatever the stack puts there (rewards.py:191-198).  wnext = weather row k+1 (first forecast row).
 // StateObservations is `np.random.rand(27)` in the reference (global numpy RNG, observations.py:57): here 27 Philox uniforms
 // keyed by (seed, global env id, step counter), draw blocks 96.. (disjoint from the noise and reset-table blocks).
+// hrow (may be NULL): the same row without the forecast block, packed.
 __device__ __forceinline__ void glg_write_obs_row(const GlgStepArgs &A, const double *hd, const double *wnext, unsigned long long env_id,
-                                                  unsigned int ctr, float *orow, double *o3) {
+                                                  unsigned int ctr, float *orow, float *hrow, double *o3) {
     const int seg0[5] = {0, 4, 7, 13, 18}, segn[5] = {4, 3, 6, 5, 5};
 #pragma unroll 1
     for (int m = 0; m < A.obs_nmod; ++m) {
         const int id = A.obs_mod[m], off = A.obs_off[m];
+        const int hoff = (A.fc_off >= 0 && off > A.fc_off) ? off - 5 * A.Np : off;
         if (id >= GLG_OBS_CLIMATE && id <= GLG_OBS_TIME) {
             const int s0 = seg0[id - GLG_OBS_CLIMATE], n = segn[id - GLG_OBS_CLIMATE];
 #pragma unroll 1
             for (int i = 0; i < n; ++i) {
                 const double v = hd[s0 + i];
                 orow[off + i] = (float)v;
+                if (hrow) hrow[hoff + i] = (float)v;
                 if (off + i < 3) o3[off + i] = v;
             }
         } else if (id == GLG_OBS_STATE) {
@@ -225,9 +229,11 @@ __device__ __forceinline__ void glg_write_obs_row(const GlgStepArgs &A, const do
                                                        (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
                 const double v0 = glg_u01(r.v[0], r.v[1]), v1 = glg_u01(r.v[2], r.v[3]);
                 orow[off + 2 * b] = (float)v0;
+                if (hrow) hrow[hoff + 2 * b] = (float)v0;
                 if (off + 2 * b < 3) o3[off + 2 * b] = v0;
                 if (2 * b + 1 < GLG_NOBS_STATE) {
                     orow[off + 2 * b + 1] = (float)v1;
+                    if (hrow) hrow[hoff + 2 * b + 1] = (float)v1;
                     if (off + 2 * b + 1 < 3) o3[off + 2 * b + 1] = v1;
                 }
             }
@@ -368,10 +374,11 @@ __device__ __forceinline__ void glg_env_epilogue(const GlgUniform &U, const GlgS
     const unsigned long long env_gid = (unsigned long long)(A.env_id_offset + e);
     // the row of this step: written to obs, or (when the env terminates and resets in place) to the terminal observation
     float *step_row = orow;
+    float *hrow = A.obs_head + (size_t)e * (A.obs_dim - (A.fc_off >= 0 ? 5 * A.Np : 0));
     // S6: termination (tomato_env.py:68-75,131-132)
     if (k >= A.N) done = 1;
     if (done && A.auto_reset) step_row = A.term_obs + (size_t)e * A.obs_dim;
-    glg_write_obs_row(A, hd, wrow + GLG_ND, env_gid, ctr, step_row, o3);
+    glg_write_obs_row(A, hd, wrow + GLG_ND, env_gid, ctr, step_row, step_row == orow ? hrow : nullptr, o3);
     // S5/S7: reward and info with the nominal parameters (rewards.py:156-231), same operation order
     double reward, info[GLG_NINFO];
     {
@@ -436,7 +443,7 @@ __device__ __forceinline__ void glg_env_epilogue(const GlgUniform &U, const GlgS
         hod = 0.0;
         glg_obs_head(x, u, d, 0, doy, hod, hd);
         double o3r[3];
-        glg_write_obs_row(A, hd, w0 + GLG_ND, env_gid, ctr + 0x80000000u, orow, o3r);
+        glg_write_obs_row(A, hd, w0 + GLG_ND, env_gid, ctr + 0x80000000u, orow, hrow, o3r);
         o.k_obs = 0;
         o.tbl_obs = tbl;
     }
@@ -619,7 +626,8 @@ __global__ void __launch_bounds__(NT) glg_reset_kernel(const __grid_constant__ G
     double hd[GLG_NOBS_FIXED];
     glg_obs_head(x, u, d, 0, doy, 0.0, hd);
     float *orow = A.obs + (size_t)e * A.obs_dim;
-    glg_write_obs_row(A, hd, w0 + GLG_ND, (unsigned long long)(A.env_id_offset + e), ctr + 0x80000000u, orow, o3);
+    glg_write_obs_row(A, hd, w0 + GLG_ND, (unsigned long long)(A.env_id_offset + e), ctr + 0x80000000u, orow,
+                      A.obs_head + (size_t)e * (A.obs_dim - (A.fc_off >= 0 ? 5 * A.Np : 0)), o3);
     if (A.fc_off >= 0) {
         const int nf = 5 * A.Np;
         for (int j = 0; j < nf; ++j) {

@@ -33,13 +33,16 @@
 #define GLG_ROLE_LANES 32
 constexpr int GLG_NO = 4;  // owner warps: warps 0..3, one per SM sub-partition
 constexpr int GLG_BAR_PARTS = 1, GLG_BAR_XS = 2, GLG_BAR_LATE = 3;
-// Experiment switches (DESIGN.md "round 2 kernel experiments": every one of them measured slower at B = 4096 -- the role loops
-// together sit at the SM's ~32 KB instruction cache, and whatever grows them costs more than it saves):
+// Layout switches, all measured at B = 4096 (DESIGN.md "Round-2 kernel experiments").  The role loops of the latency layout
+// together span ~32 KB of code, the SM's instruction-cache capacity (tools/ubench/icache2.cu): a variant whose loops span more
+// is 3-20 % slower whatever it was meant to gain, so every switch is judged with tools/sass_loop_size.py beside the timer.
 //   GLG_HREG        per-env-step constants of a group role in registers instead of re-read from shared memory per evaluation
-//   GLG_ORDER_TOKEN make the owners' barrier wait data-dependent on the work meant to precede it (ptxas sinks it otherwise)
-//   GLG_LATE_MASK   (glg_units.h) early / late split of the owners' reduction
+//                   (removes ~60 of the group warps' 139 shared-memory loads per evaluation): 1.447 -> 1.428 ms.  On.
+//   GLG_ORDER_TOKEN make the owners' barrier wait data-dependent on the work meant to precede it (ptxas sinks it behind the
+//                   barrier otherwise): the extra instructions push the loops over 32 KB, 1.524 ms.  Off.
+//   GLG_LATE_MASK   (glg_units.h) early / late split of the owners' reduction behind a third named barrier: 1.69 ms.  Off.
 #ifndef GLG_HREG
-#define GLG_HREG 0
+#define GLG_HREG 1
 #endif
 #ifndef GLG_ORDER_TOKEN
 #define GLG_ORDER_TOKEN 0
@@ -384,6 +387,9 @@ __device__ __forceinline__ void glg_group_dispatch(int gw, const GlgUniform &U, 
     }
 }
 
+__constant__ double glg_kStageC[4] = {0.5, 0.5, 1.0, 1.0 / 6.0};
+__constant__ double glg_kStageW[4] = {1.0, 2.0, 2.0, 1.0};
+
 // ---- owner: RK4 state of the NJ plan rows of owner index o for this lane's env, and the micro-step bookkeeping.
 // One nominal RK4 substep = m micro-steps of h_nom/m, m per env = max of the harvest-stiffness guard (glg_model.h; 1 unless an
 // organ sits inside its harvest window) and, with integrator = 1, the graded start of the interval and the transient-stiffness
@@ -468,8 +474,8 @@ struct GlgOwner {
     __device__ __forceinline__ void pre(int lane) {
         first = stage == 0 && q == 0;  // first evaluation of a nominal substep: the micro-step count is decided in post_late()
         last = stage == 3;
-        cs = stage == 2 ? 1.0 : (last ? 1.0 / 6.0 : 0.5);
-        w = (stage == 1 || stage == 2) ? 2.0 : 1.0;
+        cs = glg_kStageC[stage];  // 1/2, 1/2, 1, 1/6 : constant-bank lookups instead of select chains (loop code size)
+        w = glg_kStageW[stage];   // 1, 2, 2, 1
         // is this the last evaluation of the interval?  (m_cta of the last substep is known by its stage 3)
         const bool last_micro = q + 1 >= m_cta && sub + 1 >= n_sub;
         final_eval = last && last_micro;
@@ -568,37 +574,32 @@ struct GlgOwner {
                 m_cta = __reduce_max_sync(0xffffffffu, m_lane);  // every owner warp sees the same 32 envs
                 // reciprocal + multiply instead of an IEEE division; the step size differs from h_nom/m by at most 1 ulp
                 h_lane = m_lane == 1 ? h_nom : h_nom * glg_rcp((double)m_lane);
-                const double hcs = cs * h_lane;
                 // redo the stage update with the right step (first evaluation: stage 0, base = x)
+                const double hcs = cs * h_lane;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     hc[j] = hcs * scale[j];
-                    xn[j] = glg_fma(hc[j], sum[j], xo[j]);
+                    if (kHasLate) xn[j] = glg_fma(hc[j], sum[j], xo[j]);
                 }
-            } else if (!kHasLate) {
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) xn[j] = glg_fma(hc[j], sum[j], base[j]);
             }
             n_micro += m_lane;
-        } else if (!kHasLate) {
+        }
+        if (!kHasLate) {  // one copy of the stage update for all paths (the loop code must stay below the instruction cache)
 #pragma unroll
             for (int j = 0; j < NJ; ++j) xn[j] = glg_fma(hc[j], sum[j], base[j]);
         }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) xbase[j * GLG_NO * NL] = (T)xn[j];
-        if (final_eval) {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) xo[j] = xn[j];
-        }
     }
-    // final state -> s_xfin; returns 1 if any of this owner's states is not finite
+    // final state (xn of the last evaluation: the caller leaves its loop right behind that post_late()) -> s_xfin; returns 1 if
+    // any of this owner's states is not finite
     __device__ __forceinline__ int finish(double *s_xfin, int lane) const {
         int bad = 0;
         glg_static_for<0, NJ>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             const int st = row_state<j>();
-            bad |= !(fabs(xo[j]) <= 1.79769313486231570e308);
-            if (!kStateInXs && st >= 0) s_xfin[st * NL + lane] = xo[j];  // fp64 units: post_late() left it in the stage-state block
+            bad |= !(fabs(xn[j]) <= 1.79769313486231570e308);
+            if (!kStateInXs && st >= 0) s_xfin[st * NL + lane] = xn[j];  // fp64 units: post_late() left it in the stage-state block
         });
         return bad;
     }

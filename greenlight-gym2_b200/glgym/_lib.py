@@ -31,6 +31,13 @@ class GlgConfig(C.Structure):
     ]
 
 
+class GlgRolloutConfig(C.Structure):
+    """struct glg_rollout_config (include/glgym.h)."""
+    _fields_ = [("n_steps", C.c_int32), ("training", C.c_int32), ("norm_obs", C.c_int32), ("norm_reward", C.c_int32),
+                ("gamma", C.c_double), ("gae_lambda", C.c_double), ("clip_obs", C.c_double), ("clip_reward", C.c_double),
+                ("epsilon", C.c_double)]
+
+
 class GlgEnvState(C.Structure):
     """struct glg_env_state (include/glgym.h): host pointers, NULL = skip."""
     _fields_ = [("x", C.c_void_p), ("u", C.c_void_p), ("timestep", C.c_void_p), ("table", C.c_void_p), ("time", C.c_void_p),
@@ -54,6 +61,7 @@ SIGNATURES = {
     "glg_step_rule_based": (C.c_int, [C.c_void_p, _DP, _VP]),
     "glg_rule_control_batch": (C.c_int, [_DP, _DP, _DP, _DP, _DP, _DP, C.c_int32, C.c_int32, _VP]),
     "glg_step_host": (C.c_int, [C.c_void_p, _FP, _FP, _DP, _U8P]),
+    "glg_step_host_split": (C.c_int, [C.c_void_p, _FP, _FP, _IP, _IP, _DP, _U8P]),
     "glg_obs_dim": (C.c_int32, [C.c_void_p]),
     "glg_obs_dev": (C.c_void_p, [C.c_void_p]),
     "glg_terminal_obs_dev": (C.c_void_p, [C.c_void_p]),
@@ -72,6 +80,16 @@ SIGNATURES = {
     "glg_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
     "glg_get_state_ex": (C.c_int, [C.c_void_p, C.POINTER(GlgEnvState)]),
     "glg_set_state_ex": (C.c_int, [C.c_void_p, C.POINTER(GlgEnvState)]),
+    "glg_rollout_create": (C.c_int, [C.c_void_p, C.POINTER(GlgRolloutConfig)]),
+    "glg_rollout_store": (C.c_int, [C.c_void_p, C.c_int32, _VP]),
+    "glg_rollout_carry": (C.c_int, [C.c_void_p, _VP]),
+    "glg_rollout_gae": (C.c_int, [C.c_void_p, _FP, _VP]),
+    "glg_rollout_obs_dev": (C.c_void_p, [C.c_void_p]),
+    "glg_rollout_rewards_dev": (C.c_void_p, [C.c_void_p]),
+    "glg_rollout_starts_dev": (C.c_void_p, [C.c_void_p]),
+    "glg_rollout_advantages_dev": (C.c_void_p, [C.c_void_p]),
+    "glg_rollout_returns_dev": (C.c_void_p, [C.c_void_p]),
+    "glg_rollout_stats_dev": (C.c_void_p, [C.c_void_p]),
     "glg_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "glg_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "glg_allreduce_stats": (C.c_int, [C.c_void_p, _VP]),

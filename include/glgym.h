@@ -133,6 +133,15 @@ int glg_rule_control_batch(const double *settings29, const double *x_dev, const 
  * NULL.  obs_host float32 [B][obs_dim], reward_host double [B], done_host uint8 [B]. */
 int glg_step_host(glg_handle *h, const float *actions_host, float *obs_host, double *reward_host, uint8_t *done_host);
 
+/* Same step with the observation returned in SPLIT form (opt-in, for host loops that do not want 240 of 263 floats per env
+ * that are a pure function of (weather table, timestep)): head_host float32 [B][obs_dim - 5 Np] receives every column of the
+ * row except the WeatherForecastObservations block (observations.py:163-182), packed; timestep_host / table_host int32 [B]
+ * receive each env's timestep and weather table AFTER the step, from which the caller reads the forecast block out of its
+ * own copy of the weather bank: rows max(timestep, 1) .. + Np - 1, columns 0..4.  D2H per step at B = 4096: 0.43 MB instead of
+ * 4.35 MB.  Any output may be NULL. */
+int glg_step_host_split(glg_handle *h, const float *actions_host, float *head_host, int32_t *timestep_host, int32_t *table_host,
+                        double *reward_host, uint8_t *done_host);
+
 /* Output / state accessors: device pointers owned by the handle, valid until glg_destroy. */
 int32_t glg_obs_dim(const glg_handle *h);          /* 23 + 5*Np */
 float *glg_obs_dev(glg_handle *h);                 /* float32 [B][obs_dim]  (observations.py:59-182) */
@@ -173,6 +182,40 @@ typedef struct glg_env_state {
 } glg_env_state;
 int glg_get_state_ex(glg_handle *h, const glg_env_state *out_host);
 int glg_set_state_ex(glg_handle *h, const glg_env_state *in_host);
+
+/* ---- device rollout: VecNormalize statistics + normalisation, on-policy rollout buffer, GAE -------------------
+ * What the reference's training loop puts between env.step and the PPO update -- SubprocVecEnv -> VecMonitor -> VecNormalize
+ * (gl_gym/RL/utils.py:60-67; norm_obs / norm_reward / clip_obs / clip_reward / gamma from RL/experiment_manager.py:142-147) and
+ * SB3's RolloutBuffer with generalised advantage estimation (configs/agents/ppo.yml: n_steps, gamma, gae_lambda) -- as kernels
+ * on the handle's own outputs (csrc/glg_rollout.cuh), so a rollout never leaves the device.  Episode return / length
+ * bookkeeping (VecMonitor) is part of the step kernel (glg_stats_dev).
+ * Buffers (device, owned by the handle): obs float32 [T+1][B][obs_dim] (normalised, clipped; slot t = what the policy sees
+ * at step t, slot T = the observation after the last step), rewards float32 [T][B] (normalised), episode_starts float32
+ * [T+1][B], advantages / returns float32 [T][B], statistics double [obs_dim + 1][3] = running (mean, var, count) per observation
+ * column, last row = statistics of the discounted return. */
+typedef struct glg_rollout_config {
+    int32_t n_steps;     /* T */
+    int32_t training;    /* 1: update the running statistics (VecNormalize.training) */
+    int32_t norm_obs, norm_reward;
+    double gamma, gae_lambda;
+    double clip_obs, clip_reward, epsilon; /* 10, 10, 1e-8 in the reference's setup */
+} glg_rollout_config;
+int glg_rollout_create(glg_handle *h, const glg_rollout_config *cfg);
+/* After glg_reset (t = -1): statistics fed with the first observations, normalised into slot 0, returns zeroed, every env
+ * starts an episode.  After the glg_step* of rollout step t (0 <= t < T): observation statistics updated with the new raw
+ * observations, which are normalised into slot t + 1; ret <- ret gamma + reward feeds the return statistics; the normalised
+ * reward goes to slot t; episode_starts[t + 1] = done; ret[done] = 0.  Three launches on `stream`. */
+int glg_rollout_store(glg_handle *h, int32_t t, void *stream);
+/* Start the next rollout without a reset: slot T (observation, episode_starts) becomes slot 0. */
+int glg_rollout_carry(glg_handle *h, void *stream);
+/* RolloutBuffer.compute_returns_and_advantage: values_dev float32 [T+1][B] (row T = value of the slot-T observation). */
+int glg_rollout_gae(glg_handle *h, const float *values_dev, void *stream);
+float *glg_rollout_obs_dev(glg_handle *h);
+float *glg_rollout_rewards_dev(glg_handle *h);
+float *glg_rollout_starts_dev(glg_handle *h);
+float *glg_rollout_advantages_dev(glg_handle *h);
+float *glg_rollout_returns_dev(glg_handle *h);
+double *glg_rollout_stats_dev(glg_handle *h);
 
 /* Multi-GPU episode statistics: the step path has no collective; the one exchange is a sum of the 16-entry
  * statistics vector over the ranks' handles, once per logging interval -- ncclAllReduce on the handle's device buffer.

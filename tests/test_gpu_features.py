@@ -326,3 +326,28 @@ def test_nccl_stats_allreduce_entry_points():
     after = env.episode_stats()
     assert after == before
     env.close()
+
+
+@pytest.mark.parametrize("mods", [None, ["WeatherObservations", "WeatherForecastObservations", "IndoorClimateObservations", "TimeObservations"],
+                                  ["ControlObservations", "BasicCropObservations"]])
+def test_split_observation_host_path(mods, weather0):
+    """step_split(): only the per-env columns cross PCIe; the forecast block is read from the host's copy of the weather bank.
+    Rows assembled from the split form equal step()'s rows bit for bit -- through an episode end with in-place reset, with the
+    forecast block in the middle of the row, and for a stack without one."""
+    B = 37
+    kw = dict(n_sub=300, observation_modules=mods, base_env_params=dict(season_length=5 / 96.0), weather_tables=weather0, seed=4)
+    ea, eb = make_env(B, **kw), make_env(B, **kw)
+    ea.reset(); eb.reset()
+    rng = np.random.default_rng(2)
+    for s in range(9):
+        a = rng.uniform(-1, 1, (B, 6)).astype(np.float32)
+        oa, ra, da, ia = ea.step(a)
+        so, rb, db, ib = eb.step_split(a)
+        assert np.array_equal(so.full(), oa) and np.array_equal(ra, rb) and np.array_equal(da, db), s
+        assert so.head.shape == (B, ea.obs_dim - (240 if ea.forecast_offset >= 0 else 0))
+        if ea.forecast_offset >= 0:
+            assert np.array_equal(so.forecast(3), oa[3, ea.forecast_offset:ea.forecast_offset + 240])
+        if da.any():
+            assert all(np.array_equal(ia[i]["terminal_observation"], ib[i]["terminal_observation"]) for i in np.nonzero(da)[0])
+    assert da.sum() == 0 and s == 8
+    ea.close(); eb.close()

@@ -208,3 +208,23 @@ def test_results_frame_layout():
     df = to_results_frame(data, cols)
     assert df.shape == (6, 33) and df["episode"].tolist() == [0, 0, 0, 1, 1, 1]
     assert df["Rewards"].tolist() == data[:, :, 23].ravel().tolist() and df["co2_air"].iloc[4] == data[1, 1, 0]
+
+
+def test_role_loops_fit_the_instruction_cache():
+    """The latency layout's role loops (10 group loops + the owner loop) must together span less than the SM's ~32 KB
+    instruction cache: measured on B200, a build whose loops span 32.0-32.5 KB is 3-20 % slower at B = 4096 whatever else
+    changed (DESIGN.md "Round-2 kernel experiments").  A code change that grows the loops shows up here, at build time."""
+    import shutil
+    import subprocess
+    import sys
+    from glgym import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    dump = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    path = os.path.join(os.path.dirname(__file__), "..", "tools")
+    out = subprocess.run([sys.executable, os.path.join(path, "sass_loop_size.py"), "/dev/stdin"], input=dump, capture_output=True, text=True).stdout
+    import re
+    m = re.search(r"loops (0x[0-9a-f]+)\.\.(0x[0-9a-f]+)", out)
+    assert m, out
+    span = int(m.group(2), 16) - int(m.group(1), 16) + 16
+    assert span <= 32 * 1024 - 64, f"role loops span {span} B"

@@ -122,3 +122,68 @@ def test_device_vec_normalize_on_cuda_env():
         eo, er = ref.step(o2.cpu().numpy().astype(np.float64), r2.cpu().numpy(), d2.cpu().numpy().astype(bool))
         assert np.allclose(no.cpu().numpy(), eo, atol=2e-6) and np.allclose(nr.cpu().numpy(), er, rtol=1e-10, atol=1e-12), t
     env.close(); raw.close()
+
+
+def np_gae(rewards, values, starts, gamma, lam):
+    """RolloutBuffer.compute_returns_and_advantage of SB3 2.6.0 (common/buffers.py), float32 like the buffer's arrays:
+    values [T+1, B] (row T = last_values), starts [T+1, B] (row T = dones of the last step)."""
+    T = rewards.shape[0]
+    adv = np.zeros_like(rewards)
+    last = np.zeros(rewards.shape[1], dtype=np.float32)
+    for t in reversed(range(T)):
+        nnt = (1.0 - starts[t + 1]).astype(np.float32)
+        delta = rewards[t] + np.float32(gamma) * values[t + 1] * nnt - values[t]
+        last = delta + np.float32(gamma * lam) * nnt * last
+        adv[t] = last
+    return adv, adv + values[:T]
+
+
+@pytest.mark.gpu
+def test_device_rollout_kernels_match_sb3_restatement():
+    """glg_rollout_* (csrc/glg_rollout.cuh): fused running statistics + normalisation into the rollout buffer + GAE, on the real
+    CUDA env, against the numpy restatement of SB3's VecNormalize / RolloutBuffer applied to the raw outputs of an identical
+    env.  Short season so episode ends (returns reset, episode_starts) fall inside the rollout; two consecutive rollouts
+    (begin() carries slot T over)."""
+    from glgym.rollout import DeviceRollout
+    from glgym.vec_env import GreenLightVecEnv
+    B, T, gamma, lam = 200, 12, 0.9631, 0.9470
+    kw = dict(n_sub=300, integrator="fixed", seed=5, base_env_params=dict(season_length=7 / 96.0))
+    env, raw = GreenLightVecEnv(B, **kw), GreenLightVecEnv(B, **kw)
+    roll = DeviceRollout(env, T, gamma=gamma, gae_lambda=lam)
+    ref = NpVecNormalize(B, env.obs_dim, gamma)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    o = roll.reset()
+    ro = ref.reset(raw.reset_tensor().cpu().numpy().astype(np.float64))
+    assert np.allclose(o.cpu().numpy(), ro, atol=2e-6) and bool((roll.episode_starts[0] == 1).all())
+    n_done = 0
+    for rollout in range(2):
+        exp_obs, exp_rew, exp_starts = [ro], [], [roll.episode_starts[0].cpu().numpy()]
+        for t in range(T):
+            a = torch.rand(B, 6, device="cuda", generator=g) * 2 - 1
+            no, nr, d = roll.step(a)
+            o2, r2, d2 = raw.step_tensor(a)
+            eo, er = ref.step(o2.cpu().numpy().astype(np.float64), r2.cpu().numpy(), d2.cpu().numpy().astype(bool))
+            assert np.allclose(no.cpu().numpy(), eo, atol=2e-6) and np.allclose(nr.cpu().numpy(), er, rtol=1e-6, atol=1e-7), (rollout, t)
+            assert np.array_equal(d.cpu().numpy(), d2.cpu().numpy())
+            exp_obs.append(eo); exp_rew.append(er.astype(np.float32)); exp_starts.append(d2.cpu().numpy().astype(np.float32))
+            n_done += int(d2.sum().item())
+        assert np.allclose(roll.obs.cpu().numpy(), np.stack(exp_obs), atol=2e-6)
+        assert np.allclose(roll.rewards.cpu().numpy(), np.stack(exp_rew), rtol=1e-6, atol=1e-7)
+        assert np.array_equal(roll.episode_starts.cpu().numpy(), np.stack(exp_starts))
+        # running statistics (float64): observation columns and the discounted return
+        st = roll.stats.cpu().numpy()
+        assert np.allclose(st[:-1, 0], ref.obs_rms.mean, rtol=1e-9, atol=1e-9) and np.allclose(st[:-1, 1], ref.obs_rms.var, rtol=1e-7, atol=1e-12)
+        assert abs(st[-1, 0] - ref.ret_rms.mean) <= 1e-10 and abs(st[-1, 1] - ref.ret_rms.var) <= 1e-9 * ref.ret_rms.var
+        assert st[0, 2] == ref.obs_rms.count
+        values = torch.randn(T + 1, B, device="cuda", generator=g)
+        adv, ret = roll.finish(values)
+        ea, er_ = np_gae(roll.rewards.cpu().numpy(), values.cpu().numpy(), roll.episode_starts.cpu().numpy(), gamma, lam)
+        assert np.allclose(adv.cpu().numpy(), ea, rtol=1e-5, atol=1e-5) and np.allclose(ret.cpu().numpy(), er_, rtol=1e-5, atol=1e-5)
+        first = roll.begin()
+        ro = exp_obs[-1]
+        assert np.array_equal(first.cpu().numpy(), roll.obs[T].cpu().numpy()) and np.array_equal(roll.episode_starts[0].cpu().numpy(), exp_starts[-1])
+    assert n_done >= 2 * B  # episodes really ended inside the rollouts
+    with pytest.raises(RuntimeError):
+        for t in range(T + 1):
+            roll.step(torch.zeros(B, 6, device="cuda"))
+    env.close(); raw.close()

@@ -19,6 +19,11 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+        # local memory = register spills + per-thread arrays: instructions executed, L1 requests / sectors
+        "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
+        "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_local_op_st.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+        "launch__local_size", "launch__occupancy_limit_warps", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "sm__cycles_elapsed.avg", "sm__cycles_active.avg", "smsp__cycles_active.avg"]
 stall = [h for h in hdr if h.startswith("smsp__average_warp_latency_issue_stalled") or h.startswith("smsp__average_warps_issue_stalled")]
 out = []
