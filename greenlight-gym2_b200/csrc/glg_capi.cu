@@ -789,7 +789,7 @@ extern "C" int glg_rollout_store(glg_handle *h, int32_t t, void *stream) {
     a.starts_out = h->roll_starts + (size_t)(t + 1) * B;
     cudaStream_t s = (cudaStream_t)stream;
     glg_roll_moments_kernel<<<h->roll_blocks, GLG_ROLL_NT, 0, s>>>(a);
-    glg_roll_finish_kernel<<<(h->obs_dim + 1 + GLG_ROLL_NT - 1) / GLG_ROLL_NT, GLG_ROLL_NT, 0, s>>>(a);
+    glg_roll_finish_kernel<<<(h->obs_dim + 1 + GLG_ROLL_NT / 32 - 1) / (GLG_ROLL_NT / 32), GLG_ROLL_NT, 0, s>>>(a);
     glg_roll_apply_kernel<<<h->roll_blocks, GLG_ROLL_NT, 0, s>>>(a);
     h->launches += 3;
     GLG_CUDA(h, cudaGetLastError());

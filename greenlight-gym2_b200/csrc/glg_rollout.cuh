@@ -42,8 +42,21 @@ __global__ void __launch_bounds__(GLG_ROLL_NT) glg_roll_moments_kernel(const Glg
     for (int c = threadIdx.x; c < A.obs_dim; c += GLG_ROLL_NT) {
         const double m = A.stat[3 * c];
         double s1 = 0.0, s2 = 0.0;
-        for (int r = r0; r < r1; ++r) {
-            const double d = (double)A.obs[(size_t)r * A.obs_dim + c] - m;
+        const float *col = A.obs + (size_t)r0 * A.obs_dim + c;
+        int r = r0;
+        for (; r + 8 <= r1; r += 8, col += 8 * (size_t)A.obs_dim) {  // eight independent loads in flight per thread
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(col + (size_t)k * A.obs_dim);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double d = (double)v[k] - m;
+                s1 += d;
+                s2 = fma(d, d, s2);
+            }
+        }
+        for (; r < r1; ++r, col += A.obs_dim) {
+            const double d = (double)__ldg(col) - m;
             s1 += d;
             s2 = fma(d, d, s2);
         }
@@ -75,44 +88,68 @@ __global__ void __launch_bounds__(GLG_ROLL_NT) glg_roll_moments_kernel(const Glg
     }
 }
 
-// one thread per column (+ the return statistic): fixed-order sum of the partials, Chan update (running_mean_std.py)
+// one warp per column (+ the return statistic): lane l sums the partials of CTAs l, l + 32, ... in order, the lanes are combined
+// by a fixed shuffle tree (deterministic), lane 0 does the Chan update (running_mean_std.py).  (One THREAD per column walking
+// all partials serially was 250 us of dependent L2 loads at 1024 CTAs.)
 __global__ void __launch_bounds__(GLG_ROLL_NT) glg_roll_finish_kernel(const GlgRollArgs A) {
-    const int c = blockIdx.x * GLG_ROLL_NT + threadIdx.x;
+    const int c = blockIdx.x * (GLG_ROLL_NT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c > A.obs_dim) return;
     const bool is_ret = c == A.obs_dim;
     double mean = A.stat[3 * c], var = A.stat[3 * c + 1], count = A.stat[3 * c + 2];
     const bool update = A.training && (is_ret ? A.reward != nullptr : A.norm_obs != 0);
     if (update) {
         double s1 = 0.0, s2 = 0.0;
-        for (int b = 0; b < A.n_blocks; ++b) {
+#pragma unroll 4
+        for (int b = lane; b < A.n_blocks; b += 32) {
             s1 += A.partial[((size_t)b * (A.obs_dim + 1) + c) * 2];
             s2 += A.partial[((size_t)b * (A.obs_dim + 1) + c) * 2 + 1];
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_down_sync(0xffffffffu, s1, o);
+            s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        }
         const double n = (double)A.B;
-        const double dmean = s1 / n;                       // batch mean - running mean
+        const double dmean = s1 / n;                            // batch mean - running mean
         const double bvar = fmax(s2 / n - dmean * dmean, 0.0);  // population variance of the batch
         const double tot = count + n;
         const double m2 = var * count + bvar * n + dmean * dmean * count * n / tot;
         mean = mean + dmean * n / tot;
         var = m2 / tot;
         count = tot;
-        A.stat[3 * c] = mean;
-        A.stat[3 * c + 1] = var;
-        A.stat[3 * c + 2] = count;
+        if (lane == 0) {
+            A.stat[3 * c] = mean;
+            A.stat[3 * c + 1] = var;
+            A.stat[3 * c + 2] = count;
+        }
     }
-    A.norm64[2 * c] = mean;
-    A.norm64[2 * c + 1] = 1.0 / sqrt(var + A.epsilon);
+    if (lane == 0) {
+        A.norm64[2 * c] = mean;
+        A.norm64[2 * c + 1] = 1.0 / sqrt(var + A.epsilon);
+    }
 }
 
 __global__ void __launch_bounds__(GLG_ROLL_NT) glg_roll_apply_kernel(const GlgRollArgs A) {
     const int r0 = blockIdx.x * GLG_ROLL_ROWS, r1 = min(r0 + GLG_ROLL_ROWS, A.B);
     for (int c = threadIdx.x; c < A.obs_dim; c += GLG_ROLL_NT) {
         const double m = A.norm64[2 * c], is = A.norm64[2 * c + 1];
-        for (int r = r0; r < r1; ++r) {
-            const float x = A.obs[(size_t)r * A.obs_dim + c];
-            float y = x;
-            if (A.norm_obs) y = (float)fmin(fmax(((double)x - m) * is, -A.clip_obs), A.clip_obs);
-            A.obs_out[(size_t)r * A.obs_dim + c] = y;
+        const float *col = A.obs + (size_t)r0 * A.obs_dim + c;
+        float *out = A.obs_out + (size_t)r0 * A.obs_dim + c;
+        int r = r0;
+        for (; r + 8 <= r1; r += 8, col += 8 * (size_t)A.obs_dim, out += 8 * (size_t)A.obs_dim) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(col + (size_t)k * A.obs_dim);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (A.norm_obs) v[k] = (float)fmin(fmax(((double)v[k] - m) * is, -A.clip_obs), A.clip_obs);
+                out[(size_t)k * A.obs_dim] = v[k];
+            }
+        }
+        for (; r < r1; ++r, col += A.obs_dim, out += A.obs_dim) {
+            float y = __ldg(col);
+            if (A.norm_obs) y = (float)fmin(fmax(((double)y - m) * is, -A.clip_obs), A.clip_obs);
+            *out = y;
         }
     }
     if (threadIdx.x < GLG_ROLL_ROWS && r0 + (int)threadIdx.x < r1) {
