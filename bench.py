@@ -108,6 +108,28 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything this process (or a library it loads: NCCL prints a version banner to stdout when the first communicator is
+    created) writes to fd 1 goes to stderr from here on; the one JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def load_inputs():
     from glgym.params import init_default_params
     from glgym.weather import load_weather_data
@@ -179,8 +201,8 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     n_sub = args.n_sub or (300 if args.integrator == "graded" else 600)
     kind = "port-implicit"
-    probe, _, _ = cpu_rate(kind, args.integrator, n_sub, 4 * cores, 2, cores)
-    sample = max(4 * cores, int(np.ceil(12.0 * probe / max(args.steps, 1) / cores)) * cores)  # envs per step: >= 10 s in total
+    probe, _, _ = cpu_rate(kind, args.integrator, n_sub, 16 * cores, 3, cores, warmup=1)
+    sample = max(4 * cores, int(np.ceil(15.0 * probe / max(args.steps, 1) / cores)) * cores)  # envs per step: >= 10 s in total
     rate, dt, rhs = cpu_rate(kind, args.integrator, n_sub, sample, args.steps, cores, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -196,7 +218,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
@@ -438,7 +460,7 @@ def run_ours(args, rank, world, local):
                                  note="value = the faster CPU arm; 'port' runs the GPU arm's RK4 contract, 'port-implicit' an adaptive BDF at the "
                                       "reference solver's tolerances (rtol = atol = 1e-6) on the same right-hand side"),
         }
-        print(json.dumps(line))
+        emit(line)
 
 
 def main():
@@ -458,6 +480,7 @@ def main():
         args.integrator = "graded"  # == glgym.vec_env.DEFAULT_INTEGRATOR (not imported here: --impl reference must not need torch)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

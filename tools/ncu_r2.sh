@@ -10,8 +10,10 @@ cap() {  # name, kernel regex, skip, args...
   python tools/ncu_summary.py /tmp/$name.ncu-rep $O/$name.txt > /dev/null 2>&1
   ncu -i /tmp/$name.ncu-rep --page source --csv > /tmp/$name.src.csv 2>/dev/null && python tools/ncu_src_stalls.py /tmp/$name.src.csv >> $O/$name.txt 2>/dev/null
 }
+python -c "import bench; print(bench.csrc_hash())" > $O/r2_csrc_sha16.txt   # the sources these captures belong to
 cap r2_lat_graded_B4096 glg_step_units 2 B=4096 integrator=graded
 cp /tmp/r2_lat_graded_B4096.ncu-rep $O/
+cap r2_lat_fp32_graded_B4096 glg_step_units 2 B=4096 integrator=graded precision=fp32
 cap r2_lat_fixed600_B4096 glg_step_units 2 B=4096 integrator=fixed
 cap r2_tput_graded_B262144 glg_step_units 2 B=262144 integrator=graded
 cap r2_tput_fp32_unc03_B262144 glg_step_units 2 B=262144 integrator=graded precision=fp32 uncertainty_scale=0.3 tables=19
