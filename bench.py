@@ -185,7 +185,7 @@ def workload_config(args):
             "envs_per_gpu": args.envs, "n_sub": n_sub, "dt": 900, "integrator": integ, "obs_dim": 263,
             "parallelism": f"env-shard x{args.gpus}, no collective on the step path",
             "l2": "GPU arm: flushed between timed steps (256 MiB memset outside the event pair); CPU arm: not applicable",
-            "kernel": {0: "GPU arm: glg_step_units_kernel (auto: latency layout, 4 owner + 12 flux-unit warps per 32 envs, up to SMs*32 envs; "
+            "kernel": {0: "GPU arm: glg_step_units_kernel (auto: latency layout, 4 owner + 12 flux-unit warps per 32 envs, up to 2*SMs*32 envs; "
                           "else throughput layout, 4 fused warps per 32 envs x 4 CTAs per SM)",
                        1: "GPU arm: glg_step_kernel (thread per env)", 2: "GPU arm: glg_step_units_kernel latency layout",
                        3: "GPU arm: glg_step_units_kernel throughput layout"}[args.role_warps]}

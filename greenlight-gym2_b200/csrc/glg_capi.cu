@@ -436,12 +436,13 @@ static cudaError_t launch_step_units(glg_handle *h, const GlgStepArgs &a, cudaSt
 #endif
 }
 
-// Kernel variant: 1 = kernel A (one thread per env), 2 = kernel C compiled for one CTA per SM (128 registers per thread:
-// the step time of a batch that leaves SMs under-filled is the latency of one CTA), 3 = kernel C compiled for two CTAs per SM
-// (64 registers: throughput once every SM holds two).
+// Kernel variant: 1 = kernel A (one thread per env), 2 = kernel C latency layout (4 owner + 12 group warps per 32 envs, one CTA
+// per SM: the step time of a batch that leaves SMs under-filled is the latency of one CTA), 3 = kernel C throughput layout
+// (4 fused warps per 32 envs, 4 CTAs per SM).  Auto-pick: measured with tools/layout_sweep.py the latency layout wins up to two
+// waves of CTAs (B = 9472 on 148 SMs: 1.735 vs 1.814 ms), the throughput layout beyond (B = 12 288: 2.60 vs 2.18 ms).
 static int pick_role_warps(const glg_handle *h) {
     if (h->cfg.role_warps != 0) return h->cfg.role_warps;
-    return h->B <= h->sms * GLG_ROLE_LANES ? 2 : 3;
+    return h->B <= 2 * h->sms * GLG_ROLE_LANES ? 2 : 3;
 }
 
 static int step_common(glg_handle *h, const float *actions_dev, const double *controls_dev, const double *noise_dev,

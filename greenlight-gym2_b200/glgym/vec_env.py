@@ -114,8 +114,16 @@ class SplitObs:
         return out
 
 
-class GreenLightVecEnv:
-    """B TomatoEnv instances advanced in lock-step on one GPU.  See the module docstring."""
+try:  # pragma: no cover - stable-baselines3 is pinned by the reference (requirements.txt:49) but absent from this image
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase  # a real subclass where SB3 exists (isinstance checks)
+except Exception:
+    _VecEnvBase = object
+
+
+class GreenLightVecEnv(_VecEnvBase):
+    """B TomatoEnv instances advanced in lock-step on one GPU.  See the module docstring.  Subclasses SB3's `VecEnv` when
+    stable-baselines3 is importable (every abstract method of SB3 2.6.0's VecEnv is implemented below: reset, step_async,
+    step_wait, close, get_attr, set_attr, env_method, env_is_wrapped; plus seed / step / get_images-free render_mode)."""
 
     metadata = {"render_modes": []}
 
@@ -179,6 +187,8 @@ class GreenLightVecEnv:
         self.constraints_high = np.array([con["co2_max"], con["temp_max"], con["rh_max"]])
         self.render_mode = None
         self.reset_infos = [{} for _ in range(self.num_envs)]
+        self._seeds = [None for _ in range(self.num_envs)]      # attributes SB3's VecEnv.__init__ would set
+        self._options = [{} for _ in range(self.num_envs)]
         self.info_mode = info_mode or ("full" if self.num_envs <= 256 else "minimal")
 
         # --- parameters (parameters.py) : float32 table widened to float64, as pybind does for evalF
@@ -494,8 +504,16 @@ class GreenLightVecEnv:
         self._seed = int(seed)
         _lib.check(self._lib.glg_set_seed(self._h, C.c_uint64(self._seed & (2**64 - 1))), self._h, "glg_set_seed")
 
+    def set_options(self, options=None):  # SB3 VecEnv API; TomatoEnv.reset takes no options
+        self._options = [{} for _ in range(self.num_envs)]
+
     def seed(self, seed=None):
-        return [None if seed is None else seed + i for i in range(self.num_envs)]
+        """SB3 VecEnv.seed: env i is seeded with seed + i.  Here one key re-keys the handle's Philox streams and the per-env offset
+        is the global env id those streams are keyed by anyway."""
+        if seed is not None:
+            self.reseed(int(seed))
+        self._seeds = [None if seed is None else seed + i for i in range(self.num_envs)]
+        return list(self._seeds)
 
     def get_obs_names(self):
         return obs_names(self.Np, self.observation_modules)
