@@ -1,0 +1,11 @@
+#!/bin/bash
+# One gpurun call that re-validates a frozen build: GPU tests, smoke, both bench arms, ncu evidence, compute-sanitizer.
+cd "$(dirname "$0")/.."
+O=gpurun_out
+python -m pytest tests -m gpu -q --tb=short 2>&1 | cut -c1-300 | tail -6
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py > $O/bench_final.json 2> $O/bench_final.err; echo "bench rc=$?"
+python bench.py --impl reference > $O/bench_final_ref.json 2>> $O/bench_final.err; echo "ref rc=$?"
+bash tools/ncu_r2.sh > $O/ncu_r2.log 2>&1; tail -2 $O/ncu_r2.log
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $O/r2_sanitizer_memcheck.log 2>&1; tail -3 $O/r2_sanitizer_memcheck.log
+timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_run.py > $O/r2_sanitizer_racecheck.log 2>&1; tail -3 $O/r2_sanitizer_racecheck.log
