@@ -11,6 +11,7 @@
 
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #undef GLG_NX
@@ -37,7 +38,7 @@ struct glg_handle {
     unsigned int *step_ctr = nullptr;
     float *obs = nullptr, *term_obs = nullptr, *actions = nullptr, *obs_head = nullptr;
     double *reward = nullptr, *info = nullptr, *stats = nullptr;
-    unsigned char *done = nullptr;
+    unsigned char *done = nullptr, *res_block = nullptr;
     double *weather = nullptr, *start_day = nullptr;
     int *reset_tables = nullptr;
     int n_tables = 0, rows = 0, n_reset_tables = 0;
@@ -45,7 +46,16 @@ struct glg_handle {
     float *h_actions = nullptr, *h_obs = nullptr;
     double *h_reward = nullptr;
     unsigned char *h_done = nullptr;
+    // host side of glg_step_host's overlapped observation path (see there)
+    std::vector<float> fc_bank;  // [n_tables][rows][5] float32: the weather columns a forecast block shows, as the kernels cast them
+    float *h_head = nullptr;     // pinned [B][obs_dim - 5 Np]: staging of the packed columns for a pageable destination
+    unsigned char *h_res = nullptr;  // pinned [2 buffers][17 B]: reward | timestep | table | done of every env after a glg_step_host
+    int kt_cur = 0;              // buffer the last glg_step_host filled
+    bool kt_valid = false;       // h_res[kt_cur] holds this handle's last host step (a prediction source, verified after every step)
+    std::vector<int> fc_pred;    // [2][B]: (table, first weather row) the forecast blocks in the caller's buffer were filled from
+    int host_obs_mode = 0;       // glg_set_host_obs_mode
     cudaStream_t own_stream = nullptr;
+    cudaEvent_t order_event = nullptr;  // glg_host_path_after
     long long launches = 0;
     double ctrl[GLG_NCTRL];  // rule-based controller settings (defaults: configs/agents/rule_based.yml)
     int obs_nmod = 0, obs_mod[GLG_MAXOBSMOD] = {}, obs_off[GLG_MAXOBSMOD] = {}, fc_off = -1;
@@ -106,6 +116,7 @@ extern "C" void glg_default_config(glg_config *c) {
 
 extern "C" const char *glg_last_error(const glg_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+static size_t res_block_bytes(size_t B) { return 17 * B; }  // double reward[B] | int32 timestep[B] | int32 table[B] | uint8 done[B]
 template <typename T>
 static cudaError_t dev_alloc(T **p, size_t n) {
     cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
@@ -157,14 +168,17 @@ extern "C" void glg_destroy(glg_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->x); cudaFree(h->u); cudaFree(h->time); cudaFree(h->ep_return); cudaFree(h->ep_info);
-    cudaFree(h->timestep); cudaFree(h->table); cudaFree(h->ep_len); cudaFree(h->step_ctr);
+    cudaFree(h->res_block); cudaFree(h->ep_len); cudaFree(h->step_ctr);
     cudaFree(h->obs_head);
-    cudaFree(h->obs); cudaFree(h->term_obs); cudaFree(h->actions); cudaFree(h->reward); cudaFree(h->info);
-    cudaFree(h->stats); cudaFree(h->done); cudaFree(h->weather); cudaFree(h->start_day); cudaFree(h->reset_tables);
+    cudaFree(h->obs); cudaFree(h->term_obs); cudaFree(h->actions); cudaFree(h->info);
+    cudaFree(h->stats); cudaFree(h->weather); cudaFree(h->start_day); cudaFree(h->reset_tables);
     if (h->h_actions) cudaFreeHost(h->h_actions);
     if (h->h_obs) cudaFreeHost(h->h_obs);
     if (h->h_reward) cudaFreeHost(h->h_reward);
     if (h->h_done) cudaFreeHost(h->h_done);
+    if (h->h_head) cudaFreeHost(h->h_head);
+    if (h->h_res) cudaFreeHost(h->h_res);
+    if (h->order_event) cudaEventDestroy(h->order_event);
     cudaFree(h->roll_obs); cudaFree(h->roll_rew); cudaFree(h->roll_starts); cudaFree(h->roll_adv); cudaFree(h->roll_ret);
     cudaFree(h->roll_stat); cudaFree(h->roll_partial); cudaFree(h->roll_norm); cudaFree(h->roll_acc);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -247,18 +261,22 @@ extern "C" int glg_create(const glg_config *cfg, glg_handle **out) {
     if (e == cudaSuccess) e = dev_alloc(&h->time, 2 * B);
     if (e == cudaSuccess) e = dev_alloc(&h->ep_return, B);
     if (e == cudaSuccess) e = dev_alloc(&h->ep_info, GLG_NINFO * B);
-    if (e == cudaSuccess) e = dev_alloc(&h->timestep, B);
-    if (e == cudaSuccess) e = dev_alloc(&h->table, B);
+    // reward | timestep | table | done share one allocation: glg_step_host fetches them with one device->host copy
+    if (e == cudaSuccess) e = dev_alloc(&h->res_block, res_block_bytes(B));
+    if (e == cudaSuccess) {
+        h->reward = reinterpret_cast<double *>(h->res_block);
+        h->timestep = reinterpret_cast<int *>(h->res_block + 8 * B);
+        h->table = h->timestep + B;
+        h->done = h->res_block + 16 * B;
+    }
     if (e == cudaSuccess) e = dev_alloc(&h->ep_len, B);
     if (e == cudaSuccess) e = dev_alloc(&h->step_ctr, B);
     if (e == cudaSuccess) e = dev_alloc(&h->obs, (size_t)h->obs_dim * B);
     if (e == cudaSuccess) e = dev_alloc(&h->term_obs, (size_t)h->obs_dim * B);
     if (e == cudaSuccess) e = dev_alloc(&h->obs_head, (size_t)(h->obs_dim - (h->fc_off >= 0 ? 5 * cfg->Np : 0)) * B);
     if (e == cudaSuccess) e = dev_alloc(&h->actions, GLG_NU * B);
-    if (e == cudaSuccess) e = dev_alloc(&h->reward, B);
     if (e == cudaSuccess) e = dev_alloc(&h->info, GLG_NINFO * B);
     if (e == cudaSuccess) e = dev_alloc(&h->stats, (size_t)GLG_NSTATS);
-    if (e == cudaSuccess) e = dev_alloc(&h->done, B);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         g_create_error = std::string("glg_create: ") + cudaGetErrorString(e);
@@ -309,6 +327,11 @@ extern "C" int glg_set_weather(glg_handle *h, const double *tables_host, int32_t
     h->rows = rows;
     h->n_reset_tables = n_tables;
     h->have_weather = true;
+    // host copy of what glg_write_forecast shows of the bank (columns 0..4, double -> float), for glg_step_host
+    h->fc_bank.resize((size_t)n_tables * rows * 5);
+    for (size_t r = 0; r < (size_t)n_tables * rows; ++r)
+        for (int c = 0; c < 5; ++c) h->fc_bank[r * 5 + c] = (float)tables_host[r * GLG_ND + c];
+    h->kt_valid = false;
     return GLG_OK;
 }
 
@@ -379,6 +402,7 @@ extern "C" int glg_reset(glg_handle *h, const uint8_t *mask_dev, const int32_t *
     h->launches += 1;
     GLG_CUDA(h, cudaGetLastError());
     h->is_reset = true;
+    h->kt_valid = false;
     return GLG_OK;
 }
 
@@ -451,6 +475,7 @@ static int step_common(glg_handle *h, const float *actions_dev, const double *co
     if (rc) return rc;
     if (!h->is_reset) return fail(h, GLG_ERR_STATE, "step before reset");
     GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    h->kt_valid = false;
     GlgStepArgs a;
     fill_args(h, &a);
     a.actions = actions_dev;
@@ -531,12 +556,138 @@ extern "C" int glg_rule_control_batch(const double *settings29, const double *x_
 }
 
 static bool is_pinned(const void *p) {
+    // small per-thread cache: the callers pass the same few buffers every step, and a stale answer is harmless (a pageable
+    // buffer taken for page-locked makes cudaMemcpyAsync stage it itself; the reverse costs one staging copy)
+    static thread_local struct { const void *p; bool pinned; } cache[8] = {};
+    static thread_local int next = 0;
+    for (auto &c : cache)
+        if (c.p == p) return c.pinned;
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) cudaGetLastError();
+    else pinned = at.type == cudaMemoryTypeHost;
+    cache[next] = {p, pinned};
+    next = (next + 1) % 8;
+    return pinned;
+}
+
+// Rows [lo, hi) of a per-env host loop on up to `max_threads` threads; small batches run inline (a thread costs ~20 us to start).
+template <class F>
+static void host_rows(size_t n_rows, size_t bytes_per_row, const F &f) {
+    const size_t total = n_rows * bytes_per_row;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = total / ((size_t)6 << 20);  // one thread per 6 MB moved
+    const size_t cap = hw >= 4 ? (hw / 2 < 8 ? hw / 2 : 8) : 1;
+    nt = nt > cap ? cap : nt;
+    if (nt <= 1) {
+        f((size_t)0, n_rows);
+        return;
     }
-    return at.type == cudaMemoryTypeHost;
+    std::vector<std::thread> th;
+    const size_t chunk = (n_rows + nt - 1) / nt;
+    for (size_t t = 1; t < nt; ++t) {
+        const size_t lo = t * chunk, hi = lo + chunk < n_rows ? lo + chunk : n_rows;
+        if (lo < hi) th.emplace_back([&f, lo, hi] { f(lo, hi); });
+    }
+    f((size_t)0, chunk < n_rows ? chunk : n_rows);
+    for (auto &t : th) t.join();
+}
+
+extern "C" int glg_host_path_after(glg_handle *h, void *stream) {
+    if (!h) return GLG_ERR_ARG;
+    GLG_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (!h->order_event) GLG_CUDA(h, cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming));
+    GLG_CUDA(h, cudaEventRecord(h->order_event, (cudaStream_t)stream));
+    GLG_CUDA(h, cudaStreamWaitEvent(h->own_stream, h->order_event, 0));
+    return GLG_OK;
+}
+
+extern "C" int glg_set_host_obs_mode(glg_handle *h, int32_t mode) {
+    if (!h || (mode != 0 && mode != 1)) return GLG_ERR_ARG;
+    h->host_obs_mode = mode;
+    return GLG_OK;
+}
+
+// Overlapped observation path (host_obs_mode 0, the default, for stacks with a WeatherForecastObservations block): 5 Np of the
+// row's floats (240 of 263 in the default stack) are weather rows kw+1 .. kw+Np of the env's table, kw = min(timestep before the
+// step, rows - Np - 1) -- known before the kernel runs.  So only the rest of the row (glg_write_obs_row's packed copy, obs_head)
+// crosses PCIe, and WHILE THE KERNEL RUNS the host writes the forecast blocks into the caller's buffer from its float32 copy of
+// the bank, predicted from the (timestep, table) of the previous host step.  After the synchronise the packed columns are
+// scattered into the rows and every prediction is checked against the (timestep, table) the step left behind: rows that reset
+// in place (auto-reset draws a new table on the device), and all rows when something other than glg_step_host moved the envs in
+// between (reset, tensor steps, set_state), are filled again from the verified values.  The result is the same [B][obs_dim]
+// array the full device->host copy (mode 1) delivers, bit for bit (tests/test_gpu_features.py).
+static int step_host_overlapped(glg_handle *h, const float *a_src, float *obs_host, double *reward_host, uint8_t *done_host, bool o_pin) {
+    const size_t B = (size_t)h->B;
+    const int Np = h->cfg.Np, nf = 5 * Np, D = h->obs_dim, n_head = D - nf, fc = h->fc_off, rows = h->rows;
+    if (!h->h_res) {
+        GLG_CUDA(h, cudaMallocHost((void **)&h->h_res, 2 * res_block_bytes(B)));
+        h->fc_pred.assign(2 * B, -1);
+        h->kt_valid = false;
+    }
+    if (!o_pin && !h->h_head) GLG_CUDA(h, cudaMallocHost((void **)&h->h_head, (size_t)n_head * B * sizeof(float)));
+    cudaStream_t s = h->own_stream;
+    // result block of the previous host step (prediction source) / of this one
+    const unsigned char *res_cur = h->h_res + (size_t)h->kt_cur * res_block_bytes(B);
+    unsigned char *res_nxt = h->h_res + (size_t)(h->kt_cur ^ 1) * res_block_bytes(B);
+    const int *cur = reinterpret_cast<const int *>(res_cur + 8 * B);
+    const int *nxt = reinterpret_cast<const int *>(res_nxt + 8 * B);
+    const bool valid = h->kt_valid;  // every entry that moves the envs clears it (step_common included: set again below)
+    GLG_CUDA(h, cudaMemcpyAsync(h->actions, a_src, GLG_NU * B * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = step_common(h, h->actions, nullptr, nullptr, s);
+    if (rc) return rc;
+    if (o_pin) {
+        // page-locked destination: the copy engine puts the packed columns straight into the rows (strided 2-D copy)
+        if (fc > 0)
+            GLG_CUDA(h, cudaMemcpy2DAsync(obs_host, (size_t)D * sizeof(float), h->obs_head, (size_t)n_head * sizeof(float), (size_t)fc * sizeof(float), B,
+                                          cudaMemcpyDeviceToHost, s));
+        if (n_head > fc)
+            GLG_CUDA(h, cudaMemcpy2DAsync(obs_host + fc + nf, (size_t)D * sizeof(float), h->obs_head + fc, (size_t)n_head * sizeof(float),
+                                          (size_t)(n_head - fc) * sizeof(float), B, cudaMemcpyDeviceToHost, s));
+    } else {
+        GLG_CUDA(h, cudaMemcpyAsync(h->h_head, h->obs_head, (size_t)n_head * B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    GLG_CUDA(h, cudaMemcpyAsync(res_nxt, h->res_block, res_block_bytes(B), cudaMemcpyDeviceToHost, s));  // reward | timestep | table | done
+    // ---- while the GPU works: forecast blocks from the predicted (table, row)
+    const float *bank = h->fc_bank.data();
+    int *pred_t = h->fc_pred.data(), *pred_r = pred_t + B;
+    const int n_tables = h->n_tables, kmax = rows - Np - 1;
+    host_rows(B, (size_t)nf * sizeof(float), [=](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const int k = valid ? cur[i] : -1, t = valid ? cur[B + i] : -1;
+            if (k < 0 || t < 0 || t >= n_tables) {
+                pred_t[i] = -1;
+                continue;
+            }
+            const int r0 = (k < kmax ? k : kmax) + 1;
+            memcpy(obs_host + i * D + fc, bank + ((size_t)t * rows + r0) * 5, (size_t)nf * sizeof(float));
+            pred_t[i] = t;
+            pred_r[i] = r0;
+        }
+    });
+    GLG_CUDA(h, cudaStreamSynchronize(s));
+    // ---- verify every prediction against what the step left behind (and, for a pageable destination, scatter the packed columns)
+    const float *head = h->h_head;
+    host_rows(B, o_pin ? 16 : (size_t)D * sizeof(float) / 4, [=](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            float *row = obs_host + i * D;
+            if (!o_pin) {
+                const float *hd = head + i * n_head;
+                if (fc > 0) memcpy(row, hd, (size_t)fc * sizeof(float));
+                if (n_head > fc) memcpy(row + fc + nf, hd + fc, (size_t)(n_head - fc) * sizeof(float));
+            }
+            // timestep after the step: 0 = reset in place (row 1 of the new table), else the pre-step timestep + 1
+            const int kp = nxt[i], t = nxt[B + i];
+            const int r0 = kp <= 0 ? 1 : ((kp - 1 < kmax ? kp - 1 : kmax) + 1);
+            if (t != pred_t[i] || r0 != pred_r[i])
+                memcpy(row + fc, bank + ((size_t)t * rows + r0) * 5, (size_t)nf * sizeof(float));
+        }
+    });
+    if (reward_host) memcpy(reward_host, res_nxt, B * sizeof(double));
+    if (done_host) memcpy(done_host, res_nxt + 16 * B, B);
+    h->kt_cur ^= 1;
+    h->kt_valid = true;
+    return GLG_OK;
 }
 
 extern "C" int glg_step_host(glg_handle *h, const float *actions_host, float *obs_host, double *reward_host,
@@ -546,7 +697,6 @@ extern "C" int glg_step_host(glg_handle *h, const float *actions_host, float *ob
     const size_t B = (size_t)h->B;
     if (!h->h_actions) {
         GLG_CUDA(h, cudaMallocHost((void **)&h->h_actions, GLG_NU * B * sizeof(float)));
-        GLG_CUDA(h, cudaMallocHost((void **)&h->h_obs, (size_t)h->obs_dim * B * sizeof(float)));
         GLG_CUDA(h, cudaMallocHost((void **)&h->h_reward, B * sizeof(double)));
         GLG_CUDA(h, cudaMallocHost((void **)&h->h_done, B));
     }
@@ -560,15 +710,21 @@ extern "C" int glg_step_host(glg_handle *h, const float *actions_host, float *ob
         memcpy(h->h_actions, actions_host, GLG_NU * B * sizeof(float));
         a_src = h->h_actions;
     }
-    GLG_CUDA(h, cudaMemcpyAsync(h->actions, a_src, GLG_NU * B * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = step_common(h, h->actions, nullptr, nullptr, s);
-    if (rc) return rc;
-    if (obs_host)
-        GLG_CUDA(h, cudaMemcpyAsync(o_pin ? obs_host : h->h_obs, h->obs, (size_t)h->obs_dim * B * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (reward_host) GLG_CUDA(h, cudaMemcpyAsync(r_pin ? reward_host : h->h_reward, h->reward, B * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (done_host) GLG_CUDA(h, cudaMemcpyAsync(d_pin ? done_host : h->h_done, h->done, B, cudaMemcpyDeviceToHost, s));
-    GLG_CUDA(h, cudaStreamSynchronize(s));
-    if (obs_host && !o_pin) memcpy(obs_host, h->h_obs, (size_t)h->obs_dim * B * sizeof(float));
+    if (obs_host && h->host_obs_mode == 0 && h->fc_off >= 0 && !h->fc_bank.empty()) {
+        return step_host_overlapped(h, a_src, obs_host, reward_host, done_host, o_pin);
+    } else {
+        h->kt_valid = false;
+        if (obs_host && !o_pin && !h->h_obs) GLG_CUDA(h, cudaMallocHost((void **)&h->h_obs, (size_t)h->obs_dim * B * sizeof(float)));
+        GLG_CUDA(h, cudaMemcpyAsync(h->actions, a_src, GLG_NU * B * sizeof(float), cudaMemcpyHostToDevice, s));
+        int rc = step_common(h, h->actions, nullptr, nullptr, s);
+        if (rc) return rc;
+        if (obs_host)
+            GLG_CUDA(h, cudaMemcpyAsync(o_pin ? obs_host : h->h_obs, h->obs, (size_t)h->obs_dim * B * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (reward_host) GLG_CUDA(h, cudaMemcpyAsync(r_pin ? reward_host : h->h_reward, h->reward, B * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (done_host) GLG_CUDA(h, cudaMemcpyAsync(d_pin ? done_host : h->h_done, h->done, B, cudaMemcpyDeviceToHost, s));
+        GLG_CUDA(h, cudaStreamSynchronize(s));
+        if (obs_host && !o_pin) memcpy(obs_host, h->h_obs, (size_t)h->obs_dim * B * sizeof(float));
+    }
     if (reward_host && !r_pin) memcpy(reward_host, h->h_reward, B * sizeof(double));
     if (done_host && !d_pin) memcpy(done_host, h->h_done, B);
     return GLG_OK;
@@ -629,6 +785,7 @@ static void to_aos(const double *soa, double *aos, int B, int n) {
 
 extern "C" int glg_set_state(glg_handle *h, const double *x_host, const double *u_host, const int32_t *timestep_host) {
     if (!h) return GLG_ERR_ARG;
+    h->kt_valid = false;
     GLG_CUDA(h, cudaSetDevice(h->cfg.device));
     GLG_CUDA(h, cudaDeviceSynchronize());
     const int B = h->B;
@@ -711,6 +868,7 @@ static int state_ex(glg_handle *h, const glg_env_state *s, bool to_dev) {
     GLG_CUDA(h, cudaSetDevice(h->cfg.device));
     GLG_CUDA(h, cudaDeviceSynchronize());
     const int B = h->B;
+    if (to_dev) h->kt_valid = false;
     if (to_dev) {
         if (s->table) {
             if (!h->have_weather) return fail(h, GLG_ERR_STATE, "glg_set_state_ex: set the weather bank first");

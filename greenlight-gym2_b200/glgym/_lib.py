@@ -62,6 +62,8 @@ SIGNATURES = {
     "glg_rule_control_batch": (C.c_int, [_DP, _DP, _DP, _DP, _DP, _DP, C.c_int32, C.c_int32, _VP]),
     "glg_step_host": (C.c_int, [C.c_void_p, _FP, _FP, _DP, _U8P]),
     "glg_step_host_split": (C.c_int, [C.c_void_p, _FP, _FP, _IP, _IP, _DP, _U8P]),
+    "glg_set_host_obs_mode": (C.c_int, [C.c_void_p, C.c_int32]),
+    "glg_host_path_after": (C.c_int, [C.c_void_p, _VP]),
     "glg_obs_dim": (C.c_int32, [C.c_void_p]),
     "glg_obs_dev": (C.c_void_p, [C.c_void_p]),
     "glg_terminal_obs_dev": (C.c_void_p, [C.c_void_p]),

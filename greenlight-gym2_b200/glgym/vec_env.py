@@ -52,6 +52,14 @@ INFO_KEYS = ("EPI", "revenue", "variable_costs", "fixed_costs", "co2_cost", "hea
              "temp_violation", "co2_violation", "rh_violation", "lamp_violation")
 
 
+def _raw_stream(device_index):
+    """cudaStream_t of torch's current stream on the device (the cheap accessor where this torch has it)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(device_index)
+    except AttributeError:
+        return torch.cuda.current_stream(device_index).cuda_stream
+
+
 class _DevArray:
     """Zero-copy view of handle-owned device memory through __cuda_array_interface__."""
 
@@ -131,7 +139,7 @@ class GreenLightVecEnv(_VecEnvBase):
                  eval_options=None, reward_params=None, base_env_params=None, uncertainty_scale=0.0,
                  n_sub=None, device=0, seed=0, auto_reset=True, env_id_offset=0, weather_tables=None,
                  table_start_days=None, params=None, info_mode=None, role_warps=0, role_lanes=0, precision="fp64",
-                 reuse_output_buffers=False, integrator=None, obs_ring=4):
+                 reuse_output_buffers=False, integrator=None, obs_ring=4, host_obs="overlap"):
         if reward_function != "GreenhouseReward":
             raise ValueError("only GreenhouseReward exists in the reference (tomato_env.py:14)")
         mods = list(observation_modules or DEFAULT_OBSERVATION_MODULES)
@@ -285,6 +293,13 @@ class GreenLightVecEnv(_VecEnvBase):
         self.obs_ring = 2 if self.reuse_output_buffers else int(obs_ring)
         if self.obs_ring == 1 or self.obs_ring < 0:
             raise ValueError("obs_ring must be 0 (copy every step) or >= 2")
+        # host_obs: how step() (numpy path) gets the observation rows into host memory (glg_set_host_obs_mode): "overlap" (default)
+        # = the forecast block of every row is written by the host from its own copy of the weather bank while the kernel runs
+        # and only the other columns cross PCIe; "copy" = one device->host copy of the whole array.  Same array either way.
+        if host_obs not in ("overlap", "copy"):
+            raise ValueError("host_obs must be 'overlap' or 'copy'")
+        self.host_obs = host_obs
+        _lib.check(self._lib.glg_set_host_obs_mode(self._h, 0 if host_obs == "overlap" else 1), self._h, "glg_set_host_obs_mode")
         self._split = None
         self._ring = self._ring_np = None  # page-locked, allocated by the first numpy step (the tensor path never needs them)
         self._ring_pos = 0
@@ -359,8 +374,8 @@ class GreenLightVecEnv(_VecEnvBase):
         obs_buf = self._ring_np[self._ring_pos]
         self._ring_pos = (self._ring_pos + 1) % n
         # glg_step_host works on the handle's own stream: order it behind whatever the caller enqueued on torch's current
-        # stream (reset_tensor / step_tensor / episode_stats(clear=True) followed by step())
-        torch.cuda.current_stream(self.device).synchronize()
+        # stream (reset_tensor / step_tensor / episode_stats(clear=True) followed by step()) -- an event wait, no host sync
+        self._lib.glg_host_path_after(self._h, _raw_stream(self.device_index))
         _lib.check(self._lib.glg_step_host(self._h, self._actions.ctypes.data, obs_buf.ctypes.data,
                                            self._rew_host.ctypes.data, self._done_host.ctypes.data), self._h, "glg_step_host")
         dones = self._done_host.astype(bool)
@@ -393,7 +408,7 @@ class GreenLightVecEnv(_VecEnvBase):
         i = sp["pos"]
         sp["pos"] = (i + 1) % len(sp["head"])
         np.copyto(self._act_host, np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.nu))
-        torch.cuda.current_stream(self.device).synchronize()
+        self._lib.glg_host_path_after(self._h, _raw_stream(self.device_index))
         head, k, tb = sp["head"][i].numpy(), sp["k"][i].numpy(), sp["tb"][i].numpy()
         _lib.check(self._lib.glg_step_host_split(self._h, self._act_host.ctypes.data, head.ctypes.data, k.ctypes.data, tb.ctypes.data,
                                                  self._rew_host.ctypes.data, self._done_host.ctypes.data), self._h, "glg_step_host_split")

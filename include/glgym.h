@@ -128,10 +128,24 @@ int glg_step_rule_based(glg_handle *h, const double *noise_dev, void *stream);
 int glg_rule_control_batch(const double *settings29, const double *x_dev, const double *d_dev, const double *hod_dev,
                            const double *doy_dev, double *u_dev, int32_t n, int32_t device, void *stream);
 
-/* End-to-end convenience for host callers (the SB3 VecEnv numpy path): copies actions host->device, runs
- * glg_step on the handle's own stream, copies obs/reward/done device->host and synchronises.  Any output may be
- * NULL.  obs_host float32 [B][obs_dim], reward_host double [B], done_host uint8 [B]. */
+/* End-to-end convenience for host callers (the SB3 VecEnv numpy path; replaces SubprocVecEnv.step_async / step_wait over
+ * TomatoEnv.step, RL/utils.py:44-58): copies actions host->device, runs glg_step on the handle's own stream, delivers
+ * obs/reward/done in host memory and synchronises.  Any output may be NULL.  obs_host float32 [B][obs_dim], reward_host
+ * double [B], done_host uint8 [B].
+ * How the observation rows reach obs_host is set by glg_set_host_obs_mode:
+ *   0 (default) overlapped: the WeatherForecastObservations block (observations.py:163-182; 5 Np of the row's floats) is a
+ *     function of (weather table, timestep) that is known before the kernel runs, so the host writes it into obs_host from its
+ *     own float32 copy of the bank WHILE the kernel runs, only the other columns cross PCIe (0.45 MB instead of 4.35 MB per
+ *     step at B = 4096), and after the synchronise every row is checked against the (table, timestep) the step left behind
+ *     (rows that reset in place are filled again).  Same bytes in obs_host as mode 1.
+ *   1 full: one device->host copy of the [B][obs_dim] array.
+ * Stacks without a forecast block always use the full copy. */
 int glg_step_host(glg_handle *h, const float *actions_host, float *obs_host, double *reward_host, uint8_t *done_host);
+int glg_set_host_obs_mode(glg_handle *h, int32_t mode);
+/* glg_step_host / glg_step_host_split work on the handle's own stream.  A caller that has enqueued work touching the handle on
+ * another stream (glg_reset / glg_step with a stream argument, writes to the device views) orders the next host step behind it
+ * with this call: an event recorded on `stream` that the handle's stream waits for -- no host synchronisation. */
+int glg_host_path_after(glg_handle *h, void *stream);
 
 /* Same step with the observation returned in SPLIT form (opt-in, for host loops that do not want 240 of 263 floats per env
  * that are a pure function of (weather table, timestep)): head_host float32 [B][obs_dim - 5 Np] receives every column of the

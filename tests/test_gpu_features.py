@@ -351,3 +351,53 @@ def test_split_observation_host_path(mods, weather0):
             assert all(np.array_equal(ia[i]["terminal_observation"], ib[i]["terminal_observation"]) for i in np.nonzero(da)[0])
     assert da.sum() == 0 and s == 8
     ea.close(); eb.close()
+
+
+@pytest.mark.parametrize("mods", [None, ["WeatherObservations", "WeatherForecastObservations", "IndoorClimateObservations", "TimeObservations"]])
+@pytest.mark.parametrize("B", [37, 20000])
+def test_overlapped_host_observation_path(mods, B, weather0):
+    """glg_step_host, default mode: the forecast block of every row is written by the host from its copy of the weather bank while
+    the kernel runs (predicted from the previous step's timestep / table), the other columns cross PCIe, and the prediction is
+    verified after the step.  The array equals the full device->host copy (host_obs="copy") and the device's own obs_t bit for
+    bit -- through episode ends with in-place resets into other weather tables, after reset(), tensor steps and set_state in
+    between (which invalidate the prediction), with the forecast block last or in the middle of the row, with page-locked and
+    pageable caller buffers, single- and multi-threaded host loops (B = 20 000 moves 19 MB per step)."""
+    tabs = np.stack([weather0, weather0[::-1].copy(), weather0 * 0.5])
+    kw = dict(n_sub=300, observation_modules=mods, base_env_params=dict(season_length=5 / 96.0), weather_tables=tabs,
+              table_start_days=np.array([0.0, 4.0, 9.0]), seed=11)
+    ea, eb = make_env(B, host_obs="overlap", **kw), make_env(B, host_obs="copy", **kw)
+    assert ea.host_obs == "overlap"
+    ea.reset(); eb.reset()
+    rng = np.random.default_rng(5)
+    n_done = 0
+    for s in range(14):
+        a = rng.uniform(-1, 1, (B, 6)).astype(np.float32)
+        if s == 8:  # something other than step() moves the envs: the host's prediction is stale / invalid
+            at = torch.as_tensor(a, device="cuda")
+            ea.step_tensor(at); eb.step_tensor(at)
+            continue
+        if s == 10:
+            k = np.full(B, 2, dtype=np.int32); k[::3] = 4
+            ea.set_state(timestep=k); eb.set_state(timestep=k)
+        if s == 12:
+            ea.reset(); eb.reset()
+        oa, ra, da, ia = ea.step(a)
+        ob_, rb, db, ib = eb.step(a)
+        assert np.array_equal(oa, ob_), (s, np.argwhere(oa != ob_)[:4])
+        assert np.array_equal(oa, ea.obs_t.cpu().numpy()), s
+        assert np.array_equal(ra, rb) and np.array_equal(da, db)
+        n_done += int(da.sum())
+        if da.any():
+            assert len(set(ea.table_t.cpu().numpy().tolist())) > 1  # the resets drew different weather tables
+            i = int(np.nonzero(da)[0][0])
+            assert np.array_equal(ia[i]["terminal_observation"], ib[i]["terminal_observation"])
+    assert n_done >= B
+    # the C entry with pageable caller buffers
+    L = ea._lib
+    obs = np.empty((B, ea.obs_dim), dtype=np.float32); rew = np.empty(B); done = np.empty(B, dtype=np.uint8)
+    a = rng.uniform(-1, 1, (B, 6)).astype(np.float32)
+    assert L.glg_step_host(ea._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data) == 0
+    ob_, rb, db, _ = eb.step(a)
+    assert np.array_equal(obs, ob_) and np.array_equal(rew.astype(np.float32), rb) and np.array_equal(done.astype(bool), db)
+    assert L.glg_set_host_obs_mode(ea._h, 7) != 0
+    ea.close(); eb.close()
