@@ -4,7 +4,7 @@
 Headline workload (config.workload): BASELINE.json configs[1] -- "TomatoEnv 4096 batched envs fp64 parity mode, nominal
 parameters, fixed weather year": 4096 envs PER GPU (weak scaling: every rank owns its own 4096-env shard, no collective on
 the step path), Bleiswijk GL2009 weather table (start day 0), the package's default integrator contract (graded RK4 with
-zero-order hold, n_sub = 300 nominal substeps, 349 RK4 steps per 900 s control interval; DESIGN.md "Integrator contract"),
+zero-order hold, n_sub = 260 nominal substeps, 300 RK4 steps per 900 s control interval; DESIGN.md "Integrator contract"),
 U(-1,1) float32 actions through the rate-limited action->control map, observations (263 f32), reward, info, termination and
 auto-reset all inside the one fused kernel launch per step.
 
@@ -176,10 +176,10 @@ def cpu_arm(kind, integrator, n_sub, seconds, cores):
 
 def workload_config(args):
     """The `config` both arms report."""
-    nominal = 300 if args.integrator == "graded" else 600
+    nominal = 260 if args.integrator == "graded" else 600
     n_sub = args.n_sub or nominal
-    integ = (f"graded RK4, zero-order hold: {n_sub} nominal substeps, the first 15 split 16/8/8/4x4/2x8, transient-stiffness rule "
-             f"(349 RK4 steps per interval at n_sub 300)" if args.integrator == "graded" else f"RK4, {n_sub} equal substeps, zero-order hold")
+    integ = (f"graded RK4, zero-order hold: {n_sub} nominal substeps, the first 12 split 16/8/4x4/2x6, transient-stiffness rule "
+             f"(300 RK4 steps per interval at n_sub 260)" if args.integrator == "graded" else f"RK4, {n_sub} equal substeps, zero-order hold")
     return {"workload": f"TomatoEnv {args.envs} batched envs per GPU, fp64 parity mode, nominal parameters, fixed weather year "
                         "(BASELINE configs[1])",
             "envs_per_gpu": args.envs, "n_sub": n_sub, "dt": 900, "integrator": integ, "obs_dim": 263,
@@ -199,7 +199,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sub = args.n_sub or (300 if args.integrator == "graded" else 600)
+    n_sub = args.n_sub or (260 if args.integrator == "graded" else 600)
     kind = "port-implicit"
     probe, _, _ = cpu_rate(kind, args.integrator, n_sub, 16 * cores, 3, cores, warmup=1)
     sample = max(4 * cores, int(np.ceil(15.0 * probe / max(args.steps, 1) / cores)) * cores)  # envs per step: >= 10 s in total
@@ -389,7 +389,7 @@ def run_ours(args, rank, world, local):
     other = "fixed" if args.integrator == "graded" else "graded"
     configs[f"config2_{other}"] = extra_config(
         f"config2_{other}", f"BASELINE configs[1] with integrator='{other}' (" + ("RK4, 600 equal substeps: round 1's headline contract)" if other == "fixed"
-                                                                                   else "graded RK4, n_sub 300)"),
+                                                                                   else "graded RK4, n_sub 260)"),
         dict(integrator=other, precision="fp64"), B, K, Wm, flush, barrier, dev, world, rank, local, peak64)
     configs["saturated_fp64"] = extra_config(
         "saturated_fp64", "262 144 envs per GPU, fp64 parity mode, nominal parameters, one weather table (the regime the one-CTA-per-32-envs "
@@ -479,7 +479,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--integrator", default=None, choices=["graded", "fixed"], help="default: the package's default contract")
-    ap.add_argument("--n-sub", type=int, default=None, help="nominal RK4 substeps (default 300 graded / 600 fixed)")
+    ap.add_argument("--n-sub", type=int, default=None, help="nominal RK4 substeps (default 260 graded / 600 fixed)")
     ap.add_argument("--role-warps", type=int, default=0)
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
                     help="fp64 = parity mode (the BASELINE metric); fp32 = throughput mode (flux groups in fp32, RK4 state in fp64)")

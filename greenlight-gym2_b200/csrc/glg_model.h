@@ -640,12 +640,13 @@ GLG_HD double glg_rhs(const KV &K, const CV &C, const HV &H, const P &p, const d
 // Harvest-stiffness guard (same rule as the oracle's glgo_micro_steps): number of equal micro-steps a nominal RK4 substep
 // of length h is split into, so that harvest moves an organ at most half a sigmoid window-width per micro-step.
 #define GLG_MAX_MICRO 512
-// graded integrator (integrator = 1): nominal substep s of a control interval is split in glg_graded_m(s) = 16, 8 8, 4 x4,
-// 2 x8, then 1 (the controls jump at t = 0 and the fast modes relax within seconds: that is where an equal-substep grid commits
+// graded integrator (integrator = 1): nominal substep s of a control interval is split in glg_graded_m(s) = 16, 8, 4 x4,
+// 2 x6, then 1 (the controls jump at t = 0 and the fast modes relax within seconds: that is where an equal-substep grid commits
 // its error; oracle: glgo_graded_m); any nominal substep is split in 1 + floor(h lambda_est / GLG_STIFF_CFL) (RK4's real-axis
-// limit is 2.785)
-#define GLG_GRADED_SUBSTEPS 15
-GLG_HD int glg_graded_m(int s) { return s < 1 ? 16 : s < 3 ? 8 : s < 7 ? 4 : s < GLG_GRADED_SUBSTEPS ? 2 : 1; }
+// limit is 2.785).  Meant for n_sub = 260 (h = 3.46 s: the largest nominal step the cover pair's 0.653 1/s mode leaves unsplit
+// with 3 % to spare is 3.58 s): 300 RK4 steps per interval.
+#define GLG_GRADED_SUBSTEPS 12
+GLG_HD int glg_graded_m(int s) { return s < 1 ? 16 : s < 2 ? 8 : s < 6 ? 4 : s < GLG_GRADED_SUBSTEPS ? 2 : 1; }
 #define GLG_STIFF_CFL 2.5
 #define GLG_STIFF_INV_CFL 0.4  // the rule multiplies by this constant (oracle and kernels alike)
 template <class T>

@@ -23,7 +23,7 @@ class GreenLight:
         if integrator not in ("fixed", "graded"):
             raise ValueError("integrator must be 'fixed' or 'graded'")
         self.integrator = integrator  # "graded": DESIGN.md "Graded integrator" (default n_sub 300)
-        self.n_sub = int(n_sub) if n_sub is not None else (600 if integrator == "fixed" else 300)
+        self.n_sub = int(n_sub) if n_sub is not None else (600 if integrator == "fixed" else 260)
         self.device = int(device)
         self._lib = _lib.load()
 

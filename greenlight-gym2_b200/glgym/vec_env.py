@@ -26,7 +26,7 @@ from .spaces import Box
 from .weather import DEFAULT_WEATHER_DIR, load_weather_data
 
 # Integrator contract of a freshly constructed env: "graded" = classical RK4 with zero-order hold on a grid refined at the start
-# of every control interval and wherever the transient-stiffness estimate asks for it (n_sub = 300 nominal substeps, ~315 RK4
+# of every control interval and wherever the transient-stiffness estimate asks for it (n_sub = 260 nominal substeps, 300 RK4
 # steps per interval).  Chosen on accuracy grounds (DESIGN.md "Integrator contract"): against tight-tolerance solutions of 250
 # rule-based control intervals its worst-step error sits inside the reference solver's 1e-6 band, the fixed 600-substep grid's
 # does not.  integrator="fixed" keeps the equal-substep contract (n_sub = 600).
@@ -174,12 +174,12 @@ class GreenLightVecEnv(_VecEnvBase):
         self.train_years = list(range(bp["start_train_year"], bp["end_train_year"] + 1))
         self.train_days = list(range(bp["start_train_day"], bp["end_train_day"] + 1))
         # integrator: "fixed" = n_sub equal RK4 substeps (default 600, the parity contract); "graded" = RK4 with a refined
-        # start of every control interval and a transient-stiffness rule (default n_sub 300; DESIGN.md "Graded integrator")
+        # start of every control interval and a transient-stiffness rule (default n_sub 260; DESIGN.md "Graded integrator")
         integrator = integrator or DEFAULT_INTEGRATOR
         if integrator not in ("fixed", "graded"):
             raise ValueError("integrator must be 'fixed' or 'graded'")
         self.integrator = integrator
-        self.n_sub = int(n_sub) if n_sub is not None else (600 if integrator == "fixed" else 300)
+        self.n_sub = int(n_sub) if n_sub is not None else (600 if integrator == "fixed" else 260)
         self.observation_modules = mods
         # spaces: tomato_env.py:83-98 / observations.py observation_space() of each module, concatenated in stack order
         sizes = [len(OBSERVATION_MODULES[m][1]) if OBSERVATION_MODULES[m][1] is not None else 5 * self.Np for m in mods]

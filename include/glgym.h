@@ -67,10 +67,10 @@ typedef struct glg_config {
                               * 12 flux-unit warps per 32 envs) compiled for one CTA per SM (latency: small batches) / two (throughput) */
     int32_t role_lanes;      /* 0 = auto (32), or 1..32: kernel C's envs-per-CTA (tuning / tests) */
     int32_t integrator;      /* 0 = fixed-step RK4, n_sub equal substeps (the parity contract);
-                                1 = graded RK4: the first 5 nominal substeps of every control interval are split in 4 (the
-                                    controls just changed: fast transients) and any nominal substep is split further while the
-                                    top-compartment / cover stiffness estimate asks for it (DESIGN.md "Graded integrator");
-                                    meant for n_sub = 300. */
+                                1 = graded RK4: the first 12 nominal substeps of every control interval are split in 16, 8,
+                                    4 x4, 2 x6 (the controls just changed: fast transients) and any nominal substep is split
+                                    further while the top-compartment / cover stiffness estimate asks for it (DESIGN.md
+                                    "Integrator contract"); meant for n_sub = 260: 300 RK4 steps per interval. */
     int32_t reserved2;
     /* Observation stack (tomato_env.py:77-96, configs/envs/TomatoEnv.yml:26-33): ordered list of module ids, terminated by 0;
      * an empty list (obs_modules[0] == 0) is the default stack {2,3,4,5,6,7}.  ids (observations.py:35-182):

@@ -492,11 +492,13 @@ static double glgo_stiffness(const double *p, const double *a) {
 #define GLGO_STIFF_INV_CFL 0.4 /* 1/2.5; RK4's real-axis stability limit is 2.785 */
 /* graded start of a control interval: the controls (and the weather row) jump at t = 0, the fast modes (top compartment, cover
  * pair) relax within seconds, and the error of an equal-substep grid is committed there.  Nominal substep s is split in
- *   m(s) = 16, 8, 8, 4 x4, 2 x8, then 1     (s = 0, 1..2, 3..6, 7..14, >= 15): 49 extra RK4 steps per interval.
- * Measured on 249 tight-tolerance rule-based intervals (tests/golden/truth_rule_based.npz): worst step 2.7e-8 against 4.0e-6
- * for "first 5 substeps in 4" (round 1) and 8.9e-5 for 600 equal substeps. */
-#define GLGO_GRADED_SUBSTEPS 15
-static int glgo_graded_m(int s) { return s < 1 ? 16 : s < 3 ? 8 : s < 7 ? 4 : s < GLGO_GRADED_SUBSTEPS ? 2 : 1; }
+ *   m(s) = 16, 8, 4 x4, 2 x6, then 1     (s = 0, 1, 2..5, 6..11, >= 12): 40 extra RK4 steps per interval.
+ * Meant for n_sub = 260 (h = 3.46 s; beyond h = 3.58 s the stiffness rule below splits every substep because of the cover
+ * pair's constant 0.653 1/s mode): 300 RK4 steps per interval.  Measured on 249 tight-tolerance rule-based intervals
+ * (tests/golden/truth_rule_based.npz): worst step 5.2e-8 (n_sub = 300 with 16, 8, 8, 4 x4, 2 x8: 2.7e-8 at 349 steps), against
+ * 4.0e-6 for "first 5 substeps in 4" (round 1) and 8.9e-5 for 600 equal substeps. */
+#define GLGO_GRADED_SUBSTEPS 12
+static int glgo_graded_m(int s) { return s < 1 ? 16 : s < 2 ? 8 : s < 6 ? 4 : s < GLGO_GRADED_SUBSTEPS ? 2 : 1; }
 
 /* Classical RK4, n_sub equal nominal substeps over [0,dt] (each split into m micro-steps by the guards above), inputs
  * held constant (greenlight_model.cpp:59-63 passes p=[u;d;p] as integrator parameters => zero-order hold).
