@@ -514,7 +514,7 @@ GLG_HD void glg_unit(const KV &K, const CV &C, const HV &H, const P &p, const do
 // unit -> group-warp assignment.  Row w lists the units group warp w evaluates (-1 pads).  NG = number of group warps.
 // Balanced on FP64 instruction counts (tools/sasssim): each sub-partition (warp id mod 4) gets about a quarter of the work.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int GLG_MAXUNITS_PER_WARP = 4;
+constexpr int GLG_MAXUNITS_PER_WARP = 5;
 struct GlgAssign {
     int n_warps;
     int unit[16][GLG_MAXUNITS_PER_WARP];
@@ -543,10 +543,26 @@ GLG_HD constexpr GlgAssign glg_assign(int ng) {
         for (int w = 0; w < 12; ++w)
             for (int k = 0; k < 2; ++k) a.unit[w][k] = t[w][k];
     } else if (ng == 4) {  // one fat warp per sub-partition (throughput layouts: all warps of a sub-partition run the same code)
-        const int t[4][4] = {{U_FIR, U_TRANSP, U_COVER, -1}, {U_PHOTO, U_OPT, U_THSCR, -1}, {U_FLOWS, U_PIPES, U_MAINT, -1},
-                             {U_SCR, U_VENT, U_FLOOR, U_BLSCR}};
+#ifndef GLG_ASSIGN4
+#define GLG_ASSIGN4 0
+#endif
+#if GLG_ASSIGN4 == 0
+        const int t[4][5] = {{U_FIR, U_TRANSP, U_COVER, -1, -1}, {U_PHOTO, U_OPT, U_THSCR, -1, -1}, {U_FLOWS, U_PIPES, U_MAINT, -1, -1},
+                             {U_SCR, U_VENT, U_FLOOR, U_BLSCR, -1}};
+        // measured at B = 262 144 (graded, 300 RK4 steps): 0 = 30.46 ms per step; 1 = 33.31; 2 = 33.98; 3 = 30.48 -- equal FP64
+        // instruction counts per warp do not balance the roles, the dependency chains inside the units do
+#elif GLG_ASSIGN4 == 1  // FP64 instructions per warp 225 / 234 / 227 / 232 instead of 255 / 234 / 232 / 197
+        const int t[4][5] = {{U_PHOTO, U_TRANSP, -1, -1, -1}, {U_FIR, U_PIPES, U_MAINT, -1, -1}, {U_FLOWS, U_THSCR, U_BLSCR, -1, -1},
+                             {U_SCR, U_VENT, U_FLOOR, U_COVER, U_OPT}};
+#elif GLG_ASSIGN4 == 2
+        const int t[4][5] = {{U_PHOTO, U_TRANSP, -1, -1, -1}, {U_FIR, U_PIPES, U_OPT, -1, -1}, {U_FLOWS, U_THSCR, U_BLSCR, -1, -1},
+                             {U_SCR, U_VENT, U_FLOOR, U_COVER, U_MAINT}};
+#else
+        const int t[4][5] = {{U_FIR, U_TRANSP, U_OPT, -1, -1}, {U_PHOTO, U_COVER, U_THSCR, -1, -1}, {U_FLOWS, U_PIPES, U_MAINT, -1, -1},
+                             {U_SCR, U_VENT, U_FLOOR, U_BLSCR, -1}};
+#endif
         for (int w = 0; w < 4; ++w)
-            for (int k = 0; k < 4; ++k) a.unit[w][k] = t[w][k];
+            for (int k = 0; k < 5; ++k) a.unit[w][k] = t[w][k];
     } else if (ng == 8) {
         const int t[8][3] = {{U_FIR, -1, -1},          {U_PHOTO, U_FLOOR, -1}, {U_FLOWS, U_MAINT, -1}, {U_SCR, U_VENT, -1},
                              {U_THSCR, U_TRANSP, -1},  {U_OPT, U_COVER, -1},   {U_PIPES, -1, -1},      {U_BLSCR, -1, -1}};

@@ -1,6 +1,6 @@
 """Small runs of every kernel variant for compute-sanitizer (memcheck / racecheck): both layouts of the step kernel, kernel A, both
 integrator contracts, fp32 units, parametric uncertainty, the on-device rule-based controller, a non-default observation stack
-(no forecast block / StateObservations), the split host path, the device rollout kernels (store, GAE, carry), termination with
+(no forecast block / StateObservations), the overlapped and the split host path, the device rollout kernels (store, GAE, carry), termination with
 in-place reset.
     compute-sanitizer --tool memcheck python tools/sanitize_run.py ; compute-sanitizer --tool racecheck python tools/sanitize_run.py"""
 import os, sys
@@ -29,7 +29,8 @@ for kw in (dict(integrator="fixed", role_warps=2), dict(integrator="fixed", role
     if kw.get("role_warps") != 1:
         env.step_rule_based_tensor()
     a = A.cpu().numpy()
-    env.step(a)
+    for _ in range(3):  # the first host step has no prediction to work from; the following ones run the overlapped path proper
+        env.step(a)
     env.step_split(a)[0].full([0, B - 1])
     roll = DeviceRollout(env, 3, gamma=0.96, gae_lambda=0.9)
     roll.reset()
