@@ -281,6 +281,8 @@ class GreenLightVecEnv(_VecEnvBase):
         self._pin = [torch.empty((B, self.obs_dim), dtype=torch.float32).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory(),
                      torch.empty(B, dtype=torch.uint8).pin_memory(), torch.empty((B, self.nu), dtype=torch.float32).pin_memory()]
         self._obs_host, self._rew_host, self._done_host, self._act_host = (t.numpy() for t in self._pin)
+        # addresses of the fixed host buffers (`ndarray.ctypes.data` costs ~2 us per access: 9 us of a 0.86 ms step otherwise)
+        self._rew_ptr, self._done_ptr, self._act_ptr = (a.ctypes.data for a in (self._rew_host, self._done_host, self._act_host))
         # Observation arrays returned by `step()` (numpy path) -- explicit ownership, no reference counting:
         #   obs_ring = n >= 2 (default 4): the arrays ARE page-locked buffers of a ring of n, handed out round-robin; the array
         #       returned by step k stays untouched until step k + n (no host copy: 0.29 ms per step at B = 4096).  Safe for SB3's
@@ -370,14 +372,14 @@ class GreenLightVecEnv(_VecEnvBase):
             B = self.num_envs
             self._ring = [self._pin[0]] + [torch.empty((B, self.obs_dim), dtype=torch.float32).pin_memory() for _ in range(max(self.obs_ring - 1, 0))]
             self._ring_np = [t.numpy() for t in self._ring]
+            self._ring_ptr = [a.ctypes.data for a in self._ring_np]
         n = len(self._ring_np)
-        obs_buf = self._ring_np[self._ring_pos]
+        obs_buf, obs_ptr = self._ring_np[self._ring_pos], self._ring_ptr[self._ring_pos]
         self._ring_pos = (self._ring_pos + 1) % n
         # glg_step_host works on the handle's own stream: order it behind whatever the caller enqueued on torch's current
         # stream (reset_tensor / step_tensor / episode_stats(clear=True) followed by step()) -- an event wait, no host sync
         self._lib.glg_host_path_after(self._h, _raw_stream(self.device_index))
-        _lib.check(self._lib.glg_step_host(self._h, self._actions.ctypes.data, obs_buf.ctypes.data,
-                                           self._rew_host.ctypes.data, self._done_host.ctypes.data), self._h, "glg_step_host")
+        _lib.check(self._lib.glg_step_host(self._h, self._act_ptr, obs_ptr, self._rew_ptr, self._done_ptr), self._h, "glg_step_host")
         dones = self._done_host.astype(bool)
         obs = obs_buf.copy() if self.obs_ring == 0 else obs_buf
         # rewards: float64 on the device (the reference returns a Python float); the VecEnv protocol carries float32
