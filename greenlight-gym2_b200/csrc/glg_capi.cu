@@ -526,6 +526,7 @@ extern "C" int glg_step_rule_based(glg_handle *h, const double *noise_dev, void 
 // known-answer entry for the controller alone: one thread per point
 __global__ void glg_rule_control_kernel(GlgStepArgs A, const double *x, const double *d, const double *hod, const double *doy,
                                         double *u, int n) {
+    glg_exp_tbl_fill();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double xl[GLG_NX], dl[GLG_ND], ul[GLG_NU];

@@ -532,6 +532,7 @@ struct GlgStepSmem {
 
 template <bool GENERAL, bool NOISY, int NT>
 __global__ void __launch_bounds__(NT) glg_step_kernel(const __grid_constant__ GlgUniform U, const __grid_constant__ GlgStepArgs A) {
+    glg_exp_tbl_fill();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_wtile = reinterpret_cast<double *>(smem_raw);                         // [(Np+1)][10], 16-B aligned
     double *s_cols = s_wtile + (size_t)(A.Np + 1) * GLG_ND;                          // [kColRows][NT]
@@ -588,6 +589,7 @@ __global__ void __launch_bounds__(NT) glg_step_kernel(const __grid_constant__ Gl
 template <int NT>
 __global__ void __launch_bounds__(NT) glg_reset_kernel(const __grid_constant__ GlgStepArgs A, const unsigned char *mask,
                                                        const int *table_ids) {
+    glg_exp_tbl_fill();
     const int e = blockIdx.x * NT + threadIdx.x;
     if (e >= A.B) return;
     if (mask && !mask[e]) return;
@@ -650,6 +652,7 @@ template <bool GENERAL, bool PER_ENV_P, int NT>
 __global__ void __launch_bounds__(NT) glg_evalf_kernel(const __grid_constant__ GlgUniform U, const double *xin, const double *uin,
                                                        const double *din, const double *pin, double *xout,
                                                        unsigned char *bad_out, int B, double dt, int n_sub, int integrator) {
+    glg_exp_tbl_fill();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_cols = reinterpret_cast<double *>(smem_raw);  // [2*28 + H_COUNT][NT]
     const int tid = threadIdx.x;
@@ -702,6 +705,7 @@ __global__ void __launch_bounds__(256) glg_fma_peak_kernel(T *out, int iters, T 
 
 // accuracy probe for glg_math.h (tests only; not on the step path)
 __global__ void glg_math_kernel(int op, const double *in, double *out, int n) {
+    glg_exp_tbl_fill();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = glg_math_eval(op, in[i]);
 }

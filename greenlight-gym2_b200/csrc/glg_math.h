@@ -77,6 +77,20 @@ GLG_COEF double glg_kExpT[5] = {0x1.71547652b82fep+7 /*128/ln2*/, -0x1.62e42fefa
     0x1.f50765b6e4540p+0, 0x1.f7bfdad9cbe14p+0, 0x1.fa7c1819e90d8p+0, 0x1.fd3c22b8f71f1p+0
 #if defined(__CUDACC__)
 __device__ const double glg_exp_tbl_dev[128] = {GLG_EXP_TABLE_VALUES};
+// GLG_EXP_SMEM: per-CTA copy of the table in shared memory (a 32-bit address and an LDS instead of a 64-bit address and an L1 load:
+// two integer instructions fewer per exp).  Every kernel that evaluates an exp calls glg_exp_tbl_fill() before its first use.
+#ifndef GLG_EXP_SMEM
+#define GLG_EXP_SMEM 1
+#endif
+#if GLG_EXP_SMEM
+__shared__ double glg_exp_tbl_sh[128];
+#endif
+__device__ __forceinline__ void glg_exp_tbl_fill() {
+#if GLG_EXP_SMEM
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) glg_exp_tbl_sh[i] = glg_exp_tbl_dev[i];
+    __syncthreads();
+#endif
+}
 #endif
 static const double glg_exp_tbl_host[128] = {GLG_EXP_TABLE_VALUES};
 GLG_COEF double glg_kLog[9] = {
@@ -142,10 +156,26 @@ GLG_HD double glg_sqrt(double x) {
 // ---- exp (table-driven, see glg_kExpT).  2^m goes through the exponent field; m is clamped on the integer pipe so the
 //      result stays a normal number and the function saturates (~1e-308 / ~1e308) instead of wrapping for |x| > 708.
 GLG_HD double glg_exp_tbl(int j) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && GLG_EXP_SMEM
+    // address = base + 8 j as ONE multiply-add (left to itself the compiler emits shift, mask and add), 32-bit shared-window load
+    unsigned a;
+    double T;
+    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a) : "r"(j), "r"((unsigned)__cvta_generic_to_shared(glg_exp_tbl_sh)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(a));
+    return T;
+#elif defined(__CUDA_ARCH__)
     return __ldg(glg_exp_tbl_dev + j);
 #else
     return glg_exp_tbl_host[j];
+#endif
+}
+// y 2^m for y in [1, 2) and m in [-1021, 1023]: m goes into the exponent field -- of the high word alone on the device (a 64-bit
+// integer add costs a second instruction for a carry that cannot happen)
+GLG_HD double glg_scale2(double y, int m) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(y) + (m << 20), __double2loint(y));
+#else
+    return glg_bits2d(glg_d2bits(y) + ((long long)m << 52));
 #endif
 }
 GLG_HD double glg_exp(double x) {
@@ -162,7 +192,7 @@ GLG_HD double glg_exp(double x) {
     const double y = glg_fma(T, p, T);   // in [1, 2)
     int m = k >> 7;
     m = m < -1021 ? -1021 : (m > 1023 ? 1023 : m);
-    return glg_bits2d(glg_d2bits(y) + ((long long)m << 52));
+    return glg_scale2(y, m);
 }
 
 // ---- accurate exp (<= 4e-16 relative): two-constant argument reduction, degree-5 polynomial.  For once-per-env-step code
@@ -181,7 +211,7 @@ GLG_HD double glg_exp_acc(double x) {
     const double y = glg_fma(T, glg_fma(r * r, q, r), T);
     int m = k >> 7;
     m = m < -1021 ? -1021 : (m > 1023 ? 1023 : m);
-    return glg_bits2d(glg_d2bits(y) + ((long long)m << 52));
+    return glg_scale2(y, m);
 }
 
 // ---- N independent exps with their dependency chains interleaved in SOURCE order.  The hardware issues in order and
@@ -212,7 +242,7 @@ GLG_HD void glg_exp_n(const double (&x)[N], double (&y)[N]) {
         const double v = glg_fma(T[i], q[i], T[i]);
         int m = k[i] >> 7;
         m = m < -1021 ? -1021 : (m > 1023 ? 1023 : m);
-        y[i] = glg_bits2d(glg_d2bits(v) + ((long long)m << 52));
+        y[i] = glg_scale2(v, m);
     }
 }
 // N independent reciprocals, interleaved the same way

@@ -621,6 +621,7 @@ __global__ void __launch_bounds__(32 * (NG + (FUSED ? 0 : GLG_NO)), MINB) glg_st
                                                                                                  const __grid_constant__ GlgStepArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     static_assert(!FUSED || NG == GLG_NO, "fused layout: one group role per owner");
+    glg_exp_tbl_fill();
     constexpr int NL = GLG_ROLE_LANES;
     constexpr int NT = 32 * (NG + (FUSED ? 0 : GLG_NO));
     using PL = GlgPlan<NG, GENERAL>;
