@@ -11,4 +11,4 @@ bash tools/ncu_r2.sh > $O/ncu_r2.log 2>&1; tail -2 $O/ncu_r2.log
 (for w in kernels torch; do python tools/rollout_policy.py --envs 65536 --steps 16 --wrapper $w; done) > $O/r2_rollout_policy.txt 2>&1; tail -4 $O/r2_rollout_policy.txt
 python tools/layout_sweep.py > $O/r2_layout_sweep.txt 2>&1; tail -3 $O/r2_layout_sweep.txt
 timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $O/r2_sanitizer_memcheck.log 2>&1; tail -3 $O/r2_sanitizer_memcheck.log
-timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_run.py > $O/r2_sanitizer_racecheck.log 2>&1; tail -3 $O/r2_sanitizer_racecheck.log
+timeout 2000 compute-sanitizer --tool racecheck python tools/sanitize_run.py > $O/r2_sanitizer_racecheck.log 2>&1; tail -3 $O/r2_sanitizer_racecheck.log
