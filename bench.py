@@ -397,12 +397,12 @@ def run_ours(args, rank, world, local):
         barrier, dev, world, rank, local, peak64)
     configs["config3_fp32_uncertainty"] = extra_config(
         "config3_fp32_uncertainty", "BASELINE configs[2]: 262 144 envs per GPU, fp32 throughput mode (flux units fp32, RK4 state fp64), "
-        "uncertainty_scale 0.3 (device Philox, 34 draws per env-step), start day randomised over the 19 Bleiswijk GL2009 tables; 12 warm-up "
-        "steps: in the first 8 steps after a reset ~10 % of the envs are pruned by the harvest terms (cLeafMax redrawn below the initial "
-        "leaf mass), their CTAs run twice the RK4 steps (27.5 instead of 18.2 ms per step); the other 5750 steps of a season cost what is "
-        "timed here (profiles/r2_season_throughput.txt)",
+        "uncertainty_scale 0.3 (device Philox, 34 draws per env-step), start day randomised over the 19 Bleiswijk GL2009 tables; 24 warm-up "
+        "steps: in the first steps after a reset ~10 % of the envs are pruned by the harvest terms (cLeafMax redrawn below the initial "
+        "leaf mass) and their CTAs run twice the RK4 steps (27.5 ms per step; 20.5 after 12 steps); a whole season averages 18.2 ms per "
+        "step (profiles/r2_season_throughput.txt)",
         dict(integrator=args.integrator, precision="fp32", uncertainty_scale=0.3, base_env_params=dict(start_train_day=0, end_train_day=18)),
-        262144, Kx, 12, flush, barrier, dev, world, rank, local, peak32)
+        262144, Kx, 24, flush, barrier, dev, world, rank, local, peak32)
     if world >= 8:
         configs["config4_65536_per_gpu"] = extra_config(
             "config4_65536_per_gpu", "BASELINE configs[3] shape: 65 536 envs per GPU x 8 GPUs, fp64, U(-1,1) actions resident on the device",
