@@ -572,7 +572,8 @@ static bool is_pinned(const void *p) {
     return pinned;
 }
 
-// Rows [lo, hi) of a per-env host loop on up to `max_threads` threads; small batches run inline (a thread costs ~20 us to start).
+// Rows [lo, hi) of a per-env host loop on up to 8 threads; small batches run inline (a thread costs ~20 us to start).  A chunk
+// whose thread cannot be started (no exception may cross the C boundary) is done by the caller.
 template <class F>
 static void host_rows(size_t n_rows, size_t bytes_per_row, const F &f) {
     const size_t total = n_rows * bytes_per_row;
@@ -588,7 +589,12 @@ static void host_rows(size_t n_rows, size_t bytes_per_row, const F &f) {
     const size_t chunk = (n_rows + nt - 1) / nt;
     for (size_t t = 1; t < nt; ++t) {
         const size_t lo = t * chunk, hi = lo + chunk < n_rows ? lo + chunk : n_rows;
-        if (lo < hi) th.emplace_back([&f, lo, hi] { f(lo, hi); });
+        if (lo >= hi) continue;
+        try {
+            th.emplace_back([&f, lo, hi] { f(lo, hi); });
+        } catch (...) {
+            f(lo, hi);
+        }
     }
     f((size_t)0, chunk < n_rows ? chunk : n_rows);
     for (auto &t : th) t.join();
