@@ -225,6 +225,25 @@ def test_default_integrator_contract_against_tight_truth(truth_rb):
     assert DEFAULT_INTEGRATOR == "graded"
 
 
+def test_default_integrator_contract_on_random_action_intervals():
+    """The same gate on the action distribution an exploring agent produces: 120 control intervals of two free-running seasons --
+    U(-1,1) actions (what bench.py feeds) and bang-bang actions (the largest control jumps the rate limit allows) -- each solved with
+    Radau at rtol = atol = 1e-12 (tests/golden/make_truth_random.py).  Default contract: <= 1e-6 in every interval (measured 4.4e-10
+    uniform, 1.3e-9 bang-bang), exactly 300 RK4 steps each."""
+    import oracle_binding as ob
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "truth_random_actions.npz"))
+    n = len(z["k"])
+    assert n >= 100 and set(z["season"].tolist()) == {0, 1} and len(z["skipped"]) == 0
+    eg, micro = np.zeros(n), np.zeros(n)
+    for i in range(n):
+        yg, bad, m = ob.evalf_ex(z["x"][i], z["u"][i], z["d"][i], z["p"], 900.0, 260, 3)
+        assert not bad
+        eg[i], micro[i] = _rel(yg, z["y"][i]), m
+    assert eg.max() <= 1e-6                       # the gate
+    assert eg.max() <= 1e-8 and np.median(eg) <= 1e-10   # what is measured (regression guard)
+    assert micro.min() == 300 and micro.max() <= 320
+
+
 def test_implicit_cpu_baseline_solver(truth_rb):
     """oracle/glg_oracle_bdf.c -- the CVODES-class CPU baseline (variable-order BDF/NDF, rtol = atol = 1e-6): its error against
     truth sits in the band an implicit multistep solver at that tolerance delivers (2e-7 ... 2e-6 per step in quiet
