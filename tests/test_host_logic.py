@@ -228,3 +228,25 @@ def test_role_loops_fit_the_instruction_cache():
     assert m, out
     span = int(m.group(2), 16) - int(m.group(1), 16) + 16
     assert span <= 32 * 1024 - 64, f"role loops span {span} B"
+
+
+def test_bench_contract_helpers():
+    """bench.py's workload description, flop model and source hash (the pieces both arms and the committed ncu record depend on)."""
+    import argparse
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    args = argparse.Namespace(integrator="graded", n_sub=None, envs=4096, gpus=1, role_warps=0)
+    cfg = bench.workload_config(args)
+    assert cfg["n_sub"] == 260 and cfg["envs_per_gpu"] == 4096 and "300 RK4 steps" in cfg["integrator"] and "model" not in cfg
+    assert "BASELINE configs[1]" in cfg["workload"]
+    args.integrator = "fixed"
+    assert bench.workload_config(args)["n_sub"] == 600
+    assert bench.flop_per_env_step(300) == 3968 * 300 + 529 and bench.flop_per_env_step(600) == 2381329
+    assert bench.algorithmic_bytes_per_env_step(263) == 1749
+    h = bench.csrc_hash()
+    assert len(h) == 16 and int(h, 16) >= 0
+    prof = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    assert {"csrc_sha16", "graded_fp64_B4096", "fixed_fp64_B4096", "graded_fp64_B262144"} <= set(prof)
+    assert prof["csrc_sha16"] == open(os.path.join(ROOT, "profiles", "r2_csrc_sha16.txt")).read().strip()
